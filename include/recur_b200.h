@@ -1,0 +1,179 @@
+/* recur_b200.h — array-of-nets ("synchronic mini-batch") entry points and
+ * device control of librecur_b200.so.
+ *
+ * recur trains on N cloned nets that share weights and gradient arrays and
+ * are stepped one after another on one thread (rnn_new_training_set,
+ * reference recur-nn-init.c:221-243).  The loops that do the stepping live
+ * in the callers; these calls replace each such loop by one launch sequence
+ * over all streams, keeping activations, history and errors in HBM:
+ *
+ *   reference loop                                 replaced by
+ *   charmodel-predict.c:293-311 (text-predict)     rnn_batch_char_step / rnn_batch_text_train
+ *   gstclassify.c:2201-2239 (classify train)       rnn_batch_opinion + rnn_batch_set_errors
+ *                                                  + rnn_batch_calc_deltas + rnn_batch_advance
+ *   gstrnnca.c:723-728, 811-820 (rnnca)            rnn_batch_opinion / rnn_batch_get_outputs
+ *   charmodel-multi-predict.c:350-372              rnn_batch_opinion + rnn_batch_get_outputs
+ *
+ * Every function is plain C: pointers and sizes only.  Host arrays passed in
+ * are read before the call returns unless stated; nothing here is reentrant
+ * (the reference API is not either: SURVEY.md §8b "Threading").
+ *
+ * Errors follow the reference's conventions (SURVEY.md §8b "Errors"):
+ * allocation or CUDA failure prints one line to stderr and abort()s; calls
+ * that can fail for user-visible reasons return NULL / -1.
+ */
+#ifndef RECUR_B200_H
+#define RECUR_B200_H 1
+
+#include "recur-nn.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- device / library state ---------------------------------------------- */
+
+/* Number of usable CUDA devices (0 when there is no driver or no GPU).
+   Never aborts. */
+int rnn_b200_device_count(void);
+
+/* Select the CUDA device used for all subsequently created nets (default 0,
+   or $RECUR_B200_DEVICE).  Returns 0, or -1 if the ordinal does not exist. */
+int rnn_b200_set_device(int ordinal);
+
+/* Block until all queued device work of this library is complete. */
+void rnn_b200_synchronize(void);
+
+/* The CUDA stream (cudaStream_t) the library launches on, as a void*; for
+   callers that time with CUDA events or interleave their own work. */
+void *rnn_b200_stream(void);
+
+/* Library version string, e.g. "recur-b200 0.1 (sm_100a)". */
+const char *rnn_b200_version(void);
+
+/* Count of kernels launched by this library since load (monotonic). */
+uint64_t rnn_b200_kernel_launches(void);
+
+/* Choose the matrix engine for batches: 0 = automatic (tensor cores when the
+   batch has >= 64 streams and the sizes allow, FP32 FMA otherwise),
+   1 = force FP32 FMA kernels, 2 = force tensor-core kernels (aborts if the
+   shapes do not allow them).  Returns the previous setting. */
+int rnn_b200_set_engine(int engine);
+
+/* ---- mirrors --------------------------------------------------------------- */
+
+/* Refresh the host mirrors of one net (input_layer/history, hidden_layer,
+   output_layer, i/h/o_error, ih_scale, min_error_factor) from the device. */
+void rnn_b200_pull(RecurNN *net);
+
+/* Push the host mirrors of one net (history ring, hidden_layer, o_error,
+   min_error_factor) to its device slot; needed only after host code has
+   rewritten state that the per-net calls do not upload by themselves. */
+void rnn_b200_push(RecurNN *net);
+
+/* ---- array-of-nets calls --------------------------------------------------- */
+
+typedef struct RnnBatch RnnBatch;
+
+/* Sums the text-predict loop accumulates per character position
+   (charmodel-predict.c:300-303): error += e; entropy += capped_log2f(1-e);
+   correct += (winner == next). */
+typedef struct RnnBatchCharStats {
+  double error;
+  double entropy;
+  int64_t correct;
+  int64_t count;
+} RnnBatchCharStats;
+
+/* Bind n nets that share weights (a training set, or any clones of one
+   parent) into a batch.  All nets must come from the same rnn_new /
+   rnn_clone family and have the same BPTT depth.  Returns NULL (with a line
+   on stderr) if they do not.  The nets stay valid and usable one by one. */
+RnnBatch *rnn_batch_new(RecurNN **nets, int n_nets);
+void rnn_batch_delete(RnnBatch *batch);
+int rnn_batch_size(const RnnBatch *batch);
+
+/* rnn_bptt_advance (recur-nn.c:696-704) for every stream. */
+void rnn_batch_advance(RnnBatch *batch);
+
+/* Write every stream's real_inputs: `inputs` is n x input_size floats, row
+   per stream. */
+void rnn_batch_set_inputs(RnnBatch *batch, const float *inputs);
+
+/* one_hot_opinion's input half (charmodel-helpers.h:16-33): zero the inputs
+   and set inputs[hot[j]] = 1 for stream j. */
+void rnn_batch_set_one_hot(RnnBatch *batch, const u8 *hot);
+
+/* rnn_opinion(net, NULL, presynaptic_noise) (recur-nn.c:83-154) for every
+   stream; the outputs stay on the device. */
+void rnn_batch_opinion(RnnBatch *batch, float presynaptic_noise);
+
+/* Copy out n x output_size floats (one row per stream); synchronises. */
+void rnn_batch_get_outputs(RnnBatch *batch, float *outputs);
+
+/* Copy out n x hidden_size+1 floats: each stream's hidden_layer[0..hidden_size]. */
+void rnn_batch_get_hiddens(RnnBatch *batch, float *hiddens);
+
+/* net_error_bptt's second half (charmodel-predict.c:21-26) for every stream:
+   o_error = onehot(target) - softmax(output) with badmaths.h's fast_expf and
+   clamp; err[j] = o_error[target[j]]; winner[j] = argmax.  err and winner
+   may be NULL.  Synchronises only if one of them is given. */
+void rnn_batch_softmax_error(RnnBatch *batch, const u8 *target,
+    float *err, int32_t *winner);
+
+/* Write every stream's bptt->o_error: n x output_size floats. */
+void rnn_batch_set_errors(RnnBatch *batch, const float *o_error);
+
+/* rnn_bptt_calc_deltas(net, j || accumulate, NULL) (recur-nn.c:707-772) for
+   streams j = 0..n-1 in one go: with accumulate == 0 the shared ih/ho deltas
+   are overwritten by the sum over all streams, otherwise added to. */
+void rnn_batch_calc_deltas(RnnBatch *batch, int accumulate);
+
+/* rnn_apply_learning(nets[0], ...) (recur-nn.c:601-678). */
+void rnn_batch_apply_learning(RnnBatch *batch, int learning_style, float momentum);
+
+/* One character position of the synchronic text-predict loop
+   (charmodel-predict.c:293-311): advance, one-hot forward on cur[j], softmax
+   error against next[j], deltas summed over streams, one weight update.
+   `stats` (may be NULL) is ADDED to; reading it back synchronises. */
+void rnn_batch_char_step(RnnBatch *batch, const u8 *cur, const u8 *next,
+    int learning_style, float momentum, RnnBatchCharStats *stats);
+
+/* Keep an encoded text on the device for rnn_batch_text_train. */
+void rnn_batch_text_upload(RnnBatch *batch, const u8 *text, int len);
+
+/* `steps` consecutive positions of that loop over the uploaded text, stream j
+   reading position i + j * ((len - 1) / n) as rnn_char_epoch does
+   (charmodel-predict.c:273,295-298), momentum following
+   rnn_calculate_momentum_soft_start.  Nothing crosses PCIe per step.
+   Returns the position after the last step (wrapped into [0, len-1)). */
+int rnn_batch_text_train(RnnBatch *batch, int start, int steps,
+    int learning_style, float momentum, float momentum_soft_start,
+    RnnBatchCharStats *stats);
+
+/* Forward-only variant (rnn_opinion steps/sec): steps one-hot forwards per
+   stream over the uploaded text, no training. */
+int rnn_batch_text_forward(RnnBatch *batch, int start, int steps);
+
+/* Refresh host mirrors and struct scalars (generation, ih_scale,
+   min_error_factor, bptt->index) of every net in the batch. */
+void rnn_batch_pull(RnnBatch *batch);
+
+/* ---- multi-GPU: streams shard across processes, deltas are summed -------- */
+
+/* One process per GPU.  The caller obtains a 128-byte NCCL unique id on rank
+   0, distributes it by any means (bench.py uses torch.distributed), and every
+   rank joins.  After rnn_b200_comm_join, rnn_batch_calc_deltas /
+   rnn_batch_char_step / rnn_batch_text_train all-reduce (sum) the
+   concatenated [ih_delta | ho_delta] over the ranks before the update, so
+   every rank applies the identical update to its weight replica
+   (SURVEY.md §8e).  Returns 0 on success, -1 if NCCL cannot be loaded. */
+int rnn_b200_comm_unique_id(void *id128);
+int rnn_b200_comm_join(const void *id128, int rank, int n_ranks);
+void rnn_b200_comm_leave(void);
+int rnn_b200_comm_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,527 @@
+/* rb_batch.cu — the array-of-nets entry points (include/recur_b200.h).
+ *
+ * These replace the callers' `for j in streams` loops (SURVEY.md §8b "New
+ * batch entry points").  State stays in the device pool between calls; host
+ * mirrors of the nets are refreshed only by rnn_batch_pull / rnn_b200_pull
+ * (each net is flagged dev_ahead so that a later per-net call pulls first).
+ */
+#include "rb_kernels.h"
+#include "rb_host.h"
+#include "rb_comm.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define CUDA_OR_DIE(call) do {                                          \
+    cudaError_t e_ = (call);                                            \
+    if (e_ != cudaSuccess)                                              \
+      rb_die("recur-b200: %s failed at %s:%d: %s", #call, __FILE__,     \
+          __LINE__, cudaGetErrorString(e_));                            \
+  } while (0)
+
+struct RnnBatch {
+  RbNet **nets;
+  int n;
+  RbPool *pool;
+  RbGroup *group;
+  int contiguous, base;
+  int *slots_dev;        /* only when the slots are not one ascending run */
+  /* device scratch */
+  u8 *cur_dev, *next_dev;
+  float *err_dev;
+  int *winner_dev;
+  RbCharAccum *accum_dev;
+  float *lr_dev, *mef_dev;
+  float *io_dev;         /* n x max(input_size, o_size, hidden_size+1) floats */
+  size_t io_floats;
+  u8 *text_dev;
+  int text_len;
+  /* pinned staging */
+  u8 *sym_host;          /* 2n */
+  float *f_host;         /* like io_dev */
+  int *i_host;           /* n */
+  float *lr_host;        /* n, last uploaded learn rates */
+  RbCharAccum *accum_host;
+};
+
+static int g_engine = 0;
+
+extern "C" int
+rnn_b200_set_engine(int engine)
+{
+  int old = g_engine;
+  if (engine >= 0 && engine <= 2)
+    g_engine = engine;
+  return old;
+}
+
+extern "C" int
+rb_engine(void)
+{
+  return g_engine;
+}
+
+static void
+batch_view(RnnBatch *b, RbView *v)
+{
+  rb_view_of_net(b->nets[0], v);
+  v->cap = b->pool->cap; /* pools never grow while a batch exists on them... */
+  v->n = b->n;
+  v->contiguous = b->contiguous;
+  v->base = b->base;
+  v->slots = b->contiguous ? b->pool->iota + b->base : b->slots_dev;
+}
+
+static void
+mark_ahead(RnnBatch *b)
+{
+  for (int j = 0; j < b->n; j++)
+    b->nets[j]->dev_ahead = 1;
+}
+
+extern "C" RnnBatch *
+rnn_batch_new(RecurNN **nets, int n_nets)
+{
+  if (!nets || n_nets < 1) {
+    fprintf(stderr, "rnn_batch_new: need at least one net\n");
+    return NULL;
+  }
+  rb_require_device("rnn_batch_new");
+  RnnBatch *b = (RnnBatch *)calloc(1, sizeof(RnnBatch));
+  b->nets = (RbNet **)calloc(n_nets, sizeof(RbNet *));
+  b->n = n_nets;
+  for (int j = 0; j < n_nets; j++) {
+    b->nets[j] = rb_net_of(nets[j]);
+    if (b->nets[j]->pool != b->nets[0]->pool ||
+        nets[j]->ih_weights != nets[0]->ih_weights) {
+      fprintf(stderr, "rnn_batch_new: net %d does not share weights and BPTT depth "
+          "with net 0\n", j);
+      free(b->nets);
+      free(b);
+      return NULL;
+    }
+  }
+  /* a previous batch may have left the structs behind the device */
+  for (int j = 0; j < n_nets; j++)
+    if (b->nets[j]->dev_ahead)
+      rb_net_pull(b->nets[j]);
+  b->pool = b->nets[0]->pool;
+  b->group = b->nets[0]->group;
+  b->base = b->nets[0]->slot;
+  b->contiguous = 1;
+  for (int j = 0; j < n_nets; j++)
+    if (b->nets[j]->slot != b->base + j)
+      b->contiguous = 0;
+  const RbDims *d = &b->group->d;
+  size_t n = (size_t)n_nets;
+  if (!b->contiguous) {
+    int *slots = (int *)malloc(n * sizeof(int));
+    for (int j = 0; j < n_nets; j++)
+      slots[j] = b->nets[j]->slot;
+    CUDA_OR_DIE(cudaMalloc((void **)&b->slots_dev, n * sizeof(int)));
+    CUDA_OR_DIE(cudaMemcpy(b->slots_dev, slots, n * sizeof(int), cudaMemcpyHostToDevice));
+    free(slots);
+  }
+  size_t widest = d->input_size;
+  if ((size_t)d->o_size > widest) widest = d->o_size;
+  if ((size_t)d->hidden_size + 1 > widest) widest = d->hidden_size + 1;
+  b->io_floats = n * widest;
+  CUDA_OR_DIE(cudaMalloc((void **)&b->cur_dev, n));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->next_dev, n));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->err_dev, n * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->winner_dev, n * sizeof(int)));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->accum_dev, sizeof(RbCharAccum)));
+  CUDA_OR_DIE(cudaMemset(b->accum_dev, 0, sizeof(RbCharAccum)));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->lr_dev, n * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->mef_dev, n * sizeof(float)));
+  CUDA_OR_DIE(cudaMalloc((void **)&b->io_dev, b->io_floats * sizeof(float)));
+  CUDA_OR_DIE(cudaHostAlloc((void **)&b->sym_host, 2 * n, cudaHostAllocDefault));
+  CUDA_OR_DIE(cudaHostAlloc((void **)&b->f_host, b->io_floats * sizeof(float), cudaHostAllocDefault));
+  CUDA_OR_DIE(cudaHostAlloc((void **)&b->i_host, n * sizeof(int), cudaHostAllocDefault));
+  CUDA_OR_DIE(cudaHostAlloc((void **)&b->lr_host, n * sizeof(float), cudaHostAllocDefault));
+  CUDA_OR_DIE(cudaHostAlloc((void **)&b->accum_host, sizeof(RbCharAccum), cudaHostAllocDefault));
+  /* per-stream training parameters as the structs have them now */
+  if (b->pool->has_bptt) {
+    RbView v;
+    batch_view(b, &v);
+    for (int j = 0; j < n_nets; j++) {
+      b->lr_host[j] = nets[j]->bptt->learn_rate;
+      b->f_host[j] = nets[j]->bptt->min_error_factor;
+    }
+    CUDA_OR_DIE(cudaMemcpyAsync(b->lr_dev, b->lr_host, n * sizeof(float),
+            cudaMemcpyHostToDevice, rb_stream));
+    CUDA_OR_DIE(cudaMemcpyAsync(b->mef_dev, b->f_host, n * sizeof(float),
+            cudaMemcpyHostToDevice, rb_stream));
+    rbk_set_params(&v, b->lr_dev, b->mef_dev,
+        !!(nets[0]->flags & RNN_NET_FLAG_BPTT_ADAPTIVE_MIN_ERROR));
+  }
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  return b;
+}
+
+extern "C" void
+rnn_batch_delete(RnnBatch *b)
+{
+  if (!b)
+    return;
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  cudaFree(b->slots_dev);
+  cudaFree(b->cur_dev);
+  cudaFree(b->next_dev);
+  cudaFree(b->err_dev);
+  cudaFree(b->winner_dev);
+  cudaFree(b->accum_dev);
+  cudaFree(b->lr_dev);
+  cudaFree(b->mef_dev);
+  cudaFree(b->io_dev);
+  cudaFree(b->text_dev);
+  cudaFreeHost(b->sym_host);
+  cudaFreeHost(b->f_host);
+  cudaFreeHost(b->i_host);
+  cudaFreeHost(b->lr_host);
+  cudaFreeHost(b->accum_host);
+  free(b->nets);
+  free(b);
+}
+
+extern "C" int
+rnn_batch_size(const RnnBatch *b)
+{
+  return b->n;
+}
+
+/* host bookkeeping of rnn_bptt_advance for every net, one kernel for the device */
+extern "C" void
+rnn_batch_advance(RnnBatch *b)
+{
+  RbPool *p = b->pool;
+  for (int j = 0; j < b->n; j++) {
+    RecurNN *net = &b->nets[j]->pub;
+    RecurNNBPTT *bp = net->bptt;
+    bp->index++;
+    if (bp->index == bp->depth)
+      bp->index -= bp->depth;
+    net->input_layer = bp->history + (size_t)bp->index * net->i_size;
+    net->real_inputs = net->input_layer + net->hidden_size + 1;
+    int s = b->nets[j]->slot;
+    int pos = p->pos_shadow[s] + 1;
+    p->pos_shadow[s] = (pos >= p->depth) ? pos - p->depth : pos;
+  }
+  RbView v;
+  batch_view(b, &v);
+  rbk_advance(&v);
+}
+
+extern "C" void
+rnn_batch_set_inputs(RnnBatch *b, const float *inputs)
+{
+  const RbDims *d = &b->group->d;
+  size_t bytes = (size_t)b->n * d->input_size * sizeof(float);
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream)); /* staging buffer reuse */
+  memcpy(b->f_host, inputs, bytes);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->io_dev, b->f_host, bytes, cudaMemcpyHostToDevice, rb_stream));
+  RbView v;
+  batch_view(b, &v);
+  rbk_set_inputs(&v, b->io_dev);
+  mark_ahead(b);
+}
+
+extern "C" void
+rnn_batch_set_one_hot(RnnBatch *b, const u8 *hot)
+{
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  memcpy(b->sym_host, hot, b->n);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
+  RbView v;
+  batch_view(b, &v);
+  rbk_set_one_hot(&v, b->cur_dev);
+  mark_ahead(b);
+}
+
+extern "C" void rb_forward_dispatch(const RbView *v, float noise);
+extern "C" void rb_bptt_dispatch(const RbView *v, float *ih_delta, int accumulate);
+
+static void
+upload_rng_if_noisy(RnnBatch *b, float noise)
+{
+  if (noise == 0.0f)
+    return;
+  /* each stream draws from its own generator: ship the states in, and back
+     out afterwards so the structs stay the source of truth */
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  for (int j = 0; j < b->n; j++) {
+    CUDA_OR_DIE(cudaMemcpyAsync(b->pool->rng + (size_t)b->nets[j]->slot * 4,
+            &b->nets[j]->pub.rng, sizeof(rand_ctx), cudaMemcpyHostToDevice, rb_stream));
+  }
+}
+
+static void
+download_rng_if_noisy(RnnBatch *b, float noise)
+{
+  if (noise == 0.0f)
+    return;
+  for (int j = 0; j < b->n; j++) {
+    CUDA_OR_DIE(cudaMemcpyAsync(&b->nets[j]->pub.rng,
+            b->pool->rng + (size_t)b->nets[j]->slot * 4, sizeof(rand_ctx),
+            cudaMemcpyDeviceToHost, rb_stream));
+  }
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+}
+
+extern "C" void
+rnn_batch_opinion(RnnBatch *b, float presynaptic_noise)
+{
+  if (b->nets[0]->pub.bottom_layer)
+    rb_die("recur-b200: rnn_batch_opinion on a net with a bottom layer is not implemented yet");
+  rb_matrices_to_device(&b->nets[0]->pub);
+  RbView v;
+  batch_view(b, &v);
+  upload_rng_if_noisy(b, presynaptic_noise);
+  rb_forward_dispatch(&v, presynaptic_noise);
+  download_rng_if_noisy(b, presynaptic_noise);
+  mark_ahead(b);
+}
+
+static void
+gather_rows(RnnBatch *b, const float *pool_array, int row_stride, int n_cols, float *out)
+{
+  /* rows of the batch's slots -> packed host rows */
+  if (b->contiguous) {
+    CUDA_OR_DIE(cudaMemcpy2DAsync(out, (size_t)n_cols * sizeof(float),
+            pool_array + (size_t)b->base * row_stride, (size_t)row_stride * sizeof(float),
+            (size_t)n_cols * sizeof(float), b->n, cudaMemcpyDeviceToHost, rb_stream));
+  }
+  else {
+    for (int j = 0; j < b->n; j++)
+      CUDA_OR_DIE(cudaMemcpyAsync(out + (size_t)j * n_cols,
+              pool_array + (size_t)b->nets[j]->slot * row_stride, n_cols * sizeof(float),
+              cudaMemcpyDeviceToHost, rb_stream));
+  }
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+}
+
+extern "C" void
+rnn_batch_get_outputs(RnnBatch *b, float *outputs)
+{
+  const RbDims *d = &b->group->d;
+  gather_rows(b, b->pool->Y, d->o_size, d->output_size, outputs);
+}
+
+extern "C" void
+rnn_batch_get_hiddens(RnnBatch *b, float *hiddens)
+{
+  const RbDims *d = &b->group->d;
+  gather_rows(b, b->pool->Hd, d->h_size, d->hidden_size + 1, hiddens);
+}
+
+extern "C" void
+rnn_batch_softmax_error(RnnBatch *b, const u8 *target, float *err, int32_t *winner)
+{
+  RbView v;
+  batch_view(b, &v);
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  memcpy(b->sym_host + b->n, target, b->n);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice, rb_stream));
+  rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, NULL);
+  if (err)
+    CUDA_OR_DIE(cudaMemcpyAsync(err, b->err_dev, b->n * sizeof(float), cudaMemcpyDeviceToHost, rb_stream));
+  if (winner)
+    CUDA_OR_DIE(cudaMemcpyAsync(winner, b->winner_dev, b->n * sizeof(int), cudaMemcpyDeviceToHost, rb_stream));
+  if (err || winner)
+    CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  mark_ahead(b);
+}
+
+extern "C" void
+rnn_batch_set_errors(RnnBatch *b, const float *o_error)
+{
+  const RbDims *d = &b->group->d;
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  /* pad each row out to o_size with zeros, like the calloc'ed o_error */
+  for (int j = 0; j < b->n; j++) {
+    float *row = b->f_host + (size_t)j * d->o_size;
+    memcpy(row, o_error + (size_t)j * d->output_size, d->output_size * sizeof(float));
+    for (int i = d->output_size; i < d->o_size; i++)
+      row[i] = 0.0f;
+  }
+  if (b->contiguous) {
+    CUDA_OR_DIE(cudaMemcpyAsync(b->pool->OE + (size_t)b->base * d->o_size, b->f_host,
+            (size_t)b->n * d->o_size * sizeof(float), cudaMemcpyHostToDevice, rb_stream));
+  }
+  else {
+    for (int j = 0; j < b->n; j++)
+      CUDA_OR_DIE(cudaMemcpyAsync(b->pool->OE + (size_t)b->nets[j]->slot * d->o_size,
+              b->f_host + (size_t)j * d->o_size, d->o_size * sizeof(float),
+              cudaMemcpyHostToDevice, rb_stream));
+  }
+  mark_ahead(b);
+}
+
+/* learn rates live in the structs: re-upload when a caller changed one */
+static void
+refresh_learn_rates(RnnBatch *b, const RbView *v)
+{
+  int changed = 0;
+  for (int j = 0; j < b->n; j++) {
+    float lr = b->nets[j]->pub.bptt->learn_rate;
+    if (lr != b->lr_host[j])
+      changed = 1;
+  }
+  if (!changed)
+    return;
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  for (int j = 0; j < b->n; j++)
+    b->lr_host[j] = b->nets[j]->pub.bptt->learn_rate;
+  CUDA_OR_DIE(cudaMemcpyAsync(b->lr_dev, b->lr_host, b->n * sizeof(float),
+          cudaMemcpyHostToDevice, rb_stream));
+  rbk_set_params(v, b->lr_dev, NULL, -1);
+}
+
+static void
+calc_deltas_async(RnnBatch *b, int accumulate)
+{
+  RecurNN *proto = &b->nets[0]->pub;
+  RecurNNBPTT *bp = proto->bptt;
+  if (proto->bottom_layer)
+    rb_die("recur-b200: rnn_batch_calc_deltas on a net with a bottom layer is not implemented yet");
+  rb_matrices_to_device(proto);
+  RbView v;
+  batch_view(b, &v);
+  refresh_learn_rates(b, &v);
+  rbk_top_layer(&v, bp->ho_delta, accumulate, NULL, 0);
+  rb_bptt_dispatch(&v, bp->ih_delta, accumulate);
+  /* [ih_delta | ho_delta] are adjacent in the prototype's delta block */
+  if (rb_comm_size() > 1)
+    rb_comm_allreduce_sum(bp->ih_delta, (size_t)proto->ih_size + proto->ho_size);
+  for (int j = 0; j < b->n; j++)
+    b->nets[j]->pub.generation++;
+  mark_ahead(b);
+}
+
+extern "C" void
+rnn_batch_calc_deltas(RnnBatch *b, int accumulate)
+{
+  calc_deltas_async(b, accumulate);
+  if (b->nets[0]->pub.log) {
+    /* only the prototype logs (recur-nn-init.c:237): bring its scalars back */
+    rb_net_pull(b->nets[0]);
+    b->nets[0]->dev_ahead = 1;
+  }
+}
+
+extern "C" void
+rnn_batch_apply_learning(RnnBatch *b, int learning_style, float momentum)
+{
+  rb_apply_learning_async(&b->nets[0]->pub, learning_style, momentum);
+}
+
+static void
+fetch_stats(RnnBatch *b, RnnBatchCharStats *stats)
+{
+  CUDA_OR_DIE(cudaMemcpyAsync(b->accum_host, b->accum_dev, sizeof(RbCharAccum),
+          cudaMemcpyDeviceToHost, rb_stream));
+  CUDA_OR_DIE(cudaMemsetAsync(b->accum_dev, 0, sizeof(RbCharAccum), rb_stream));
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  stats->error += b->accum_host->error;
+  stats->entropy += b->accum_host->entropy;
+  stats->correct += b->accum_host->correct;
+  stats->count += b->accum_host->count;
+}
+
+/* advance .. update for one character position, symbols already on device */
+static void
+char_step_device(RnnBatch *b, int learning_style, float momentum)
+{
+  RecurNN *proto = &b->nets[0]->pub;
+  rnn_batch_advance(b);
+  RbView v;
+  batch_view(b, &v);
+  rb_matrices_to_device(proto);
+  rbk_set_one_hot(&v, b->cur_dev);
+  float noise = proto->presynaptic_noise;
+  upload_rng_if_noisy(b, noise);
+  rb_forward_dispatch(&v, noise);
+  download_rng_if_noisy(b, noise);
+  rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
+  calc_deltas_async(b, 0);
+  rb_apply_learning_async(proto, learning_style, momentum);
+}
+
+extern "C" void
+rnn_batch_char_step(RnnBatch *b, const u8 *cur, const u8 *next, int learning_style,
+    float momentum, RnnBatchCharStats *stats)
+{
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  memcpy(b->sym_host, cur, b->n);
+  memcpy(b->sym_host + b->n, next, b->n);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
+  CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice, rb_stream));
+  char_step_device(b, learning_style, momentum);
+  if (stats)
+    fetch_stats(b, stats);
+}
+
+extern "C" void
+rnn_batch_text_upload(RnnBatch *b, const u8 *text, int len)
+{
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  cudaFree(b->text_dev);
+  CUDA_OR_DIE(cudaMalloc((void **)&b->text_dev, len));
+  CUDA_OR_DIE(cudaMemcpy(b->text_dev, text, len, cudaMemcpyHostToDevice));
+  b->text_len = len;
+}
+
+extern "C" int
+rnn_batch_text_train(RnnBatch *b, int start, int steps, int learning_style,
+    float momentum, float momentum_soft_start, RnnBatchCharStats *stats)
+{
+  if (!b->text_dev)
+    rb_die("recur-b200: rnn_batch_text_train before rnn_batch_text_upload");
+  RecurNN *proto = &b->nets[0]->pub;
+  int len = b->text_len;
+  int spacing = (len - 1) / b->n;
+  int i = start;
+  for (int s = 0; s < steps; s++, i++) {
+    if (i >= len - 1)
+      i = 0;
+    float m = rnn_calculate_momentum_soft_start(proto->generation, momentum,
+        momentum_soft_start);
+    rbk_text_symbols(b->text_dev, len, i, spacing, b->n, b->cur_dev, b->next_dev);
+    char_step_device(b, learning_style, m);
+  }
+  if (stats)
+    fetch_stats(b, stats);
+  return (i >= len - 1) ? 0 : i;
+}
+
+extern "C" int
+rnn_batch_text_forward(RnnBatch *b, int start, int steps)
+{
+  if (!b->text_dev)
+    rb_die("recur-b200: rnn_batch_text_forward before rnn_batch_text_upload");
+  int len = b->text_len;
+  int spacing = (len - 1) / b->n;
+  int i = start;
+  RbView v;
+  batch_view(b, &v);
+  rb_matrices_to_device(&b->nets[0]->pub);
+  for (int s = 0; s < steps; s++, i++) {
+    if (i >= len - 1)
+      i = 0;
+    rbk_text_symbols(b->text_dev, len, i, spacing, b->n, b->cur_dev, b->next_dev);
+    rbk_set_one_hot(&v, b->cur_dev);
+    rb_forward_dispatch(&v, 0.0f);
+  }
+  mark_ahead(b);
+  return (i >= len - 1) ? 0 : i;
+}
+
+extern "C" void
+rnn_batch_pull(RnnBatch *b)
+{
+  for (int j = 0; j < b->n; j++) {
+    b->nets[j]->dev_ahead = 1;
+    rb_net_pull(b->nets[j]);
+  }
+}

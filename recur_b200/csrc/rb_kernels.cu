@@ -1,0 +1,1313 @@
+/* rb_kernels.cu — FP32 FMA kernels of the recur hot path for sm_100a.
+ *
+ * This file is the "FMA engine": every stage of the path as CUDA-core
+ * kernels that are exact FP32 and work for any number of streams.  Batches
+ * of >= 64 streams route the three big contractions (forward, BPTT chain,
+ * weight gradient) to the tensor-core engine in rb_tc.cu instead; everything
+ * else (gathers, soft clips, softmax, top layer, per-stream BPTT control,
+ * optimisers, conditioning) is always done here.
+ *
+ * Reference stages -> kernels:
+ *   a1  rnn_bptt_advance            k_advance
+ *   a2  one_hot_opinion (inputs)    k_set_one_hot / k_set_inputs
+ *   a3  rnn_opinion                 k_prepare_x, k_gemm<FWD>, k_out
+ *   a4  calculate_interlayer        (zero rows are skipped in k_out; masked
+ *                                    rows cost nothing in the GEMM tiles)
+ *   a5  maybe_scale_inputs          k_prepare_x
+ *   a6  softmax/net_error_bptt      k_softmax_error
+ *   a7  backprop_top_layer          k_top
+ *   a8  top soft clip               k_top
+ *   a9  single_layer_sgd            k_ho_delta
+ *   a10 bptt_and_accumulate_error   k_gemm<CHAIN> + k_chain_decide per step,
+ *                                   then k_gemm<DW> (the outer products of all
+ *                                   steps and streams as one contraction)
+ *   a11 delta fold (ih_scale)       inside k_gemm<DW> (row scale)
+ *   a13 rnn_apply_learning          k_apply_learning
+ *   a14 rnn_bptt_calculate          k_sgd_top_apply + the above
+ *   a15 rnn_condition_net           k_scale / k_zero_small / k_clamp / k_tall_poppy
+ *   a16 rnn_bptt_clear_deltas       k_fill
+ */
+#include "rb_kernels.h"
+#include "rb_rng.h"
+#include <math.h>
+
+#define RB_WARP 32
+
+static inline int
+cdiv(int a, int b)
+{
+  return (a + b - 1) / b;
+}
+
+/* ------------------------------------------------------------------------ */
+/* small device helpers                                                       */
+
+__device__ __forceinline__ float
+warp_sum(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float
+warp_max(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float
+warp_min(float v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+/* block-wide sum for blockDim.x <= 1024; every thread gets the result */
+__device__ __forceinline__ float
+block_sum(float v, float *scratch /* >= 33 floats */)
+{
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0)
+    scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    float t = (lane < nw) ? scratch[lane] : 0.0f;
+    t = warp_sum(t);
+    if (lane == 0)
+      scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+/* recur-nn-helpers.h:104-113: 2x / (1 + x^2 (0.99 + x^2/100)), x = sum/halfmax */
+__device__ __forceinline__ float
+soft_clip_dev(float sum, float halfmax)
+{
+  if (halfmax == 0.0f)
+    return sum;
+  float x = sum / halfmax;
+  float fudge = (float)(0.99 + (double)(x * x / 100.0f));
+  return 2.0f * x / (1.0f + x * x * fudge);
+}
+
+/* badmaths.h:14-29: Pade(2,2) of exp on |x| < 0.2 after dividing by 8^count,
+   then count rounds of three squarings.  The comparison in the reference is
+   made in double against 0.2, which for a float means >= 0.2f. */
+__device__ __forceinline__ float
+fast_expf_dev(float x)
+{
+  int count = 0;
+  while (fabsf(x) >= 0.2f && count < 48) {
+    x *= 0.125f;
+    count++;
+  }
+  float a = ((x + 3.0f) * (x + 3.0f) + 3.0f) / ((x - 3.0f) * (x - 3.0f) + 3.0f);
+  while (count) {
+    a *= a;
+    a *= a;
+    a *= a;
+    count--;
+  }
+  return a;
+}
+
+__device__ __forceinline__ float *
+x_row(const RbView &v, int s, int back)
+{
+  int p = v.pos[s] - back;
+  if (p < 0)
+    p += v.depth;
+  return v.X + ((size_t)p * v.cap + s) * v.d.i_size;
+}
+
+__device__ __forceinline__ float *
+e_row(const RbView &v, int s, int k)
+{
+  return v.E + ((size_t)k * v.cap + s) * v.d.i_size;
+}
+
+/* ------------------------------------------------------------------------ */
+/* a1, a2: ring position and inputs                                           */
+
+__global__ void
+k_advance(RbView v)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < v.n) {
+    int s = v.slots[j];
+    int p = v.pos[s] + 1;
+    v.pos[s] = (p >= v.depth) ? p - v.depth : p;
+  }
+}
+
+__global__ void
+k_fill_iota(int *iota, int n)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n)
+    iota[j] = j;
+}
+
+__global__ void
+k_set_one_hot(RbView v, const u8 *hot)
+{
+  int s = v.slots[blockIdx.x];
+  float *in = x_row(v, s, 0) + v.d.hidden_size + 1;
+  int h = hot[blockIdx.x];
+  for (int i = threadIdx.x; i < v.d.input_size; i += blockDim.x)
+    in[i] = (i == h) ? 1.0f : 0.0f;
+}
+
+__global__ void
+k_set_inputs(RbView v, const float *inputs)
+{
+  int s = v.slots[blockIdx.x];
+  float *in = x_row(v, s, 0) + v.d.hidden_size + 1;
+  const float *src = inputs + (size_t)blockIdx.x * v.d.input_size;
+  for (int i = threadIdx.x; i < v.d.input_size; i += blockDim.x)
+    in[i] = src[i];
+}
+
+/* stream j reads text position i + j*spacing, wrapped as charmodel-predict.c:295-298 */
+__global__ void
+k_text_symbols(const u8 *text, int len, int i, int spacing, int n, u8 *cur, u8 *next)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    long long off = (long long)i + (long long)j * spacing;
+    if (off >= len - 1)
+      off -= len - 1;
+    cur[j] = text[off];
+    next[j] = text[off + 1];
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* a3 (first half), a5: build the input row [1 | hidden(t-1) | inputs | 0..]
+   in the ring and soft-clip it in emergencies (recur-nn.c:68-81,108-115).   */
+
+__global__ void __launch_bounds__(256)
+k_prepare_x(RbView v)
+{
+  __shared__ float scratch[33];
+  int s = v.slots[blockIdx.x];
+  float *x = x_row(v, s, 0);
+  const float *h = v.Hd + (size_t)s * v.d.h_size;
+  int n_copy = v.d.hidden_size + 1;
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < v.d.i_size; i += blockDim.x) {
+    float val;
+    if (i < n_copy) {
+      val = (i == 0) ? 1.0f : h[i];
+      x[i] = val;
+    }
+    else {
+      val = x[i];
+    }
+    sum += val;
+  }
+  sum = block_sum(sum, scratch);
+  float softclip = v.d.i_size * INPUT_MEAN_SOFT_TOP;
+  if (sum > softclip) {
+    float scale = soft_clip_dev(sum, softclip);
+    for (int i = threadIdx.x; i < v.d.i_size; i += blockDim.x)
+      x[i] *= scale;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* The three big contractions as one tiled FP32 kernel.
+ *
+ *  FWD    hidden[b, h]  = act( sum_y x[b, y]   * Wih[y, h] )        K = i_size
+ *  CHAIN  E(k+1)[b, y]  = mask * sum_x E(k)[b, x] * Wih[y, x]       K = h_size
+ *  DW     delta[y, x]  += sum_r scale_r * x_r[y] * E_r[x]           K = n * depth
+ *
+ * 64x64 output tile, 16-deep K slices, 256 threads, 4x4 per thread, global
+ * loads of the next slice overlapped with the FMAs of the current one. */
+
+#define TM 64
+#define TN 64
+#define TK 16
+#define TPAD 4
+
+enum { G_FWD = 0, G_CHAIN = 1, G_DW = 2 };
+
+struct GemmArgs {
+  RbView v;
+  int k;          /* CHAIN: BPTT step */
+  float *delta;   /* DW: output [i_size][h_size] */
+  int accumulate; /* DW: add to delta instead of overwriting */
+  int use_noise;  /* FWD: add v.noise before the activation */
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_gemm(GemmArgs g)
+{
+  const RbView &v = g.v;
+  __shared__ __align__(16) float As[TK][TM + TPAD];
+  __shared__ __align__(16) float Bs[TK][TN + TPAD];
+  __shared__ int s_any_live;
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int I = v.d.i_size, H = v.d.h_size;
+
+  int M, N, K;
+  if (MODE == G_FWD) { M = v.n; N = H; K = I; }
+  else if (MODE == G_CHAIN) { M = v.n; N = I; K = H; }
+  else { M = I; N = H; K = v.n * v.depth; }
+
+  /* --- per-thread load coordinates --- */
+  /* "row" loaders: 64 rows x 16 k, thread -> (row = tid/4, kq = (tid%4)*4)
+     "flat" loaders: 16 k x 64 cols, thread -> (k = tid/16, cq = (tid%16)*4) */
+  const int lr = tid >> 2, lkq = (tid & 3) * 4;
+  const int fk = tid >> 4, fcq = (tid & 15) * 4;
+
+  const float *a_ptr = NULL; /* row loaders of A (FWD, CHAIN) */
+  const float *b_ptr = NULL; /* row loader of B (CHAIN) / flat loader base (FWD) */
+  bool a_ok = false, b_ok = false;
+
+  if (MODE == G_CHAIN) {
+    if (tid == 0)
+      s_any_live = 0;
+    __syncthreads();
+  }
+  if (MODE == G_FWD || MODE == G_CHAIN) {
+    int m = m0 + lr;
+    if (m < M) {
+      int s = v.slots[m];
+      if (MODE == G_FWD) {
+        a_ptr = x_row(v, s, 0);
+        a_ok = true;
+      }
+      else {
+        a_ok = v.sc[s].live != 0;
+        a_ptr = e_row(v, s, g.k);
+        if (a_ok)
+          s_any_live = 1;
+      }
+    }
+  }
+  if (MODE == G_CHAIN) {
+    int n = n0 + lr;
+    b_ok = n < N;
+    b_ptr = v.Wih + (size_t)n * H;
+    __syncthreads();
+    if (!s_any_live)
+      return; /* every stream of this tile has stopped */
+  }
+
+  float4 ra = make_float4(0.f, 0.f, 0.f, 0.f), rb = ra;
+
+  auto load_tile = [&](int k0) {
+    ra = make_float4(0.f, 0.f, 0.f, 0.f);
+    rb = ra;
+    if (MODE == G_FWD) {
+      int k = k0 + lkq;
+      if (a_ok && k < K)
+        ra = *(const float4 *)(a_ptr + k);
+      int kb = k0 + fk, c = n0 + fcq;
+      if (kb < K && c < N)
+        rb = *(const float4 *)(v.Wih + (size_t)kb * H + c);
+    }
+    else if (MODE == G_CHAIN) {
+      int k = k0 + lkq;
+      if (k < K) {
+        if (a_ok)
+          ra = *(const float4 *)(a_ptr + k);
+        if (b_ok)
+          rb = *(const float4 *)(b_ptr + k);
+      }
+    }
+    else {
+      int r = k0 + fk;
+      if (r < K) {
+        int step = r / v.n, b = r - step * v.n;
+        int s = v.slots[b];
+        if (step < v.sc[s].n_steps) {
+          float scale = v.sc[s].ih_scale;
+          int ca = m0 + fcq, cb = n0 + fcq;
+          if (ca < M) {
+            ra = *(const float4 *)(x_row(v, s, step) + ca);
+            ra.x *= scale; ra.y *= scale; ra.z *= scale; ra.w *= scale;
+          }
+          if (cb < N)
+            rb = *(const float4 *)(e_row(v, s, step) + cb);
+        }
+      }
+    }
+  };
+
+  auto store_tile = [&]() {
+    if (MODE == G_FWD) {
+      As[lkq + 0][lr] = ra.x; As[lkq + 1][lr] = ra.y;
+      As[lkq + 2][lr] = ra.z; As[lkq + 3][lr] = ra.w;
+      *(float4 *)&Bs[fk][fcq] = rb;
+    }
+    else if (MODE == G_CHAIN) {
+      As[lkq + 0][lr] = ra.x; As[lkq + 1][lr] = ra.y;
+      As[lkq + 2][lr] = ra.z; As[lkq + 3][lr] = ra.w;
+      Bs[lkq + 0][lr] = rb.x; Bs[lkq + 1][lr] = rb.y;
+      Bs[lkq + 2][lr] = rb.z; Bs[lkq + 3][lr] = rb.w;
+    }
+    else {
+      *(float4 *)&As[fk][fcq] = ra;
+      *(float4 *)&Bs[fk][fcq] = rb;
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      acc[i][j] = 0.0f;
+
+  const int n_tiles = (K + TK - 1) / TK;
+  load_tile(0);
+  store_tile();
+  __syncthreads();
+  for (int t = 0; t < n_tiles; t++) {
+    if (t + 1 < n_tiles)
+      load_tile((t + 1) * TK);
+#pragma unroll
+    for (int kk = 0; kk < TK; kk++) {
+      float4 a = *(const float4 *)&As[kk][ty * 4];
+      float4 b = *(const float4 *)&Bs[kk][tx * 4];
+      acc[0][0] += a.x * b.x; acc[0][1] += a.x * b.y; acc[0][2] += a.x * b.z; acc[0][3] += a.x * b.w;
+      acc[1][0] += a.y * b.x; acc[1][1] += a.y * b.y; acc[1][2] += a.y * b.z; acc[1][3] += a.y * b.w;
+      acc[2][0] += a.z * b.x; acc[2][1] += a.z * b.y; acc[2][2] += a.z * b.z; acc[2][3] += a.z * b.w;
+      acc[3][0] += a.w * b.x; acc[3][1] += a.w * b.y; acc[3][2] += a.w * b.z; acc[3][3] += a.w * b.w;
+    }
+    __syncthreads();
+    if (t + 1 < n_tiles) {
+      store_tile();
+      __syncthreads();
+    }
+  }
+
+  /* --- epilogues --- */
+  if (MODE == G_FWD) {
+    /* activation, recur-nn.c:120-148 */
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int m = m0 + ty * 4 + i;
+      if (m >= M)
+        continue;
+      int s = v.slots[m];
+      int c = n0 + tx * 4;
+      if (c >= N)
+        continue;
+      float out[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float h = acc[i][j];
+        int col = c + j;
+        if (g.use_noise && col >= 1)
+          h += v.noise[(size_t)s * H + col];
+        if (v.activation == RNN_RESQRT) {
+          h = (h > 0.0f) ? sqrtf(h + 1.0f) - 1.0f : 0.0f;
+        }
+        else if (v.activation == RNN_RECLIP20) {
+          if (col >= 1) {
+            h = h - RNN_HIDDEN_PENALTY;
+            h = h < 20.0f ? h : 20.0f;
+            h = (h > 0.0f) ? h : 0.0f;
+          }
+        }
+        else {
+          if (col >= 1) {
+            h = h - RNN_HIDDEN_PENALTY;
+            h = (h > 0.0f) ? h : 0.0f;
+          }
+        }
+        if (col == 0)
+          h = 1.0f;
+        out[j] = h;
+      }
+      *(float4 *)(v.Hd + (size_t)s * H + c) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+  }
+  else if (MODE == G_CHAIN) {
+    /* recur-nn.c:338-376 for one ring row: mask by the input that fed the
+       row, ReSQRT derivative, squared-error partial sums per stream */
+    const int hs1 = v.d.hidden_size + 1;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int m = m0 + ty * 4 + i;
+      bool row_ok = false;
+      int s = 0;
+      if (m < M) {
+        s = v.slots[m];
+        row_ok = v.sc[s].live != 0;
+      }
+      float sq = 0.0f;
+      int c = n0 + tx * 4;
+      if (row_ok && c < N) {
+        const float4 xin = *(const float4 *)(x_row(v, s, g.k) + c);
+        float xi[4] = {xin.x, xin.y, xin.z, xin.w};
+        float out[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float e = 0.0f;
+          float input = xi[j];
+          if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
+            e = acc[i][j];
+            if (v.activation == RNN_RESQRT)
+              e /= 2.0f * (input + 1.0f);
+            sq += e * e;
+          }
+          int col = c + j;
+          /* the next step reads this row as h_error: bias and pad columns
+             are cleared there (recur-nn.c:334-337) */
+          if (col == 0 || (col >= hs1 && col < H))
+            e = 0.0f;
+          out[j] = e;
+        }
+        *(float4 *)(e_row(v, s, g.k + 1) + c) = make_float4(out[0], out[1], out[2], out[3]);
+      }
+      /* the 16 threads with equal ty hold one row of the tile */
+      sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      if (tx == 0 && row_ok)
+        v.partial[(size_t)s * v.n_part + blockIdx.x] = sq;
+    }
+  }
+  else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int m = m0 + ty * 4 + i;
+      int c = n0 + tx * 4;
+      if (m >= M || c >= N)
+        continue;
+      float *dst = g.delta + (size_t)m * H + c;
+      float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (g.accumulate) {
+        float4 d = *(const float4 *)dst;
+        o.x += d.x; o.y += d.y; o.z += d.z; o.w += d.w;
+      }
+      *(float4 *)dst = o;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* a3 (second half): output = hidden . Who; hidden rows that are zero are
+   skipped, which is the reference's row-skipping (recur-nn.c:39-48) — the
+   branch is uniform across the block because the block is one stream.     */
+
+__global__ void __launch_bounds__(256)
+k_out(RbView v)
+{
+  extern __shared__ float sh[]; /* h_size hidden + reduction space */
+  int s = v.slots[blockIdx.x];
+  const int H = v.d.h_size, O = v.d.o_size;
+  float *hid = sh;
+  float *red = sh + H;
+  for (int i = threadIdx.x; i < H; i += blockDim.x)
+    hid[i] = v.Hd[(size_t)s * H + i];
+  __syncthreads();
+  const int CW = (O >= 256) ? 256 : O;
+  const int G = 256 / CW;
+  const int col = threadIdx.x % CW, grp = threadIdx.x / CW;
+  float *y = v.Y + (size_t)s * O;
+  for (int c0 = 0; c0 < O; c0 += CW) {
+    int c = c0 + col;
+    float acc = 0.0f;
+    if (grp < G && c < O) {
+      for (int r = grp; r < H; r += G) {
+        float h = hid[r];
+        if (h != 0.0f)
+          acc += h * v.Who[(size_t)r * O + c];
+      }
+    }
+    if (G > 1) {
+      if (grp < G)
+        red[grp * CW + col] = acc;
+      __syncthreads();
+      if (grp == 0 && c < O) {
+        float t = 0.0f;
+        for (int q = 0; q < G; q++)
+          t += red[q * CW + col];
+        y[c] = t;
+      }
+      __syncthreads();
+    }
+    else if (c < O) {
+      y[c] = acc;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* a6: softmax with badmaths.h's clamp and fast_expf, error = onehot - p,
+   argmax; one warp per stream, warp-shuffle reductions
+   (badmaths.h:71-141, charmodel-predict.c:18-27).                          */
+
+__global__ void __launch_bounds__(128)
+k_softmax_error(RbView v, const u8 *target, float *err_out, int *winner_out)
+{
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (j >= v.n)
+    return;
+  int s = v.slots[j];
+  const int len = v.d.output_size, O = v.d.o_size;
+  const float *src = v.Y + (size_t)s * O;
+  float *err = v.OE + (size_t)s * O;
+
+  float mx = -INFINITY, mn = INFINITY;
+  for (int i = lane; i < len; i += 32) {
+    float y = src[i];
+    mx = fmaxf(mx, y);
+    mn = fminf(mn, y);
+  }
+  mx = warp_max(mx);
+  mn = warp_min(mn);
+  const float max_exp = 50.0f, min_exp = -60.0f;
+  float adj = 0.0f;
+  if (mx > max_exp)
+    adj = max_exp - mx;
+  else if (mn < min_exp)
+    adj = fminf(min_exp - mn, max_exp - mx);
+
+  float sum = 0.0f;
+  for (int i = lane; i < len; i += 32) {
+    float x = fast_expf_dev(src[i] + adj);
+    err[i] = x;
+    sum += x;
+  }
+  sum = warp_sum(sum);
+  float best = -INFINITY;
+  int best_i = 0x7fffffff;
+  int tgt = target ? (int)target[j] : -1;
+  float e_t = 0.0f;
+  for (int i = lane; i < len; i += 32) {
+    float p = err[i] / sum;
+    if (p > best) { /* first maximum wins within a lane: indices ascend */
+      best = p;
+      best_i = i;
+    }
+    float e = -p;
+    if (i == tgt) {
+      e += 1.0f;
+      e_t = e;
+    }
+    err[i] = e;
+  }
+  for (int i = len + lane; i < O; i += 32)
+    err[i] = 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) {
+      best = ob;
+      best_i = oi;
+    }
+  }
+  e_t = warp_sum(e_t);
+  if (lane == 0) {
+    if (err_out)
+      err_out[j] = e_t;
+    if (winner_out)
+      winner_out[j] = best_i;
+  }
+}
+
+/* sums of charmodel-predict.c:301-303 over the batch, in a fixed order */
+__global__ void __launch_bounds__(256)
+k_char_accum(const float *err, const int *winner, const u8 *target, int n,
+    RbCharAccum *acc)
+{
+  __shared__ double s_err[256], s_ent[256];
+  __shared__ int s_cor[256];
+  double e = 0.0, h = 0.0;
+  int c = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    float ej = err[j];
+    e += ej;
+    float x = 1.0f - ej;
+    h += (x < 1e-30f) ? -100.0f : log2f(x);
+    c += (winner[j] == (int)target[j]);
+  }
+  s_err[threadIdx.x] = e;
+  s_ent[threadIdx.x] = h;
+  s_cor[threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_err[threadIdx.x] += s_err[threadIdx.x + o];
+      s_ent[threadIdx.x] += s_ent[threadIdx.x + o];
+      s_cor[threadIdx.x] += s_cor[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    acc->error += s_err[0];
+    acc->entropy += s_ent[0];
+    acc->correct += s_cor[0];
+    acc->count += n;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* a7, a8: top layer back-propagation into E[0] with the soft clip, and the
+   per-stream set-up of the BPTT walk (recur-nn.c:199-228, 318-322, 719-721) */
+
+__global__ void __launch_bounds__(256)
+k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
+{
+  extern __shared__ float sh[]; /* o_size errors + 33 scratch */
+  int s = v.slots[blockIdx.x];
+  const int H = v.d.h_size, O = v.d.o_size, I = v.d.i_size;
+  float *oe = sh;
+  float *scratch = sh + O;
+  for (int i = threadIdx.x; i < O; i += blockDim.x)
+    oe[i] = v.OE[(size_t)s * O + i];
+  __syncthreads();
+  const float *hid = v.Hd + (size_t)s * H;
+  float *e0 = e_row(v, s, 0);
+  float abs_sum = 0.0f, hsum = 0.0f, hmag = 0.0f;
+  int hzero = 0;
+  for (int y = threadIdx.x; y < I; y += blockDim.x) {
+    float e = 0.0f;
+    if (y < H) {
+      float h = hid[y];
+      hsum += h;
+      hmag += h * h;
+      hzero += (h == 0.0f);
+      if (y >= 1 && h != 0.0f) {
+        const float *row = v.Who + (size_t)y * O;
+        if (n_ranges == 0) {
+          for (int x = 0; x < O; x += 4) {
+            float4 w = *(const float4 *)(row + x);
+            e += w.x * oe[x] + w.y * oe[x + 1] + w.z * oe[x + 2] + w.w * oe[x + 3];
+          }
+          abs_sum += fabsf(e);
+        }
+        else {
+          /* recur-nn.c:178-191: the running dot product is added to the
+             error sum once per range */
+          for (int q = 0; q < n_ranges; q++) {
+            int start = ranges[q].start & ~3;
+            int len = (ranges[q].len + 3) & ~3;
+            for (int x = start; x < start + len; x++)
+              e += row[x] * oe[x];
+            abs_sum += fabsf(e);
+          }
+        }
+      }
+    }
+    e0[y] = e;
+  }
+  abs_sum = block_sum(abs_sum, scratch);
+  hsum = block_sum(hsum, scratch);
+  hmag = block_sum(hmag, scratch);
+  float hz = block_sum((float)hzero, scratch);
+  float halfmax = H * MAX_TOP_ERROR_FACTOR;
+  float top_scaled = abs_sum;
+  if (abs_sum > halfmax) {
+    float scale = soft_clip_dev(abs_sum, halfmax);
+    for (int y = threadIdx.x; y < H; y += blockDim.x)
+      e0[y] *= scale;
+    top_scaled = scale * abs_sum;
+  }
+  if (threadIdx.x == 0) {
+    RbScalars *sc = v.sc + s;
+    sc->top_raw = abs_sum;
+    sc->top_scaled = top_scaled;
+    sc->hidden_sum = hsum;
+    sc->hidden_mag = sqrtf(hmag);
+    sc->hidden_zeros = (int)(hz + 0.5f);
+    float min_gain = MIN_ERROR_GAIN * top_scaled;
+    sc->min_sum = fminf(sc->mef / sc->lr, min_gain);
+    sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
+    sc->cum_error = 0.0f;
+    sc->err_sum = 0.0f;
+    sc->live = (v.depth > 0);
+    sc->n_steps = 0;
+    sc->t_left = v.depth;
+    sc->ih_scale = 1.0f;
+  }
+}
+
+/* a9: ho_delta[y, :] (+)= sum over streams hidden[y] * o_error[:]
+   (recur-nn.c:256-301).  One thread per (y, x) element, streams in order. */
+__global__ void __launch_bounds__(256)
+k_ho_delta(RbView v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges, int n_ranges)
+{
+  const int H = v.d.h_size, O = v.d.o_size;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * O)
+    return;
+  int y = idx / O, x = idx - y * O;
+  if (n_ranges) {
+    bool inside = false;
+    for (int q = 0; q < n_ranges; q++) {
+      int start = ranges[q].start & ~3;
+      int len = (ranges[q].len + 3) & ~3;
+      inside |= (x >= start && x < start + len);
+    }
+    if (!inside) {
+      if (!accumulate)
+        ho_delta[idx] = 0.0f;
+      return;
+    }
+  }
+  float acc = accumulate ? ho_delta[idx] : 0.0f;
+  for (int j = 0; j < v.n; j++) {
+    int s = v.slots[j];
+    float h = v.Hd[(size_t)s * H + y];
+    if (h != 0.0f)
+      acc += h * v.OE[(size_t)s * O + x];
+  }
+  ho_delta[idx] = acc;
+}
+
+/* a14: the single-net path updates the top layer straight away
+   (recur-nn.c:941-964); rows of silent hidden units only decay momentum. */
+__global__ void __launch_bounds__(256)
+k_sgd_top_apply(RbView v, float *weights, float *momentums, float rate,
+    float momentum, float momentum_weight)
+{
+  const int H = v.d.h_size, O = v.d.o_size;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= H * O)
+    return;
+  int s = v.slots[0];
+  int y = idx / O, x = idx - y * O;
+  float h = (y == 0) ? 1.0f : v.Hd[(size_t)s * H + y];
+  float mm = momentums[idx];
+  float w = weights[idx];
+  if (h != 0.0f) {
+    float m = h * rate;
+    float d = v.OE[(size_t)s * O + x] * m;
+    w += d + mm * momentum_weight;
+    mm += d;
+  }
+  else {
+    w += mm * momentum_weight;
+  }
+  weights[idx] = w;
+  momentums[idx] = mm * momentum;
+}
+
+/* ------------------------------------------------------------------------ */
+/* a10 control: after each chain step, per stream: accumulate cum_error,
+   decide whether to walk further (recur-nn.c:383-389) and on the last step
+   settle ih_scale / min_error_factor (recur-nn.c:393-413).                 */
+
+__global__ void
+k_chain_decide(RbView v, int k)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n)
+    return;
+  int s = v.slots[j];
+  RbScalars *sc = v.sc + s;
+  if (!sc->live)
+    return;
+  float es = 0.0f;
+  const float *p = v.partial + (size_t)s * v.n_part;
+  for (int q = 0; q < v.n_part; q++)
+    es += p[q];
+  sc->err_sum = es;
+  sc->cum_error += sqrtf(es);
+  sc->n_steps = k + 1;
+  int t = v.depth - k; /* the reference's loop counter during this step */
+  bool stop = (es <= sc->min_sum || es > sc->max_sum);
+  bool last = (k == v.depth - 1);
+  if (!stop && !last)
+    return;
+  sc->live = 0;
+  int t_left = stop ? t : 0;
+  sc->t_left = t_left;
+  float ceiling = ERROR_GAIN_CEILING * sc->top_scaled;
+  if (es > ceiling) {
+    sc->ih_scale = soft_clip_dev(es, sc->max_sum);
+  }
+  else {
+    sc->ih_scale = 1.0f;
+    if (sc->adaptive) {
+      int depth_error = v.depth / 4 - t_left;
+      float min_gain = MIN_ERROR_GAIN * sc->top_scaled;
+      float mef = sc->mef;
+      if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc->min_sum || depth_error < 0))
+        mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
+      sc->mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+    }
+  }
+}
+
+/* per-stream training parameters the host owns (bptt->learn_rate,
+   bptt->min_error_factor, the ADAPTIVE flag) */
+__global__ void
+k_set_params(RbView v, const float *lr, const float *mef, int adaptive)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n)
+    return;
+  RbScalars *sc = v.sc + v.slots[j];
+  if (lr)
+    sc->lr = lr[j];
+  if (mef)
+    sc->mef = mef[j];
+  if (adaptive >= 0)
+    sc->adaptive = adaptive;
+}
+
+__global__ void
+k_set_params_scalar(RbView v, float lr, float mef, int adaptive)
+{
+  RbScalars *sc = v.sc + v.slots[0];
+  sc->lr = lr;
+  sc->mef = mef;
+  sc->adaptive = adaptive;
+}
+
+/* ------------------------------------------------------------------------ */
+/* a13: the seven optimisers (recur-nn.c:454-593), elementwise.             */
+
+__global__ void __launch_bounds__(256)
+k_apply_learning(int method, float *__restrict__ weights,
+    const float *__restrict__ delta, float *__restrict__ momentums,
+    float *__restrict__ aux, int size, float rate, float momentum,
+    float momentum_weight, const float *rate_scale)
+{
+  if (rate_scale)
+    rate *= *rate_scale;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size;
+       i += gridDim.x * blockDim.x) {
+    float d = delta[i];
+    float w = weights[i];
+    if (method == RNN_MOMENTUM_NESTEROV) {
+      float t = d * rate;
+      float m = (momentums[i] + t) * momentum;
+      w += t;
+      w += m;
+      momentums[i] = m;
+    }
+    else if (method == RNN_ADAGRAD) {
+      float a = momentums[i] + d * d;
+      w += d * rate / sqrtf(a);
+      momentums[i] = a;
+    }
+    else if (method == RNN_ADADELTA) {
+      const float decay = momentum, renewal = 1.0f - decay;
+      float gacc = momentums[i] * decay;
+      float sacc = aux[i] * decay;
+      gacc += fabsf(d) * renewal + rate;
+      float step = sacc / gacc * d;
+      sacc += fabsf(step) * renewal + rate;
+      momentums[i] = gacc;
+      aux[i] = sacc;
+      w += step;
+    }
+    else if (method == RNN_RPROP) {
+      const float max_step = 1.0f * rate;
+      const float min_step = (float)(1e-6 * (double)rate);
+      float p = momentums[i];
+      float step = aux[i];
+      if (d * p > 0.0f) {
+        step = fminf(step * 1.2f, max_step);
+      }
+      else if (d * p < 0.0f) {
+        step = fmaxf(step * 0.5f, min_step);
+        d = 0.0f;
+      }
+      if (d > 0.0f)
+        w += step;
+      else
+        w -= step;
+      aux[i] = step;
+      momentums[i] = d;
+    }
+    else { /* weighted / simplified Nesterov / classical: recur-nn.c:482-487 */
+      float t = d * rate;
+      float m = momentums[i];
+      w += t + m * momentum_weight;
+      momentums[i] = (m + t) * momentum;
+    }
+    weights[i] = w;
+  }
+}
+
+/* ------------------------------------------------------------------------ */
+/* a15, a16 and array helpers (recur-nn-helpers.h:22-168)                   */
+
+__global__ void
+k_scale(float *a, int n, float s)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    a[i] *= s;
+}
+
+__global__ void
+k_zero_small(float *a, int n)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x = a[i];
+    a[i] = (fabsf(x) > 1e-34f) ? x : 0.0f;
+  }
+}
+
+__global__ void
+k_clamp(float *a, int n, float lo, float hi)
+{
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    a[i] = fminf(fmaxf(a[i], lo), hi);
+}
+
+__global__ void
+k_fill(float *a, size_t n, float value)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    a[i] = value;
+}
+
+__global__ void
+k_axpy(float *dst, const float *src, int n, float s, const float *s_dev)
+{
+  if (s_dev)
+    s *= *s_dev;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    dst[i] += src[i] * s;
+}
+
+__global__ void
+k_add_at(float *a, int index, float value)
+{
+  a[index] += value;
+}
+
+/* recur-nn.c:828-844: shrink the single largest |weight| (first one wins) */
+__global__ void __launch_bounds__(1024)
+k_tall_poppy(float *a, int n, float threshold, float scale)
+{
+  __shared__ float s_v[1024];
+  __shared__ int s_i[1024];
+  float bv = -1.0f;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float x = fabsf(a[i]);
+    if (x > bv) {
+      bv = x;
+      bi = i;
+    }
+  }
+  s_v[threadIdx.x] = bv;
+  s_i[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      float ov = s_v[threadIdx.x + o];
+      int oi = s_i[threadIdx.x + o];
+      if (ov > s_v[threadIdx.x] || (ov == s_v[threadIdx.x] && oi < s_i[threadIdx.x])) {
+        s_v[threadIdx.x] = ov;
+        s_i[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && s_v[0] > threshold)
+    a[s_i[0]] *= scale;
+}
+
+__global__ void __launch_bounds__(1024)
+k_abs_sum(const float *a, int n, float *out)
+{
+  __shared__ float scratch[33];
+  float t = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    t += fabsf(a[i]);
+  t = block_sum(t, scratch);
+  if (threadIdx.x == 0)
+    *out = t;
+}
+
+/* presynaptic noise: each stream draws its row from its own generator, in
+   the reference's order (recur-nn-helpers.h:170-181, recur-nn.c:120).       */
+__global__ void
+k_gen_noise(RbView v, float deviation, int first_col, int n_cols)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= v.n)
+    return;
+  int s = v.slots[j];
+  rb_rng_state st;
+  st.a = v.rng[s * 4 + 0];
+  st.b = v.rng[s * 4 + 1];
+  st.c = v.rng[s * 4 + 2];
+  st.d = v.rng[s * 4 + 3];
+  float *row = v.noise + (size_t)s * v.d.h_size;
+  for (int i = 0; i < n_cols; i++)
+    row[first_col + i] = rb_rng_cheap_gaussian(&st) * deviation;
+  v.rng[s * 4 + 0] = st.a;
+  v.rng[s * 4 + 1] = st.b;
+  v.rng[s * 4 + 2] = st.c;
+  v.rng[s * 4 + 3] = st.d;
+}
+
+/* ------------------------------------------------------------------------ */
+/* launchers                                                                  */
+
+#define LAUNCH_CHECK(name) do {                                         \
+    cudaError_t e_ = cudaGetLastError();                                \
+    if (e_ != cudaSuccess)                                              \
+      rb_die("recur-b200: launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    rb_count_launch(1);                                                 \
+  } while (0)
+
+static inline int
+grid1d(long long n, int block)
+{
+  long long g = (n + block - 1) / block;
+  if (g > 148 * 16)
+    g = 148 * 16;
+  if (g < 1)
+    g = 1;
+  return (int)g;
+}
+
+extern "C" void
+rbk_advance(const RbView *v)
+{
+  k_advance<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v);
+  LAUNCH_CHECK("k_advance");
+}
+
+extern "C" void
+rbk_fill_iota(int *iota, int n)
+{
+  k_fill_iota<<<cdiv(n, 256), 256, 0, rb_stream>>>(iota, n);
+  LAUNCH_CHECK("k_fill_iota");
+}
+
+extern "C" void
+rbk_set_one_hot(const RbView *v, const u8 *hot_dev)
+{
+  k_set_one_hot<<<v->n, 64, 0, rb_stream>>>(*v, hot_dev);
+  LAUNCH_CHECK("k_set_one_hot");
+}
+
+extern "C" void
+rbk_set_inputs(const RbView *v, const float *inputs_dev)
+{
+  k_set_inputs<<<v->n, 64, 0, rb_stream>>>(*v, inputs_dev);
+  LAUNCH_CHECK("k_set_inputs");
+}
+
+extern "C" void
+rbk_text_symbols(const u8 *text_dev, int len, int i, int spacing, int n,
+    u8 *cur_dev, u8 *next_dev)
+{
+  k_text_symbols<<<cdiv(n, 128), 128, 0, rb_stream>>>(text_dev, len, i, spacing, n,
+      cur_dev, next_dev);
+  LAUNCH_CHECK("k_text_symbols");
+}
+
+extern "C" void
+rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols)
+{
+  k_gen_noise<<<cdiv(v->n, 32), 32, 0, rb_stream>>>(*v, deviation, first_col, n_cols);
+  LAUNCH_CHECK("k_gen_noise");
+}
+
+extern "C" void
+rbk_forward(const RbView *v, float presynaptic_noise)
+{
+  k_prepare_x<<<v->n, 256, 0, rb_stream>>>(*v);
+  LAUNCH_CHECK("k_prepare_x");
+  GemmArgs g;
+  g.v = *v;
+  g.k = 0;
+  g.delta = NULL;
+  g.accumulate = 0;
+  g.use_noise = 0;
+  if (presynaptic_noise != 0.0f) {
+    rbk_gen_noise(v, presynaptic_noise, 1, v->d.h_size - 1);
+    g.use_noise = 1;
+  }
+  dim3 grid(cdiv(v->d.h_size, TN), cdiv(v->n, TM));
+  k_gemm<G_FWD><<<grid, 256, 0, rb_stream>>>(g);
+  LAUNCH_CHECK("k_gemm<FWD>");
+  size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
+  k_out<<<v->n, 256, sh, rb_stream>>>(*v);
+  LAUNCH_CHECK("k_out");
+}
+
+static int *rb_winner_scratch = NULL;
+static float *rb_err_scratch = NULL;
+static int rb_scratch_cap = 0;
+
+extern "C" void
+rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
+    int *winner_dev, RbCharAccum *accum_dev)
+{
+  if (accum_dev && (!err_dev || !winner_dev)) {
+    if (rb_scratch_cap < v->n) {
+      if (rb_winner_scratch) {
+        cudaFree(rb_winner_scratch);
+        cudaFree(rb_err_scratch);
+      }
+      rb_scratch_cap = v->n + 64;
+      if (cudaMalloc(&rb_winner_scratch, rb_scratch_cap * sizeof(int)) != cudaSuccess ||
+          cudaMalloc(&rb_err_scratch, rb_scratch_cap * sizeof(float)) != cudaSuccess)
+        rb_die("recur-b200: out of device memory for softmax scratch");
+    }
+    if (!err_dev)
+      err_dev = rb_err_scratch;
+    if (!winner_dev)
+      winner_dev = rb_winner_scratch;
+  }
+  k_softmax_error<<<cdiv(v->n, 4), 128, 0, rb_stream>>>(*v, target_dev, err_dev, winner_dev);
+  LAUNCH_CHECK("k_softmax_error");
+  if (accum_dev) {
+    k_char_accum<<<1, 256, 0, rb_stream>>>(err_dev, winner_dev, target_dev, v->n, accum_dev);
+    LAUNCH_CHECK("k_char_accum");
+  }
+}
+
+extern "C" void
+rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges)
+{
+  size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
+  k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
+  LAUNCH_CHECK("k_top");
+  if (ho_delta) {
+    int total = v->d.h_size * v->d.o_size;
+    k_ho_delta<<<cdiv(total, 256), 256, 0, rb_stream>>>(*v, ho_delta, accumulate,
+        ranges_dev, n_ranges);
+    LAUNCH_CHECK("k_ho_delta");
+  }
+}
+
+extern "C" void
+rbk_sgd_top_apply(const RbView *v, float *ho_weights, float *ho_momentum,
+    float rate, float momentum, float momentum_weight)
+{
+  int total = v->d.h_size * v->d.o_size;
+  k_sgd_top_apply<<<cdiv(total, 256), 256, 0, rb_stream>>>(*v, ho_weights, ho_momentum,
+      rate, momentum, momentum_weight);
+  LAUNCH_CHECK("k_sgd_top_apply");
+}
+
+extern "C" void
+rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
+{
+  GemmArgs g;
+  g.v = *v;
+  g.delta = ih_delta;
+  g.accumulate = accumulate;
+  g.use_noise = 0;
+  dim3 cgrid(cdiv(v->d.i_size, TN), cdiv(v->n, TM));
+  for (int k = 0; k < v->depth; k++) {
+    g.k = k;
+    k_gemm<G_CHAIN><<<cgrid, 256, 0, rb_stream>>>(g);
+    LAUNCH_CHECK("k_gemm<CHAIN>");
+    k_chain_decide<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, k);
+    LAUNCH_CHECK("k_chain_decide");
+  }
+  dim3 dgrid(cdiv(v->d.h_size, TN), cdiv(v->d.i_size, TM));
+  k_gemm<G_DW><<<dgrid, 256, 0, rb_stream>>>(g);
+  LAUNCH_CHECK("k_gemm<DW>");
+}
+
+extern "C" void
+rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive)
+{
+  k_set_params<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, lr_dev, mef_dev, adaptive);
+  LAUNCH_CHECK("k_set_params");
+}
+
+extern "C" void
+rbk_set_params_scalar(const RbView *v, float lr, float mef, int adaptive)
+{
+  k_set_params_scalar<<<1, 1, 0, rb_stream>>>(*v, lr, mef, adaptive);
+  LAUNCH_CHECK("k_set_params_scalar");
+}
+
+extern "C" void
+rbk_apply_learning(int method, float *weights, const float *delta,
+    float *momentums, float *aux, int size, float rate, float momentum,
+    float momentum_weight, const float *rate_scale_dev)
+{
+  k_apply_learning<<<grid1d(size, 256), 256, 0, rb_stream>>>(method, weights, delta,
+      momentums, aux, size, rate, momentum, momentum_weight, rate_scale_dev);
+  LAUNCH_CHECK("k_apply_learning");
+}
+
+extern "C" void
+rbk_scale(float *a, int n, float s)
+{
+  k_scale<<<grid1d(n, 256), 256, 0, rb_stream>>>(a, n, s);
+  LAUNCH_CHECK("k_scale");
+}
+
+extern "C" void
+rbk_zero_small(float *a, int n)
+{
+  k_zero_small<<<grid1d(n, 256), 256, 0, rb_stream>>>(a, n);
+  LAUNCH_CHECK("k_zero_small");
+}
+
+extern "C" void
+rbk_clamp(float *a, int n, float lo, float hi)
+{
+  k_clamp<<<grid1d(n, 256), 256, 0, rb_stream>>>(a, n, lo, hi);
+  LAUNCH_CHECK("k_clamp");
+}
+
+extern "C" void
+rbk_tall_poppy(float *a, int n, float threshold, float scale)
+{
+  k_tall_poppy<<<1, 1024, 0, rb_stream>>>(a, n, threshold, scale);
+  LAUNCH_CHECK("k_tall_poppy");
+}
+
+extern "C" void
+rbk_add_at(float *a, int index, float value)
+{
+  k_add_at<<<1, 1, 0, rb_stream>>>(a, index, value);
+  LAUNCH_CHECK("k_add_at");
+}
+
+extern "C" void
+rbk_axpy(float *dst, const float *src, int n, float s, const float *s_dev)
+{
+  k_axpy<<<grid1d(n, 256), 256, 0, rb_stream>>>(dst, src, n, s, s_dev);
+  LAUNCH_CHECK("k_axpy");
+}
+
+extern "C" void
+rbk_fill(float *a, size_t n, float value)
+{
+  k_fill<<<grid1d((long long)n, 256), 256, 0, rb_stream>>>(a, n, value);
+  LAUNCH_CHECK("k_fill");
+}
+
+extern "C" void
+rbk_abs_sum(const float *a, int n, float *out_dev)
+{
+  k_abs_sum<<<1, 1024, 0, rb_stream>>>(a, n, out_dev);
+  LAUNCH_CHECK("k_abs_sum");
+}

@@ -1,0 +1,79 @@
+/* rb_kernels.h — launchers of the sm_100a kernels (rb_kernels.cu, rb_tc.cu).
+ * All launch asynchronously on the library stream. */
+#ifndef RB_KERNELS_H
+#define RB_KERNELS_H
+
+#include "rb_internal.h"
+#include <cuda_runtime.h>
+
+/* A batch of streams of one pool, as the kernels see it. */
+typedef struct RbView {
+  RbDims d;
+  int cap, depth, n_part;
+  float *X, *Hd, *Y, *OE, *E, *partial, *noise;
+  int *pos;
+  RbScalars *sc;
+  uint64_t *rng;
+  const int *slots; /* device: n pool slots */
+  int n;
+  int contiguous;   /* slots[j] == slots[0] + j */
+  int base;         /* slots[0] when contiguous */
+  const float *Wih; /* [i_size][h_size] */
+  const float *Who; /* [h_size][o_size] */
+  int activation;
+} RbView;
+
+/* device accumulators of the text-predict report sums */
+typedef struct RbCharAccum {
+  double error;
+  double entropy;
+  long long correct;
+  long long count;
+} RbCharAccum;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+extern cudaStream_t rb_stream;
+void rb_view_of_net(RbNet *rn, RbView *v);
+void rb_count_launch(int n);
+
+void rbk_advance(const RbView *v);
+void rbk_fill_iota(int *iota, int n);
+void rbk_set_one_hot(const RbView *v, const u8 *hot_dev);
+void rbk_set_inputs(const RbView *v, const float *inputs_dev);
+void rbk_text_symbols(const u8 *text_dev, int len, int i, int spacing, int n,
+    u8 *cur_dev, u8 *next_dev);
+void rbk_forward(const RbView *v, float presynaptic_noise); /* a3..a5 */
+void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
+    int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
+void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges);       /* a7..a9 */
+void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */
+void rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive);
+void rbk_set_params_scalar(const RbView *v, float lr, float mef, int adaptive);
+void rbk_sgd_top_apply(const RbView *v, float *ho_weights, float *ho_momentum,
+    float rate, float momentum, float momentum_weight);     /* a14 (recur-nn.c:941-964) */
+
+/* a13: one optimiser step over `size` elements.  rate_scale_dev (may be NULL)
+   points at a device float multiplied into the rate (ih_scale, a14). */
+void rbk_apply_learning(int method, float *weights, const float *delta,
+    float *momentums, float *aux, int size, float rate, float momentum,
+    float momentum_weight, const float *rate_scale_dev);
+
+/* a15 / a16 and friends */
+void rbk_scale(float *a, int n, float s);
+void rbk_zero_small(float *a, int n);
+void rbk_clamp(float *a, int n, float lo, float hi);
+void rbk_tall_poppy(float *a, int n, float threshold, float scale);
+void rbk_add_at(float *a, int index, float value);
+void rbk_axpy(float *dst, const float *src, int n, float s, const float *s_dev);
+void rbk_fill(float *a, size_t n, float value);
+void rbk_abs_sum(const float *a, int n, float *out_dev);
+void rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
