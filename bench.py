@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py — text-predict BPTT chars/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" is one character position of recur's synchronic text-predict loop
+(reference charmodel-predict.c:293-311) over all streams of this rank:
+advance, one-hot forward, softmax error, truncated BPTT, one weight update.
+The workload is BASELINE.json configs[1]: hidden 1023, 512 synchronic streams
+per GPU, BPTT depth 30, 42-symbol alphabet, synthetic order-1 Markov text,
+random-initialised weights (rnn_randomise_weights_auto, seed 1).
+
+  value  whole-job chars/sec with the text resident in HBM
+         (rnn_batch_text_train), CUDA-event timed on the library's stream,
+         max over ranks.
+  e2e    the same metric through rnn_batch_char_step with HOST symbol arrays:
+         every step copies this step's 2*n symbol bytes host->device and reads
+         the step's report sums (32 bytes) back.
+  roofline / cpu_baseline: see DESIGN.md "Measurement".
+
+N > 1: one process per GPU (torchrun), streams sharded 512 per rank (weak
+scaling), [ih_delta | ho_delta] all-reduced over NCCL each step.  The only
+thing torch.distributed carries is the NCCL unique id, the barriers and the
+max-over-ranks of the timings.
+
+--impl reference times the reference's own CPU implementation of the same
+loop (oracle/_ref, the unmodified reference compiled in place) on the host
+cores: one independent replica per core, bounded sample.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+HIDDEN = 1023
+STREAMS = 512
+DEPTH = 30
+ALPHABET = 42
+TEXT_LEN = 2_000_000
+LEARN_RATE = 1e-6     # deltas are summed over streams: 1e-5 diverges
+MOMENTUM = 0.95
+SOFT_START = 2000.0
+METRIC = "text-predict BPTT chars/sec"
+UNIT = "chars/s"
+
+
+def markov_text(n, n_symbols, seed):
+    """Order-1 Markov chain, vectorised enough for 2M symbols."""
+    rng = np.random.RandomState(seed)
+    trans = rng.dirichlet(np.ones(n_symbols) * 0.3, size=n_symbols)
+    cum = np.cumsum(trans, axis=1)
+    cum[:, -1] = 1.0
+    u = rng.random_sample(n)
+    out = np.empty(n, dtype=np.uint8)
+    s = 0
+    for i in range(n):
+        s = int(np.searchsorted(cum[s], u[i]))
+        out[i] = s if s < n_symbols else n_symbols - 1
+    return out
+
+
+def synthetic_text(n=TEXT_LEN, seed=2):
+    cache = os.path.join(ROOT, "gpurun_out", "bench_text_%d_%d.npy" % (n, seed))
+    try:
+        t = np.load(cache)
+        if len(t) == n:
+            return t
+    except Exception:
+        pass
+    # generate a 200k chunk and tile it with different offsets: the loop only
+    # needs a learnable symbol stream, and 2M python iterations take too long
+    base = markov_text(200_000, ALPHABET, seed)
+    reps = (n + len(base) - 1) // len(base)
+    t = np.concatenate([np.roll(base, 7919 * r) for r in range(reps)])[:n].copy()
+    try:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        np.save(cache, t)
+    except Exception:
+        pass
+    return t
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler
+
+class ClockSampler(threading.Thread):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.samples.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for k, name in enumerate(names):
+                    if s[5 + k].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# the reference arm / CPU baseline: replicas of the reference's own loop
+
+def _ref_replica(args):
+    seed, hidden, n_streams, depth, warm, steps, text = args
+    import oracle
+    from recur_b200 import abi
+    from helpers import make_net, u8ptr
+    ref = oracle.load_ref(strict=False)   # the reference's own flags
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    os.dup2(devnull, 2)
+    net = make_net(ref, input_size=ALPHABET, hidden=hidden, output=ALPHABET, depth=depth,
+                   seed=seed, lr=LEARN_RATE)
+    nets = ref.rnn_new_training_set(net, n_streams)
+    if warm:
+        ref.ref_multi_tap_train(nets, n_streams, u8ptr(text), len(text), 0, warm,
+                                abi.RNN_MOMENTUM_WEIGHTED, MOMENTUM, SOFT_START, None, None, None)
+    secs = ref.ref_multi_tap_train(nets, n_streams, u8ptr(text), len(text), warm, steps,
+                                   abi.RNN_MOMENTUM_WEIGHTED, MOMENTUM, SOFT_START,
+                                   None, None, None)
+    return secs, steps * n_streams
+
+
+def reference_cpu_throughput(cores, n_streams, warm, steps, hidden=HIDDEN, depth=DEPTH):
+    """Aggregate chars/s of `cores` independent replicas of the reference's
+    multi-tap loop (it is single-threaded by construction: streams alias
+    shared delta arrays)."""
+    import oracle
+    if not oracle.have_ref():
+        raise RuntimeError("oracle/_ref is not built")
+    text = synthetic_text(200_000)
+    jobs = [(100 + r, hidden, n_streams, depth, warm, steps, text) for r in range(cores)]
+    t0 = time.time()
+    if cores == 1:
+        res = [_ref_replica(jobs[0])]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_ref_replica, jobs)
+    wall = time.time() - t0
+    # every replica ran concurrently: aggregate = sum of per-replica rates
+    rate = sum(chars / secs for secs, chars in res)
+    return rate, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    # bounded sample: 8 streams per replica; 30 warm-up positions fill the
+    # BPTT ring (steady-state cost), then a few timed positions per "step"
+    n_streams, warm = 8, DEPTH
+    per_step = 4
+    t_all = []
+    total_chars = 0
+    t0 = time.time()
+    steps_done = 0
+    rate, wall = reference_cpu_throughput(cores, n_streams, warm + per_step * args.warmup,
+                                          per_step * args.steps)
+    ms_per_step = 1e3 * (per_step * n_streams * cores) / rate
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d independent replicas (one per core) of the reference "
+                                   "multi-tap loop, H%d D%d, %d streams each, %d warm-up + %d timed "
+                                   "positions" % (cores, HIDDEN, DEPTH, n_streams,
+                                                  warm + per_step * args.warmup,
+                                                  per_step * args.steps)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, scaling="weak"):
+    return {
+        "workload": "text-predict BPTT training, hidden %d, %d synchronic streams per GPU, "
+                    "BPTT depth %d, %d-symbol alphabet (BASELINE.json configs[1])"
+                    % (HIDDEN, STREAMS, DEPTH, ALPHABET),
+        "hidden": HIDDEN, "streams_per_gpu": STREAMS, "global_streams": STREAMS * n_gpus,
+        "bptt_depth": DEPTH, "alphabet": ALPHABET, "learn_rate": LEARN_RATE,
+        "learning_style": "weighted momentum 0.95", "text": "order-1 Markov chain, seed 2",
+        "parallelism": "streams sharded over %d GPU(s), deltas all-reduced (NCCL)" % n_gpus
+        if n_gpus > 1 else "1 GPU",
+        "l2": "working set per step (history ring 66 MB + error chain 66 MB + weights, "
+              "momentum, deltas 18 MB) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+# ---------------------------------------------------------------------------
+# our arm
+
+def run_ours(args):
+    import torch
+    from recur_b200 import api, abi
+    from helpers import make_net, u8ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    L = api.load_library()
+    if L.rnn_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if L.rnn_b200_set_device(local_rank) != 0:
+        raise SystemExit("cannot select GPU %d" % local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idbuf = (C.c_uint8 * 128)()
+        if rank == 0 and L.rnn_b200_comm_unique_id(idbuf) != 0:
+            raise SystemExit("NCCL not loadable")
+        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        raw = bytes(t.cpu().tolist())
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(raw)
+        if L.rnn_b200_comm_join(idbuf, rank, world) != 0:
+            raise SystemExit("rnn_b200_comm_join failed")
+
+    def barrier():
+        L.rnn_b200_synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if args.engine is not None:
+        L.rnn_b200_set_engine(args.engine)
+    n = args.streams
+    text = synthetic_text()
+    devnull_fd = os.dup(2)
+    os.dup2(os.open(os.devnull, os.O_WRONLY), 2)   # the reference-style init chatter
+    net = make_net(L, input_size=ALPHABET, hidden=args.hidden, output=ALPHABET, depth=DEPTH,
+                   seed=1, lr=LEARN_RATE / world)
+    os.dup2(devnull_fd, 2)
+    nets = L.rnn_new_training_set(net, n)
+    batch = L.rnn_batch_new(nets, n)
+    # each rank reads its own stretch of the text
+    shard = len(text) // world
+    my_text = np.ascontiguousarray(text[rank * shard:(rank + 1) * shard])
+    L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
+    stream = torch.cuda.ExternalStream(L.rnn_b200_stream())
+    style = abi.RNN_MOMENTUM_WEIGHTED
+
+    # ---- device-resident arm (value) ---------------------------------------
+    pos = L.rnn_batch_text_train(batch, 0, max(args.warmup, 3), style, MOMENTUM, SOFT_START, None)
+    # fill the BPTT ring so that every timed step walks the full depth
+    if args.warmup < DEPTH and not args.cold:
+        pos = L.rnn_batch_text_train(batch, pos, DEPTH - args.warmup, style, MOMENTUM,
+                                     SOFT_START, None)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = L.rnn_b200_kernel_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stats = api.RnnBatchCharStats()
+    barrier()
+    ev0.record(stream)
+    pos = L.rnn_batch_text_train(batch, pos, args.steps, style, MOMENTUM, SOFT_START,
+                                 C.byref(stats))
+    ev1.record(stream)
+    barrier()
+    launches = L.rnn_b200_kernel_launches() - launches0
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    value = (args.steps * n * world) / (ms * 1e-3)
+
+    # ---- end-to-end arm (host symbols in, report sums out, every step) -----
+    spacing = (len(my_text) - 1) // n
+    offs = (np.arange(n, dtype=np.int64) * spacing)
+    est = api.RnnBatchCharStats()
+    e2e_steps = args.steps
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        idx = (pos + k + offs) % (len(my_text) - 1)
+        cur = my_text[idx]
+        nxt = my_text[idx + 1]
+        m = L.rnn_calculate_momentum_soft_start(float(net.contents.generation), MOMENTUM, SOFT_START)
+        L.rnn_batch_char_step(batch, u8ptr(cur), u8ptr(nxt), style, m, C.byref(est))
+    L.rnn_b200_synchronize()
+    t1 = time.perf_counter()
+    barrier()
+    e2e_ms = max_over_ranks((t1 - t0) * 1e3)
+    e2e_value = (e2e_steps * n * world) / (e2e_ms * 1e-3)
+    sampler.stop()
+
+    # ---- per-kernel timing for the roofline (separate, instrumented pass) --
+    prof_steps = min(args.steps, 10)
+    L.rnn_b200_profile_enable(1)
+    pev0, pev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pev0.record(stream)
+    L.rnn_batch_text_train(batch, pos, prof_steps, style, MOMENTUM, SOFT_START, None)
+    pev1.record(stream)
+    pms = (C.c_double * 8)()
+    pln = (C.c_uint64 * 8)()
+    ncls = L.rnn_b200_profile_read(pms, pln, 8)
+    L.rnn_b200_profile_enable(0)
+    prof_total = pev0.elapsed_time(pev1)
+    L.rnn_batch_pull(batch)
+    # executed BPTT depth per stream (n_steps of the last step), from the log scalars
+    kernels = {}
+    for c in range(ncls):
+        name = L.rnn_b200_profile_class_name(c).decode()
+        if pln[c]:
+            kernels[name] = {"ms_total": pms[c], "launches": int(pln[c]),
+                             "ms_per_launch": pms[c] / pln[c],
+                             "share_of_step": pms[c] / prof_total}
+    hs1 = args.hidden + 1
+    i_alg = hs1 + 1               # bias + hidden rows + the one hot input row
+    flops_pair = 2.0 * i_alg * hs1  # one stream, one ring row: one of {error back, outer product}
+    alg = {
+        "forward": (2.0 * i_alg * hs1) * n,                  # per launch (one step)
+        "bptt_chain": flops_pair * n,                        # per launch (one depth step)
+        "weight_grad": flops_pair * n * DEPTH,               # per launch (all depth steps)
+    }
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_bf16 = float(peaks["bf16_tflops_sustained"])
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)"
+    except Exception:
+        peak_bf16 = 1400.0
+        peak_src = "fallback 1.4 PFLOP/s sustained bf16 / 2"
+    dominant = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_total"],
+                   default=None)
+    roofline = None
+    if dominant:
+        per_launch_s = kernels[dominant]["ms_per_launch"] * 1e-3
+        achieved = alg[dominant] / per_launch_s / 1e12
+        peak = peak_bf16 / 2.0
+        roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src,
+                    "note": "achieved = algorithmic FP32 FLOPs (unpadded, 2 per multiply-add) "
+                            "per launch / CUDA-event time per launch; a 3xTF32 kernel issues 3 "
+                            "MMAs per logical one, so its ceiling against this peak is 1/3",
+                    "kernels": kernels}
+
+    line = None
+    if rank == 0:
+        step_flops = (alg["forward"] + DEPTH * alg["bptt_chain"] + alg["weight_grad"]) * world
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n,
+                    "d2h_bytes_per_step": C.sizeof(api.RnnBatchCharStats),
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "algorithmic_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12,
+            "train": {"t_entropy": -stats.entropy / max(stats.count, 1),
+                      "accuracy": stats.correct / max(stats.count, 1)},
+            "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],
+        }
+        if args.hidden != HIDDEN or n != STREAMS:
+            line["config"]["workload"] += " [OVERRIDDEN: hidden %d streams %d]" % (args.hidden, n)
+    L.rnn_batch_delete(batch)
+    if dist:
+        barrier()
+    L.rnn_b200_comm_leave()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ------------------------
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cores = host_cores()
+                rate, wall = reference_cpu_throughput(cores, 8, DEPTH, 4)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "sample": "%d independent replicas (one per core) of the reference multi-tap "
+                              "loop, H%d D%d, 8 streams each, %d warm-up + 4 timed positions, "
+                              "%.1f s wall" % (cores, HIDDEN, DEPTH, DEPTH, wall)}
+            except Exception as e:  # the oracle .so did not travel
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
+                                        "kind": "reference", "sample": "unavailable: %s" % e}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", type=int, default=None, help="0 auto, 1 FMA, 2 tensor")
+    ap.add_argument("--hidden", type=int, default=HIDDEN)
+    ap.add_argument("--streams", type=int, default=STREAMS)
+    ap.add_argument("--cold", action="store_true", help="do not pre-fill the BPTT ring")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

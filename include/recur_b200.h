@@ -60,6 +60,17 @@ uint64_t rnn_b200_kernel_launches(void);
    shapes do not allow them).  Returns the previous setting. */
 int rnn_b200_set_engine(int engine);
 
+/* Per-kernel-class device timing (for bench.py's roofline): when enabled,
+   every launch of the big contractions and of the update kernel is bracketed
+   by CUDA events on the library stream.  rnn_b200_profile_read synchronises
+   and fills, per class, the summed milliseconds and the launch count since
+   enabling; it returns the number of classes.  Classes: see
+   rnn_b200_profile_class_name (0 "forward", 1 "bptt_chain", 2 "weight_grad",
+   3 "update"). */
+void rnn_b200_profile_enable(int on);
+int rnn_b200_profile_read(double *ms, uint64_t *launches, int max_classes);
+const char *rnn_b200_profile_class_name(int cls);
+
 /* ---- mirrors --------------------------------------------------------------- */
 
 /* Refresh the host mirrors of one net (input_layer/history, hidden_layer,

@@ -24,6 +24,7 @@ B200_API_SYMBOLS = [
     "rnn_b200_device_count", "rnn_b200_set_device", "rnn_b200_synchronize",
     "rnn_b200_stream", "rnn_b200_version", "rnn_b200_kernel_launches",
     "rnn_b200_set_engine", "rnn_b200_pull", "rnn_b200_push",
+    "rnn_b200_profile_enable", "rnn_b200_profile_read", "rnn_b200_profile_class_name",
     "rnn_batch_new", "rnn_batch_delete", "rnn_batch_size", "rnn_batch_advance",
     "rnn_batch_set_inputs", "rnn_batch_set_one_hot", "rnn_batch_opinion",
     "rnn_batch_get_outputs", "rnn_batch_get_hiddens", "rnn_batch_softmax_error",
@@ -52,6 +53,12 @@ def _declare_b200(lib):
     lib.rnn_b200_kernel_launches.argtypes = []
     lib.rnn_b200_set_engine.restype = C.c_int
     lib.rnn_b200_set_engine.argtypes = [C.c_int]
+    lib.rnn_b200_profile_enable.restype = None
+    lib.rnn_b200_profile_enable.argtypes = [C.c_int]
+    lib.rnn_b200_profile_read.restype = C.c_int
+    lib.rnn_b200_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    lib.rnn_b200_profile_class_name.restype = C.c_char_p
+    lib.rnn_b200_profile_class_name.argtypes = [C.c_int]
     lib.rnn_b200_pull.restype = None
     lib.rnn_b200_pull.argtypes = [P]
     lib.rnn_b200_push.restype = None

@@ -427,3 +427,76 @@ rb_pool_release_slot(RbPool *p, int slot)
     p->n_live--;
   }
 }
+
+/* ---- per-class kernel timing ------------------------------------------------ */
+
+#define RB_PROF_CLASSES 4
+static int prof_on = 0;
+static cudaEvent_t *prof_ev = NULL; /* pairs */
+static int *prof_cls = NULL;
+static size_t prof_n = 0, prof_cap = 0;
+
+extern "C" void
+rnn_b200_profile_enable(int on)
+{
+  if (rb_have_device())
+    CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  prof_on = on && rb_have_device();
+  prof_n = 0;
+}
+
+extern "C" const char *
+rnn_b200_profile_class_name(int cls)
+{
+  static const char *names[RB_PROF_CLASSES] = {"forward", "bptt_chain", "weight_grad", "update"};
+  return (cls >= 0 && cls < RB_PROF_CLASSES) ? names[cls] : NULL;
+}
+
+extern "C" void
+rb_prof_begin(int cls)
+{
+  if (!prof_on)
+    return;
+  if (prof_n == prof_cap) {
+    size_t cap = prof_cap ? prof_cap * 2 : 1024;
+    prof_ev = (cudaEvent_t *)realloc(prof_ev, cap * 2 * sizeof(cudaEvent_t));
+    prof_cls = (int *)realloc(prof_cls, cap * sizeof(int));
+    for (size_t i = prof_cap * 2; i < cap * 2; i++)
+      CUDA_OR_DIE(cudaEventCreate(&prof_ev[i]));
+    prof_cap = cap;
+  }
+  prof_cls[prof_n] = cls;
+  CUDA_OR_DIE(cudaEventRecord(prof_ev[prof_n * 2], rb_stream));
+}
+
+extern "C" void
+rb_prof_end(int cls)
+{
+  (void)cls;
+  if (!prof_on)
+    return;
+  CUDA_OR_DIE(cudaEventRecord(prof_ev[prof_n * 2 + 1], rb_stream));
+  prof_n++;
+}
+
+extern "C" int
+rnn_b200_profile_read(double *ms, uint64_t *launches, int max_classes)
+{
+  for (int c = 0; c < max_classes; c++) {
+    ms[c] = 0;
+    launches[c] = 0;
+  }
+  if (!rb_have_device())
+    return RB_PROF_CLASSES;
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  for (size_t i = 0; i < prof_n; i++) {
+    float t = 0;
+    CUDA_OR_DIE(cudaEventElapsedTime(&t, prof_ev[i * 2], prof_ev[i * 2 + 1]));
+    int c = prof_cls[i];
+    if (c < max_classes) {
+      ms[c] += t;
+      launches[c]++;
+    }
+  }
+  return RB_PROF_CLASSES;
+}

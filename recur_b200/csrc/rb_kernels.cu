@@ -1147,8 +1147,10 @@ rbk_forward(const RbView *v, float presynaptic_noise)
     g.use_noise = 1;
   }
   dim3 grid(cdiv(v->d.h_size, TN), cdiv(v->n, TM));
+  rb_prof_begin(RB_PROF_FWD);
   k_gemm<G_FWD><<<grid, 256, 0, rb_stream>>>(g);
   LAUNCH_CHECK("k_gemm<FWD>");
+  rb_prof_end(RB_PROF_FWD);
   size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
   k_out<<<v->n, 256, sh, rb_stream>>>(*v);
   LAUNCH_CHECK("k_out");
@@ -1222,14 +1224,18 @@ rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
   dim3 cgrid(cdiv(v->d.i_size, TN), cdiv(v->n, TM));
   for (int k = 0; k < v->depth; k++) {
     g.k = k;
+    rb_prof_begin(RB_PROF_CHAIN);
     k_gemm<G_CHAIN><<<cgrid, 256, 0, rb_stream>>>(g);
     LAUNCH_CHECK("k_gemm<CHAIN>");
+    rb_prof_end(RB_PROF_CHAIN);
     k_chain_decide<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, k);
     LAUNCH_CHECK("k_chain_decide");
   }
   dim3 dgrid(cdiv(v->d.h_size, TN), cdiv(v->d.i_size, TM));
+  rb_prof_begin(RB_PROF_DW);
   k_gemm<G_DW><<<dgrid, 256, 0, rb_stream>>>(g);
   LAUNCH_CHECK("k_gemm<DW>");
+  rb_prof_end(RB_PROF_DW);
 }
 
 extern "C" void
@@ -1251,9 +1257,11 @@ rbk_apply_learning(int method, float *weights, const float *delta,
     float *momentums, float *aux, int size, float rate, float momentum,
     float momentum_weight, const float *rate_scale_dev)
 {
+  rb_prof_begin(RB_PROF_UPDATE);
   k_apply_learning<<<grid1d(size, 256), 256, 0, rb_stream>>>(method, weights, delta,
       momentums, aux, size, rate, momentum, momentum_weight, rate_scale_dev);
   LAUNCH_CHECK("k_apply_learning");
+  rb_prof_end(RB_PROF_UPDATE);
 }
 
 extern "C" void
