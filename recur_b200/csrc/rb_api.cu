@@ -67,6 +67,7 @@ rb_view_of_net(RbNet *rn, RbView *v)
   v->Wih = rn->pub.ih_weights;
   v->Who = rn->pub.ho_weights;
   v->activation = rn->pub.activation;
+  v->pool = p;
 }
 
 static float *

@@ -261,6 +261,7 @@ pool_free_device(RbPool *p)
 {
   if (!rb_have_device())
     return;
+  rb_tc_pool_release(p);
   cudaFree(p->X);
   cudaFree(p->Hd);
   cudaFree(p->Y);

@@ -1,7 +1,8 @@
 /* rb_dispatch.cu — picks the matrix engine for the three big contractions.
  *
- * FMA engine (rb_kernels.cu): exact FP32 on CUDA cores, any batch size.
- * Tensor engine (rb_tc.cu): tcgen05 3xTF32 for batches of >= 64 streams.
+ * FMA engine (rb_kernels.cu): exact FP32 on CUDA cores, any batch.
+ * Tensor engine (rb_tc.cu): tcgen05 3xTF32; needs >= 64 streams, a multiple
+ * of 32, in one contiguous run of pool slots that advance in lockstep.
  */
 #include "rb_kernels.h"
 #include "rb_host.h"
@@ -14,14 +15,43 @@ rb_weights_changed(RecurNN *net)
   rb_net_of(net)->group->weights_version++;
 }
 
+static int
+lockstep(const RbView *v)
+{
+  const int *pos = v->pool->pos_shadow;
+  for (int j = 1; j < v->n; j++)
+    if (pos[v->base + j] != pos[v->base])
+      return 0;
+  return 1;
+}
+
+static int
+use_tensor_engine(const RbView *v)
+{
+  int engine = rb_engine();
+  if (engine == 1)
+    return 0;
+  int ok = rb_tc_usable(v) && lockstep(v);
+  if (engine == 2 && !ok)
+    rb_die("recur-b200: the tensor engine was forced but this batch (%d streams%s) cannot "
+        "use it", v->n, v->contiguous ? "" : ", scattered slots");
+  return ok;
+}
+
 extern "C" void
 rb_forward_dispatch(const RbView *v, float noise)
 {
-  rbk_forward(v, noise);
+  if (use_tensor_engine(v))
+    rb_tc_forward(v->pool, v, noise);
+  else
+    rbk_forward(v, noise);
 }
 
 extern "C" void
 rb_bptt_dispatch(const RbView *v, float *ih_delta, int accumulate)
 {
-  rbk_bptt(v, ih_delta, accumulate);
+  if (use_tensor_engine(v) && v->pool->has_bptt)
+    rb_tc_bptt(v->pool, v, ih_delta, accumulate);
+  else
+    rbk_bptt(v, ih_delta, accumulate);
 }

@@ -71,6 +71,7 @@ typedef struct RbPool {
   RbScalars *sc;  /* [cap] */
   uint64_t *rng;  /* [cap][4] per-stream PRNG state when noise runs on device */
   int n_part;
+  void *tc;        /* tensor-core engine state (rb_tc.cu), made on first use */
 } RbPool;
 
 typedef struct RbGroup {

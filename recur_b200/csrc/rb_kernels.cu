@@ -1132,10 +1132,31 @@ rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols)
 }
 
 extern "C" void
-rbk_forward(const RbView *v, float presynaptic_noise)
+rbk_prepare_x(const RbView *v)
 {
   k_prepare_x<<<v->n, 256, 0, rb_stream>>>(*v);
   LAUNCH_CHECK("k_prepare_x");
+}
+
+extern "C" void
+rbk_output(const RbView *v)
+{
+  size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
+  k_out<<<v->n, 256, sh, rb_stream>>>(*v);
+  LAUNCH_CHECK("k_out");
+}
+
+extern "C" void
+rbk_chain_decide(const RbView *v, int k)
+{
+  k_chain_decide<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, k);
+  LAUNCH_CHECK("k_chain_decide");
+}
+
+extern "C" void
+rbk_forward(const RbView *v, float presynaptic_noise)
+{
+  rbk_prepare_x(v);
   GemmArgs g;
   g.v = *v;
   g.k = 0;
@@ -1151,9 +1172,7 @@ rbk_forward(const RbView *v, float presynaptic_noise)
   k_gemm<G_FWD><<<grid, 256, 0, rb_stream>>>(g);
   LAUNCH_CHECK("k_gemm<FWD>");
   rb_prof_end(RB_PROF_FWD);
-  size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
-  k_out<<<v->n, 256, sh, rb_stream>>>(*v);
-  LAUNCH_CHECK("k_out");
+  rbk_output(v);
 }
 
 static int *rb_winner_scratch = NULL;
@@ -1228,8 +1247,7 @@ rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
     k_gemm<G_CHAIN><<<cgrid, 256, 0, rb_stream>>>(g);
     LAUNCH_CHECK("k_gemm<CHAIN>");
     rb_prof_end(RB_PROF_CHAIN);
-    k_chain_decide<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, k);
-    LAUNCH_CHECK("k_chain_decide");
+    rbk_chain_decide(v, k);
   }
   dim3 dgrid(cdiv(v->d.h_size, TN), cdiv(v->d.i_size, TM));
   rb_prof_begin(RB_PROF_DW);

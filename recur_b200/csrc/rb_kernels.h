@@ -21,6 +21,7 @@ typedef struct RbView {
   const float *Wih; /* [i_size][h_size] */
   const float *Who; /* [h_size][o_size] */
   int activation;
+  RbPool *pool;     /* host-side owner (not used by kernels) */
 } RbView;
 
 /* device accumulators of the text-predict report sums */
@@ -49,6 +50,9 @@ void rbk_set_inputs(const RbView *v, const float *inputs_dev);
 void rbk_text_symbols(const u8 *text_dev, int len, int i, int spacing, int n,
     u8 *cur_dev, u8 *next_dev);
 void rbk_forward(const RbView *v, float presynaptic_noise); /* a3..a5 */
+void rbk_prepare_x(const RbView *v);
+void rbk_output(const RbView *v);
+void rbk_chain_decide(const RbView *v, int k);
 void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
 void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
@@ -75,6 +79,12 @@ void rbk_axpy(float *dst, const float *src, int n, float s, const float *s_dev);
 void rbk_fill(float *a, size_t n, float value);
 void rbk_abs_sum(const float *a, int n, float *out_dev);
 void rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols);
+
+/* tensor-core engine (rb_tc.cu) */
+int rb_tc_usable(const RbView *v);
+void rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise);
+void rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate);
+void rb_tc_pool_release(RbPool *p);
 
 #ifdef __cplusplus
 }
