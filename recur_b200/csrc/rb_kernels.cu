@@ -232,6 +232,7 @@ k_prepare_x(RbView v)
  *  FWD    hidden[b, h]  = act( sum_y x[b, y]   * Wih[y, h] )        K = i_size
  *  CHAIN  E(k+1)[b, y]  = mask * sum_x E(k)[b, x] * Wih[y, x]       K = h_size
  *  DW     delta[y, x]  += sum_r scale_r * x_r[y] * E_r[x]           K = n * depth
+ *  HO     ho_delta[y,o] += sum_b hidden[b, y] * o_error[b, o]       K = n
  *
  * 64x64 output tile, 16-deep K slices, 256 threads, 4x4 per thread, global
  * loads of the next slice overlapped with the FMAs of the current one. */
@@ -241,7 +242,7 @@ k_prepare_x(RbView v)
 #define TK 16
 #define TPAD 4
 
-enum { G_FWD = 0, G_CHAIN = 1, G_DW = 2 };
+enum { G_FWD = 0, G_CHAIN = 1, G_DW = 2, G_HO = 3 };
 
 struct GemmArgs {
   RbView v;
@@ -268,7 +269,8 @@ k_gemm(GemmArgs g)
   int M, N, K;
   if (MODE == G_FWD) { M = v.n; N = H; K = I; }
   else if (MODE == G_CHAIN) { M = v.n; N = I; K = H; }
-  else { M = I; N = H; K = v.n * v.depth; }
+  else if (MODE == G_DW) { M = I; N = H; K = v.n * v.depth; }
+  else { M = H; N = v.d.o_size; K = v.n; }
 
   /* --- per-thread load coordinates --- */
   /* "row" loaders: 64 rows x 16 k, thread -> (row = tid/4, kq = (tid%4)*4)
@@ -330,6 +332,17 @@ k_gemm(GemmArgs g)
           ra = *(const float4 *)(a_ptr + k);
         if (b_ok)
           rb = *(const float4 *)(b_ptr + k);
+      }
+    }
+    else if (MODE == G_HO) {
+      int r = k0 + fk;
+      if (r < K) {
+        int s = v.slots[r];
+        int ca = m0 + fcq, cb = n0 + fcq;
+        if (ca < M)
+          ra = *(const float4 *)(v.Hd + (size_t)s * H + ca);
+        if (cb < N)
+          rb = *(const float4 *)(v.OE + (size_t)s * N + cb);
       }
     }
     else {
@@ -489,13 +502,14 @@ k_gemm(GemmArgs g)
     }
   }
   else {
+    const int ldd = (MODE == G_HO) ? N : H;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
       int m = m0 + ty * 4 + i;
       int c = n0 + tx * 4;
       if (m >= M || c >= N)
         continue;
-      float *dst = g.delta + (size_t)m * H + c;
+      float *dst = g.delta + (size_t)m * ldd + c;
       float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
       if (g.accumulate) {
         float4 d = *(const float4 *)dst;
@@ -1214,7 +1228,19 @@ rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
   size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
   k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
   LAUNCH_CHECK("k_top");
-  if (ho_delta) {
+  if (ho_delta && n_ranges == 0 && v->n >= 8) {
+    /* the sum over streams as a tiled contraction */
+    GemmArgs g;
+    g.v = *v;
+    g.k = 0;
+    g.delta = ho_delta;
+    g.accumulate = accumulate;
+    g.use_noise = 0;
+    dim3 grid(cdiv(v->d.o_size, TN), cdiv(v->d.h_size, TM));
+    k_gemm<G_HO><<<grid, 256, 0, rb_stream>>>(g);
+    LAUNCH_CHECK("k_gemm<HO>");
+  }
+  else if (ho_delta) {
     int total = v->d.h_size * v->d.o_size;
     k_ho_delta<<<cdiv(total, 256), 256, 0, rb_stream>>>(*v, ho_delta, accumulate,
         ranges_dev, n_ranges);

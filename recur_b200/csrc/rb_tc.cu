@@ -102,6 +102,16 @@ tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1)
 }
 
 __device__ __forceinline__ void
+tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void
 tma_prefetch_desc(const CUtensorMap *map)
 {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -218,16 +228,43 @@ split_tf32(float a, float &hi, float &lo)
   lo = __uint_as_float(l);
 }
 
+__device__ __forceinline__ float
+block_sum_tc(float v, float *scratch /* >= 33 floats */)
+{
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0)
+    scratch[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    float t = (lane < nw) ? scratch[lane] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+      t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0)
+      scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
 /* ======================================================================== */
 /* the engine's extra state per pool                                          */
 
 #define TC_BM 128      /* tile rows (TMEM lanes) */
 #define TC_BK 32       /* K per stage: 32 floats = one 128-byte swizzle row */
-#define TC_NT_BN 64    /* FWD / CHAIN tile columns */
-#define TC_NT_STAGES 4
-#define TC_DW_BN 128   /* DW tile columns */
-#define TC_DW_STAGES 3
-#define TC_DW_SPLITS 2
+#define TC_FWD_BN 64      /* FWD tile columns */
+#define TC_FWD_STAGES 4
+#define TC_CHAIN_BN 128   /* CHAIN tile columns */
+#define TC_CHAIN_STAGES 3
+#define TC_CHAIN_SPLITS 4 /* split-K: 4 x 9 x 4 = 144 CTAs at 512 streams, H1023 */
+#define TC_DW_BN 256      /* DW tile columns */
+#define TC_DW_BK 16       /* DW ring rows per stage */
+#define TC_DW_STAGES 4
+#define TC_DW_SPLITS 4
 
 typedef struct RbTc {
   int cap, depth;
@@ -236,12 +273,13 @@ typedef struct RbTc {
   float *Whi, *Wlo;     /* [i_size][h_size] */
   float *WThi, *WTlo;   /* [h_size][i_size] */
   float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
+  float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size] split-K partial sums of a chain step */
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
   CUtensorMap mXhi_k, mXlo_k;   /* ring rows as K-major A of FWD: box 32 x 128 */
   CUtensorMap mEhi_k, mElo_k;   /* error rows as K-major A of CHAIN (width h_size) */
-  CUtensorMap mWhi_k, mWlo_k;   /* Wih rows as K-major B of CHAIN: box 32 x 64 */
+  CUtensorMap mWhi_k, mWlo_k;   /* Wih rows as K-major B of CHAIN: box 32 x 128 */
   CUtensorMap mWThi_k, mWTlo_k; /* Wih^T rows as K-major B of FWD: box 32 x 64 */
   CUtensorMap mXhi_mn, mXlo_mn; /* ring rows as MN-major A of DW: box 32 x 32 */
   CUtensorMap mEhi_mn, mElo_mn; /* error rows as MN-major B of DW (width h_size) */
@@ -283,6 +321,26 @@ make_map(CUtensorMap *m, float *base, uint64_t width, uint64_t rows, uint64_t pi
         (unsigned long long)width, (unsigned long long)rows, (unsigned long long)pitch);
 }
 
+/* The same rows seen as [chunk of 32 columns][row][32 floats], so that one
+   TMA fetches n_chunks column chunks of box_rows rows into consecutive
+   (chunk-major) shared memory: the MN-major operand layout of DW.  A chunk
+   that straddles the end of a row reads on into the next row; those columns
+   only ever feed output rows/columns that are discarded. */
+static void
+make_map_chunked(CUtensorMap *m, float *base, uint64_t width, uint64_t rows, uint64_t pitch,
+    uint32_t box_rows, uint32_t n_chunks)
+{
+  cuuint64_t dims[3] = {32, rows, (width + 31) / 32};
+  cuuint64_t strides[2] = {pitch * sizeof(float), 32 * sizeof(float)};
+  cuuint32_t box[3] = {32, box_rows, n_chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    rb_die("recur-b200: cuTensorMapEncodeTiled (chunked) failed (%d)", (int)r);
+}
+
 template <typename T>
 static T *
 dmalloc0(size_t n)
@@ -303,6 +361,7 @@ tc_free(RbTc *t)
   cudaFree(t->Xhi); cudaFree(t->Xlo); cudaFree(t->Ehi); cudaFree(t->Elo);
   cudaFree(t->Whi); cudaFree(t->Wlo); cudaFree(t->WThi); cudaFree(t->WTlo);
   cudaFree(t->partial);
+  cudaFree(t->cpartial);
   free(t);
 }
 
@@ -329,29 +388,30 @@ tc_state(RbPool *p)
   t->cap = p->cap;
   t->depth = p->depth;
   size_t ring = (size_t)p->depth * p->cap * I, chain = (size_t)(p->depth + 1) * p->cap * I;
-  t->Xhi = dmalloc0<float>(ring);
-  t->Xlo = dmalloc0<float>(ring);
-  t->Ehi = dmalloc0<float>(chain);
-  t->Elo = dmalloc0<float>(chain);
+  t->Xhi = dmalloc0<float>(ring + 64);
+  t->Xlo = dmalloc0<float>(ring + 64);
+  t->Ehi = dmalloc0<float>(chain + 64);
+  t->Elo = dmalloc0<float>(chain + 64);
   t->Whi = dmalloc0<float>(I * H);
   t->Wlo = dmalloc0<float>(I * H);
   t->WThi = dmalloc0<float>(I * H);
   t->WTlo = dmalloc0<float>(I * H);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
+  t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * I);
   t->w_src = NULL;
   uint64_t ring_rows = (uint64_t)p->depth * p->cap, chain_rows = (uint64_t)(p->depth + 1) * p->cap;
   make_map(&t->mXhi_k, t->Xhi, I, ring_rows, I, TC_BM);
   make_map(&t->mXlo_k, t->Xlo, I, ring_rows, I, TC_BM);
   make_map(&t->mEhi_k, t->Ehi, H, chain_rows, I, TC_BM);
   make_map(&t->mElo_k, t->Elo, H, chain_rows, I, TC_BM);
-  make_map(&t->mWhi_k, t->Whi, H, I, H, TC_NT_BN);
-  make_map(&t->mWlo_k, t->Wlo, H, I, H, TC_NT_BN);
-  make_map(&t->mWThi_k, t->WThi, I, H, I, TC_NT_BN);
-  make_map(&t->mWTlo_k, t->WTlo, I, H, I, TC_NT_BN);
-  make_map(&t->mXhi_mn, t->Xhi, I, ring_rows, I, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  make_map(&t->mXlo_mn, t->Xlo, I, ring_rows, I, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  make_map(&t->mEhi_mn, t->Ehi, H, chain_rows, I, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-  make_map(&t->mElo_mn, t->Elo, H, chain_rows, I, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  make_map(&t->mWhi_k, t->Whi, H, I, H, TC_CHAIN_BN);
+  make_map(&t->mWlo_k, t->Wlo, H, I, H, TC_CHAIN_BN);
+  make_map(&t->mWThi_k, t->WThi, I, H, I, TC_FWD_BN);
+  make_map(&t->mWTlo_k, t->WTlo, I, H, I, TC_FWD_BN);
+  make_map_chunked(&t->mXhi_mn, t->Xhi, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
+  make_map_chunked(&t->mXlo_mn, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
+  make_map_chunked(&t->mEhi_mn, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
+  make_map_chunked(&t->mElo_mn, t->Elo, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
   p->tc = t;
   return t;
 }
@@ -438,39 +498,54 @@ k_finalize_rows(RbView v, float *Ehi, float *Elo)
 }
 
 /* ======================================================================== */
-/* FWD and CHAIN: C[128 x 64] tiles, both operands K-major                    */
+/* FWD and CHAIN: C[128 x BN] tiles, both operands K-major.
+ *
+ * FWD  (BN 64): activation epilogue straight from tensor memory.
+ * CHAIN (BN 128, split-K over blockIdx.z): one BPTT step is too small to
+ * fill 148 SMs with tiles the tensor pipe likes, so K is split four ways and
+ * each CTA writes its raw partial tile; k_chain_finish_step sums the
+ * partials and does the row-wise part of the step.                          */
 
 struct NtArgs {
   RbView v;
   int mode;        /* 0 FWD, 1 CHAIN */
   int k;           /* CHAIN: step */
   int use_noise;
-  float *Ehi, *Elo;
+  float *cpartial; /* CHAIN: [splits][cap][i_size] */
 };
 
-#define NT_A_BYTES (TC_BM * TC_BK * 4)        /* 16 KB */
-#define NT_B_BYTES (TC_NT_BN * TC_BK * 4)     /* 8 KB */
-#define NT_STAGE_BYTES (2 * NT_A_BYTES + 2 * NT_B_BYTES)
-#define NT_SMEM_BYTES (TC_NT_STAGES * NT_STAGE_BYTES + 1024 + 256)
+template <int BN, int STAGES>
+struct NtCfg {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
 
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtensorMap mAlo,
     const __grid_constant__ CUtensorMap mBhi, const __grid_constant__ CUtensorMap mBlo,
     NtArgs g)
 {
+  using Cfg = NtCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const RbView &v = g.v;
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = (uint64_t *)(smem + TC_NT_STAGES * NT_STAGE_BYTES);
-  uint64_t *empty = full + TC_NT_STAGES;
-  uint64_t *acc_ready = empty + TC_NT_STAGES;
+  uint64_t *full = (uint64_t *)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_ready = empty + STAGES;
   uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int I = v.d.i_size, H = v.d.h_size;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_NT_BN;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int K = (g.mode == 0) ? I : H;
-  const int n_kb = (K + TC_BK - 1) / TC_BK;
+  const int n_kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
+  const int n_kb = max(0, kb_end - kb_begin);
 
   /* CHAIN: a tile whose streams have all stopped has nothing to do */
   if (g.mode == 1) {
@@ -485,7 +560,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_NT_STAGES; s++) {
+    for (int s = 0; s < STAGES; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
@@ -497,7 +572,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     tma_prefetch_desc(&mBlo);
   }
   if (warp == 1)
-    tmem_alloc(tmem_slot, TC_NT_BN);
+    tmem_alloc(tmem_slot, BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -511,31 +586,32 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
         ring_row = v.pos[v.base] * v.cap + v.base + m0;
       else
         ring_row = g.k * v.cap + v.base + m0;
-      for (int kb = 0; kb < n_kb; kb++) {
-        int s = kb % TC_NT_STAGES;
-        uint32_t ph = (kb / TC_NT_STAGES) & 1;
+      for (int it = 0; it < n_kb; it++) {
+        int kb = kb_begin + it;
+        int s = it % STAGES;
+        uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        uint8_t *st = smem + s * NT_STAGE_BYTES;
-        mbar_expect_tx(&full[s], NT_STAGE_BYTES);
+        uint8_t *st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
         tma_load_2d(&mAhi, &full[s], st, kb * TC_BK, ring_row);
-        tma_load_2d(&mAlo, &full[s], st + NT_A_BYTES, kb * TC_BK, ring_row);
-        tma_load_2d(&mBhi, &full[s], st + 2 * NT_A_BYTES, kb * TC_BK, n0);
-        tma_load_2d(&mBlo, &full[s], st + 2 * NT_A_BYTES + NT_B_BYTES, kb * TC_BK, n0);
+        tma_load_2d(&mAlo, &full[s], st + Cfg::A_BYTES, kb * TC_BK, ring_row);
+        tma_load_2d(&mBhi, &full[s], st + 2 * Cfg::A_BYTES, kb * TC_BK, n0);
+        tma_load_2d(&mBlo, &full[s], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * TC_BK, n0);
       }
     }
   }
   else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_NT_BN, 0, 0);
-      for (int kb = 0; kb < n_kb; kb++) {
-        int s = kb % TC_NT_STAGES;
-        uint32_t ph = (kb / TC_NT_STAGES) & 1;
+      const uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
+      for (int it = 0; it < n_kb; it++) {
+        int s = it % STAGES;
+        uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        uint32_t a_hi = smem_u32(smem + s * NT_STAGE_BYTES);
-        uint32_t a_lo = a_hi + NT_A_BYTES;
-        uint32_t b_hi = a_hi + 2 * NT_A_BYTES;
-        uint32_t b_lo = b_hi + NT_B_BYTES;
+        uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        uint32_t a_lo = a_hi + Cfg::A_BYTES;
+        uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+        uint32_t b_lo = b_hi + Cfg::B_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 8; kk++) {
           /* K-major, 128B swizzle: 8-row groups 1024 B apart; a K step of 8
@@ -544,7 +620,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
           uint64_t dal = umma_desc(a_lo + kk * 32, 16, 1024);
           uint64_t dbh = umma_desc(b_hi + kk * 32, 16, 1024);
           uint64_t dbl = umma_desc(b_lo + kk * 32, 16, 1024);
-          umma_tf32(tmem_base, dal, dbh, idesc, (kb | kk) ? 1u : 0u);
+          umma_tf32(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
           umma_tf32(tmem_base, dah, dbl, idesc, 1u);
           umma_tf32(tmem_base, dah, dbh, idesc, 1u);
         }
@@ -560,12 +636,14 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     const int m = m0 + row;
     const bool row_ok = m < v.n;
     const int sidx = v.base + (row_ok ? m : 0);
-    mbar_wait(acc_ready, 0);
-    tc_fence_after();
+    if (n_kb > 0) {
+      mbar_wait(acc_ready, 0);
+      tc_fence_after();
+    }
     float acc[32];
     if (g.mode == 0) {
 #pragma unroll 1
-      for (int c = 0; c < TC_NT_BN; c += 32) {
+      for (int c = 0; c < BN; c += 32) {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
         int col0 = n0 + c;
         if (!row_ok || col0 >= H)
@@ -603,69 +681,142 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
       }
     }
     else {
-      const int hs1 = v.d.hidden_size + 1;
+      /* raw partial sums of this K split; masks and the rest happen row-wise
+         in k_chain_finish_step */
       const bool live = row_ok && v.sc[sidx].live != 0;
-      const int p = v.pos[sidx] - g.k;
-      const float *xk = v.X + ((size_t)(p < 0 ? p + v.depth : p) * v.cap + sidx) * I;
-      const size_t eoff = ((size_t)(g.k + 1) * v.cap + sidx) * I;
-      float sq = 0.0f;
+      float *dst = g.cpartial + ((size_t)blockIdx.z * v.cap + sidx) * I;
 #pragma unroll 1
-      for (int c = 0; c < TC_NT_BN; c += 32) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+      for (int c = 0; c < BN; c += 32) {
+        if (n_kb > 0)
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+        else {
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            acc[j] = 0.0f;
+        }
         int col0 = n0 + c;
         if (!live || col0 >= I)
           continue;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          if (col0 + j >= I)
-            break;
-          float4 xin = *(const float4 *)(xk + col0 + j);
-          float xi[4] = {xin.x, xin.y, xin.z, xin.w};
-          float o[4], ohi[4], olo[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            float e = 0.0f;
-            float input = xi[u];
-            if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
-              e = acc[j + u];
-              if (v.activation == RNN_RESQRT)
-                e /= 2.0f * (input + 1.0f);
-              sq += e * e;
-            }
-            int col = col0 + j + u;
-            if (col == 0 || (col >= hs1 && col < H))
-              e = 0.0f;
-            o[u] = e;
-            split_tf32(e, ohi[u], olo[u]);
-          }
-          *(float4 *)(v.E + eoff + col0 + j) = make_float4(o[0], o[1], o[2], o[3]);
-          *(float4 *)(g.Ehi + eoff + col0 + j) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
-          *(float4 *)(g.Elo + eoff + col0 + j) = make_float4(olo[0], olo[1], olo[2], olo[3]);
+          if (col0 + j < I)
+            *(float4 *)(dst + col0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
         }
       }
-      if (live)
-        v.partial[(size_t)sidx * v.n_part + blockIdx.x] = sq;
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_NT_BN);
+    tmem_dealloc(tmem_base, BN);
   }
 }
 
+/* The row-wise half of a BPTT step (recur-nn.c:338-389, 393-413), one block
+   per stream: sum the split-K partials in a fixed order, mask by the input
+   that fed each row, ReSQRT derivative, write E(k+1) with its hi/lo planes,
+   sum the squares, and decide whether this stream walks further.           */
+__global__ void __launch_bounds__(256)
+k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int splits,
+    float *__restrict__ Ehi, float *__restrict__ Elo)
+{
+  __shared__ float scratch[33];
+  const int s = v.slots[blockIdx.x];
+  RbScalars *scp = v.sc + s;
+  RbScalars scv = *scp; /* one read up front; thread 0 writes the changes back */
+  RbScalars *sc = &scv;
+  if (!sc->live)
+    return;
+  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  int p = v.pos[s] - k;
+  if (p < 0)
+    p += v.depth;
+  const float *xk = v.X + ((size_t)p * v.cap + s) * I;
+  const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
+  const size_t split_stride = (size_t)v.cap * I;
+  const float *part = cpartial + (size_t)s * I;
+  float sq = 0.0f;
+  for (int c = threadIdx.x * 4; c < I; c += blockDim.x * 4) {
+    float4 a = *(const float4 *)(part + c);
+    for (int z = 1; z < splits; z++) {
+      float4 b = *(const float4 *)(part + z * split_stride + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 xin = *(const float4 *)(xk + c);
+    float acc[4] = {a.x, a.y, a.z, a.w};
+    float xi[4] = {xin.x, xin.y, xin.z, xin.w};
+    float o[4], ohi[4], olo[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      float e = 0.0f;
+      float input = xi[u];
+      if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
+        e = acc[u];
+        if (v.activation == RNN_RESQRT)
+          e /= 2.0f * (input + 1.0f);
+        sq += e * e;
+      }
+      int col = c + u;
+      if (col == 0 || (col >= hs1 && col < H))
+        e = 0.0f;
+      o[u] = e;
+      split_tf32(e, ohi[u], olo[u]);
+    }
+    *(float4 *)(v.E + eoff + c) = make_float4(o[0], o[1], o[2], o[3]);
+    *(float4 *)(Ehi + eoff + c) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
+    *(float4 *)(Elo + eoff + c) = make_float4(olo[0], olo[1], olo[2], olo[3]);
+  }
+  float es = block_sum_tc(sq, scratch);
+  if (threadIdx.x != 0)
+    return;
+  sc->err_sum = es;
+  sc->cum_error += sqrtf(es);
+  sc->n_steps = k + 1;
+  int t = v.depth - k;
+  bool stop = (es <= sc->min_sum || es > sc->max_sum);
+  bool last = (k == v.depth - 1);
+  if (!stop && !last) {
+    *scp = scv;
+    return;
+  }
+  sc->live = 0;
+  int t_left = stop ? t : 0;
+  sc->t_left = t_left;
+  float ceiling = ERROR_GAIN_CEILING * sc->top_scaled;
+  if (es > ceiling) {
+    float halfmax = sc->max_sum;
+    float x = es / halfmax;
+    float fudge = (float)(0.99 + (double)(x * x / 100.0f));
+    sc->ih_scale = (halfmax == 0.0f) ? es : 2.0f * x / (1.0f + x * x * fudge);
+  }
+  else {
+    sc->ih_scale = 1.0f;
+    if (sc->adaptive) {
+      int depth_error = v.depth / 4 - t_left;
+      float min_gain = MIN_ERROR_GAIN * sc->top_scaled;
+      float mef = sc->mef;
+      if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc->min_sum || depth_error < 0))
+        mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
+      sc->mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+    }
+  }
+  *scp = scv;
+}
+
 /* ======================================================================== */
-/* DW: delta tile [128 y x 128 x] += X^T . E over (step, stream) rows;
-   both operands MN-major, split-K across blockIdx.z                          */
+/* DW: delta tile [128 y x 256 x] += X^T . E over (step, stream) rows;
+   both operands MN-major, 16 ring rows per stage, split-K across blockIdx.z  */
 
 struct DwArgs {
   RbView v;
   float *partial; /* [splits][i_size][h_size] */
 };
 
-#define DW_OP_BYTES (TC_BM * TC_BK * 4) /* 16 KB: 4 chunks of 32(MN) x 32(K) */
-#define DW_STAGE_BYTES (4 * DW_OP_BYTES)
+#define DW_CHUNK_BYTES (32 * TC_DW_BK * 4)          /* one TMA box: 32 floats x 16 rows */
+#define DW_A_BYTES ((TC_BM / 32) * DW_CHUNK_BYTES)    /* 8 KB */
+#define DW_B_BYTES ((TC_DW_BN / 32) * DW_CHUNK_BYTES) /* 16 KB */
+#define DW_STAGE_BYTES (2 * DW_A_BYTES + 2 * DW_B_BYTES)
 #define DW_SMEM_BYTES (TC_DW_STAGES * DW_STAGE_BYTES + 1024 + 256)
 
 __global__ void __launch_bounds__(192, 1)
@@ -684,7 +835,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int I = v.d.i_size, H = v.d.h_size;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_DW_BN;
-  const int kb_per_step = v.n / TC_BK;
+  const int kb_per_step = v.n / TC_DW_BK;
   const int n_kb_total = v.depth * kb_per_step;
   const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
   const int kb_begin = blockIdx.z * kb_per_split;
@@ -717,7 +868,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
         uint32_t ph = (it / TC_DW_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         int step = kb / kb_per_step;
-        int b0 = (kb - step * kb_per_step) * TC_BK;
+        int b0 = (kb - step * kb_per_step) * TC_DW_BK;
         int slot = pos - step;
         if (slot < 0)
           slot += v.depth;
@@ -725,13 +876,10 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
         int erow = step * v.cap + v.base + b0;
         uint8_t *st = smem + s * DW_STAGE_BYTES;
         mbar_expect_tx(&full[s], DW_STAGE_BYTES);
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-          tma_load_2d(&mXhi, &full[s], st + c * 4096, m0 + c * 32, xrow);
-          tma_load_2d(&mXlo, &full[s], st + DW_OP_BYTES + c * 4096, m0 + c * 32, xrow);
-          tma_load_2d(&mEhi, &full[s], st + 2 * DW_OP_BYTES + c * 4096, n0 + c * 32, erow);
-          tma_load_2d(&mElo, &full[s], st + 3 * DW_OP_BYTES + c * 4096, n0 + c * 32, erow);
-        }
+        tma_load_3d(&mXhi, &full[s], st, 0, xrow, m0 / 32);
+        tma_load_3d(&mXlo, &full[s], st + DW_A_BYTES, 0, xrow, m0 / 32);
+        tma_load_3d(&mEhi, &full[s], st + 2 * DW_A_BYTES, 0, erow, n0 / 32);
+        tma_load_3d(&mElo, &full[s], st + 2 * DW_A_BYTES + DW_B_BYTES, 0, erow, n0 / 32);
       }
     }
   }
@@ -744,19 +892,19 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
         mbar_wait(&full[s], ph);
         tc_fence_after();
         uint32_t a_hi = smem_u32(smem + s * DW_STAGE_BYTES);
-        uint32_t a_lo = a_hi + DW_OP_BYTES;
-        uint32_t b_hi = a_hi + 2 * DW_OP_BYTES;
-        uint32_t b_lo = a_hi + 3 * DW_OP_BYTES;
+        uint32_t a_lo = a_hi + DW_A_BYTES;
+        uint32_t b_hi = a_hi + 2 * DW_A_BYTES;
+        uint32_t b_lo = b_hi + DW_B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; kk++) {
+        for (int kk = 0; kk < TC_DW_BK / 8; kk++) {
           /* MN-major 32-bit operands (SWIZZLE_128B_BASE32B): each K row is one
              128-byte line of 32 floats along M/N; 32-float chunks along M/N
-             are 4096 B apart (leading offset), groups of 4 K rows 512 B apart
-             (stride offset); one MMA consumes 8 K rows = 1024 B */
-          uint64_t dah = umma_desc(a_hi + kk * 1024, 4096, 512, UMMA_SW128_BASE32);
-          uint64_t dal = umma_desc(a_lo + kk * 1024, 4096, 512, UMMA_SW128_BASE32);
-          uint64_t dbh = umma_desc(b_hi + kk * 1024, 4096, 512, UMMA_SW128_BASE32);
-          uint64_t dbl = umma_desc(b_lo + kk * 1024, 4096, 512, UMMA_SW128_BASE32);
+             are one TMA box apart (leading offset), groups of 4 K rows 512 B
+             apart (stride offset); one MMA consumes 8 K rows = 1024 B */
+          uint64_t dah = umma_desc(a_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dal = umma_desc(a_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dbh = umma_desc(b_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dbl = umma_desc(b_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
           umma_tf32(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
           umma_tf32(tmem_base, dah, dbl, idesc, 1u);
           umma_tf32(tmem_base, dah, dbh, idesc, 1u);
@@ -841,7 +989,9 @@ refresh_weight_planes(RbTc *t, RbPool *p, const RbView *v)
   t->w_version = g->weights_version;
 }
 
-static int nt_attr_done = 0, dw_attr_done = 0;
+static int fwd_attr_done = 0, chain_attr_done = 0, dw_attr_done = 0;
+typedef NtCfg<TC_FWD_BN, TC_FWD_STAGES> FwdCfg;
+typedef NtCfg<TC_CHAIN_BN, TC_CHAIN_STAGES> ChainCfg;
 
 extern "C" void
 rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
@@ -856,19 +1006,20 @@ rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
   g.mode = 0;
   g.k = 0;
   g.use_noise = 0;
-  g.Ehi = g.Elo = NULL;
+  g.cpartial = NULL;
   if (presynaptic_noise != 0.0f) {
     rbk_gen_noise(v, presynaptic_noise, 1, v->d.h_size - 1);
     g.use_noise = 1;
   }
-  if (!nt_attr_done) {
-    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            NT_SMEM_BYTES));
-    nt_attr_done = 1;
+  if (!fwd_attr_done) {
+    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_FWD_BN, TC_FWD_STAGES>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, FwdCfg::SMEM_BYTES));
+    fwd_attr_done = 1;
   }
-  dim3 grid(cdiv(v->d.h_size, TC_NT_BN), cdiv(v->n, TC_BM));
+  dim3 grid(cdiv(v->d.h_size, TC_FWD_BN), cdiv(v->n, TC_BM), 1);
   rb_prof_begin(RB_PROF_FWD);
-  k_tc_nt<<<grid, 192, NT_SMEM_BYTES, rb_stream>>>(t->mXhi_k, t->mXlo_k, t->mWThi_k, t->mWTlo_k, g);
+  k_tc_nt<TC_FWD_BN, TC_FWD_STAGES><<<grid, 192, FwdCfg::SMEM_BYTES, rb_stream>>>(t->mXhi_k,
+      t->mXlo_k, t->mWThi_k, t->mWTlo_k, g);
   LAUNCH_CHECK("k_tc_nt<FWD>");
   rb_prof_end(RB_PROF_FWD);
   rbk_output(v);
@@ -882,25 +1033,31 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
   /* E[0] (written by k_top) -> planes */
   k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 1, t->Ehi, t->Elo);
   LAUNCH_CHECK("k_split_rows");
-  if (!nt_attr_done) {
-    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            NT_SMEM_BYTES));
-    nt_attr_done = 1;
+  if (!chain_attr_done) {
+    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
+    chain_attr_done = 1;
   }
   NtArgs g;
   g.v = *v;
   g.mode = 1;
   g.use_noise = 0;
-  g.Ehi = t->Ehi;
-  g.Elo = t->Elo;
-  dim3 cgrid(cdiv(v->d.i_size, TC_NT_BN), cdiv(v->n, TC_BM));
+  g.cpartial = t->cpartial;
+  /* split K only as far as there are K blocks to share out */
+  int n_kb = cdiv(v->d.h_size, TC_BK);
+  int splits = TC_CHAIN_SPLITS;
+  while (splits > 1 && n_kb / splits < 2)
+    splits /= 2;
+  dim3 cgrid(cdiv(v->d.i_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
   for (int k = 0; k < v->depth; k++) {
     g.k = k;
     rb_prof_begin(RB_PROF_CHAIN);
-    k_tc_nt<<<cgrid, 192, NT_SMEM_BYTES, rb_stream>>>(t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, g);
+    k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, 192, ChainCfg::SMEM_BYTES, rb_stream>>>(
+        t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, g);
     LAUNCH_CHECK("k_tc_nt<CHAIN>");
+    k_chain_finish_step<<<v->n, 256, 0, rb_stream>>>(*v, k, t->cpartial, splits, t->Ehi, t->Elo);
+    LAUNCH_CHECK("k_chain_finish_step");
     rb_prof_end(RB_PROF_CHAIN);
-    rbk_chain_decide(v, k);
   }
   dim3 fgrid(v->n, v->depth);
   k_finalize_rows<<<fgrid, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo);
