@@ -274,6 +274,8 @@ typedef struct RbTc {
   float *WThi, *WTlo;   /* [h_size][i_size] */
   float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
   float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size] split-K partial sums of a chain step */
+  unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
+  int persistent_ok;    /* -1 unknown, 0 no, 1 yes */
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
@@ -362,6 +364,7 @@ tc_free(RbTc *t)
   cudaFree(t->Whi); cudaFree(t->Wlo); cudaFree(t->WThi); cudaFree(t->WTlo);
   cudaFree(t->partial);
   cudaFree(t->cpartial);
+  cudaFree(t->sync);
   free(t);
 }
 
@@ -398,6 +401,8 @@ tc_state(RbPool *p)
   t->WTlo = dmalloc0<float>(I * H);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
   t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * I);
+  t->sync = dmalloc0<unsigned int>(p->depth + 8);
+  t->persistent_ok = -1;
   t->w_src = NULL;
   uint64_t ring_rows = (uint64_t)p->depth * p->cap, chain_rows = (uint64_t)(p->depth + 1) * p->cap;
   make_map(&t->mXhi_k, t->Xhi, I, ring_rows, I, TC_BM);
@@ -805,6 +810,301 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
 }
 
 /* ======================================================================== */
+/* The whole BPTT walk as ONE persistent, grid-synchronised kernel.
+ *
+ * A BPTT step is a small dependent GEMM; launched per step it spends more
+ * time on launch gaps, pipeline prologues and cold tensor-map fetches than on
+ * MMAs.  Here 144 CTAs (n-tiles x m-tiles x K-splits, one per SM, co-resident
+ * through a cooperative launch) stay alive for all `depth` steps.  Per step:
+ *   phase A  the split-K tcgen05 GEMM of k_tc_nt (TMEM allocated once, mbarrier
+ *            pipeline state carried across steps), partial tiles to L2;
+ *   grid barrier;
+ *   phase B  the row-wise half (k_chain_finish_step's body), one row per
+ *            epilogue warp across the grid, which also counts the streams
+ *            that walk on;
+ *   grid barrier; stop when no stream is left.
+ * E(k+1)'s hi/lo planes are written with generic stores and read by the next
+ * step's TMA, hence the generic->async proxy fence before the barrier.       */
+
+/* per-stream scalars change between steps inside one launch: read them past L1 */
+__device__ __forceinline__ RbScalars
+load_scalars_cg(const RbScalars *p)
+{
+  static_assert(sizeof(RbScalars) == 64, "RbScalars is read as four 16-byte words");
+  union { RbScalars s; int4 w[4]; } u;
+  const int4 *src = (const int4 *)p;
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+    u.w[i] = __ldcg(src + i);
+  return u.s;
+}
+
+struct ChainArgs {
+  RbView v;
+  float *cpartial;
+  float *Ehi, *Elo;
+  unsigned int *sync;   /* [0] barrier counter, [1 + k] streams alive at step k */
+};
+
+__device__ __forceinline__ void
+grid_barrier(unsigned int *counter, unsigned int target)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    while (*(volatile unsigned int *)counter < target)
+      ;
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
+    const __grid_constant__ CUtensorMap mAlo, const __grid_constant__ CUtensorMap mBhi,
+    const __grid_constant__ CUtensorMap mBlo, ChainArgs g)
+{
+  using Cfg = NtCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const RbView &v = g.v;
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t *empty = full + STAGES;
+  uint64_t *acc_ready = empty + STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int n_ctas = gridDim.x * gridDim.y * gridDim.z;
+  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const int n_kb_total = (H + TC_BK - 1) / TC_BK;
+  const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
+  const int n_kb = max(0, kb_end - kb_begin);
+  const size_t split_stride = (size_t)v.cap * I;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mAhi);
+    tma_prefetch_desc(&mAlo);
+    tma_prefetch_desc(&mBhi);
+    tma_prefetch_desc(&mBlo);
+  }
+  if (warp == 1)
+    tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  unsigned int it = 0;       /* pipeline iterations so far (producer and MMA keep equal counts) */
+  unsigned int n_gemms = 0;  /* accumulators completed by this CTA */
+  unsigned int n_bar = 0;
+
+  for (int k = 0; k < v.depth; k++) {
+    /* ---- phase A: partial tile of E(k) . Wih^T over this CTA's K range ---- */
+    int alive = 0;
+    for (int r = lane; r < TC_BM; r += 32) {
+      int m = m0 + r;
+      if (m < v.n && __ldcg(&v.sc[v.base + m].live))
+        alive = 1;
+    }
+    const bool tile_alive = __any_sync(0xffffffffu, alive) && n_kb > 0;
+
+    if (tile_alive) {
+      if (warp == 0) {
+        if (lane == 0) {
+          const int ring_row = k * v.cap + v.base + m0;
+          for (int j = 0; j < n_kb; j++) {
+            unsigned int i2 = it + j;
+            int s = i2 % STAGES;
+            uint32_t ph = (i2 / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t *st = smem + s * Cfg::STAGE_BYTES;
+            int kb = kb_begin + j;
+            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
+            tma_load_2d(&mAhi, &full[s], st, kb * TC_BK, ring_row);
+            tma_load_2d(&mAlo, &full[s], st + Cfg::A_BYTES, kb * TC_BK, ring_row);
+            tma_load_2d(&mBhi, &full[s], st + 2 * Cfg::A_BYTES, kb * TC_BK, n0);
+            tma_load_2d(&mBlo, &full[s], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * TC_BK, n0);
+          }
+        }
+      }
+      else if (warp == 1) {
+        if (lane == 0) {
+          const uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
+          for (int j = 0; j < n_kb; j++) {
+            unsigned int i2 = it + j;
+            int s = i2 % STAGES;
+            uint32_t ph = (i2 / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
+            uint32_t a_lo = a_hi + Cfg::A_BYTES;
+            uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
+            uint32_t b_lo = b_hi + Cfg::B_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 8; kk++) {
+              uint64_t dah = umma_desc(a_hi + kk * 32, 16, 1024);
+              uint64_t dal = umma_desc(a_lo + kk * 32, 16, 1024);
+              uint64_t dbh = umma_desc(b_hi + kk * 32, 16, 1024);
+              uint64_t dbl = umma_desc(b_lo + kk * 32, 16, 1024);
+              umma_tf32(tmem_base, dal, dbh, idesc, (j | kk) ? 1u : 0u);
+              umma_tf32(tmem_base, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_base, dah, dbh, idesc, 1u);
+            }
+            umma_commit(&empty[s]);
+          }
+          umma_commit(acc_ready);
+        }
+      }
+      else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool row_ok = m < v.n;
+        const int sidx = v.base + (row_ok ? m : 0);
+        mbar_wait(acc_ready, n_gemms & 1);
+        tc_fence_after();
+        const bool live = row_ok && __ldcg(&v.sc[sidx].live) != 0;
+        float *dst = g.cpartial + (size_t)blockIdx.z * split_stride + (size_t)sidx * I;
+        float acc[32];
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+          int col0 = n0 + c;
+          if (!live || col0 >= I)
+            continue;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (col0 + j < I)
+              __stcg((float4 *)(dst + col0 + j),
+                  make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+          }
+        }
+        tc_fence_before();
+      }
+      it += n_kb;
+      n_gemms++;
+    }
+    n_bar++;
+    grid_barrier(g.sync, n_bar * n_ctas);
+
+    /* ---- phase B: rows of E(k+1), one per epilogue warp across the grid ---- */
+    if (warp >= 2) {
+      const int gw = cta * 4 + (warp - 2);
+      for (int m = gw; m < v.n; m += n_ctas * 4) {
+        const int s = v.base + m;
+        RbScalars *scp = v.sc + s;
+        if (!__ldcg(&scp->live))
+          continue;
+        int p = v.pos[s] - k;
+        if (p < 0)
+          p += v.depth;
+        const float *xk = v.X + ((size_t)p * v.cap + s) * I;
+        const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
+        const float *part = g.cpartial + (size_t)s * I;
+        float sq = 0.0f;
+        for (int c = lane * 4; c < I; c += 128) {
+          /* K splits whose tile was skipped do not exist: gridDim.z splits
+             always ran for a live row, in order */
+          float4 a = __ldcg((const float4 *)(part + c));
+          for (int z = 1; z < (int)gridDim.z; z++) {
+            float4 b = __ldcg((const float4 *)(part + z * split_stride + c));
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          float4 xin = *(const float4 *)(xk + c);
+          float av[4] = {a.x, a.y, a.z, a.w};
+          float xi[4] = {xin.x, xin.y, xin.z, xin.w};
+          float o[4], ohi[4], olo[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            float e = 0.0f;
+            float input = xi[u];
+            if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
+              e = av[u];
+              if (v.activation == RNN_RESQRT)
+                e /= 2.0f * (input + 1.0f);
+              sq += e * e;
+            }
+            int col = c + u;
+            if (col == 0 || (col >= hs1 && col < H))
+              e = 0.0f;
+            o[u] = e;
+            split_tf32(e, ohi[u], olo[u]);
+          }
+          *(float4 *)(v.E + eoff + c) = make_float4(o[0], o[1], o[2], o[3]);
+          *(float4 *)(g.Ehi + eoff + c) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
+          *(float4 *)(g.Elo + eoff + c) = make_float4(olo[0], olo[1], olo[2], olo[3]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) {
+          RbScalars sc = load_scalars_cg(scp);
+          float es = sq;
+          sc.err_sum = es;
+          sc.cum_error += sqrtf(es);
+          sc.n_steps = k + 1;
+          int t = v.depth - k;
+          bool stop = (es <= sc.min_sum || es > sc.max_sum);
+          bool last = (k == v.depth - 1);
+          if (stop || last) {
+            sc.live = 0;
+            int t_left = stop ? t : 0;
+            sc.t_left = t_left;
+            float ceiling = ERROR_GAIN_CEILING * sc.top_scaled;
+            if (es > ceiling) {
+              float halfmax = sc.max_sum;
+              float x = es / halfmax;
+              float fudge = (float)(0.99 + (double)(x * x / 100.0f));
+              sc.ih_scale = (halfmax == 0.0f) ? es : 2.0f * x / (1.0f + x * x * fudge);
+            }
+            else {
+              sc.ih_scale = 1.0f;
+              if (sc.adaptive) {
+                int depth_error = v.depth / 4 - t_left;
+                float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
+                float mef = sc.mef;
+                if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc.min_sum || depth_error < 0))
+                  mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
+                sc.mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+              }
+            }
+          }
+          else {
+            atomicAdd(&g.sync[1 + k], 1u);
+          }
+          *scp = sc;
+        }
+      }
+      /* E(k+1) planes were written through the generic proxy; the next step's
+         TMA reads them through the async proxy */
+      asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    n_bar++;
+    grid_barrier(g.sync, n_bar * n_ctas);
+    if (__ldcg(&g.sync[1 + k]) == 0)
+      break; /* every stream has stopped (uniform across the grid) */
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+/* ======================================================================== */
 /* DW: delta tile [128 y x 256 x] += X^T . E over (step, stream) rows;
    both operands MN-major, 16 ring rows per stage, split-K across blockIdx.z  */
 
@@ -1049,6 +1349,36 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
   while (splits > 1 && n_kb / splits < 2)
     splits /= 2;
   dim3 cgrid(cdiv(v->d.i_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
+  int n_ctas = cgrid.x * cgrid.y * cgrid.z;
+  if (t->persistent_ok < 0) {
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    CUDA_OR_DIE(cudaGetDevice(&dev));
+    CUDA_OR_DIE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
+    CUDA_OR_DIE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+            k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, 192, ChainCfg::SMEM_BYTES));
+    t->persistent_ok = (coop && per_sm * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
+  }
+  if (t->persistent_ok) {
+    ChainArgs ca;
+    ca.v = *v;
+    ca.cpartial = t->cpartial;
+    ca.Ehi = t->Ehi;
+    ca.Elo = t->Elo;
+    ca.sync = t->sync;
+    CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0, (v->depth + 8) * sizeof(unsigned int), rb_stream));
+    void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
+                      (void *)&t->mWlo_k, (void *)&ca};
+    rb_prof_begin(RB_PROF_CHAIN);
+    CUDA_OR_DIE(cudaLaunchCooperativeKernel(
+            (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(192),
+            params, ChainCfg::SMEM_BYTES, rb_stream));
+    LAUNCH_CHECK("k_tc_chain_persistent");
+    rb_prof_end(RB_PROF_CHAIN);
+  }
+  else
   for (int k = 0; k < v->depth; k++) {
     g.k = k;
     rb_prof_begin(RB_PROF_CHAIN);
