@@ -209,8 +209,8 @@ def run_reference(args):
     total_chars = 0
     t0 = time.time()
     steps_done = 0
-    rate, wall = reference_cpu_throughput(cores, n_streams, warm + per_step * args.warmup,
-                                          per_step * args.steps)
+    timed = max(4, min(per_step * args.steps, 48))   # bounded: ~10-20 s of CPU work
+    rate, wall = reference_cpu_throughput(cores, n_streams, warm, timed)
     ms_per_step = 1e3 * (per_step * n_streams * cores) / rate
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
@@ -221,9 +221,8 @@ def run_reference(args):
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": "%d independent replicas (one per core) of the reference "
                                    "multi-tap loop, H%d D%d, %d streams each, %d warm-up + %d timed "
-                                   "positions" % (cores, HIDDEN, DEPTH, n_streams,
-                                                  warm + per_step * args.warmup,
-                                                  per_step * args.steps)},
+                                   "positions, %.1f s wall" % (cores, HIDDEN, DEPTH, n_streams,
+                                                  warm, timed, wall)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -319,7 +318,10 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.time()
+    while not sampler.samples and time.time() - t_wait < 5.0:
+        time.sleep(0.05)          # nvidia-smi takes a moment to print its first line
+    sampler.samples.clear()
     launches0 = L.rnn_b200_kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = api.RnnBatchCharStats()
@@ -354,7 +356,7 @@ def run_ours(args):
     sampler.stop()
 
     # ---- per-kernel timing for the roofline (separate, instrumented pass) --
-    prof_steps = min(args.steps, 10)
+    prof_steps = min(args.steps, 50)
     L.rnn_b200_profile_enable(1)
     pev0, pev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pev0.record(stream)
@@ -436,11 +438,11 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cores = host_cores()
-                rate, wall = reference_cpu_throughput(cores, 8, DEPTH, 4)
+                rate, wall = reference_cpu_throughput(cores, 8, DEPTH, 24)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
                     "sample": "%d independent replicas (one per core) of the reference multi-tap "
-                              "loop, H%d D%d, 8 streams each, %d warm-up + 4 timed positions, "
+                              "loop, H%d D%d, 8 streams each, %d warm-up + 24 timed positions, "
                               "%.1f s wall" % (cores, HIDDEN, DEPTH, DEPTH, wall)}
             except Exception as e:  # the oracle .so did not travel
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
@@ -456,8 +458,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", type=int, default=None, help="0 auto, 1 FMA, 2 tensor")
     ap.add_argument("--hidden", type=int, default=HIDDEN)

@@ -273,7 +273,7 @@ typedef struct RbTc {
   float *Whi, *Wlo;     /* [i_size][h_size] */
   float *WThi, *WTlo;   /* [h_size][i_size] */
   float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
-  float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size] split-K partial sums of a chain step */
+  float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
   unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
   int persistent_ok;    /* -1 unknown, 0 no, 1 yes */
   const float *w_src;   /* weights the planes were made from */
@@ -400,7 +400,7 @@ tc_state(RbPool *p)
   t->WThi = dmalloc0<float>(I * H);
   t->WTlo = dmalloc0<float>(I * H);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
-  t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * I);
+  t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * ((I + 31) & ~(size_t)31));
   t->sync = dmalloc0<unsigned int>(p->depth + 8);
   t->persistent_ok = -1;
   t->w_src = NULL;
@@ -689,7 +689,8 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
       /* raw partial sums of this K split; masks and the rest happen row-wise
          in k_chain_finish_step */
       const bool live = row_ok && v.sc[sidx].live != 0;
-      float *dst = g.cpartial + ((size_t)blockIdx.z * v.cap + sidx) * I;
+      const int cpitch = (I + 31) & ~31;
+      float *dst = g.cpartial + ((size_t)blockIdx.z * v.cap + sidx) * cpitch;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         if (n_kb > 0)
@@ -739,8 +740,9 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
     p += v.depth;
   const float *xk = v.X + ((size_t)p * v.cap + s) * I;
   const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
-  const size_t split_stride = (size_t)v.cap * I;
-  const float *part = cpartial + (size_t)s * I;
+  const int cpitch = (I + 31) & ~31;
+  const size_t split_stride = (size_t)v.cap * cpitch;
+  const float *part = cpartial + (size_t)s * cpitch;
   float sq = 0.0f;
   for (int c = threadIdx.x * 4; c < I; c += blockDim.x * 4) {
     float4 a = *(const float4 *)(part + c);
@@ -826,6 +828,24 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
  * E(k+1)'s hi/lo planes are written with generic stores and read by the next
  * step's TMA, hence the generic->async proxy fence before the barrier.       */
 
+/* 32 bytes per lane per instruction: whole L2 sectors even when every lane
+   writes its own row */
+__device__ __forceinline__ void
+st_global_v8(float *p, const float *a)
+{
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]),
+      "f"(a[7]) : "memory");
+}
+
+__device__ __forceinline__ unsigned int
+ld_acquire_gpu(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 /* per-stream scalars change between steps inside one launch: read them past L1 */
 __device__ __forceinline__ RbScalars
 load_scalars_cg(const RbScalars *p)
@@ -844,7 +864,31 @@ struct ChainArgs {
   float *cpartial;
   float *Ehi, *Elo;
   unsigned int *sync;   /* [0] barrier counter, [1 + k] streams alive at step k */
+  unsigned long long *dbg; /* optional: 5 globaltimer stamps per step from CTA 0 */
 };
+
+__device__ __forceinline__ unsigned long long
+globaltimer_ns(void)
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+#define ROLE_STAMP(slot) do {                                           \
+    if (g.dbg && cta == 0 && k == 5)                                    \
+      g.dbg[1200 + (slot)] = globaltimer_ns();                          \
+  } while (0)
+
+#define CHAIN_STAMP(slot) do {                                          \
+    if (g.dbg && threadIdx.x == 0) {                                    \
+      unsigned long long now_ = globaltimer_ns();                       \
+      if (cta == 0)                                                     \
+        g.dbg[k * 5 + (slot)] = now_;                                   \
+      if (k == 5)                                                       \
+        g.dbg[320 + cta * 5 + (slot)] = now_;                           \
+    }                                                                   \
+  } while (0)
 
 __device__ __forceinline__ void
 grid_barrier(unsigned int *counter, unsigned int target)
@@ -853,9 +897,8 @@ grid_barrier(unsigned int *counter, unsigned int target)
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
-    while (*(volatile unsigned int *)counter < target)
+    while (ld_acquire_gpu(counter) < target)
       ;
-    __threadfence();
   }
   __syncthreads();
 }
@@ -885,7 +928,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
   const int n_kb = max(0, kb_end - kb_begin);
-  const size_t split_stride = (size_t)v.cap * I;
+  const int cpitch = (I + 31) & ~31; /* rows of the partial planes start on 128-byte lines */
+  const size_t split_stride = (size_t)v.cap * cpitch;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -906,19 +950,20 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  const int pos0 = v.pos[v.base]; /* the batch advances in lockstep */
   unsigned int it = 0;       /* pipeline iterations so far (producer and MMA keep equal counts) */
   unsigned int n_gemms = 0;  /* accumulators completed by this CTA */
   unsigned int n_bar = 0;
 
   for (int k = 0; k < v.depth; k++) {
     /* ---- phase A: partial tile of E(k) . Wih^T over this CTA's K range ---- */
-    int alive = 0;
-    for (int r = lane; r < TC_BM; r += 32) {
-      int m = m0 + r;
-      if (m < v.n && __ldcg(&v.sc[v.base + m].live))
-        alive = 1;
-    }
-    const bool tile_alive = __any_sync(0xffffffffu, alive) && n_kb > 0;
+    CHAIN_STAMP(0);
+    /* no per-tile liveness test here: it would put an L2 round trip in front
+       of the first TMA; dead rows are simply not stored, and the walk ends
+       for the whole grid once no stream is left */
+    const bool tile_alive = n_kb > 0;
+    if (threadIdx.x == 0)
+      ROLE_STAMP(0);
 
     if (tile_alive) {
       if (warp == 0) {
@@ -948,6 +993,10 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
             uint32_t ph = (i2 / STAGES) & 1;
             mbar_wait(&full[s], ph);
             tc_fence_after();
+            if (j == 0)
+              ROLE_STAMP(1);
+            if (j == n_kb - 1)
+              ROLE_STAMP(2);
             uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
             uint32_t a_lo = a_hi + Cfg::A_BYTES;
             uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
@@ -973,10 +1022,12 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         const int m = m0 + row;
         const bool row_ok = m < v.n;
         const int sidx = v.base + (row_ok ? m : 0);
+        const bool live = row_ok && __ldcg(&v.sc[sidx].live) != 0;
         mbar_wait(acc_ready, n_gemms & 1);
         tc_fence_after();
-        const bool live = row_ok && __ldcg(&v.sc[sidx].live) != 0;
-        float *dst = g.cpartial + (size_t)blockIdx.z * split_stride + (size_t)sidx * I;
+        if (threadIdx.x == 64)
+          ROLE_STAMP(3);
+        float *dst = g.cpartial + (size_t)blockIdx.z * split_stride + (size_t)sidx * cpitch;
         float acc[32];
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -985,19 +1036,26 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           if (!live || col0 >= I)
             continue;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < I)
+          for (int j = 0; j < 32; j += 8) {
+            if (col0 + j + 8 <= I)
+              st_global_v8(dst + col0 + j, acc + j);
+            else if (col0 + j < I)
               __stcg((float4 *)(dst + col0 + j),
                   make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
           }
         }
         tc_fence_before();
+        if (threadIdx.x == 64)
+          ROLE_STAMP(4);
       }
       it += n_kb;
       n_gemms++;
     }
+    __syncthreads();
+    CHAIN_STAMP(1);
     n_bar++;
     grid_barrier(g.sync, n_bar * n_ctas);
+    CHAIN_STAMP(2);
 
     /* ---- phase B: rows of E(k+1), one per epilogue warp across the grid ---- */
     if (warp >= 2) {
@@ -1005,52 +1063,80 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
       for (int m = gw; m < v.n; m += n_ctas * 4) {
         const int s = v.base + m;
         RbScalars *scp = v.sc + s;
-        if (!__ldcg(&scp->live))
+        RbScalars sc = load_scalars_cg(scp);
+        if (!sc.live)
           continue;
-        int p = v.pos[s] - k;
+        int p = pos0 - k;
         if (p < 0)
           p += v.depth;
         const float *xk = v.X + ((size_t)p * v.cap + s) * I;
         const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
-        const float *part = g.cpartial + (size_t)s * I;
+        const float *part = g.cpartial + (size_t)s * cpitch;
         float sq = 0.0f;
-        for (int c = lane * 4; c < I; c += 128) {
-          /* K splits whose tile was skipped do not exist: gridDim.z splits
-             always ran for a live row, in order */
-          float4 a = __ldcg((const float4 *)(part + c));
-          for (int z = 1; z < (int)gridDim.z; z++) {
-            float4 b = __ldcg((const float4 *)(part + z * split_stride + c));
-            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          }
-          float4 xin = *(const float4 *)(xk + c);
-          float av[4] = {a.x, a.y, a.z, a.w};
-          float xi[4] = {xin.x, xin.y, xin.z, xin.w};
-          float o[4], ohi[4], olo[4];
+        /* all loads of a group of column chunks are issued before any of
+           their results is used or stored: the row costs a few L2 round
+           trips instead of one per chunk */
+        constexpr int GRP = 5;
+        for (int c0 = lane * 4; c0 < I; c0 += 128 * GRP) {
+          float4 a[GRP], xin[GRP], pz[TC_CHAIN_SPLITS - 1][GRP];
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            float e = 0.0f;
-            float input = xi[u];
-            if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
-              e = av[u];
-              if (v.activation == RNN_RESQRT)
-                e /= 2.0f * (input + 1.0f);
-              sq += e * e;
+          for (int i = 0; i < GRP; i++) {
+            int c = c0 + 128 * i;
+            if (c < I) {
+              a[i] = __ldcg((const float4 *)(part + c));
+              xin[i] = __ldg((const float4 *)(xk + c));
+#pragma unroll
+              for (int z = 1; z < TC_CHAIN_SPLITS; z++)
+                if (z < (int)gridDim.z)
+                  pz[z - 1][i] = __ldcg((const float4 *)(part + z * split_stride + c));
             }
-            int col = c + u;
-            if (col == 0 || (col >= hs1 && col < H))
-              e = 0.0f;
-            o[u] = e;
-            split_tf32(e, ohi[u], olo[u]);
           }
-          *(float4 *)(v.E + eoff + c) = make_float4(o[0], o[1], o[2], o[3]);
-          *(float4 *)(g.Ehi + eoff + c) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
-          *(float4 *)(g.Elo + eoff + c) = make_float4(olo[0], olo[1], olo[2], olo[3]);
+#pragma unroll
+          for (int z = 1; z < TC_CHAIN_SPLITS; z++) {
+            if (z < (int)gridDim.z) {
+#pragma unroll
+              for (int i = 0; i < GRP; i++) {
+                int c = c0 + 128 * i;
+                if (c < I) {
+                  a[i].x += pz[z - 1][i].x; a[i].y += pz[z - 1][i].y;
+                  a[i].z += pz[z - 1][i].z; a[i].w += pz[z - 1][i].w;
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < GRP; i++) {
+            int c = c0 + 128 * i;
+            if (c >= I)
+              continue;
+            float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+            float xi[4] = {xin[i].x, xin[i].y, xin[i].z, xin[i].w};
+            float o[4], ohi[4], olo[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              float e = 0.0f;
+              float input = xi[u];
+              if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
+                e = av[u];
+                if (v.activation == RNN_RESQRT)
+                  e /= 2.0f * (input + 1.0f);
+                sq += e * e;
+              }
+              int col = c + u;
+              if (col == 0 || (col >= hs1 && col < H))
+                e = 0.0f;
+              o[u] = e;
+              split_tf32(e, ohi[u], olo[u]);
+            }
+            __stcg((float4 *)(v.E + eoff + c), make_float4(o[0], o[1], o[2], o[3]));
+            __stcg((float4 *)(g.Ehi + eoff + c), make_float4(ohi[0], ohi[1], ohi[2], ohi[3]));
+            __stcg((float4 *)(g.Elo + eoff + c), make_float4(olo[0], olo[1], olo[2], olo[3]));
+          }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (lane == 0) {
-          RbScalars sc = load_scalars_cg(scp);
           float es = sq;
           sc.err_sum = es;
           sc.cum_error += sqrtf(es);
@@ -1091,8 +1177,11 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
          TMA reads them through the async proxy */
       asm volatile("fence.proxy.async;" ::: "memory");
     }
+    __syncthreads();
+    CHAIN_STAMP(3);
     n_bar++;
     grid_barrier(g.sync, n_bar * n_ctas);
+    CHAIN_STAMP(4);
     if (__ldcg(&g.sync[1 + k]) == 0)
       break; /* every stream has stopped (uniform across the grid) */
   }
@@ -1368,15 +1457,58 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
     ca.Ehi = t->Ehi;
     ca.Elo = t->Elo;
     ca.sync = t->sync;
+    ca.dbg = NULL;
+    static unsigned long long *dbg_dev = NULL;
+    static int dbg_calls = 0;
+    const bool timing = getenv("RECUR_B200_CHAIN_TIMING") != NULL;
+    if (timing) {
+      if (!dbg_dev)
+        CUDA_OR_DIE(cudaMalloc((void **)&dbg_dev, (1280) * sizeof(unsigned long long)));
+      CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, (1280) * sizeof(unsigned long long), rb_stream));
+      ca.dbg = dbg_dev;
+    }
     CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0, (v->depth + 8) * sizeof(unsigned int), rb_stream));
     void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
                       (void *)&t->mWlo_k, (void *)&ca};
     rb_prof_begin(RB_PROF_CHAIN);
-    CUDA_OR_DIE(cudaLaunchCooperativeKernel(
-            (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(192),
-            params, ChainCfg::SMEM_BYTES, rb_stream));
+    if (getenv("RECUR_B200_COOP_LAUNCH")) {
+      CUDA_OR_DIE(cudaLaunchCooperativeKernel(
+              (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(192),
+              params, ChainCfg::SMEM_BYTES, rb_stream));
+    }
+    else {
+      /* co-residency was established above (occupancy x SM count >= grid and
+         this stream runs nothing else alongside), so a plain launch is safe
+         and avoids the cooperative launch's queue drain */
+      k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, 192, ChainCfg::SMEM_BYTES,
+        rb_stream>>>(t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, ca);
+    }
     LAUNCH_CHECK("k_tc_chain_persistent");
     rb_prof_end(RB_PROF_CHAIN);
+    if (timing && (++dbg_calls % 100) == 60) {
+      static unsigned long long h[1280];
+      CUDA_OR_DIE(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, rb_stream));
+      CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+      double a = 0, b1 = 0, b = 0, b2 = 0;
+      int steps = 0;
+      for (int k = 0; k < v->depth && k < 64 && h[k * 5 + 4]; k++, steps++) {
+        a += (double)(h[k * 5 + 1] - h[k * 5 + 0]);
+        b1 += (double)(h[k * 5 + 2] - h[k * 5 + 1]);
+        b += (double)(h[k * 5 + 3] - h[k * 5 + 2]);
+        b2 += (double)(h[k * 5 + 4] - h[k * 5 + 3]);
+      }
+      if (steps)
+        fprintf(stderr, "chain timing (CTA 0, %d steps): phase A %.2f us, barrier %.2f us, "
+            "phase B %.2f us, barrier %.2f us per step\n", steps, a / steps * 1e-3,
+            b1 / steps * 1e-3, b / steps * 1e-3, b2 / steps * 1e-3);
+      {
+        const unsigned long long *q = h + 1200, t0 = h[320];
+        fprintf(stderr, "step 5 CTA 0 phase A: alive check done +%.2f, first stage landed +%.2f, "
+            "last stage landed +%.2f, accumulator ready +%.2f, epilogue done +%.2f, phase end +%.2f us\n",
+            (double)(q[0] - t0) * 1e-3, (double)(q[1] - t0) * 1e-3, (double)(q[2] - t0) * 1e-3,
+            (double)(q[3] - t0) * 1e-3, (double)(q[4] - t0) * 1e-3, (double)(h[321] - t0) * 1e-3);
+      }
+    }
   }
   else
   for (int k = 0; k < v->depth; k++) {
