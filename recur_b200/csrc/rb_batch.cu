@@ -240,7 +240,8 @@ rnn_batch_set_one_hot(RnnBatch *b, const u8 *hot)
 }
 
 extern "C" void rb_forward_dispatch(const RbView *v, float noise);
-extern "C" void rb_bptt_dispatch(const RbView *v, float *ih_delta, int accumulate);
+extern "C" void rb_top_and_bptt_dispatch(const RbView *v, float *ho_delta, float *ih_delta,
+    int accumulate);
 
 static void
 upload_rng_if_noisy(RnnBatch *b, float noise)
@@ -389,8 +390,7 @@ calc_deltas_async(RnnBatch *b, int accumulate)
   RbView v;
   batch_view(b, &v);
   refresh_learn_rates(b, &v);
-  rbk_top_layer(&v, bp->ho_delta, accumulate, NULL, 0);
-  rb_bptt_dispatch(&v, bp->ih_delta, accumulate);
+  rb_top_and_bptt_dispatch(&v, bp->ho_delta, bp->ih_delta, accumulate);
   /* [ih_delta | ho_delta] are adjacent in the prototype's delta block */
   if (rb_comm_size() > 1)
     rb_comm_allreduce_sum(bp->ih_delta, (size_t)proto->ih_size + proto->ho_size);

@@ -47,11 +47,15 @@ rb_forward_dispatch(const RbView *v, float noise)
     rbk_forward(v, noise);
 }
 
+/* a7..a11 for a batch without error ranges */
 extern "C" void
-rb_bptt_dispatch(const RbView *v, float *ih_delta, int accumulate)
+rb_top_and_bptt_dispatch(const RbView *v, float *ho_delta, float *ih_delta, int accumulate)
 {
-  if (use_tensor_engine(v) && v->pool->has_bptt)
-    rb_tc_bptt(v->pool, v, ih_delta, accumulate);
-  else
+  if (use_tensor_engine(v) && v->pool->has_bptt) {
+    rb_tc_top_and_bptt(v->pool, v, ho_delta, ih_delta, accumulate);
+  }
+  else {
+    rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
     rbk_bptt(v, ih_delta, accumulate);
+  }
 }

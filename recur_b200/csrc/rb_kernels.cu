@@ -795,6 +795,240 @@ k_ho_delta(RbView v, float *ho_delta, int accumulate,
   ho_delta[idx] = acc;
 }
 
+/* ------------------------------------------------------------------------ */
+/* Batch versions of the two top-layer kernels: eight streams per block share
+   every Who row they read, which turns 512 passes over Who into 64.         */
+
+#define OS 8 /* streams per block */
+
+__global__ void __launch_bounds__(256)
+k_out_multi(RbView v)
+{
+  extern __shared__ float sh[]; /* OS x h_size hidden rows, then reduction space */
+  const int H = v.d.h_size, O = v.d.o_size;
+  const int j0 = blockIdx.x * OS;
+  const int ns = min(OS, v.n - j0);
+  float *hid = sh;
+  float *red = sh + (size_t)OS * H;
+  for (int i = threadIdx.x; i < OS * H; i += blockDim.x) {
+    int q = i / H, r = i - q * H;
+    hid[i] = (q < ns) ? v.Hd[(size_t)v.slots[j0 + q] * H + r] : 0.0f;
+  }
+  __syncthreads();
+  const int CW = (O >= 256) ? 256 : O;
+  const int G = 256 / CW;
+  const int col = threadIdx.x % CW, grp = threadIdx.x / CW;
+  for (int c0 = 0; c0 < O; c0 += CW) {
+    int c = c0 + col;
+    float acc[OS];
+#pragma unroll
+    for (int q = 0; q < OS; q++)
+      acc[q] = 0.0f;
+    if (grp < G && c < O) {
+      for (int r = grp; r < H; r += G) {
+        float w = v.Who[(size_t)r * O + c];
+#pragma unroll
+        for (int q = 0; q < OS; q++)
+          acc[q] += hid[q * H + r] * w;
+      }
+    }
+    if (G > 1) {
+      if (grp < G) {
+#pragma unroll
+        for (int q = 0; q < OS; q++)
+          red[(grp * OS + q) * CW + col] = acc[q];
+      }
+      __syncthreads();
+      if (grp == 0 && c < O) {
+        for (int q = 0; q < ns; q++) {
+          float t = 0.0f;
+          for (int gq = 0; gq < G; gq++)
+            t += red[(gq * OS + q) * CW + col];
+          v.Y[(size_t)v.slots[j0 + q] * O + c] = t;
+        }
+      }
+      __syncthreads();
+    }
+    else if (c < O) {
+      for (int q = 0; q < ns; q++)
+        v.Y[(size_t)v.slots[j0 + q] * O + c] = acc[q];
+    }
+  }
+}
+
+/* a7/a8 for OS streams per block (dense error only); optionally also writes
+   the hi/lo planes of E[0] for the tensor engine */
+__global__ void __launch_bounds__(256)
+k_top_multi(RbView v, float *Ehi, float *Elo)
+{
+  extern __shared__ float sh[]; /* OS x o_size errors, 33 scratch, OS x 4 sums */
+  const int H = v.d.h_size, O = v.d.o_size, I = v.d.i_size;
+  const int j0 = blockIdx.x * OS;
+  const int ns = min(OS, v.n - j0);
+  float *oe = sh;
+  float *scratch = sh + OS * O;
+  float *sums = scratch + 40;
+  int slot[OS];
+#pragma unroll
+  for (int q = 0; q < OS; q++)
+    slot[q] = v.slots[j0 + (q < ns ? q : 0)];
+  for (int i = threadIdx.x; i < OS * O; i += blockDim.x) {
+    int q = i / O, x = i - q * O;
+    oe[i] = (q < ns) ? v.OE[(size_t)slot[q] * O + x] : 0.0f;
+  }
+  __syncthreads();
+  float abs_sum[OS], hsum[OS], hmag[OS], hzero[OS];
+#pragma unroll
+  for (int q = 0; q < OS; q++)
+    abs_sum[q] = hsum[q] = hmag[q] = hzero[q] = 0.0f;
+  for (int y = threadIdx.x; y < I; y += blockDim.x) {
+    float e[OS];
+#pragma unroll
+    for (int q = 0; q < OS; q++)
+      e[q] = 0.0f;
+    if (y < H) {
+      float h[OS];
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < OS; q++) {
+        h[q] = (q < ns) ? v.Hd[(size_t)slot[q] * H + y] : 0.0f;
+        if (q < ns) {
+          hsum[q] += h[q];
+          hmag[q] += h[q] * h[q];
+          hzero[q] += (h[q] == 0.0f);
+        }
+        any |= (h[q] != 0.0f);
+      }
+      if (y >= 1 && any) {
+        const float *row = v.Who + (size_t)y * O;
+        for (int x = 0; x < O; x += 4) {
+          float4 w = *(const float4 *)(row + x);
+#pragma unroll
+          for (int q = 0; q < OS; q++) {
+            const float *o = oe + q * O + x;
+            e[q] += w.x * o[0] + w.y * o[1] + w.z * o[2] + w.w * o[3];
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < OS; q++) {
+          if (h[q] == 0.0f)
+            e[q] = 0.0f;
+          abs_sum[q] += fabsf(e[q]);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < OS; q++)
+      if (q < ns)
+        v.E[(size_t)slot[q] * I + y] = e[q];
+  }
+#pragma unroll
+  for (int q = 0; q < OS; q++) {
+    float a = block_sum(abs_sum[q], scratch);
+    float b = block_sum(hsum[q], scratch);
+    float c = block_sum(hmag[q], scratch);
+    float d = block_sum(hzero[q], scratch);
+    if (threadIdx.x == 0) {
+      sums[q * 4 + 0] = a;
+      sums[q * 4 + 1] = b;
+      sums[q * 4 + 2] = c;
+      sums[q * 4 + 3] = d;
+    }
+  }
+  __syncthreads();
+  const float halfmax = H * MAX_TOP_ERROR_FACTOR;
+  for (int q = 0; q < ns; q++) {
+    float total = sums[q * 4 + 0];
+    float scale = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
+    float *e0 = v.E + (size_t)slot[q] * I;
+    if (scale != 1.0f || Ehi) {
+      for (int y = threadIdx.x; y < I; y += blockDim.x) {
+        float e = e0[y];
+        if (scale != 1.0f && y < H) {
+          e *= scale;
+          e0[y] = e;
+        }
+        if (Ehi) {
+          uint32_t hb, lb;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e));
+          float hi = __uint_as_float(hb);
+          float rem = e - hi;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+          Ehi[(size_t)slot[q] * I + y] = hi;
+          Elo[(size_t)slot[q] * I + y] = __uint_as_float(lb);
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      RbScalars *sc = v.sc + slot[q];
+      float top_scaled = (total > halfmax) ? scale * total : total;
+      sc->top_raw = total;
+      sc->top_scaled = top_scaled;
+      sc->hidden_sum = sums[q * 4 + 1];
+      sc->hidden_mag = sqrtf(sums[q * 4 + 2]);
+      sc->hidden_zeros = (int)(sums[q * 4 + 3] + 0.5f);
+      float min_gain = MIN_ERROR_GAIN * top_scaled;
+      sc->min_sum = fminf(sc->mef / sc->lr, min_gain);
+      sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
+      sc->cum_error = 0.0f;
+      sc->err_sum = 0.0f;
+      sc->live = (v.depth > 0);
+      sc->n_steps = 0;
+      sc->t_left = v.depth;
+      sc->ih_scale = 1.0f;
+    }
+  }
+}
+
+/* a9 for a batch that fits in shared memory: a block owns 16 hidden rows of
+   ho_delta, pulls its slab of the hidden activations and all output errors
+   into shared memory in one round of loads, then sums over the streams. */
+#define HO_ROWS 16
+
+__global__ void __launch_bounds__(256)
+k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
+{
+  extern __shared__ float sh[]; /* n x HO_ROWS hidden, n x o_size errors */
+  const int H = v.d.h_size, O = v.d.o_size, n = v.n;
+  const int y0 = blockIdx.x * HO_ROWS;
+  float *sH = sh;
+  float *sO = sh + (size_t)n * HO_ROWS;
+  for (int i = threadIdx.x; i < n * (HO_ROWS / 4); i += blockDim.x) {
+    int b = i / (HO_ROWS / 4), q = (i - b * (HO_ROWS / 4)) * 4;
+    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (y0 + q < H)
+      h = *(const float4 *)(v.Hd + (size_t)v.slots[b] * H + y0 + q);
+    *(float4 *)(sH + b * HO_ROWS + q) = h;
+  }
+  for (int i = threadIdx.x; i < n * (O / 4); i += blockDim.x) {
+    int b = i / (O / 4), q = (i - b * (O / 4)) * 4;
+    *(float4 *)(sO + (size_t)b * O + q) = *(const float4 *)(v.OE + (size_t)v.slots[b] * O + q);
+  }
+  __syncthreads();
+  const int yl = threadIdx.x % HO_ROWS, og = threadIdx.x / HO_ROWS; /* 16 column groups */
+  if (y0 + yl >= H)
+    return;
+  for (int o0 = og; o0 < O; o0 += 16 * 4) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int b = 0; b < n; b++) {
+      float h = sH[b * HO_ROWS + yl];
+      const float *e = sO + (size_t)b * O + o0;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (o0 + u * 16 < O)
+          acc[u] += h * e[u * 16];
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int o = o0 + u * 16;
+      if (o < O) {
+        size_t idx = (size_t)(y0 + yl) * O + o;
+        ho_delta[idx] = (accumulate ? ho_delta[idx] : 0.0f) + acc[u];
+      }
+    }
+  }
+}
+
 /* a14: the single-net path updates the top layer straight away
    (recur-nn.c:941-964); rows of silent hidden units only decay momentum. */
 __global__ void __launch_bounds__(256)
@@ -1155,6 +1389,12 @@ rbk_prepare_x(const RbView *v)
 extern "C" void
 rbk_output(const RbView *v)
 {
+  size_t multi = ((size_t)OS * v->d.h_size + (size_t)OS * 256 + 8) * sizeof(float);
+  if (v->n >= 2 * OS && multi <= 48 * 1024) {
+    k_out_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v);
+    LAUNCH_CHECK("k_out_multi");
+    return;
+  }
   size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
   k_out<<<v->n, 256, sh, rb_stream>>>(*v);
   LAUNCH_CHECK("k_out");
@@ -1221,14 +1461,35 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
   }
 }
 
+static int ho_slab_attr_done = 0;
+
 extern "C" void
-rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
-    const RecurErrorRange *ranges_dev, int n_ranges)
+rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo)
 {
-  size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
-  k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
-  LAUNCH_CHECK("k_top");
-  if (ho_delta && n_ranges == 0 && v->n >= 8) {
+  size_t multi = ((size_t)OS * v->d.o_size + 40 + OS * 4 + 8) * sizeof(float);
+  if (n_ranges == 0 && v->n >= 2 * OS && multi <= 48 * 1024) {
+    k_top_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v, Ehi, Elo);
+    LAUNCH_CHECK("k_top_multi");
+  }
+  else {
+    if (Ehi)
+      rb_die("recur-b200: internal: E[0] planes requested from the per-stream top kernel");
+    size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
+    k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
+    LAUNCH_CHECK("k_top");
+  }
+  size_t slab = (size_t)v->n * (HO_ROWS + v->d.o_size) * sizeof(float);
+  if (ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024) {
+    if (!ho_slab_attr_done) {
+      cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          200 * 1024);
+      ho_slab_attr_done = 1;
+    }
+    k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, rb_stream>>>(*v, ho_delta, accumulate);
+    LAUNCH_CHECK("k_ho_delta_slab");
+  }
+  else if (ho_delta && n_ranges == 0 && v->n >= 8) {
     /* the sum over streams as a tiled contraction */
     GemmArgs g;
     g.v = *v;
@@ -1246,6 +1507,20 @@ rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
         ranges_dev, n_ranges);
     LAUNCH_CHECK("k_ho_delta");
   }
+}
+
+extern "C" int
+rbk_top_layer_can_write_planes(const RbView *v)
+{
+  size_t multi = ((size_t)OS * v->d.o_size + 40 + OS * 4 + 8) * sizeof(float);
+  return v->n >= 2 * OS && multi <= 48 * 1024;
+}
+
+extern "C" void
+rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges)
+{
+  rbk_top_layer_planes(v, ho_delta, accumulate, ranges_dev, n_ranges, NULL, NULL);
 }
 
 extern "C" void

@@ -57,6 +57,9 @@ void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
 void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges);       /* a7..a9 */
+void rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo);
+int rbk_top_layer_can_write_planes(const RbView *v);
 void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */
 void rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive);
 void rbk_set_params_scalar(const RbView *v, float lr, float mef, int adaptive);
@@ -83,7 +86,8 @@ void rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols);
 /* tensor-core engine (rb_tc.cu) */
 int rb_tc_usable(const RbView *v);
 void rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise);
-void rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate);
+void rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
+    int accumulate);
 void rb_tc_pool_release(RbPool *p);
 
 #ifdef __cplusplus

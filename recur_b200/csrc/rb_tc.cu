@@ -480,26 +480,48 @@ k_split_rows(RbView v, int which /* 0: current x row, 1: E[0] */, float *hi_plan
    the weight gradient (zero them), and a stream whose gradient is clipped
    (ih_scale != 1, recur-nn.c:393-402) has its rows rescaled and re-split. */
 __global__ void __launch_bounds__(256)
-k_finalize_rows(RbView v, float *Ehi, float *Elo)
+k_finalize_rows(RbView v, float *Ehi, float *Elo, const unsigned int *kmax_dev)
 {
-  int s = v.slots[blockIdx.x];
-  int step = blockIdx.y;
+  const int s = v.slots[blockIdx.x];
   const RbScalars sc = v.sc[s];
-  size_t off = ((size_t)step * v.cap + s) * v.d.i_size;
-  if (step >= sc.n_steps) {
-    for (int i = threadIdx.x; i < v.d.h_size; i += blockDim.x) {
-      Ehi[off + i] = 0.0f;
-      Elo[off + i] = 0.0f;
+  const int kmax = min((int)*kmax_dev, v.depth);
+  /* rows this stream never reached, up to the deepest step any stream took
+     (the weight gradient stops there) */
+  for (int step = sc.n_steps; step < kmax; step++) {
+    size_t off = ((size_t)step * v.cap + s) * v.d.i_size;
+    for (int i = threadIdx.x * 4; i < v.d.h_size; i += blockDim.x * 4) {
+      *(float4 *)(Ehi + off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *(float4 *)(Elo + off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  else if (sc.ih_scale != 1.0f) {
-    for (int i = threadIdx.x; i < v.d.h_size; i += blockDim.x) {
-      float hi, lo;
-      split_tf32(v.E[off + i] * sc.ih_scale, hi, lo);
-      Ehi[off + i] = hi;
-      Elo[off + i] = lo;
+  if (sc.ih_scale != 1.0f) {
+    for (int step = 0; step < sc.n_steps; step++) {
+      size_t off = ((size_t)step * v.cap + s) * v.d.i_size;
+      for (int i = threadIdx.x; i < v.d.h_size; i += blockDim.x) {
+        float hi, lo;
+        split_tf32(v.E[off + i] * sc.ih_scale, hi, lo);
+        Ehi[off + i] = hi;
+        Elo[off + i] = lo;
+      }
     }
   }
+}
+
+/* deepest BPTT step any stream of the batch executed */
+__global__ void __launch_bounds__(256)
+k_compute_kmax(RbView v, unsigned int *kmax_dev)
+{
+  __shared__ int s_max;
+  if (threadIdx.x == 0)
+    s_max = 0;
+  __syncthreads();
+  int m = 0;
+  for (int j = threadIdx.x; j < v.n; j += blockDim.x)
+    m = max(m, v.sc[v.slots[j]].n_steps);
+  atomicMax(&s_max, m);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    *kmax_dev = (unsigned int)s_max;
 }
 
 /* ======================================================================== */
@@ -865,6 +887,7 @@ struct ChainArgs {
   float *Ehi, *Elo;
   unsigned int *sync;   /* [0] barrier counter, [1 + k] streams alive at step k */
   unsigned long long *dbg; /* optional: 5 globaltimer stamps per step from CTA 0 */
+  unsigned int *kmax;   /* out: steps executed before every stream had stopped */
 };
 
 __device__ __forceinline__ unsigned long long
@@ -1182,8 +1205,11 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     n_bar++;
     grid_barrier(g.sync, n_bar * n_ctas);
     CHAIN_STAMP(4);
-    if (__ldcg(&g.sync[1 + k]) == 0)
+    if (__ldcg(&g.sync[1 + k]) == 0) {
+      if (cta == 0 && threadIdx.x == 0)
+        *g.kmax = (unsigned int)(k + 1);
       break; /* every stream has stopped (uniform across the grid) */
+    }
   }
 
   __syncthreads();
@@ -1200,6 +1226,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
 struct DwArgs {
   RbView v;
   float *partial; /* [splits][i_size][h_size] */
+  const unsigned int *kmax; /* deepest step any stream executed: rows beyond contribute nothing */
 };
 
 #define DW_CHUNK_BYTES (32 * TC_DW_BK * 4)          /* one TMA box: 32 floats x 16 rows */
@@ -1225,7 +1252,8 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
   const int I = v.d.i_size, H = v.d.h_size;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_DW_BN;
   const int kb_per_step = v.n / TC_DW_BK;
-  const int n_kb_total = v.depth * kb_per_step;
+  const int n_steps_max = min((int)*g.kmax, v.depth);
+  const int n_kb_total = n_steps_max * kb_per_step;
   const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
@@ -1415,13 +1443,19 @@ rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
 }
 
 extern "C" void
-rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
+rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta, int accumulate)
 {
   RbTc *t = tc_state(p);
   refresh_weight_planes(t, p, v);
-  /* E[0] (written by k_top) -> planes */
-  k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 1, t->Ehi, t->Elo);
-  LAUNCH_CHECK("k_split_rows");
+  /* top layer: E[0] and, where the batch kernel applies, its planes too */
+  if (rbk_top_layer_can_write_planes(v)) {
+    rbk_top_layer_planes(v, ho_delta, accumulate, NULL, 0, t->Ehi, t->Elo);
+  }
+  else {
+    rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
+    k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 1, t->Ehi, t->Elo);
+    LAUNCH_CHECK("k_split_rows");
+  }
   if (!chain_attr_done) {
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
@@ -1468,6 +1502,7 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
       ca.dbg = dbg_dev;
     }
     CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0, (v->depth + 8) * sizeof(unsigned int), rb_stream));
+    ca.kmax = t->sync + v->depth + 4;
     void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
                       (void *)&t->mWlo_k, (void *)&ca};
     rb_prof_begin(RB_PROF_CHAIN);
@@ -1521,8 +1556,12 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
     LAUNCH_CHECK("k_chain_finish_step");
     rb_prof_end(RB_PROF_CHAIN);
   }
-  dim3 fgrid(v->n, v->depth);
-  k_finalize_rows<<<fgrid, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo);
+  unsigned int *kmax_dev = t->sync + v->depth + 4;
+  if (!t->persistent_ok) {
+    k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
+    LAUNCH_CHECK("k_compute_kmax");
+  }
+  k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo, kmax_dev);
   LAUNCH_CHECK("k_finalize_rows");
   if (!dw_attr_done) {
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1532,6 +1571,7 @@ rb_tc_bptt(RbPool *p, const RbView *v, float *ih_delta, int accumulate)
   DwArgs d;
   d.v = *v;
   d.partial = t->partial;
+  d.kmax = kmax_dev;
   dim3 dgrid(cdiv(v->d.h_size, TC_DW_BN), cdiv(v->d.i_size, TC_BM), TC_DW_SPLITS);
   rb_prof_begin(RB_PROF_DW);
   k_tc_dw<<<dgrid, 192, DW_SMEM_BYTES, rb_stream>>>(t->mXhi_mn, t->mXlo_mn, t->mEhi_mn, t->mElo_mn, d);
