@@ -796,23 +796,59 @@ k_ho_delta(RbView v, float *ho_delta, int accumulate,
 }
 
 /* ------------------------------------------------------------------------ */
-/* Batch versions of the two top-layer kernels: eight streams per block share
-   every Who row they read, which turns 512 passes over Who into 64.         */
+/* Batch versions of the two top-layer kernels.  A block serves OS streams and
+   first stages the whole of Who in shared memory (one round of coalesced
+   loads), so Who is read once per OS streams instead of once per stream and
+   the inner loops run out of shared memory.  Used when Who fits (h_size x
+   o_size floats + the streams' vectors <= 200 KB); otherwise the per-stream
+   kernels above do the job.                                                 */
 
-#define OS 8 /* streams per block */
+#define OS 4 /* streams per block */
+
+__device__ __forceinline__ int
+slot_of(const RbView &v, int j)
+{
+  return v.contiguous ? v.base + j : v.slots[j];
+}
+
+__device__ __forceinline__ void
+stage_matrix(float *dst, const float *__restrict__ src, int n_floats)
+{
+  const float4 *s4 = (const float4 *)src;
+  float4 *d4 = (float4 *)dst;
+  const int n4 = n_floats >> 2;
+  int i = threadIdx.x;
+  /* eight independent 16-byte loads in flight per thread */
+  for (; i + 7 * (int)blockDim.x < n4; i += 8 * blockDim.x) {
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      t[u] = __ldg(s4 + i + u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      d4[i + u * blockDim.x] = t[u];
+  }
+  for (; i < n4; i += blockDim.x)
+    d4[i] = __ldg(s4 + i);
+}
 
 __global__ void __launch_bounds__(256)
 k_out_multi(RbView v)
 {
-  extern __shared__ float sh[]; /* OS x h_size hidden rows, then reduction space */
+  extern __shared__ __align__(16) float sh[]; /* Who | OS hidden rows | reduction space */
   const int H = v.d.h_size, O = v.d.o_size;
   const int j0 = blockIdx.x * OS;
   const int ns = min(OS, v.n - j0);
-  float *hid = sh;
-  float *red = sh + (size_t)OS * H;
-  for (int i = threadIdx.x; i < OS * H; i += blockDim.x) {
-    int q = i / H, r = i - q * H;
-    hid[i] = (q < ns) ? v.Hd[(size_t)v.slots[j0 + q] * H + r] : 0.0f;
+  float *who = sh;
+  float *hid = sh + (size_t)H * O;
+  float *red = hid + (size_t)OS * H;
+  stage_matrix(who, v.Who, H * O);
+  for (int q = 0; q < OS; q++) {
+    if (q < ns)
+      stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot_of(v, j0 + q) * H, H);
+    else
+      for (int i = threadIdx.x; i < H; i += blockDim.x)
+        hid[(size_t)q * H + i] = 0.0f;
   }
   __syncthreads();
   const int CW = (O >= 256) ? 256 : O;
@@ -826,7 +862,7 @@ k_out_multi(RbView v)
       acc[q] = 0.0f;
     if (grp < G && c < O) {
       for (int r = grp; r < H; r += G) {
-        float w = v.Who[(size_t)r * O + c];
+        float w = who[(size_t)r * O + c];
 #pragma unroll
         for (int q = 0; q < OS; q++)
           acc[q] += hid[q * H + r] * w;
@@ -844,14 +880,14 @@ k_out_multi(RbView v)
           float t = 0.0f;
           for (int gq = 0; gq < G; gq++)
             t += red[(gq * OS + q) * CW + col];
-          v.Y[(size_t)v.slots[j0 + q] * O + c] = t;
+          v.Y[(size_t)slot_of(v, j0 + q) * O + c] = t;
         }
       }
       __syncthreads();
     }
     else if (c < O) {
       for (int q = 0; q < ns; q++)
-        v.Y[(size_t)v.slots[j0 + q] * O + c] = acc[q];
+        v.Y[(size_t)slot_of(v, j0 + q) * O + c] = acc[q];
     }
   }
 }
@@ -861,20 +897,31 @@ k_out_multi(RbView v)
 __global__ void __launch_bounds__(256)
 k_top_multi(RbView v, float *Ehi, float *Elo)
 {
-  extern __shared__ float sh[]; /* OS x o_size errors, 33 scratch, OS x 4 sums */
+  extern __shared__ __align__(16) float sh[]; /* Who | OS errors | OS hidden | scratch | sums */
   const int H = v.d.h_size, O = v.d.o_size, I = v.d.i_size;
   const int j0 = blockIdx.x * OS;
   const int ns = min(OS, v.n - j0);
-  float *oe = sh;
-  float *scratch = sh + OS * O;
+  float *who = sh;
+  float *oe = who + (size_t)H * O;
+  float *hid = oe + OS * O;
+  float *scratch = hid + (size_t)OS * H;
   float *sums = scratch + 40;
   int slot[OS];
 #pragma unroll
   for (int q = 0; q < OS; q++)
-    slot[q] = v.slots[j0 + (q < ns ? q : 0)];
-  for (int i = threadIdx.x; i < OS * O; i += blockDim.x) {
-    int q = i / O, x = i - q * O;
-    oe[i] = (q < ns) ? v.OE[(size_t)slot[q] * O + x] : 0.0f;
+    slot[q] = slot_of(v, j0 + (q < ns ? q : 0));
+  stage_matrix(who, v.Who, H * O);
+  for (int q = 0; q < OS; q++) {
+    if (q < ns) {
+      stage_matrix(oe + q * O, v.OE + (size_t)slot[q] * O, O);
+      stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot[q] * H, H);
+    }
+    else {
+      for (int i = threadIdx.x; i < O; i += blockDim.x)
+        oe[q * O + i] = 0.0f;
+      for (int i = threadIdx.x; i < H; i += blockDim.x)
+        hid[(size_t)q * H + i] = 0.0f;
+    }
   }
   __syncthreads();
   float abs_sum[OS], hsum[OS], hmag[OS], hzero[OS];
@@ -891,7 +938,7 @@ k_top_multi(RbView v, float *Ehi, float *Elo)
       bool any = false;
 #pragma unroll
       for (int q = 0; q < OS; q++) {
-        h[q] = (q < ns) ? v.Hd[(size_t)slot[q] * H + y] : 0.0f;
+        h[q] = hid[(size_t)q * H + y];
         if (q < ns) {
           hsum[q] += h[q];
           hmag[q] += h[q] * h[q];
@@ -900,14 +947,17 @@ k_top_multi(RbView v, float *Ehi, float *Elo)
         any |= (h[q] != 0.0f);
       }
       if (y >= 1 && any) {
-        const float *row = v.Who + (size_t)y * O;
-        for (int x = 0; x < O; x += 4) {
-          float4 w = *(const float4 *)(row + x);
+        /* consecutive threads read consecutive rows of o_size floats: rotate
+           the starting column by the row so that a warp spreads over banks */
+        const float *row = who + (size_t)y * O;
+        for (int xx = 0; xx < O; xx++) {
+          int x = xx + y;
+          if (x >= O)
+            x -= O * (x / O);
+          float w = row[x];
 #pragma unroll
-          for (int q = 0; q < OS; q++) {
-            const float *o = oe + q * O + x;
-            e[q] += w.x * o[0] + w.y * o[1] + w.z * o[2] + w.w * o[3];
-          }
+          for (int q = 0; q < OS; q++)
+            e[q] += w * oe[q * O + x];
         }
 #pragma unroll
         for (int q = 0; q < OS; q++) {
@@ -993,16 +1043,38 @@ k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
   const int y0 = blockIdx.x * HO_ROWS;
   float *sH = sh;
   float *sO = sh + (size_t)n * HO_ROWS;
-  for (int i = threadIdx.x; i < n * (HO_ROWS / 4); i += blockDim.x) {
-    int b = i / (HO_ROWS / 4), q = (i - b * (HO_ROWS / 4)) * 4;
-    float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (y0 + q < H)
-      h = *(const float4 *)(v.Hd + (size_t)v.slots[b] * H + y0 + q);
-    *(float4 *)(sH + b * HO_ROWS + q) = h;
-  }
-  for (int i = threadIdx.x; i < n * (O / 4); i += blockDim.x) {
-    int b = i / (O / 4), q = (i - b * (O / 4)) * 4;
-    *(float4 *)(sO + (size_t)b * O + q) = *(const float4 *)(v.OE + (size_t)v.slots[b] * O + q);
+  {
+    /* every load of the slab is issued before the first use */
+    const int per = HO_ROWS / 4;
+    for (int i0 = threadIdx.x; i0 < n * per; i0 += 8 * blockDim.x) {
+      float4 t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int i = i0 + u * blockDim.x;
+        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < n * per) {
+          int b = i / per, q = (i - b * per) * 4;
+          if (y0 + q < H)
+            t[u] = __ldg((const float4 *)(v.Hd + (size_t)slot_of(v, b) * H + y0 + q));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int i = i0 + u * blockDim.x;
+        if (i < n * per)
+          *(float4 *)(sH + (size_t)i * 4) = t[u];
+      }
+    }
+    if (v.contiguous) {
+      stage_matrix(sO, v.OE + (size_t)v.base * O, n * O);
+    }
+    else {
+      for (int i = threadIdx.x; i < n * (O / 4); i += blockDim.x) {
+        int b = i / (O / 4), q = (i - b * (O / 4)) * 4;
+        *(float4 *)(sO + (size_t)b * O + q) =
+          *(const float4 *)(v.OE + (size_t)v.slots[b] * O + q);
+      }
+    }
   }
   __syncthreads();
   const int yl = threadIdx.x % HO_ROWS, og = threadIdx.x / HO_ROWS; /* 16 column groups */
@@ -1389,8 +1461,14 @@ rbk_prepare_x(const RbView *v)
 extern "C" void
 rbk_output(const RbView *v)
 {
-  size_t multi = ((size_t)OS * v->d.h_size + (size_t)OS * 256 + 8) * sizeof(float);
-  if (v->n >= 2 * OS && multi <= 48 * 1024) {
+  size_t multi = ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.h_size +
+      (size_t)OS * 256 + 8) * sizeof(float);
+  if (v->n >= 4 * OS && multi <= 200 * 1024) {
+    static int attr_done = 0;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_out_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = 1;
+    }
     k_out_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v);
     LAUNCH_CHECK("k_out_multi");
     return;
@@ -1463,12 +1541,24 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
 
 static int ho_slab_attr_done = 0;
 
+static size_t
+top_multi_smem(const RbView *v)
+{
+  return ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.o_size +
+      (size_t)OS * v->d.h_size + 40 + OS * 4 + 8) * sizeof(float);
+}
+
 extern "C" void
 rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo)
 {
-  size_t multi = ((size_t)OS * v->d.o_size + 40 + OS * 4 + 8) * sizeof(float);
-  if (n_ranges == 0 && v->n >= 2 * OS && multi <= 48 * 1024) {
+  size_t multi = top_multi_smem(v);
+  if (n_ranges == 0 && v->n >= 4 * OS && multi <= 200 * 1024) {
+    static int attr_done = 0;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_top_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_done = 1;
+    }
     k_top_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v, Ehi, Elo);
     LAUNCH_CHECK("k_top_multi");
   }
@@ -1512,8 +1602,7 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
 extern "C" int
 rbk_top_layer_can_write_planes(const RbView *v)
 {
-  size_t multi = ((size_t)OS * v->d.o_size + 40 + OS * 4 + 8) * sizeof(float);
-  return v->n >= 2 * OS && multi <= 48 * 1024;
+  return v->n >= 4 * OS && top_multi_smem(v) <= 200 * 1024;
 }
 
 extern "C" void

@@ -1099,7 +1099,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         /* all loads of a group of column chunks are issued before any of
            their results is used or stored: the row costs a few L2 round
            trips instead of one per chunk */
-        constexpr int GRP = 5;
+        constexpr int GRP = 9; /* 9 x 128 columns: a whole row at H1023 in one round of loads */
         for (int c0 = lane * 4; c0 < I; c0 += 128 * GRP) {
           float4 a[GRP], xin[GRP], pz[TC_CHAIN_SPLITS - 1][GRP];
 #pragma unroll
