@@ -264,19 +264,12 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     if L.rnn_b200_set_device(local_rank) != 0:
         raise SystemExit("cannot select GPU %d" % local_rank)
+    from recur_b200 import dist as rdist
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idbuf = (C.c_uint8 * 128)()
-        if rank == 0 and L.rnn_b200_comm_unique_id(idbuf) != 0:
-            raise SystemExit("NCCL not loadable")
-        t = torch.tensor(list(idbuf), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        raw = bytes(t.cpu().tolist())
-        idbuf = (C.c_uint8 * 128).from_buffer_copy(raw)
-        if L.rnn_b200_comm_join(idbuf, rank, world) != 0:
-            raise SystemExit("rnn_b200_comm_join failed")
+        rdist.join_comm(L, dist, rank, world, device="cuda")
 
     def barrier():
         L.rnn_b200_synchronize()
@@ -285,11 +278,7 @@ def run_ours(args):
             dist.barrier()
 
     def max_over_ranks(x):
-        if not dist:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return rdist.max_over_ranks(dist, x, device="cuda")
 
     if args.engine is not None:
         L.rnn_b200_set_engine(args.engine)
@@ -303,8 +292,8 @@ def run_ours(args):
     nets = L.rnn_new_training_set(net, n)
     batch = L.rnn_batch_new(nets, n)
     # each rank reads its own stretch of the text
-    shard = len(text) // world
-    my_text = np.ascontiguousarray(text[rank * shard:(rank + 1) * shard])
+    lo, hi = rdist.shard_bounds(len(text), rank, world)
+    my_text = np.ascontiguousarray(text[lo:hi])
     L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
     stream = torch.cuda.ExternalStream(L.rnn_b200_stream())
     style = abi.RNN_MOMENTUM_WEIGHTED
@@ -367,7 +356,11 @@ def run_ours(args):
     ncls = L.rnn_b200_profile_read(pms, pln, 8)
     L.rnn_b200_profile_enable(0)
     prof_total = pev0.elapsed_time(pev1)
-    L.rnn_batch_pull(batch)
+    depths = (C.c_int32 * n)()
+    L.rnn_batch_bptt_depths(batch, depths)
+    depths = np.array(list(depths), dtype=np.float64)
+    mean_depth = float(depths.mean())
+    max_depth = float(depths.max())
     # executed BPTT depth per stream (n_steps of the last step), from the log scalars
     kernels = {}
     for c in range(ncls):
@@ -379,11 +372,17 @@ def run_ours(args):
     hs1 = args.hidden + 1
     i_alg = hs1 + 1               # bias + hidden rows + the one hot input row
     flops_pair = 2.0 * i_alg * hs1  # one stream, one ring row: one of {error back, outer product}
+    # algorithmic work counts the BPTT steps each stream really executed (the
+    # adaptive early exit of recur-nn.c:387 is part of the algorithm, and the
+    # CPU reference takes the same exit), not the nominal depth
     alg = {
         "forward": (2.0 * i_alg * hs1) * n,                  # per launch (one step)
-        "bptt_chain": flops_pair * n,                        # per launch (one depth step)
-        "weight_grad": flops_pair * n * DEPTH,               # per launch (all depth steps)
+        "bptt_chain": flops_pair * n * mean_depth,           # per launch (the whole walk)
+        "weight_grad": flops_pair * n * mean_depth,          # per launch (all executed steps)
     }
+    chain_launches_per_step = kernels.get("bptt_chain", {}).get("launches", prof_steps) / prof_steps
+    if chain_launches_per_step > 1.5:   # one launch per BPTT step (per-step kernels)
+        alg["bptt_chain"] = flops_pair * n
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         peak_bf16 = float(peaks["bf16_tflops_sustained"])
@@ -408,7 +407,7 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        step_flops = (alg["forward"] + DEPTH * alg["bptt_chain"] + alg["weight_grad"]) * world
+        step_flops = (alg["forward"] + 2 * flops_pair * n * mean_depth) * world
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -422,6 +421,9 @@ def run_ours(args):
             "clocks": sampler.summary(),
             "roofline": roofline,
             "algorithmic_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12,
+            "bptt": {"nominal_depth": DEPTH, "mean_executed_depth": mean_depth,
+                     "max_executed_depth": max_depth,
+                     "mflop_per_stream_char": (alg["forward"] / n + 2 * flops_pair * mean_depth) / 1e6},
             "train": {"t_entropy": -stats.entropy / max(stats.count, 1),
                       "accuracy": stats.correct / max(stats.count, 1)},
             "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],

@@ -166,6 +166,12 @@ int rnn_batch_text_train(RnnBatch *batch, int start, int steps,
    stream over the uploaded text, no training. */
 int rnn_batch_text_forward(RnnBatch *batch, int start, int steps);
 
+/* Number of BPTT steps each stream executed in the most recent
+   rnn_batch_calc_deltas / training step (the value the reference logs as
+   "depth", plus one when the walk stopped early; recur-nn.c:387,416): n
+   int32 values.  Synchronises. */
+void rnn_batch_bptt_depths(RnnBatch *batch, int32_t *depths);
+
 /* Refresh host mirrors and struct scalars (generation, ih_scale,
    min_error_factor, bptt->index) of every net in the batch. */
 void rnn_batch_pull(RnnBatch *batch);

@@ -30,7 +30,7 @@ B200_API_SYMBOLS = [
     "rnn_batch_get_outputs", "rnn_batch_get_hiddens", "rnn_batch_softmax_error",
     "rnn_batch_set_errors", "rnn_batch_calc_deltas", "rnn_batch_apply_learning",
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
-    "rnn_batch_text_forward", "rnn_batch_pull",
+    "rnn_batch_text_forward", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
     "rnn_b200_comm_size",
 ]
@@ -101,6 +101,8 @@ def _declare_b200(lib):
                                          C.POINTER(RnnBatchCharStats)]
     lib.rnn_batch_text_forward.restype = C.c_int
     lib.rnn_batch_text_forward.argtypes = [vp, C.c_int, C.c_int]
+    lib.rnn_batch_bptt_depths.restype = None
+    lib.rnn_batch_bptt_depths.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.rnn_batch_pull.restype = None
     lib.rnn_batch_pull.argtypes = [vp]
     lib.rnn_b200_comm_unique_id.restype = C.c_int

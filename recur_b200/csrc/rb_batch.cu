@@ -518,6 +518,18 @@ rnn_batch_text_forward(RnnBatch *b, int start, int steps)
 }
 
 extern "C" void
+rnn_batch_bptt_depths(RnnBatch *b, int32_t *depths)
+{
+  RbScalars *sc = (RbScalars *)malloc(sizeof(RbScalars) * b->pool->cap);
+  CUDA_OR_DIE(cudaMemcpyAsync(sc, b->pool->sc, sizeof(RbScalars) * b->pool->cap,
+          cudaMemcpyDeviceToHost, rb_stream));
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  for (int j = 0; j < b->n; j++)
+    depths[j] = sc[b->nets[j]->slot].n_steps;
+  free(sc);
+}
+
+extern "C" void
 rnn_batch_pull(RnnBatch *b)
 {
   for (int j = 0; j < b->n; j++) {

@@ -1,0 +1,189 @@
+"""The other BASELINE.json configurations as parity cases: the stream loops of
+gstclassify (config 3), the multi-head charmodel forward (config 4) and the
+rnnca per-cell forward (config 5), replayed over the reference API on the CPU
+(oracle/_ref) and over this library's array-of-nets calls on the GPU.  The
+elements themselves need GStreamer and cannot be built, so
+the loops are restated here in the order the reference runs them."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from recur_b200 import abi
+from helpers import make_net, weights, arr, fptr, rel_err, copy_weights, STD_FLAGS
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def grouped_softmax_error(out, target):
+    """train_channel's error for one class group (gstclassify.c:2104-2124):
+    error = onehot(target) - softmax(outputs)."""
+    e = np.exp(out - out.max())
+    p = e / e.sum()
+    err = -p
+    err[target] += 1.0
+    return err.astype(np.float32)
+
+
+@pytest.mark.parametrize("n_channels", [10, 96])
+def test_config3_classify_training_loop(gpu_lib, ref, n_channels):
+    """gstclassify.c:2201-2239: clear deltas; per channel forward on dense
+    features, grouped softmax error, rnn_bptt_calc_deltas(net, 1, NULL),
+    advance; then Nesterov update and rnn_condition_net."""
+    lib = gpu_lib
+    F, Hn, classes, depth, chunks = 32, 199, 4, 10, 6
+    rs = np.random.RandomState(3)
+    feats = np.log1p(rs.random_sample((chunks, n_channels, F)) * 400).astype(np.float32)
+    targets = rs.randint(0, classes, size=(chunks, n_channels))
+    flags = STD_FLAGS
+    r = make_net(ref, input_size=F, hidden=Hn, output=classes, depth=depth, seed=11, lr=1e-5,
+                 flags=flags)
+    a = make_net(lib, input_size=F, hidden=Hn, output=classes, depth=depth, seed=11, lr=1e-5,
+                 flags=flags)
+    rn = ref.rnn_new_training_set(r, n_channels)
+    an = lib.rnn_new_training_set(a, n_channels)
+    batch = lib.rnn_batch_new(an, n_channels)
+    for t in range(chunks):
+        # reference, channel by channel
+        ref.rnn_bptt_clear_deltas(r)
+        for j in range(n_channels):
+            c = rn[j].contents
+            out = ref.rnn_opinion(rn[j], fptr(feats[t, j]), 0.0)
+            err = arr(c.bptt.contents.o_error, c.o_size)
+            err[:classes] = grouped_softmax_error(arr(out, classes), targets[t, j])
+            ref.rnn_bptt_calc_deltas(rn[j], 1, None)
+            ref.rnn_bptt_advance(rn[j])
+        ref.rnn_apply_learning(r, abi.RNN_MOMENTUM_NESTEROV, 0.9)
+        ref.rnn_condition_net(r)
+        # this library, all channels at once
+        lib.rnn_batch_set_inputs(batch, fptr(np.ascontiguousarray(feats[t])))
+        lib.rnn_batch_opinion(batch, 0.0)
+        outs = np.zeros((n_channels, classes), dtype=np.float32)
+        lib.rnn_batch_get_outputs(batch, fptr(outs))
+        errs = np.stack([grouped_softmax_error(outs[j], targets[t, j]) for j in range(n_channels)])
+        lib.rnn_batch_set_errors(batch, fptr(np.ascontiguousarray(errs)))
+        lib.rnn_batch_calc_deltas(batch, 0)
+        lib.rnn_batch_advance(batch)
+        lib.rnn_apply_learning(a, abi.RNN_MOMENTUM_NESTEROV, 0.9)
+        lib.rnn_condition_net(a)
+        ref_outs = np.stack([arr(rn[j].contents.output_layer, classes).copy()
+                             for j in range(n_channels)])
+        assert rel_err(outs, ref_outs) < TOL, t
+    for x, y in zip(weights(a), weights(r)):
+        assert rel_err(x, y) < TOL
+    assert a.contents.generation == r.contents.generation
+    lib.rnn_batch_delete(batch)
+
+
+def test_config4_multi_head_forward(gpu_lib, ref):
+    """The shape of test/multi-text-6c34c563i73-h99-o3650.net (i73 / h99 /
+    o3650 = 50 classes x 73 symbols, ReSQRT): forward over independent
+    texts and the per-class cross entropy of
+    rnn_char_multi_cross_entropy (charmodel-multi-predict.c:350-372)."""
+    lib = gpu_lib
+    n_texts, steps, n_classes, alpha = 6, 12, 50, 73
+    shape = dict(input_size=alpha, hidden=99, output=n_classes * alpha, depth=5, seed=7,
+                 activation=abi.RNN_RESQRT)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    rc = [ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n_texts)]
+    ac = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n_texts)]
+    arr_t = (abi.RecurNN_p * n_texts)(*ac)
+    batch = lib.rnn_batch_new(arr_t, n_texts)
+    assert batch
+    rs = np.random.RandomState(7)
+    text = rs.randint(0, alpha, size=(n_texts, steps + 1)).astype(np.uint8)
+    ent_ref = np.zeros((n_texts, n_classes))
+    ent_got = np.zeros((n_texts, n_classes))
+    for t in range(steps):
+        hot = np.ascontiguousarray(text[:, t])
+        lib.rnn_batch_set_one_hot(batch, hot.ctypes.data_as(abi.u8_p))
+        lib.rnn_batch_opinion(batch, 0.0)
+        outs = np.zeros((n_texts, n_classes * alpha), dtype=np.float32)
+        lib.rnn_batch_get_outputs(batch, fptr(outs))
+        for j in range(n_texts):
+            c = rc[j].contents
+            x = arr(c.real_inputs, alpha)
+            x[:] = 0
+            x[text[j, t]] = 1.0
+            o = arr(ref.rnn_opinion(rc[j], None, 0.0), n_classes * alpha).copy()
+            assert rel_err(outs[j], o) < TOL
+            for k in range(n_classes):
+                for src, dst in ((o, ent_ref), (outs[j], ent_got)):
+                    g = src[k * alpha:(k + 1) * alpha].astype(np.float64)
+                    p = np.exp(g - g.max())
+                    p /= p.sum()
+                    dst[j, k] -= np.log2(max(p[text[j, t + 1]], 1e-30))
+    assert rel_err(ent_got, ent_ref) < TOL
+    lib.rnn_batch_delete(batch)
+
+
+def test_config5_rnnca_cells_forward(gpu_lib, ref):
+    """gstrnnca.c:805-820: one forward-only clone per cell, all sharing the
+    trainers' weights; I35 / H51 / O3 (gstrnnca.h:13-51)."""
+    lib = gpu_lib
+    n_cells, frames = 600, 3
+    shape = dict(input_size=35, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    ac = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n_cells)]
+    batch = lib.rnn_batch_new((abi.RecurNN_p * n_cells)(*ac), n_cells)
+    probe = [0, 1, 17, 299, 599]
+    rc = {j: ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None) for j in probe}
+    rs = np.random.RandomState(5)
+    for f in range(frames):
+        inputs = rs.random_sample((n_cells, 35)).astype(np.float32)
+        lib.rnn_batch_set_inputs(batch, fptr(inputs))
+        lib.rnn_batch_opinion(batch, 0.0)
+        outs = np.zeros((n_cells, 3), dtype=np.float32)
+        lib.rnn_batch_get_outputs(batch, fptr(outs))
+        for j in probe:
+            o = arr(ref.rnn_opinion(rc[j], fptr(inputs[j]), 0.0), 3)
+            assert rel_err(outs[j], o) < TOL, (f, j)
+    lib.rnn_batch_delete(batch)
+
+
+def test_presynaptic_noise_draws_match_reference(gpu_lib, ref):
+    """the per-stream Jenkins generator runs on the device;
+    same seed, same draws, same noisy hidden state (recur-nn.c:120)."""
+    lib = gpu_lib
+    shape = dict(input_size=7, hidden=21, output=7, depth=4, seed=4, noise=0.1)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    rn = ref.rnn_new_training_set(r, 3)
+    an = lib.rnn_new_training_set(a, 3)
+    batch = lib.rnn_batch_new(an, 3)
+    for t in range(4):
+        hot = np.array([(t + j) % 7 for j in range(3)], dtype=np.uint8)
+        lib.rnn_batch_advance(batch)
+        lib.rnn_batch_set_one_hot(batch, hot.ctypes.data_as(abi.u8_p))
+        lib.rnn_batch_opinion(batch, 0.1)
+        for j in range(3):
+            c = rn[j].contents
+            ref.rnn_bptt_advance(rn[j])
+            x = arr(c.real_inputs, 7)
+            x[:] = 0
+            x[hot[j]] = 1.0
+            ref.rnn_opinion(rn[j], None, 0.1)
+    lib.rnn_batch_pull(batch)
+    for j in range(3):
+        ca, cr = an[j].contents, rn[j].contents
+        assert (ca.rng.a, ca.rng.b, ca.rng.c, ca.rng.d) == (cr.rng.a, cr.rng.b, cr.rng.c, cr.rng.d)
+        assert rel_err(arr(ca.hidden_layer, ca.h_size), arr(cr.hidden_layer, cr.h_size)) < TOL
+    # and through the per-net call
+    b = make_net(lib, **shape)
+    r2 = make_net(ref, **shape)
+    for L, net in ((lib, b), (ref, r2)):
+        c = net.contents
+        for t in range(3):
+            L.rnn_bptt_advance(net)
+            x = arr(c.real_inputs, 7)
+            x[:] = 0
+            x[t] = 1.0
+            L.rnn_opinion(net, None, 0.2)
+    assert (b.contents.rng.a, b.contents.rng.d) == (r2.contents.rng.a, r2.contents.rng.d)
+    assert rel_err(arr(b.contents.hidden_layer, 24), arr(r2.contents.hidden_layer, 24)) < TOL
+    lib.rnn_batch_delete(batch)
