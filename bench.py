@@ -291,6 +291,28 @@ def run_ours(args):
     os.dup2(devnull_fd, 2)
     nets = L.rnn_new_training_set(net, n)
     batch = L.rnn_batch_new(nets, n)
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl all-reduce"
+        if not args.no_p2p:
+            # fused split-K reduction + all-reduce over NVLink peer memory
+            hb = (C.c_uint8 * 192)()
+            ok = L.rnn_batch_p2p_export(batch, hb) == 0
+            mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            flag = torch.tensor([1 if ok else 0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+                buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+                ok = L.rnn_batch_p2p_attach(batch, buf, rank, world) == 0
+                flag = torch.tensor([1 if ok else 0], device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()):
+                    exchange = "fused reduce + all-reduce kernel over NVLink peer memory"
+                else:
+                    raise SystemExit("peer attach succeeded on some ranks only")
     # each rank reads its own stretch of the text
     lo, hi = rdist.shard_bounds(len(text), rank, world)
     my_text = np.ascontiguousarray(text[lo:hi])
@@ -427,6 +449,7 @@ def run_ours(args):
             "train": {"t_entropy": -stats.entropy / max(stats.count, 1),
                       "accuracy": stats.correct / max(stats.count, 1)},
             "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],
+            "gradient_exchange": exchange,
         }
         if args.hidden != HIDDEN or n != STREAMS:
             line["config"]["workload"] += " [OVERRIDDEN: hidden %d streams %d]" % (args.hidden, n)
@@ -468,6 +491,7 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--cold", action="store_true", help="do not pre-fill the BPTT ring")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="exchange deltas with NCCL only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -190,6 +190,19 @@ int rnn_b200_comm_join(const void *id128, int rank, int n_ranks);
 void rnn_b200_comm_leave(void);
 int rnn_b200_comm_size(void);
 
+/* Fused gradient exchange over NVLink peer memory (optional, after
+   rnn_b200_comm_join).  Instead of "sum the split-K partials, then call
+   ncclAllReduce", ONE kernel per rank finishes the weight-gradient GEMM's
+   split-K reduction into a peer-visible staging buffer, reduces its 1/N slice
+   over all ranks with peer loads, and scatters the result to every rank with
+   peer stores (SURVEY.md §5 "natural fusion").  Each rank exports
+   RNN_B200_P2P_HANDLE_BYTES of CUDA IPC handles for its batch; the launcher
+   gathers them from all ranks (rank order) and every rank attaches.  Returns
+   0 on success, -1 when peer access is not possible (NCCL keeps being used). */
+#define RNN_B200_P2P_HANDLE_BYTES 192
+int rnn_batch_p2p_export(RnnBatch *batch, void *handles_out);
+int rnn_batch_p2p_attach(RnnBatch *batch, const void *all_handles, int rank, int n_ranks);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,7 +32,7 @@ B200_API_SYMBOLS = [
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
     "rnn_batch_text_forward", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
-    "rnn_b200_comm_size",
+    "rnn_b200_comm_size", "rnn_batch_p2p_export", "rnn_batch_p2p_attach",
 ]
 
 
@@ -113,6 +113,10 @@ def _declare_b200(lib):
     lib.rnn_b200_comm_leave.argtypes = []
     lib.rnn_b200_comm_size.restype = C.c_int
     lib.rnn_b200_comm_size.argtypes = []
+    lib.rnn_batch_p2p_export.restype = C.c_int
+    lib.rnn_batch_p2p_export.argtypes = [vp, vp]
+    lib.rnn_batch_p2p_attach.restype = C.c_int
+    lib.rnn_batch_p2p_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     return lib
 
 

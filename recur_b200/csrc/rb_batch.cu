@@ -43,6 +43,7 @@ struct RnnBatch {
   int *i_host;           /* n */
   float *lr_host;        /* n, last uploaded learn rates */
   RbCharAccum *accum_host;
+  void *p2p;             /* fused gradient exchange (multi-GPU), or NULL */
 };
 
 static int g_engine = 0;
@@ -71,6 +72,7 @@ batch_view(RnnBatch *b, RbView *v)
   v->contiguous = b->contiguous;
   v->base = b->base;
   v->slots = b->contiguous ? b->pool->iota + b->base : b->slots_dev;
+  v->p2p = b->p2p;
 }
 
 static void
@@ -176,6 +178,7 @@ rnn_batch_delete(RnnBatch *b)
   cudaFree(b->mef_dev);
   cudaFree(b->io_dev);
   cudaFree(b->text_dev);
+  rb_p2p_delete(b->p2p);
   cudaFreeHost(b->sym_host);
   cudaFreeHost(b->f_host);
   cudaFreeHost(b->i_host);
@@ -183,6 +186,26 @@ rnn_batch_delete(RnnBatch *b)
   cudaFreeHost(b->accum_host);
   free(b->nets);
   free(b);
+}
+
+extern "C" int
+rnn_batch_p2p_export(RnnBatch *b, void *handles_out)
+{
+  RecurNN *proto = &b->nets[0]->pub;
+  if (!b->p2p)
+    b->p2p = rb_p2p_new((size_t)proto->ih_size + proto->ho_size);
+  /* the exchange treats [ih_delta | ho_delta] as one block */
+  if (!proto->bptt || proto->bptt->ho_delta != proto->bptt->ih_delta + proto->ih_size)
+    return -1;
+  return rb_p2p_export(b->p2p, handles_out);
+}
+
+extern "C" int
+rnn_batch_p2p_attach(RnnBatch *b, const void *all_handles, int rank, int n_ranks)
+{
+  if (!b->p2p)
+    return -1;
+  return rb_p2p_attach(b->p2p, all_handles, rank, n_ranks);
 }
 
 extern "C" int
@@ -240,6 +263,7 @@ rnn_batch_set_one_hot(RnnBatch *b, const u8 *hot)
 }
 
 extern "C" void rb_forward_dispatch(const RbView *v, float noise);
+extern "C" int rb_last_bptt_used_tensor_engine(void);
 extern "C" void rb_top_and_bptt_dispatch(const RbView *v, float *ho_delta, float *ih_delta,
     int accumulate);
 
@@ -391,8 +415,10 @@ calc_deltas_async(RnnBatch *b, int accumulate)
   batch_view(b, &v);
   refresh_learn_rates(b, &v);
   rb_top_and_bptt_dispatch(&v, bp->ho_delta, bp->ih_delta, accumulate);
-  /* [ih_delta | ho_delta] are adjacent in the prototype's delta block */
-  if (rb_comm_size() > 1)
+  /* [ih_delta | ho_delta] are adjacent in the prototype's delta block; when
+     the peer-memory exchange is attached and the tensor engine ran, the sum
+     over ranks already happened inside the weight-gradient reduction */
+  if (rb_comm_size() > 1 && !(rb_p2p_ready(b->p2p) && rb_last_bptt_used_tensor_engine()))
     rb_comm_allreduce_sum(bp->ih_delta, (size_t)proto->ih_size + proto->ho_size);
   for (int j = 0; j < b->n; j++)
     b->nets[j]->pub.generation++;

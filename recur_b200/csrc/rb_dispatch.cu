@@ -47,11 +47,20 @@ rb_forward_dispatch(const RbView *v, float noise)
     rbk_forward(v, noise);
 }
 
+static int last_bptt_tensor = 0;
+
+extern "C" int
+rb_last_bptt_used_tensor_engine(void)
+{
+  return last_bptt_tensor;
+}
+
 /* a7..a11 for a batch without error ranges */
 extern "C" void
 rb_top_and_bptt_dispatch(const RbView *v, float *ho_delta, float *ih_delta, int accumulate)
 {
-  if (use_tensor_engine(v) && v->pool->has_bptt) {
+  last_bptt_tensor = use_tensor_engine(v) && v->pool->has_bptt;
+  if (last_bptt_tensor) {
     rb_tc_top_and_bptt(v->pool, v, ho_delta, ih_delta, accumulate);
   }
   else {

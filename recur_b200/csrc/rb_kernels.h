@@ -22,6 +22,7 @@ typedef struct RbView {
   const float *Who; /* [h_size][o_size] */
   int activation;
   RbPool *pool;     /* host-side owner (not used by kernels) */
+  void *p2p;        /* fused gradient exchange state of the batch, or NULL */
 } RbView;
 
 /* device accumulators of the text-predict report sums */
@@ -89,6 +90,15 @@ void rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise);
 void rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     int accumulate);
 void rb_tc_pool_release(RbPool *p);
+
+/* fused split-K reduction + all-reduce over peer memory (rb_p2p.cu) */
+void *rb_p2p_new(size_t n_floats);
+int rb_p2p_export(void *state, void *handles_out);
+int rb_p2p_attach(void *state, const void *all_handles, int rank, int n_ranks);
+int rb_p2p_ready(void *state);
+void rb_p2p_reduce(void *state, const float *partial, int splits, int ih_size, int ho_size,
+    float *ih_delta, int accumulate);
+void rb_p2p_delete(void *state);
 
 #ifdef __cplusplus
 }

@@ -401,7 +401,7 @@ tc_state(RbPool *p)
   t->WTlo = dmalloc0<float>(I * H);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
   t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * ((I + 31) & ~(size_t)31));
-  t->sync = dmalloc0<unsigned int>(p->depth + 8);
+  t->sync = dmalloc0<unsigned int>((size_t)(cdiv(p->cap, TC_BM) + 1) * (p->depth + 8) + 8);
   t->persistent_ok = -1;
   t->w_src = NULL;
   uint64_t ring_rows = (uint64_t)p->depth * p->cap, chain_rows = (uint64_t)(p->depth + 1) * p->cap;
@@ -946,6 +946,15 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int n_ctas = gridDim.x * gridDim.y * gridDim.z;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  /* The streams of one m-tile form an independent chain: only the CTAs that
+     share blockIdx.y exchange data, so they synchronise among themselves and
+     the four groups drift apart, one group's latency-bound row phase hiding
+     under another group's loads. */
+  const int grp = blockIdx.y;
+  const int grp_ctas = gridDim.x * gridDim.z;
+  const int grp_cta = blockIdx.z * gridDim.x + blockIdx.x;
+  const int sync_stride = v.depth + 8;
+  unsigned int *gsync = g.sync + (size_t)grp * sync_stride;
   const int n_kb_total = (H + TC_BK - 1) / TC_BK;
   const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
   const int kb_begin = blockIdx.z * kb_per_split;
@@ -1077,13 +1086,16 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     __syncthreads();
     CHAIN_STAMP(1);
     n_bar++;
-    grid_barrier(g.sync, n_bar * n_ctas);
+    grid_barrier(gsync, n_bar * grp_ctas);
     CHAIN_STAMP(2);
 
     /* ---- phase B: rows of E(k+1), one per epilogue warp across the grid ---- */
     if (warp >= 2) {
-      const int gw = cta * 4 + (warp - 2);
-      for (int m = gw; m < v.n; m += n_ctas * 4) {
+      const int gw = grp_cta * 4 + (warp - 2);
+      for (int r = gw; r < TC_BM; r += grp_ctas * 4) {
+        const int m = m0 + r;
+        if (m >= v.n)
+          break;
         const int s = v.base + m;
         RbScalars *scp = v.sc + s;
         RbScalars sc = load_scalars_cg(scp);
@@ -1191,7 +1203,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
             }
           }
           else {
-            atomicAdd(&g.sync[1 + k], 1u);
+            atomicAdd(&gsync[1 + k], 1u);
           }
           *scp = sc;
         }
@@ -1203,12 +1215,12 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     __syncthreads();
     CHAIN_STAMP(3);
     n_bar++;
-    grid_barrier(g.sync, n_bar * n_ctas);
+    grid_barrier(gsync, n_bar * grp_ctas);
     CHAIN_STAMP(4);
-    if (__ldcg(&g.sync[1 + k]) == 0) {
-      if (cta == 0 && threadIdx.x == 0)
-        *g.kmax = (unsigned int)(k + 1);
-      break; /* every stream has stopped (uniform across the grid) */
+    if (__ldcg(&gsync[1 + k]) == 0) {
+      if (grp_cta == 0 && threadIdx.x == 0)
+        atomicMax(g.kmax, (unsigned int)(k + 1));
+      break; /* every stream of this group has stopped (uniform across the group) */
     }
   }
 
@@ -1501,8 +1513,9 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
       CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, (1280) * sizeof(unsigned long long), rb_stream));
       ca.dbg = dbg_dev;
     }
-    CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0, (v->depth + 8) * sizeof(unsigned int), rb_stream));
-    ca.kmax = t->sync + v->depth + 4;
+    CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0,
+            ((size_t)(cgrid.y + 1) * (v->depth + 8) + 8) * sizeof(unsigned int), rb_stream));
+    ca.kmax = t->sync + (size_t)cgrid.y * (v->depth + 8) + 4;
     void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
                       (void *)&t->mWlo_k, (void *)&ca};
     rb_prof_begin(RB_PROF_CHAIN);
@@ -1556,7 +1569,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     LAUNCH_CHECK("k_chain_finish_step");
     rb_prof_end(RB_PROF_CHAIN);
   }
-  unsigned int *kmax_dev = t->sync + v->depth + 4;
+  unsigned int *kmax_dev = t->sync + (size_t)cdiv(v->n, TC_BM) * (v->depth + 8) + 4;
   if (!t->persistent_ok) {
     k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
     LAUNCH_CHECK("k_compute_kmax");
@@ -1577,8 +1590,15 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   k_tc_dw<<<dgrid, 192, DW_SMEM_BYTES, rb_stream>>>(t->mXhi_mn, t->mXlo_mn, t->mEhi_mn, t->mElo_mn, d);
   LAUNCH_CHECK("k_tc_dw");
   int size = v->d.i_size * v->d.h_size;
-  k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
-      TC_DW_SPLITS, accumulate);
-  LAUNCH_CHECK("k_dw_reduce");
+  if (rb_p2p_ready(v->p2p)) {
+    /* multi-GPU: the split-K sum is the first phase of the exchange kernel */
+    rb_p2p_reduce(v->p2p, t->partial, TC_DW_SPLITS, size, v->d.h_size * v->d.o_size, ih_delta,
+        accumulate);
+  }
+  else {
+    k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
+        TC_DW_SPLITS, accumulate);
+    LAUNCH_CHECK("k_dw_reduce");
+  }
   rb_prof_end(RB_PROF_DW);
 }

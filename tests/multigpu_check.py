@@ -1,0 +1,94 @@
+"""Run under torchrun with 2+ ranks (tests/test_gpu_multi.py does that):
+every rank trains its shard of streams for a few steps with the deltas summed
+across ranks, once through NCCL and once through the fused peer-memory
+kernel; rank 0 replays ALL streams of ALL ranks on the CPU oracle and prints
+the worst relative weight difference of each variant as one JSON line."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from recur_b200 import api, abi, dist as rdist
+    from helpers import make_net, weights, arr, fptr, u8ptr, markov_text, rel_err
+
+    rank, world, local = rdist.env_rank()
+    torch.cuda.set_device(local)
+    L = api.load_library()
+    L.rnn_b200_set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rdist.join_comm(L, dist, rank, world, device="cuda")
+
+    n, steps, lr = 64, 5, 1e-4
+    shape = dict(input_size=42, hidden=127, output=42, depth=12)
+    text = markov_text(4000, 42, seed=2)
+    lo, hi = rdist.shard_bounds(len(text), rank, world)
+    my_text = np.ascontiguousarray(text[lo:hi])
+    results = {}
+    for variant in ("nccl", "p2p"):
+        net = make_net(L, seed=1, lr=lr, **shape)
+        ih0, ho0 = [w.copy() for w in weights(net)]
+        nets = L.rnn_new_training_set(net, n)
+        batch = L.rnn_batch_new(nets, n)
+        if variant == "p2p":
+            hb = (C.c_uint8 * 192)()
+            assert L.rnn_batch_p2p_export(batch, hb) == 0
+            mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
+            allh = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+            buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+            assert L.rnn_batch_p2p_attach(batch, buf, rank, world) == 0
+        L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
+        L.rnn_batch_text_train(batch, 0, steps, 0, 0.9, 0.0, None)
+        L.rnn_b200_synchronize()
+        ih, ho = [w.copy() for w in weights(net)]
+        # every replica must hold the same weights
+        t = torch.tensor(ih, device="cuda")
+        tmax, tmin = t.clone(), t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        results[variant] = dict(ih=ih, ho=ho, replicas_equal=bool(torch.equal(tmax, tmin)),
+                                ih0=ih0, ho0=ho0)
+        L.rnn_batch_delete(batch)
+        L.rnn_delete_training_set(nets, n, 0)
+        dist.barrier()
+    if rank == 0:
+        port = oracle.load_port()
+        s = port.oracle_set_new(42, 127, 42, n * world, 12, lr, abi.RNN_RELU, 1,
+                                fptr(results["nccl"]["ih0"]), fptr(results["nccl"]["ho0"]))
+        for i in range(steps):
+            cur, nxt = [], []
+            for r in range(world):
+                a, b = rdist.shard_bounds(len(text), r, world)
+                t_r = text[a:b]
+                for p in rdist.stream_positions(len(t_r), n, i):
+                    cur.append(t_r[p])
+                    nxt.append(t_r[p + 1])
+            cur = np.array(cur, dtype=np.uint8)
+            nxt = np.array(nxt, dtype=np.uint8)
+            port.oracle_set_char_step(s, u8ptr(cur), u8ptr(nxt), 0.9, None, None, None)
+        want_ih = arr(port.oracle_set_wih(s), len(results["nccl"]["ih"])).copy()
+        want_ho = arr(port.oracle_set_who(s), len(results["nccl"]["ho"])).copy()
+        out = {"world": world}
+        for variant, r in results.items():
+            out[variant] = {"ih_rel": rel_err(r["ih"], want_ih), "ho_rel": rel_err(r["ho"], want_ho),
+                            "replicas_equal": r["replicas_equal"]}
+        print("MULTIGPU_CHECK " + json.dumps(out))
+    dist.barrier()
+    L.rnn_b200_comm_leave()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
