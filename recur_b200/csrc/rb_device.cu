@@ -431,7 +431,7 @@ rb_pool_release_slot(RbPool *p, int slot)
 
 /* ---- per-class kernel timing ------------------------------------------------ */
 
-#define RB_PROF_CLASSES 4
+#define RB_PROF_CLASSES 8
 static int prof_on = 0;
 static cudaEvent_t *prof_ev = NULL; /* pairs */
 static int *prof_cls = NULL;
@@ -449,7 +449,8 @@ rnn_b200_profile_enable(int on)
 extern "C" const char *
 rnn_b200_profile_class_name(int cls)
 {
-  static const char *names[RB_PROF_CLASSES] = {"forward", "bptt_chain", "weight_grad", "update"};
+  static const char *names[RB_PROF_CLASSES] = {"forward", "bptt_chain", "weight_grad", "update",
+    "top_layer", "output_layer", "ho_delta", "small_kernels"};
   return (cls >= 0 && cls < RB_PROF_CLASSES) ? names[cls] : NULL;
 }
 

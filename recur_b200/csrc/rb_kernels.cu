@@ -233,6 +233,7 @@ k_prepare_x(RbView v)
  *  CHAIN  E(k+1)[b, y]  = mask * sum_x E(k)[b, x] * Wih[y, x]       K = h_size
  *  DW     delta[y, x]  += sum_r scale_r * x_r[y] * E_r[x]           K = n * depth
  *  HO     ho_delta[y,o] += sum_b hidden[b, y] * o_error[b, o]       K = n
+ *  TOP    E(0)[b, y]    = mask * sum_o o_error[b, o] * Who[y, o]    K = o_size
  *
  * 64x64 output tile, 16-deep K slices, 256 threads, 4x4 per thread, global
  * loads of the next slice overlapped with the FMAs of the current one. */
@@ -242,7 +243,7 @@ k_prepare_x(RbView v)
 #define TK 16
 #define TPAD 4
 
-enum { G_FWD = 0, G_CHAIN = 1, G_DW = 2, G_HO = 3 };
+enum { G_FWD = 0, G_CHAIN = 1, G_DW = 2, G_HO = 3, G_TOP = 4 };
 
 struct GemmArgs {
   RbView v;
@@ -270,6 +271,7 @@ k_gemm(GemmArgs g)
   if (MODE == G_FWD) { M = v.n; N = H; K = I; }
   else if (MODE == G_CHAIN) { M = v.n; N = I; K = H; }
   else if (MODE == G_DW) { M = I; N = H; K = v.n * v.depth; }
+  else if (MODE == G_TOP) { M = v.n; N = H; K = v.d.o_size; }
   else { M = H; N = v.d.o_size; K = v.n; }
 
   /* --- per-thread load coordinates --- */
@@ -286,6 +288,16 @@ k_gemm(GemmArgs g)
     if (tid == 0)
       s_any_live = 0;
     __syncthreads();
+  }
+  if (MODE == G_TOP) {
+    int m = m0 + lr;
+    if (m < M) {
+      a_ptr = v.OE + (size_t)v.slots[m] * K;
+      a_ok = true;
+    }
+    int n = n0 + lr;
+    b_ok = n < N;
+    b_ptr = v.Who + (size_t)n * K;
   }
   if (MODE == G_FWD || MODE == G_CHAIN) {
     int m = m0 + lr;
@@ -325,7 +337,7 @@ k_gemm(GemmArgs g)
       if (kb < K && c < N)
         rb = *(const float4 *)(v.Wih + (size_t)kb * H + c);
     }
-    else if (MODE == G_CHAIN) {
+    else if (MODE == G_CHAIN || MODE == G_TOP) {
       int k = k0 + lkq;
       if (k < K) {
         if (a_ok)
@@ -370,7 +382,7 @@ k_gemm(GemmArgs g)
       As[lkq + 2][lr] = ra.z; As[lkq + 3][lr] = ra.w;
       *(float4 *)&Bs[fk][fcq] = rb;
     }
-    else if (MODE == G_CHAIN) {
+    else if (MODE == G_CHAIN || MODE == G_TOP) {
       As[lkq + 0][lr] = ra.x; As[lkq + 1][lr] = ra.y;
       As[lkq + 2][lr] = ra.z; As[lkq + 3][lr] = ra.w;
       Bs[lkq + 0][lr] = rb.x; Bs[lkq + 1][lr] = rb.y;
@@ -452,6 +464,38 @@ k_gemm(GemmArgs g)
         out[j] = h;
       }
       *(float4 *)(v.Hd + (size_t)s * H + c) = make_float4(out[0], out[1], out[2], out[3]);
+    }
+  }
+  else if (MODE == G_TOP) {
+    /* recur-nn.c:199-228: error reaches only hidden units that fired (and not
+       the bias node); sum |e| per stream in column-block partials */
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int m = m0 + ty * 4 + i;
+      float ab = 0.0f;
+      int s = 0;
+      int c = n0 + tx * 4;
+      if (m < M) {
+        s = v.slots[m];
+        if (c < N) {
+          const float4 hv = *(const float4 *)(v.Hd + (size_t)s * H + c);
+          float h[4] = {hv.x, hv.y, hv.z, hv.w};
+          float o[4];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            float e = (h[j] != 0.0f && c + j >= 1) ? acc[i][j] : 0.0f;
+            ab += fabsf(e);
+            o[j] = e;
+          }
+          *(float4 *)(e_row(v, s, 0) + c) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      ab += __shfl_xor_sync(0xffffffffu, ab, 8);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 4);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 2);
+      ab += __shfl_xor_sync(0xffffffffu, ab, 1);
+      if (tx == 0 && m < M)
+        v.partial[(size_t)s * v.n_part + blockIdx.x] = ab;
     }
   }
   else if (MODE == G_CHAIN) {
@@ -761,6 +805,73 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
   }
 }
 
+/* a8 and the set-up of the BPTT walk after k_gemm<TOP>: per stream, total
+   |e| from the column-block partials, the hidden statistics the log wants,
+   the soft clip (recur-nn.c:720-721), optional hi/lo planes of E[0] for the
+   tensor engine, and the walk's thresholds (recur-nn.c:318-322).            */
+__global__ void __launch_bounds__(256)
+k_top_finish(RbView v, int n_col_blocks, float *Ehi, float *Elo)
+{
+  __shared__ float scratch[33];
+  const int s = v.slots[blockIdx.x];
+  const int H = v.d.h_size, I = v.d.i_size;
+  const float *hid = v.Hd + (size_t)s * H;
+  float hsum = 0.0f, hmag = 0.0f, hzero = 0.0f;
+  for (int y = threadIdx.x; y < H; y += blockDim.x) {
+    float h = hid[y];
+    hsum += h;
+    hmag += h * h;
+    hzero += (h == 0.0f);
+  }
+  float total = 0.0f;
+  if (threadIdx.x == 0)
+    for (int q = 0; q < n_col_blocks; q++)
+      total += v.partial[(size_t)s * v.n_part + q];
+  total = block_sum(total, scratch);
+  hsum = block_sum(hsum, scratch);
+  hmag = block_sum(hmag, scratch);
+  hzero = block_sum(hzero, scratch);
+  const float halfmax = H * MAX_TOP_ERROR_FACTOR;
+  const float scale = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
+  float *e0 = e_row(v, s, 0);
+  if (scale != 1.0f || Ehi) {
+    for (int y = threadIdx.x; y < H; y += blockDim.x) {
+      float e = e0[y];
+      if (scale != 1.0f) {
+        e *= scale;
+        e0[y] = e;
+      }
+      if (Ehi) {
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e));
+        float hi = __uint_as_float(hb);
+        float rem = e - hi;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+        Ehi[(size_t)s * I + y] = hi;
+        Elo[(size_t)s * I + y] = __uint_as_float(lb);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    RbScalars *sc = v.sc + s;
+    float top_scaled = (total > halfmax) ? scale * total : total;
+    sc->top_raw = total;
+    sc->top_scaled = top_scaled;
+    sc->hidden_sum = hsum;
+    sc->hidden_mag = sqrtf(hmag);
+    sc->hidden_zeros = (int)(hzero + 0.5f);
+    float min_gain = MIN_ERROR_GAIN * top_scaled;
+    sc->min_sum = fminf(sc->mef / sc->lr, min_gain);
+    sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
+    sc->cum_error = 0.0f;
+    sc->err_sum = 0.0f;
+    sc->live = (v.depth > 0);
+    sc->n_steps = 0;
+    sc->t_left = v.depth;
+    sc->ih_scale = 1.0f;
+  }
+}
+
 /* a9: ho_delta[y, :] (+)= sum over streams hidden[y] * o_error[:]
    (recur-nn.c:256-301).  One thread per (y, x) element, streams in order. */
 __global__ void __launch_bounds__(256)
@@ -828,8 +939,17 @@ stage_matrix(float *dst, const float *__restrict__ src, int n_floats)
     for (int u = 0; u < 8; u++)
       d4[i + u * blockDim.x] = t[u];
   }
-  for (; i < n4; i += blockDim.x)
-    d4[i] = __ldg(s4 + i);
+  if (i < n4) { /* the last, partial batch: still all loads before all stores */
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (i + u * (int)blockDim.x < n4)
+        t[u] = __ldg(s4 + i + u * blockDim.x);
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+      if (i + u * (int)blockDim.x < n4)
+        d4[i + u * blockDim.x] = t[u];
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1033,7 +1153,7 @@ k_top_multi(RbView v, float *Ehi, float *Elo)
 /* a9 for a batch that fits in shared memory: a block owns 16 hidden rows of
    ho_delta, pulls its slab of the hidden activations and all output errors
    into shared memory in one round of loads, then sums over the streams. */
-#define HO_ROWS 16
+#define HO_ROWS 8
 
 __global__ void __launch_bounds__(256)
 k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
@@ -1077,22 +1197,23 @@ k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
     }
   }
   __syncthreads();
-  const int yl = threadIdx.x % HO_ROWS, og = threadIdx.x / HO_ROWS; /* 16 column groups */
+  const int NG = 256 / HO_ROWS; /* column groups */
+  const int yl = threadIdx.x % HO_ROWS, og = threadIdx.x / HO_ROWS;
   if (y0 + yl >= H)
     return;
-  for (int o0 = og; o0 < O; o0 += 16 * 4) {
+  for (int o0 = og; o0 < O; o0 += NG * 4) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int b = 0; b < n; b++) {
       float h = sH[b * HO_ROWS + yl];
       const float *e = sO + (size_t)b * O + o0;
 #pragma unroll
       for (int u = 0; u < 4; u++)
-        if (o0 + u * 16 < O)
-          acc[u] += h * e[u * 16];
+        if (o0 + u * NG < O)
+          acc[u] += h * e[u * NG];
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      int o = o0 + u * 16;
+      int o = o0 + u * NG;
       if (o < O) {
         size_t idx = (size_t)(y0 + yl) * O + o;
         ho_delta[idx] = (accumulate ? ho_delta[idx] : 0.0f) + acc[u];
@@ -1410,8 +1531,10 @@ grid1d(long long n, int block)
 extern "C" void
 rbk_advance(const RbView *v)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_advance<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v);
   LAUNCH_CHECK("k_advance");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void
@@ -1424,24 +1547,30 @@ rbk_fill_iota(int *iota, int n)
 extern "C" void
 rbk_set_one_hot(const RbView *v, const u8 *hot_dev)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_set_one_hot<<<v->n, 64, 0, rb_stream>>>(*v, hot_dev);
   LAUNCH_CHECK("k_set_one_hot");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void
 rbk_set_inputs(const RbView *v, const float *inputs_dev)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_set_inputs<<<v->n, 64, 0, rb_stream>>>(*v, inputs_dev);
   LAUNCH_CHECK("k_set_inputs");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void
 rbk_text_symbols(const u8 *text_dev, int len, int i, int spacing, int n,
     u8 *cur_dev, u8 *next_dev)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_text_symbols<<<cdiv(n, 128), 128, 0, rb_stream>>>(text_dev, len, i, spacing, n,
       cur_dev, next_dev);
   LAUNCH_CHECK("k_text_symbols");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void
@@ -1454,8 +1583,10 @@ rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols)
 extern "C" void
 rbk_prepare_x(const RbView *v)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_prepare_x<<<v->n, 256, 0, rb_stream>>>(*v);
   LAUNCH_CHECK("k_prepare_x");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void
@@ -1469,13 +1600,17 @@ rbk_output(const RbView *v)
       cudaFuncSetAttribute(k_out_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       attr_done = 1;
     }
+    rb_prof_begin(RB_PROF_OUT);
     k_out_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v);
     LAUNCH_CHECK("k_out_multi");
+    rb_prof_end(RB_PROF_OUT);
     return;
   }
   size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
+  rb_prof_begin(RB_PROF_OUT);
   k_out<<<v->n, 256, sh, rb_stream>>>(*v);
   LAUNCH_CHECK("k_out");
+  rb_prof_end(RB_PROF_OUT);
 }
 
 extern "C" void
@@ -1531,11 +1666,15 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     if (!winner_dev)
       winner_dev = rb_winner_scratch;
   }
+  rb_prof_begin(RB_PROF_SMALL);
   k_softmax_error<<<cdiv(v->n, 4), 128, 0, rb_stream>>>(*v, target_dev, err_dev, winner_dev);
   LAUNCH_CHECK("k_softmax_error");
+  rb_prof_end(RB_PROF_SMALL);
   if (accum_dev) {
+    rb_prof_begin(RB_PROF_SMALL);
     k_char_accum<<<1, 256, 0, rb_stream>>>(err_dev, winner_dev, target_dev, v->n, accum_dev);
     LAUNCH_CHECK("k_char_accum");
+    rb_prof_end(RB_PROF_SMALL);
   }
 }
 
@@ -1552,22 +1691,30 @@ extern "C" void
 rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo)
 {
-  size_t multi = top_multi_smem(v);
-  if (n_ranges == 0 && v->n >= 4 * OS && multi <= 200 * 1024) {
-    static int attr_done = 0;
-    if (!attr_done) {
-      cudaFuncSetAttribute(k_top_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = 1;
-    }
-    k_top_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v, Ehi, Elo);
-    LAUNCH_CHECK("k_top_multi");
+  if (n_ranges == 0 && v->n >= 4 * OS && v->pool && v->pool->has_bptt) {
+    /* a batch: E(0) = mask * (o_error . Who^T) as a tiled contraction */
+    GemmArgs g;
+    g.v = *v;
+    g.k = 0;
+    g.delta = NULL;
+    g.accumulate = 0;
+    g.use_noise = 0;
+    dim3 grid(cdiv(v->d.h_size, TN), cdiv(v->n, TM));
+    rb_prof_begin(RB_PROF_TOP);
+    k_gemm<G_TOP><<<grid, 256, 0, rb_stream>>>(g);
+    LAUNCH_CHECK("k_gemm<TOP>");
+    k_top_finish<<<v->n, 256, 0, rb_stream>>>(*v, (int)grid.x, Ehi, Elo);
+    LAUNCH_CHECK("k_top_finish");
+    rb_prof_end(RB_PROF_TOP);
   }
   else {
     if (Ehi)
       rb_die("recur-b200: internal: E[0] planes requested from the per-stream top kernel");
     size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
+    rb_prof_begin(RB_PROF_TOP);
     k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
     LAUNCH_CHECK("k_top");
+    rb_prof_end(RB_PROF_TOP);
   }
   size_t slab = (size_t)v->n * (HO_ROWS + v->d.o_size) * sizeof(float);
   if (ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024) {
@@ -1576,8 +1723,10 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
           200 * 1024);
       ho_slab_attr_done = 1;
     }
+    rb_prof_begin(RB_PROF_HO);
     k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, rb_stream>>>(*v, ho_delta, accumulate);
     LAUNCH_CHECK("k_ho_delta_slab");
+    rb_prof_end(RB_PROF_HO);
   }
   else if (ho_delta && n_ranges == 0 && v->n >= 8) {
     /* the sum over streams as a tiled contraction */
@@ -1588,21 +1737,25 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     g.accumulate = accumulate;
     g.use_noise = 0;
     dim3 grid(cdiv(v->d.o_size, TN), cdiv(v->d.h_size, TM));
+    rb_prof_begin(RB_PROF_HO);
     k_gemm<G_HO><<<grid, 256, 0, rb_stream>>>(g);
     LAUNCH_CHECK("k_gemm<HO>");
+    rb_prof_end(RB_PROF_HO);
   }
   else if (ho_delta) {
     int total = v->d.h_size * v->d.o_size;
+    rb_prof_begin(RB_PROF_HO);
     k_ho_delta<<<cdiv(total, 256), 256, 0, rb_stream>>>(*v, ho_delta, accumulate,
         ranges_dev, n_ranges);
     LAUNCH_CHECK("k_ho_delta");
+    rb_prof_end(RB_PROF_HO);
   }
 }
 
 extern "C" int
 rbk_top_layer_can_write_planes(const RbView *v)
 {
-  return v->n >= 4 * OS && top_multi_smem(v) <= 200 * 1024;
+  return v->n >= 4 * OS && v->pool && v->pool->has_bptt;
 }
 
 extern "C" void
@@ -1649,8 +1802,10 @@ rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 extern "C" void
 rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive)
 {
+  rb_prof_begin(RB_PROF_SMALL);
   k_set_params<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, lr_dev, mef_dev, adaptive);
   LAUNCH_CHECK("k_set_params");
+  rb_prof_end(RB_PROF_SMALL);
 }
 
 extern "C" void

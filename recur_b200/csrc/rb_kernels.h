@@ -42,7 +42,8 @@ void rb_view_of_net(RbNet *rn, RbView *v);
 void rb_count_launch(int n);
 void rb_prof_begin(int cls);
 void rb_prof_end(int cls);
-enum { RB_PROF_FWD = 0, RB_PROF_CHAIN = 1, RB_PROF_DW = 2, RB_PROF_UPDATE = 3 };
+enum { RB_PROF_FWD = 0, RB_PROF_CHAIN = 1, RB_PROF_DW = 2, RB_PROF_UPDATE = 3,
+       RB_PROF_TOP = 4, RB_PROF_OUT = 5, RB_PROF_HO = 6, RB_PROF_SMALL = 7 };
 
 void rbk_advance(const RbView *v);
 void rbk_fill_iota(int *iota, int n);

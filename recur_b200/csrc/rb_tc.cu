@@ -1412,8 +1412,10 @@ refresh_weight_planes(RbTc *t, RbPool *p, const RbView *v)
     return;
   const int I = v->d.i_size, H = v->d.h_size;
   dim3 grid(cdiv(H, 32), cdiv(I, 32));
+  rb_prof_begin(RB_PROF_SMALL);
   k_split_weights<<<grid, 256, 0, rb_stream>>>(v->Wih, I, H, t->Whi, t->Wlo, t->WThi, t->WTlo);
   LAUNCH_CHECK("k_split_weights");
+  rb_prof_end(RB_PROF_SMALL);
   t->w_src = v->Wih;
   t->w_version = g->weights_version;
 }
@@ -1428,8 +1430,10 @@ rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
   RbTc *t = tc_state(p);
   refresh_weight_planes(t, p, v);
   rbk_prepare_x(v);
+  rb_prof_begin(RB_PROF_SMALL);
   k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 0, t->Xhi, t->Xlo);
   LAUNCH_CHECK("k_split_rows");
+  rb_prof_end(RB_PROF_SMALL);
   NtArgs g;
   g.v = *v;
   g.mode = 0;
@@ -1465,8 +1469,10 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   }
   else {
     rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
+    rb_prof_begin(RB_PROF_SMALL);
     k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 1, t->Ehi, t->Elo);
     LAUNCH_CHECK("k_split_rows");
+    rb_prof_end(RB_PROF_SMALL);
   }
   if (!chain_attr_done) {
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
@@ -1574,8 +1580,10 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
     LAUNCH_CHECK("k_compute_kmax");
   }
+  rb_prof_begin(RB_PROF_SMALL);
   k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo, kmax_dev);
   LAUNCH_CHECK("k_finalize_rows");
+  rb_prof_end(RB_PROF_SMALL);
   if (!dw_attr_done) {
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize,
             DW_SMEM_BYTES));
