@@ -214,9 +214,8 @@ rnn_batch_size(const RnnBatch *b)
   return b->n;
 }
 
-/* host bookkeeping of rnn_bptt_advance for every net, one kernel for the device */
-extern "C" void
-rnn_batch_advance(RnnBatch *b)
+static void
+advance_host_side(RnnBatch *b)
 {
   RbPool *p = b->pool;
   for (int j = 0; j < b->n; j++) {
@@ -231,6 +230,13 @@ rnn_batch_advance(RnnBatch *b)
     int pos = p->pos_shadow[s] + 1;
     p->pos_shadow[s] = (pos >= p->depth) ? pos - p->depth : pos;
   }
+}
+
+/* host bookkeeping of rnn_bptt_advance for every net, one kernel for the device */
+extern "C" void
+rnn_batch_advance(RnnBatch *b)
+{
+  advance_host_side(b);
   RbView v;
   batch_view(b, &v);
   rbk_advance(&v);
@@ -455,19 +461,23 @@ fetch_stats(RnnBatch *b, RnnBatchCharStats *stats)
   stats->count += b->accum_host->count;
 }
 
-/* advance .. update for one character position, symbols already on device */
+extern "C" void rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos,
+    int spacing, u8 *cur_dev, u8 *next_dev, float noise);
+
+/* advance .. update for one character position; the symbols come from the
+   uploaded text at position `pos` (text != 0) or are already in cur/next */
 static void
-char_step_device(RnnBatch *b, int learning_style, float momentum)
+char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text, int pos)
 {
   RecurNN *proto = &b->nets[0]->pub;
-  rnn_batch_advance(b);
+  advance_host_side(b);
   RbView v;
   batch_view(b, &v);
   rb_matrices_to_device(proto);
-  rbk_set_one_hot(&v, b->cur_dev);
   float noise = proto->presynaptic_noise;
   upload_rng_if_noisy(b, noise);
-  rb_forward_dispatch(&v, noise);
+  rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
+      from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
   download_rng_if_noisy(b, noise);
   rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
   calc_deltas_async(b, 0);
@@ -483,7 +493,7 @@ rnn_batch_char_step(RnnBatch *b, const u8 *cur, const u8 *next, int learning_sty
   memcpy(b->sym_host + b->n, next, b->n);
   CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
   CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice, rb_stream));
-  char_step_device(b, learning_style, momentum);
+  char_step_device(b, learning_style, momentum, 0, 0);
   if (stats)
     fetch_stats(b, stats);
 }
@@ -513,8 +523,7 @@ rnn_batch_text_train(RnnBatch *b, int start, int steps, int learning_style,
       i = 0;
     float m = rnn_calculate_momentum_soft_start(proto->generation, momentum,
         momentum_soft_start);
-    rbk_text_symbols(b->text_dev, len, i, spacing, b->n, b->cur_dev, b->next_dev);
-    char_step_device(b, learning_style, m);
+    char_step_device(b, learning_style, m, 1, i);
   }
   if (stats)
     fetch_stats(b, stats);

@@ -1197,28 +1197,42 @@ k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
     }
   }
   __syncthreads();
-  const int NG = 256 / HO_ROWS; /* column groups */
-  const int yl = threadIdx.x % HO_ROWS, og = threadIdx.x / HO_ROWS;
-  if (y0 + yl >= H)
-    return;
-  for (int o0 = og; o0 < O; o0 += NG * 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int b = 0; b < n; b++) {
+  /* thread = (hidden row of the slab, group of 12 output columns, slice of the
+     streams): 12 accumulators per thread keep the FMA pipe busier than the
+     shared-memory pipe; the slices are then summed in a fixed order */
+  const int n_cg = (O + 11) / 12;
+  const int S = 256 / (HO_ROWS * n_cg);
+  const int yl = threadIdx.x % HO_ROWS;
+  const int cg = (threadIdx.x / HO_ROWS) % n_cg;
+  const int sl = threadIdx.x / (HO_ROWS * n_cg);
+  float *red = sO + (size_t)n * O + 16;
+  float acc[12];
+#pragma unroll
+  for (int u = 0; u < 12; u++)
+    acc[u] = 0.0f;
+  if (sl < S) {
+    for (int b = sl; b < n; b += S) {
       float h = sH[b * HO_ROWS + yl];
-      const float *e = sO + (size_t)b * O + o0;
-#pragma unroll
-      for (int u = 0; u < 4; u++)
-        if (o0 + u * NG < O)
-          acc[u] += h * e[u * NG];
+      const float4 *e4 = (const float4 *)(sO + (size_t)b * O + cg * 12);
+      float4 e0 = e4[0], e1 = e4[1], e2 = e4[2];
+      acc[0] += h * e0.x; acc[1] += h * e0.y; acc[2] += h * e0.z; acc[3] += h * e0.w;
+      acc[4] += h * e1.x; acc[5] += h * e1.y; acc[6] += h * e1.z; acc[7] += h * e1.w;
+      acc[8] += h * e2.x; acc[9] += h * e2.y; acc[10] += h * e2.z; acc[11] += h * e2.w;
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      int o = o0 + u * NG;
-      if (o < O) {
-        size_t idx = (size_t)(y0 + yl) * O + o;
-        ho_delta[idx] = (accumulate ? ho_delta[idx] : 0.0f) + acc[u];
-      }
-    }
+    for (int u = 0; u < 12; u++)
+      red[((size_t)sl * HO_ROWS + yl) * (n_cg * 12) + cg * 12 + u] = acc[u];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HO_ROWS * O; i += blockDim.x) {
+    int y = i / O, o = i - y * O;
+    if (y0 + y >= H)
+      continue;
+    float t = 0.0f;
+    for (int q = 0; q < S; q++)
+      t += red[((size_t)q * HO_ROWS + y) * (n_cg * 12) + o];
+    size_t idx = (size_t)(y0 + y) * O + o;
+    ho_delta[idx] = (accumulate ? ho_delta[idx] : 0.0f) + t;
   }
 }
 
@@ -1580,6 +1594,121 @@ rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols)
   LAUNCH_CHECK("k_gen_noise");
 }
 
+/* The start of a text-predict step for every stream in one launch: advance
+   the ring (a1), pick this stream's symbol pair out of the text
+   (charmodel-predict.c:295-298), write the one-hot input (a2), build the
+   input row [1 | hidden(t-1) | inputs | 0..] with the emergency soft clip
+   (a3/a5), and, for the tensor engine, the row's hi/lo planes.             */
+struct StepBeginArgs {
+  RbView v;
+  const u8 *text; /* NULL: symbols are already in cur/next */
+  int len, pos, spacing;
+  u8 *cur, *next;
+  float *Xhi, *Xlo;
+};
+
+__global__ void __launch_bounds__(256)
+k_step_begin(StepBeginArgs a)
+{
+  __shared__ float scratch[33];
+  __shared__ int s_pos, s_hot;
+  const RbView &v = a.v;
+  const int j = blockIdx.x;
+  const int s = v.contiguous ? v.base + j : v.slots[j];
+  if (threadIdx.x == 0) {
+    int p = v.pos[s] + 1;
+    if (p >= v.depth)
+      p -= v.depth;
+    v.pos[s] = p;
+    s_pos = p;
+    int hot;
+    if (a.text) {
+      long long off = (long long)a.pos + (long long)j * a.spacing;
+      if (off >= a.len - 1)
+        off -= a.len - 1;
+      hot = a.text[off];
+      a.cur[j] = (u8)hot;
+      a.next[j] = a.text[off + 1];
+    }
+    else {
+      hot = a.cur[j];
+    }
+    s_hot = hot;
+  }
+  __syncthreads();
+  const int I = v.d.i_size, hs1 = v.d.hidden_size + 1;
+  const size_t off = ((size_t)s_pos * v.cap + s) * I;
+  float *x = v.X + off;
+  const float *h = v.Hd + (size_t)s * v.d.h_size;
+  const int hot_col = hs1 + s_hot;
+  const int in_end = hs1 + v.d.input_size;
+  float vals[8]; /* i_size <= 8 * 256 on this path */
+  float sum = 0.0f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    int i = threadIdx.x + u * 256;
+    float val = 0.0f;
+    if (i < I) {
+      if (i == 0)
+        val = 1.0f;
+      else if (i < hs1)
+        val = h[i];
+      else if (i < in_end)
+        val = (i == hot_col) ? 1.0f : 0.0f;
+    }
+    vals[u] = val;
+    sum += val;
+  }
+  sum = block_sum(sum, scratch);
+  const float softclip = I * INPUT_MEAN_SOFT_TOP;
+  const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
+#pragma unroll
+  for (int u = 0; u < 8; u++) {
+    int i = threadIdx.x + u * 256;
+    if (i < I) {
+      float val = vals[u];
+      if (scale != 1.0f)
+        val *= scale;
+      x[i] = val;
+      if (a.Xhi) {
+        uint32_t hb, lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(val));
+        float hi = __uint_as_float(hb);
+        float rem = val - hi;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+        a.Xhi[off + i] = hi;
+        a.Xlo[off + i] = __uint_as_float(lb);
+      }
+    }
+  }
+}
+
+extern "C" int
+rbk_step_begin_usable(const RbView *v)
+{
+  return v->d.i_size <= 8 * 256;
+}
+
+extern "C" void
+rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
+    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo)
+{
+  StepBeginArgs a;
+  a.v = *v;
+  a.text = text_dev;
+  a.len = len;
+  a.pos = pos;
+  a.spacing = spacing;
+  a.cur = cur_dev;
+  a.next = next_dev;
+  a.Xhi = Xhi;
+  a.Xlo = Xlo;
+  rb_prof_begin(RB_PROF_SMALL);
+  k_step_begin<<<v->n, 256, 0, rb_stream>>>(a);
+  LAUNCH_CHECK("k_step_begin");
+  rb_prof_end(RB_PROF_SMALL);
+}
+
 extern "C" void
 rbk_prepare_x(const RbView *v)
 {
@@ -1624,6 +1753,13 @@ extern "C" void
 rbk_forward(const RbView *v, float presynaptic_noise)
 {
   rbk_prepare_x(v);
+  rbk_forward_core(v, presynaptic_noise);
+}
+
+/* everything of a3 after the input row is in place */
+extern "C" void
+rbk_forward_core(const RbView *v, float presynaptic_noise)
+{
   GemmArgs g;
   g.v = *v;
   g.k = 0;
@@ -1716,8 +1852,10 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     LAUNCH_CHECK("k_top");
     rb_prof_end(RB_PROF_TOP);
   }
-  size_t slab = (size_t)v->n * (HO_ROWS + v->d.o_size) * sizeof(float);
-  if (ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024) {
+  /* hidden slab + errors + slack + per-slice partial sums */
+  size_t slab = ((size_t)v->n * (HO_ROWS + v->d.o_size) + 16 +
+      (size_t)256 * 12) * sizeof(float);
+  if (ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024 && v->d.o_size <= 384) {
     if (!ho_slab_attr_done) {
       cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
           200 * 1024);

@@ -53,6 +53,10 @@ void rbk_text_symbols(const u8 *text_dev, int len, int i, int spacing, int n,
     u8 *cur_dev, u8 *next_dev);
 void rbk_forward(const RbView *v, float presynaptic_noise); /* a3..a5 */
 void rbk_prepare_x(const RbView *v);
+void rbk_forward_core(const RbView *v, float presynaptic_noise);
+int rbk_step_begin_usable(const RbView *v);
+void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
+    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo);
 void rbk_output(const RbView *v);
 void rbk_chain_decide(const RbView *v, int k);
 void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
@@ -88,6 +92,8 @@ void rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols);
 /* tensor-core engine (rb_tc.cu) */
 int rb_tc_usable(const RbView *v);
 void rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise);
+void rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise);
+void rb_tc_x_planes(RbPool *p, float **Xhi, float **Xlo);
 void rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     int accumulate);
 void rb_tc_pool_release(RbPool *p);

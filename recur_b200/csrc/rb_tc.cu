@@ -1425,15 +1425,31 @@ typedef NtCfg<TC_FWD_BN, TC_FWD_STAGES> FwdCfg;
 typedef NtCfg<TC_CHAIN_BN, TC_CHAIN_STAGES> ChainCfg;
 
 extern "C" void
+rb_tc_x_planes(RbPool *p, float **Xhi, float **Xlo)
+{
+  RbTc *t = tc_state(p);
+  *Xhi = t->Xhi;
+  *Xlo = t->Xlo;
+}
+
+extern "C" void
 rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
 {
   RbTc *t = tc_state(p);
-  refresh_weight_planes(t, p, v);
   rbk_prepare_x(v);
   rb_prof_begin(RB_PROF_SMALL);
   k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 0, t->Xhi, t->Xlo);
   LAUNCH_CHECK("k_split_rows");
   rb_prof_end(RB_PROF_SMALL);
+  rb_tc_forward_core(p, v, presynaptic_noise);
+}
+
+/* the forward contraction once the input row and its planes are in the ring */
+extern "C" void
+rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise)
+{
+  RbTc *t = tc_state(p);
+  refresh_weight_planes(t, p, v);
   NtArgs g;
   g.v = *v;
   g.mode = 0;
