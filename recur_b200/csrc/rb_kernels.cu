@@ -741,6 +741,13 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
   __syncthreads();
   const float *hid = v.Hd + (size_t)s * H;
   float *e0 = e_row(v, s, 0);
+  /* With error ranges the reference leaves h_error[y] of silent hidden units
+     untouched (no else branch, recur-nn.c:175-193), i.e. whatever the previous
+     BPTT walk of this stream left in that buffer.  The two error buffers swap
+     each step (recur-nn.c:384-386), so after n steps the one called h_error
+     holds E(n) for even n and E(n-1) for odd n. */
+  const int n_prev = v.sc[s].n_steps;
+  const float *stale = e_row(v, s, (n_prev & 1) ? n_prev - 1 : n_prev);
   float abs_sum = 0.0f, hsum = 0.0f, hmag = 0.0f;
   int hzero = 0;
   for (int y = threadIdx.x; y < I; y += blockDim.x) {
@@ -750,6 +757,8 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
       hsum += h;
       hmag += h * h;
       hzero += (h == 0.0f);
+      if (n_ranges != 0 && !(y >= 1 && h != 0.0f))
+        e = stale[y];
       if (y >= 1 && h != 0.0f) {
         const float *row = v.Who + (size_t)y * O;
         if (n_ranges == 0) {

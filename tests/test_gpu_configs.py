@@ -187,3 +187,60 @@ def test_presynaptic_noise_draws_match_reference(gpu_lib, ref):
     assert (b.contents.rng.a, b.contents.rng.d) == (r2.contents.rng.a, r2.contents.rng.d)
     assert rel_err(arr(b.contents.hidden_layer, 24), arr(r2.contents.hidden_layer, 24)) < TOL
     lib.rnn_batch_delete(batch)
+
+
+def test_config4_multi_head_training_with_error_ranges(gpu_lib, ref):
+    """text_train of charmodel-multi-predict.c:234-281 for one text: per
+    step a softmax error on the target class's output range only
+    (multi_softmax_error, 18-58), rnn_bptt_calc_deltas with RecurErrorRange,
+    adagrad every batch_size steps.  Exercises the sparse top layer with its
+    stale-row behaviour (recur-nn.c:156-196, 275-301) and ReSQRT backward."""
+    lib = gpu_lib
+    alpha, n_classes, target, batch_size, steps = 13, 5, 2, 4, 14
+    shape = dict(input_size=alpha, hidden=31, output=n_classes * alpha, depth=6, seed=9,
+                 lr=0.05, activation=abi.RNN_RESQRT)
+    rs = np.random.RandomState(1)
+    text = rs.randint(0, alpha, size=steps + 1)
+    off = target * alpha
+    ranges = (abi.RecurErrorRange * 2)()
+    ranges[0].start = off & ~3
+    ranges[0].len = ((off + alpha + 3) & ~3) - (off & ~3)
+    ranges[1].start = -1
+    res = []
+    for L in (lib, ref):
+        net = make_net(L, **shape)
+        ih, ho = weights(net)
+        ih *= 2.0   # livelier hidden layer: some units silent, some not
+        L.rnn_set_momentum_values(net, 0.5)   # adagrad ballast
+        c = net.contents
+        b = c.bptt.contents
+        countdown = batch_size
+        trace = []
+        for i in range(steps):
+            L.rnn_bptt_advance(net)
+            x = arr(c.real_inputs, alpha)
+            x[:] = 0
+            x[text[i]] = 1.0
+            answer = arr(L.rnn_opinion(net, None, 0.0), c.o_size)
+            err = arr(b.o_error, c.o_size)
+            err[:] = 0
+            seg = np.zeros(alpha, dtype=np.float32)
+            ref.ref_softmax_best_guess(fptr(seg), fptr(np.ascontiguousarray(answer[off:off + alpha])), alpha)
+            seg[text[i + 1]] += 1.0
+            err[off:off + alpha] = seg
+            countdown -= 1
+            if countdown == 0:
+                L.rnn_apply_learning(net, abi.RNN_ADAGRAD, b.momentum)
+                countdown = batch_size
+                L.rnn_bptt_calc_deltas(net, 0, ranges)
+            else:
+                L.rnn_bptt_calc_deltas(net, 1, ranges)
+            trace.append((arr(b.ih_delta, c.ih_size).copy(), arr(b.ho_delta, c.ho_size).copy(),
+                          b.ih_scale))
+        res.append((trace, [w.copy() for w in weights(net)]))
+    for i, (a, r) in enumerate(zip(res[0][0], res[1][0])):
+        assert rel_err(a[0], r[0]) < TOL, ("ih_delta", i)
+        assert rel_err(a[1], r[1]) < TOL, ("ho_delta", i)
+        assert abs(a[2] - r[2]) < TOL
+    for x, y in zip(res[0][1], res[1][1]):
+        assert rel_err(x, y) < TOL
