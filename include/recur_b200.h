@@ -140,6 +140,13 @@ void rnn_batch_set_errors(RnnBatch *batch, const float *o_error);
    are overwritten by the sum over all streams, otherwise added to. */
 void rnn_batch_calc_deltas(RnnBatch *batch, int accumulate);
 
+/* The same with some streams sitting the step out: active[j] == 0 means
+   stream j's rnn_bptt_calc_deltas call is skipped altogether, as
+   rnn_char_classify_epoch does for characters without a class
+   (charmodel-classify.c:124-148); its generation, min_error_factor and
+   contribution to the deltas stay untouched.  active == NULL: all train. */
+void rnn_batch_calc_deltas_masked(RnnBatch *batch, int accumulate, const u8 *active);
+
 /* rnn_apply_learning(nets[0], ...) (recur-nn.c:601-678). */
 void rnn_batch_apply_learning(RnnBatch *batch, int learning_style, float momentum);
 

@@ -28,7 +28,8 @@ B200_API_SYMBOLS = [
     "rnn_batch_new", "rnn_batch_delete", "rnn_batch_size", "rnn_batch_advance",
     "rnn_batch_set_inputs", "rnn_batch_set_one_hot", "rnn_batch_opinion",
     "rnn_batch_get_outputs", "rnn_batch_get_hiddens", "rnn_batch_softmax_error",
-    "rnn_batch_set_errors", "rnn_batch_calc_deltas", "rnn_batch_apply_learning",
+    "rnn_batch_set_errors", "rnn_batch_calc_deltas", "rnn_batch_calc_deltas_masked",
+    "rnn_batch_apply_learning",
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
     "rnn_batch_text_forward", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
@@ -88,6 +89,8 @@ def _declare_b200(lib):
     lib.rnn_batch_set_errors.argtypes = [vp, c_float_p]
     lib.rnn_batch_calc_deltas.restype = None
     lib.rnn_batch_calc_deltas.argtypes = [vp, C.c_int]
+    lib.rnn_batch_calc_deltas_masked.restype = None
+    lib.rnn_batch_calc_deltas_masked.argtypes = [vp, C.c_int, u8_p]
     lib.rnn_batch_apply_learning.restype = None
     lib.rnn_batch_apply_learning.argtypes = [vp, C.c_int, C.c_float]
     lib.rnn_batch_char_step.restype = None

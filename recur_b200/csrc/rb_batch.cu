@@ -44,6 +44,7 @@ struct RnnBatch {
   float *lr_host;        /* n, last uploaded learn rates */
   RbCharAccum *accum_host;
   void *p2p;             /* fused gradient exchange (multi-GPU), or NULL */
+  int masked;            /* the last calc_deltas left skip bits on the device */
 };
 
 static int g_engine = 0;
@@ -410,7 +411,7 @@ refresh_learn_rates(RnnBatch *b, const RbView *v)
 }
 
 static void
-calc_deltas_async(RnnBatch *b, int accumulate)
+calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
 {
   RecurNN *proto = &b->nets[0]->pub;
   RecurNNBPTT *bp = proto->bptt;
@@ -420,6 +421,18 @@ calc_deltas_async(RnnBatch *b, int accumulate)
   RbView v;
   batch_view(b, &v);
   refresh_learn_rates(b, &v);
+  if (active || b->masked) {
+    /* upload the mask (or clear the one a previous call left) */
+    const u8 *mask_dev = NULL;
+    if (active) {
+      CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+      memcpy(b->sym_host, active, b->n);
+      CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
+      mask_dev = b->cur_dev;
+    }
+    rbk_mask_streams(&v, mask_dev);
+    b->masked = active != NULL;
+  }
   rb_top_and_bptt_dispatch(&v, bp->ho_delta, bp->ih_delta, accumulate);
   /* [ih_delta | ho_delta] are adjacent in the prototype's delta block; when
      the peer-memory exchange is attached and the tensor engine ran, the sum
@@ -427,8 +440,15 @@ calc_deltas_async(RnnBatch *b, int accumulate)
   if (rb_comm_size() > 1 && !(rb_p2p_ready(b->p2p) && rb_last_bptt_used_tensor_engine()))
     rb_comm_allreduce_sum(bp->ih_delta, (size_t)proto->ih_size + proto->ho_size);
   for (int j = 0; j < b->n; j++)
-    b->nets[j]->pub.generation++;
+    if (!active || active[j])
+      b->nets[j]->pub.generation++;
   mark_ahead(b);
+}
+
+extern "C" void
+rnn_batch_calc_deltas_masked(RnnBatch *b, int accumulate, const u8 *active)
+{
+  calc_deltas_async(b, accumulate, active);
 }
 
 extern "C" void

@@ -807,7 +807,7 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
     sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
     sc->cum_error = 0.0f;
     sc->err_sum = 0.0f;
-    sc->live = (v.depth > 0);
+    sc->live = (v.depth > 0) && !(sc->adaptive & 2);
     sc->n_steps = 0;
     sc->t_left = v.depth;
     sc->ih_scale = 1.0f;
@@ -874,7 +874,7 @@ k_top_finish(RbView v, int n_col_blocks, float *Ehi, float *Elo)
     sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
     sc->cum_error = 0.0f;
     sc->err_sum = 0.0f;
-    sc->live = (v.depth > 0);
+    sc->live = (v.depth > 0) && !(sc->adaptive & 2);
     sc->n_steps = 0;
     sc->t_left = v.depth;
     sc->ih_scale = 1.0f;
@@ -1309,7 +1309,7 @@ k_chain_decide(RbView v, int k)
   }
   else {
     sc->ih_scale = 1.0f;
-    if (sc->adaptive) {
+    if (sc->adaptive & 1) {
       int depth_error = v.depth / 4 - t_left;
       float min_gain = MIN_ERROR_GAIN * sc->top_scaled;
       float mef = sc->mef;
@@ -1334,7 +1334,24 @@ k_set_params(RbView v, const float *lr, const float *mef, int adaptive)
   if (mef)
     sc->mef = mef[j];
   if (adaptive >= 0)
-    sc->adaptive = adaptive;
+    sc->adaptive = (sc->adaptive & 2) | (adaptive & 1);
+}
+
+/* streams that sit this step out (charmodel-classify.c:124-148: characters
+   without a class are run forward but not trained on) */
+__global__ void
+k_mask_streams(RbView v, const u8 *active)
+{
+  int j = blockIdx.x;
+  int s = v.slots[j];
+  bool skip = active && !active[j];
+  if (threadIdx.x == 0) {
+    int a = v.sc[s].adaptive & 1;
+    v.sc[s].adaptive = a | (skip ? 2 : 0);
+  }
+  if (skip)
+    for (int i = threadIdx.x; i < v.d.o_size; i += blockDim.x)
+      v.OE[(size_t)s * v.d.o_size + i] = 0.0f;
 }
 
 __global__ void
@@ -1953,6 +1970,13 @@ rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int a
   k_set_params<<<cdiv(v->n, 128), 128, 0, rb_stream>>>(*v, lr_dev, mef_dev, adaptive);
   LAUNCH_CHECK("k_set_params");
   rb_prof_end(RB_PROF_SMALL);
+}
+
+extern "C" void
+rbk_mask_streams(const RbView *v, const u8 *active_dev)
+{
+  k_mask_streams<<<v->n, 64, 0, rb_stream>>>(*v, active_dev);
+  LAUNCH_CHECK("k_mask_streams");
 }
 
 extern "C" void

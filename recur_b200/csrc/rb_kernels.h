@@ -68,6 +68,7 @@ void rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
 int rbk_top_layer_can_write_planes(const RbView *v);
 void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */
 void rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive);
+void rbk_mask_streams(const RbView *v, const u8 *active_dev);
 void rbk_set_params_scalar(const RbView *v, float lr, float mef, int adaptive);
 void rbk_sgd_top_apply(const RbView *v, float *ho_weights, float *ho_momentum,
     float rate, float momentum, float momentum_weight);     /* a14 (recur-nn.c:941-964) */

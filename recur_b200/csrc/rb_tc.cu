@@ -821,7 +821,7 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
   }
   else {
     sc->ih_scale = 1.0f;
-    if (sc->adaptive) {
+    if (sc->adaptive & 1) {
       int depth_error = v.depth / 4 - t_left;
       float min_gain = MIN_ERROR_GAIN * sc->top_scaled;
       float mef = sc->mef;
@@ -1192,7 +1192,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
             }
             else {
               sc.ih_scale = 1.0f;
-              if (sc.adaptive) {
+              if (sc.adaptive & 1) {
                 int depth_error = v.depth / 4 - t_left;
                 float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
                 float mef = sc.mef;

@@ -244,3 +244,58 @@ def test_config4_multi_head_training_with_error_ranges(gpu_lib, ref):
         assert abs(a[2] - r[2]) < TOL
     for x, y in zip(res[0][1], res[1][1]):
         assert rel_err(x, y) < TOL
+
+
+@pytest.mark.parametrize("n_nets", [6, 64])
+def test_f1_char_classify_epoch_with_unlabelled_characters(gpu_lib, ref, n_nets):
+    """rnn_char_classify_epoch (charmodel-classify.c:73-154): every stream runs
+    forward on its character; only characters that carry a class are trained
+    on, rnn_bptt_calc_deltas(n, j ? 1 : 0, NULL) — so when stream 0 sits a
+    step out the deltas are NOT cleared that step (the reference's quirk,
+    SURVEY.md §8a notes), which the masked batch call reproduces through its
+    accumulate argument."""
+    lib = gpu_lib
+    alpha, classes, steps = 11, 3, 7
+    NO_CLASS = 255
+    shape = dict(input_size=alpha, hidden=67, output=classes, depth=5, seed=2, lr=0.01)
+    rs = np.random.RandomState(n_nets)
+    sym = rs.randint(0, alpha, size=(steps, n_nets)).astype(np.uint8)
+    cls = rs.randint(0, classes, size=(steps, n_nets)).astype(np.uint8)
+    cls[rs.random_sample((steps, n_nets)) < 0.3] = NO_CLASS
+    cls[2, 0] = NO_CLASS      # stream 0 unlabelled: the stale-delta quirk
+    cls[3, :] = NO_CLASS      # a step nobody trains on
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    rn = ref.rnn_new_training_set(r, n_nets)
+    an = lib.rnn_new_training_set(a, n_nets)
+    batch = lib.rnn_batch_new(an, n_nets)
+    for t in range(steps):
+        for j in range(n_nets):
+            c = rn[j].contents
+            ref.rnn_bptt_advance(rn[j])
+            x = arr(c.real_inputs, alpha)
+            x[:] = 0
+            x[sym[t, j]] = 1.0
+            answer = ref.rnn_opinion(rn[j], None, 0.0)
+            if cls[t, j] != NO_CLASS:
+                ref.ref_softmax_best_guess(c.bptt.contents.o_error, answer, classes)
+                arr(c.bptt.contents.o_error, c.o_size)[cls[t, j]] += 1.0
+                ref.rnn_bptt_calc_deltas(rn[j], 1 if j else 0, None)
+        ref.rnn_apply_learning(r, 0, 0.9)
+        lib.rnn_batch_advance(batch)
+        lib.rnn_batch_set_one_hot(batch, np.ascontiguousarray(sym[t]).ctypes.data_as(abi.u8_p))
+        lib.rnn_batch_opinion(batch, 0.0)
+        tgt = np.where(cls[t] == NO_CLASS, 0, cls[t]).astype(np.uint8)
+        lib.rnn_batch_softmax_error(batch, tgt.ctypes.data_as(abi.u8_p), None, None)
+        active = (cls[t] != NO_CLASS).astype(np.uint8)
+        lib.rnn_batch_calc_deltas_masked(batch, 0 if active[0] else 1,
+                                         active.ctypes.data_as(abi.u8_p))
+        lib.rnn_apply_learning(a, 0, 0.9)
+        for x, y in zip(weights(a), weights(r)):
+            assert rel_err(x, y) < TOL, t
+    lib.rnn_batch_pull(batch)
+    for j in range(n_nets):
+        assert an[j].contents.generation == rn[j].contents.generation
+        assert rel_err(an[j].contents.bptt.contents.min_error_factor,
+                       rn[j].contents.bptt.contents.min_error_factor) < TOL
+    lib.rnn_batch_delete(batch)
