@@ -68,6 +68,8 @@ rb_view_of_net(RbNet *rn, RbView *v)
   v->Who = rn->pub.ho_weights;
   v->activation = rn->pub.activation;
   v->pool = p;
+  if (rb_have_device())
+    rb_bottom_attach(v, &rn->pub);
 }
 
 static float *
@@ -471,25 +473,30 @@ rnn_new_extra_layer(int input_size, int output_size, int overlap, u32 flags)
   layer->o_size = (int)align4(output_size);
   size_t matrix = (size_t)layer->i_size * layer->o_size;
   int with_aux = !!(flags & RNN_NET_FLAG_AUX_ARRAYS);
-  size_t total = matrix * (3 + with_aux) + 2 * (size_t)(layer->i_size + layer->o_size);
-  float *m = rb_alloc_matrix(total);
+  /* matrices: managed memory, like the recurrent layer's; the four small
+     vectors: pinned host memory the kernels reach directly, because callers
+     write inputs / read outputs around every call (one_hot_opinion writes
+     bottom_layer->inputs, charmodel-helpers.h:19-31) and must not drag
+     matrix pages back and forth.  (The reference never frees a bottom
+     layer, recur-nn-init.c:145-155; neither does this library.) */
+  float *m = rb_alloc_matrix(matrix * (3 + with_aux));
   layer->mem = m;
   layer->momentums = m;
   m += matrix;
-  layer->inputs = m;
-  m += layer->i_size;
   layer->weights = m;
   m += matrix;
-  layer->outputs = m;
-  m += layer->o_size;
   layer->delta = m;
   m += matrix;
-  layer->i_error = m;
-  m += layer->i_size;
-  layer->o_error = m;
-  m += layer->o_size;
   if (with_aux)
     layer->aux = m;
+  float *vec = (float *)rb_alloc_mirror(2 * (size_t)(layer->i_size + layer->o_size) * sizeof(float));
+  layer->inputs = vec;
+  vec += layer->i_size;
+  layer->outputs = vec;
+  vec += layer->o_size;
+  layer->i_error = vec;
+  vec += layer->i_size;
+  layer->o_error = vec;
   return layer;
 }
 
@@ -553,35 +560,36 @@ rnn_bptt_advance(RecurNN *net)
 
 /* ---- a3 -------------------------------------------------------------------- */
 
-static void
-no_bottom_layer_yet(RecurNN *net, const char *what)
-{
-  if (net->bottom_layer)
-    rb_die("recur-b200: %s on a net with a bottom layer is not implemented yet "
-        "(SURVEY.md §8 f2)", what);
-}
-
 /* reference recur-nn.c:83-154 */
 extern "C" float *
 rnn_opinion(RecurNN *net, const float *inputs, float presynaptic_noise)
 {
   rb_require_device("rnn_opinion");
-  no_bottom_layer_yet(net, "rnn_opinion");
   RbNet *rn = rb_net_of(net);
   catch_up(rn);
   rb_matrices_to_device(net);
   RbPool *p = rn->pool;
   const RbDims *d = &rn->group->d;
   int s = rn->slot;
-  if (inputs)
+  RecurExtraLayer *bl = net->bottom_layer;
+  if (bl) {
+    /* recur-nn.c:88-94: the layer's own (shared) input vector is the source */
+    bl->inputs[0] = 1.0f;
+    if (inputs)
+      memcpy(bl->inputs + 1, inputs, bl->input_size * sizeof(float));
+  }
+  else if (inputs)
     memcpy(net->real_inputs, inputs, net->input_size * sizeof(float));
   float *xrow = dev_x_row(rn, 0);
   h2d(p->Hd + (size_t)s * d->h_size, net->hidden_layer, d->h_size * sizeof(float));
-  h2d(xrow + d->hidden_size + 1, net->real_inputs, d->input_size * sizeof(float));
+  if (!bl)
+    h2d(xrow + d->hidden_size + 1, net->real_inputs, d->input_size * sizeof(float));
   RbView v;
   rb_view_of_net(rn, &v);
   if (presynaptic_noise != 0.0f)
     h2d(p->rng + (size_t)s * 4, &net->rng, sizeof(rand_ctx));
+  if (bl)
+    rb_bottom_forward(&v, net, bl->inputs, presynaptic_noise);
   rbk_forward(&v, presynaptic_noise);
   if (presynaptic_noise != 0.0f)
     d2h(&net->rng, p->rng + (size_t)s * 4, sizeof(rand_ctx));
@@ -654,6 +662,12 @@ log_bptt_block(RecurNN *net, const RbScalars *sc)
   rnn_log_float(net, "min_error_threshold", sc->min_sum);
   rnn_log_float(net, "min_error_factor", sc->mef);
   rnn_log_float(net, "cum_error", sc->cum_error);
+  if (net->bottom_layer) {
+    float cie = 0;
+    for (int y = 0; y < net->input_size; y++)
+      cie += net->bottom_layer->o_error[y];
+    rnn_log_float(net, "cum_input_error", cie);
+  }
   if (net->flags & RNN_NET_FLAG_LOG_HIDDEN_SUM) {
     rnn_log_float(net, "hidden_sum", sc->hidden_sum);
     rnn_log_float(net, "hidden_magnitude", sc->hidden_mag);
@@ -676,7 +690,6 @@ extern "C" void
 rnn_bptt_calc_deltas(RecurNN *net, int accumulate_delta, RecurErrorRange *top_error_ranges)
 {
   rb_require_device("rnn_bptt_calc_deltas");
-  no_bottom_layer_yet(net, "rnn_bptt_calc_deltas");
   RbNet *rn = rb_net_of(net);
   catch_up(rn);
   rb_matrices_to_device(net);
@@ -692,12 +705,21 @@ rnn_bptt_calc_deltas(RecurNN *net, int accumulate_delta, RecurErrorRange *top_er
   int n_ranges = upload_ranges(top_error_ranges);
   rbk_top_layer(&v, b->ho_delta, accumulate_delta, ranges_dev, n_ranges);
   rbk_bptt(&v, b->ih_delta, accumulate_delta);
+  if (net->bottom_layer)
+    rb_bottom_backward(&v, net, accumulate_delta);
   RbScalars sc;
   d2h(&sc, p->sc + s, sizeof(sc));
   sync_stream();
   b->ih_scale = sc.ih_scale;
   b->min_error_factor = sc.mef;
   log_bptt_block(net, &sc);
+  if (net->bottom_layer && net->log) {
+    RecurExtraLayer *bl = net->bottom_layer;
+    float be = 0;
+    for (int i = 0; i < bl->output_size; i++)
+      be += fabsf(bl->o_error[i]);
+    rnn_log_float(net, "bottom_error", be);
+  }
   net->generation++;
   if (net->log) {
     rnn_log_float(net, "error_gain", sc.err_sum / (sc.top_scaled + 1e-6));
@@ -788,7 +810,6 @@ extern "C" void
 rnn_bptt_calculate(RecurNN *net, uint batch_size)
 {
   rb_require_device("rnn_bptt_calculate");
-  no_bottom_layer_yet(net, "rnn_bptt_calculate");
   RbNet *rn = rb_net_of(net);
   catch_up(rn);
   rb_matrices_to_device(net);

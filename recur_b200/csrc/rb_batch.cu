@@ -74,6 +74,7 @@ batch_view(RnnBatch *b, RbView *v)
   v->base = b->base;
   v->slots = b->contiguous ? b->pool->iota + b->base : b->slots_dev;
   v->p2p = b->p2p;
+  rb_bottom_attach(v, &b->nets[0]->pub);
 }
 
 static void
@@ -127,6 +128,8 @@ rnn_batch_new(RecurNN **nets, int n_nets)
     free(slots);
   }
   size_t widest = d->input_size;
+  if (nets[0]->bottom_layer && (size_t)nets[0]->bottom_layer->input_size > widest)
+    widest = nets[0]->bottom_layer->input_size;
   if ((size_t)d->o_size > widest) widest = d->o_size;
   if ((size_t)d->hidden_size + 1 > widest) widest = d->hidden_size + 1;
   b->io_floats = n * widest;
@@ -247,13 +250,18 @@ extern "C" void
 rnn_batch_set_inputs(RnnBatch *b, const float *inputs)
 {
   const RbDims *d = &b->group->d;
-  size_t bytes = (size_t)b->n * d->input_size * sizeof(float);
+  RecurExtraLayer *bl = b->nets[0]->pub.bottom_layer;
+  int width = bl ? bl->input_size : d->input_size; /* rows feed the bottom layer if there is one */
+  size_t bytes = (size_t)b->n * width * sizeof(float);
   CUDA_OR_DIE(cudaStreamSynchronize(rb_stream)); /* staging buffer reuse */
   memcpy(b->f_host, inputs, bytes);
   CUDA_OR_DIE(cudaMemcpyAsync(b->io_dev, b->f_host, bytes, cudaMemcpyHostToDevice, rb_stream));
   RbView v;
   batch_view(b, &v);
-  rbk_set_inputs(&v, b->io_dev);
+  if (bl)
+    rb_bottom_set_inputs(&v, b->io_dev, width);
+  else
+    rbk_set_inputs(&v, b->io_dev);
   mark_ahead(b);
 }
 
@@ -265,7 +273,10 @@ rnn_batch_set_one_hot(RnnBatch *b, const u8 *hot)
   CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
   RbView v;
   batch_view(b, &v);
-  rbk_set_one_hot(&v, b->cur_dev);
+  if (b->nets[0]->pub.bottom_layer)
+    rb_bottom_one_hot(&v, b->cur_dev);
+  else
+    rbk_set_one_hot(&v, b->cur_dev);
   mark_ahead(b);
 }
 
@@ -304,12 +315,12 @@ download_rng_if_noisy(RnnBatch *b, float noise)
 extern "C" void
 rnn_batch_opinion(RnnBatch *b, float presynaptic_noise)
 {
-  if (b->nets[0]->pub.bottom_layer)
-    rb_die("recur-b200: rnn_batch_opinion on a net with a bottom layer is not implemented yet");
   rb_matrices_to_device(&b->nets[0]->pub);
   RbView v;
   batch_view(b, &v);
   upload_rng_if_noisy(b, presynaptic_noise);
+  if (b->nets[0]->pub.bottom_layer)
+    rb_bottom_forward(&v, &b->nets[0]->pub, NULL, presynaptic_noise);
   rb_forward_dispatch(&v, presynaptic_noise);
   download_rng_if_noisy(b, presynaptic_noise);
   mark_ahead(b);
@@ -415,8 +426,8 @@ calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
 {
   RecurNN *proto = &b->nets[0]->pub;
   RecurNNBPTT *bp = proto->bptt;
-  if (proto->bottom_layer)
-    rb_die("recur-b200: rnn_batch_calc_deltas on a net with a bottom layer is not implemented yet");
+  if (proto->bottom_layer && rb_comm_size() > 1)
+    rb_die("recur-b200: the bottom layer's deltas are not exchanged between GPUs yet");
   rb_matrices_to_device(proto);
   RbView v;
   batch_view(b, &v);
@@ -434,6 +445,8 @@ calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
     b->masked = active != NULL;
   }
   rb_top_and_bptt_dispatch(&v, bp->ho_delta, bp->ih_delta, accumulate);
+  if (proto->bottom_layer)
+    rb_bottom_backward(&v, proto, accumulate);
   /* [ih_delta | ho_delta] are adjacent in the prototype's delta block; when
      the peer-memory exchange is attached and the tensor engine ran, the sum
      over ranks already happened inside the weight-gradient reduction */
@@ -496,8 +509,18 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
   rb_matrices_to_device(proto);
   float noise = proto->presynaptic_noise;
   upload_rng_if_noisy(b, noise);
-  rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
-      from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
+  if (proto->bottom_layer) {
+    if (from_text)
+      rbk_text_symbols(b->text_dev, b->text_len, pos, (b->text_len - 1) / b->n, b->n,
+          b->cur_dev, b->next_dev);
+    rbk_advance(&v);
+    rb_bottom_one_hot(&v, b->cur_dev);
+    rb_bottom_forward(&v, proto, NULL, noise);
+    rb_forward_dispatch(&v, noise);
+  }
+  else
+    rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
+        from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
   download_rng_if_noisy(b, noise);
   rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
   calc_deltas_async(b, 0);

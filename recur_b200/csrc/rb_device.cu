@@ -262,6 +262,7 @@ pool_free_device(RbPool *p)
   if (!rb_have_device())
     return;
   rb_tc_pool_release(p);
+  rb_bottom_pool_release(p);
   cudaFree(p->X);
   cudaFree(p->Hd);
   cudaFree(p->Y);

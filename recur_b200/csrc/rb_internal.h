@@ -72,6 +72,13 @@ typedef struct RbPool {
   uint64_t *rng;  /* [cap][4] per-stream PRNG state when noise runs on device */
   int n_part;
   void *tc;        /* tensor-core engine state (rb_tc.cu), made on first use */
+  /* bottom layer (recur-nn.c:88-103,377-382,751-764), made on first use */
+  float *BI;      /* [cap][bl_i] bottom inputs [1 | inputs] per stream */
+  float *BO;      /* [cap][bl_o] bottom outputs (pre-ReLU) */
+  float *BN;      /* [cap][bl_o] bottom presynaptic noise */
+  float *CIE;     /* [cap][bl_o] cumulative input error of the current walk */
+  float *BR;      /* [cap][bl_o] the shared accumulator as it stood after each stream */
+  int bl_i, bl_o, bl_cap;
 } RbPool;
 
 typedef struct RbGroup {

@@ -485,6 +485,11 @@ k_gemm(GemmArgs g)
           for (int j = 0; j < 4; j++) {
             float e = (h[j] != 0.0f && c + j >= 1) ? acc[i][j] : 0.0f;
             ab += fabsf(e);
+            /* pad units can fire when presynaptic noise is on; they count
+               in the error sum (recur-nn.c:215-226) but the walk clears
+               their error before using it (recur-nn.c:335-337) */
+            if (c + j > v.d.hidden_size)
+              e = 0.0f;
             o[j] = e;
           }
           *(float4 *)(e_row(v, s, 0) + c) = make_float4(o[0], o[1], o[2], o[3]);
@@ -528,6 +533,9 @@ k_gemm(GemmArgs g)
             sq += e * e;
           }
           int col = c + j;
+          /* input-row errors feed the bottom layer (recur-nn.c:377-382) */
+          if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
+            v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
           /* the next step reads this row as h_error: bias and pad columns
              are cleared there (recur-nn.c:334-337) */
           if (col == 0 || (col >= hs1 && col < H))
@@ -781,6 +789,8 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
         }
       }
     }
+    if (y > v.d.hidden_size)
+      e = 0.0f; /* pad units: counted above, cleared before the walk (recur-nn.c:335-337) */
     e0[y] = e;
   }
   abs_sum = block_sum(abs_sum, scratch);
@@ -795,6 +805,9 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
       e0[y] *= scale;
     top_scaled = scale * abs_sum;
   }
+  if (v.CIE)
+    for (int i = threadIdx.x; i < v.bl_o; i += blockDim.x)
+      v.CIE[(size_t)s * v.bl_o + i] = 0.0f;
   if (threadIdx.x == 0) {
     RbScalars *sc = v.sc + s;
     sc->top_raw = abs_sum;
@@ -861,6 +874,9 @@ k_top_finish(RbView v, int n_col_blocks, float *Ehi, float *Elo)
       }
     }
   }
+  if (v.CIE)
+    for (int i = threadIdx.x; i < v.bl_o; i += blockDim.x)
+      v.CIE[(size_t)s * v.bl_o + i] = 0.0f;
   if (threadIdx.x == 0) {
     RbScalars *sc = v.sc + s;
     float top_scaled = (total > halfmax) ? scale * total : total;

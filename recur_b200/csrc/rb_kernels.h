@@ -23,6 +23,9 @@ typedef struct RbView {
   int activation;
   RbPool *pool;     /* host-side owner (not used by kernels) */
   void *p2p;        /* fused gradient exchange state of the batch, or NULL */
+  /* bottom layer, or CIE == NULL */
+  float *BI, *BO, *BN, *CIE, *BR;
+  int bl_i, bl_o;
 } RbView;
 
 /* device accumulators of the text-predict report sums */
@@ -89,6 +92,15 @@ void rbk_axpy(float *dst, const float *src, int n, float s, const float *s_dev);
 void rbk_fill(float *a, size_t n, float value);
 void rbk_abs_sum(const float *a, int n, float *out_dev);
 void rbk_gen_noise(const RbView *v, float deviation, int first_col, int n_cols);
+
+/* bottom layer (rb_bottom.cu) */
+void rb_bottom_attach(RbView *v, RecurNN *net);
+void rb_bottom_forward(const RbView *v, RecurNN *net, const float *shared_inputs_or_null,
+    float presynaptic_noise);
+void rb_bottom_one_hot(const RbView *v, const u8 *hot_dev);
+void rb_bottom_set_inputs(const RbView *v, const float *inputs_dev, int input_size);
+void rb_bottom_backward(const RbView *v, RecurNN *net, int accumulate);
+void rb_bottom_pool_release(RbPool *p);
 
 /* tensor-core engine (rb_tc.cu) */
 int rb_tc_usable(const RbView *v);

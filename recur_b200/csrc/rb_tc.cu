@@ -787,6 +787,8 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
         sq += e * e;
       }
       int col = c + u;
+      if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
+        v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
       if (col == 0 || (col >= hs1 && col < H))
         e = 0.0f;
       o[u] = e;
@@ -1158,6 +1160,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
                 sq += e * e;
               }
               int col = c + u;
+              if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
+                v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
               if (col == 0 || (col >= hs1 && col < H))
                 e = 0.0f;
               o[u] = e;

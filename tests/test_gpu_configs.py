@@ -299,3 +299,30 @@ def test_f1_char_classify_epoch_with_unlabelled_characters(gpu_lib, ref, n_nets)
         assert rel_err(an[j].contents.bptt.contents.min_error_factor,
                        rn[j].contents.bptt.contents.min_error_factor) < TOL
     lib.rnn_batch_delete(batch)
+
+
+@pytest.mark.parametrize("n", [3, 64])
+def test_training_with_presynaptic_noise_matches_reference(gpu_lib, ref, n):
+    """charmodel trains with presynaptic noise 0.1 (py-recur-text.c:443): noisy
+    pad units fire too and must be handled as the reference does
+    (recur-nn.c:120, 215-226, 335-337)."""
+    lib = gpu_lib
+    from helpers import markov_text, u8ptr
+    text = markov_text(900, 11, seed=12)
+    shape = dict(input_size=11, hidden=66, output=11, depth=5, seed=6, lr=0.01, noise=0.1)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    rn = ref.rnn_new_training_set(r, n)
+    an = lib.rnn_new_training_set(a, n)
+    batch = lib.rnn_batch_new(an, n)
+    steps = 5
+    ref.ref_multi_tap_train(rn, n, u8ptr(text), len(text), 0, steps, 0, 0.9, 0.0, None, None, None)
+    lib.rnn_batch_text_upload(batch, u8ptr(text), len(text))
+    lib.rnn_batch_text_train(batch, 0, steps, 0, 0.9, 0.0, None)
+    lib.rnn_batch_pull(batch)
+    for x, y in zip(weights(a), weights(r)):
+        assert rel_err(x, y) < TOL
+    for j in range(n):
+        ca, cr = an[j].contents, rn[j].contents
+        assert (ca.rng.a, ca.rng.d) == (cr.rng.a, cr.rng.d)
+    lib.rnn_batch_delete(batch)
