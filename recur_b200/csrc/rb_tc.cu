@@ -183,6 +183,31 @@ tmem_ld32(uint32_t taddr, float *v)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+/* the same load without the wait, so that the next one can be in flight while
+   this one's registers are being stored; tmem_wait_ld() before touching them */
+__device__ __forceinline__ void
+tmem_ld32_nowait(uint32_t taddr, float *v)
+{
+  uint32_t *r = (uint32_t *)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31},"
+      " [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+__device__ __forceinline__ void
+tmem_wait_ld(void)
+{
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 /* Shared-memory matrix descriptor for a 128B-swizzled operand tile
    (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, leading and
    stride byte offsets in 16-byte units, version 1, layout SWIZZLE_128B. */
@@ -275,7 +300,7 @@ typedef struct RbTc {
   float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
   float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
   unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
-  int persistent_ok;    /* -1 unknown, 0 no, 1 yes */
+  int persistent_ok;    /* decided per call */
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
@@ -928,6 +953,59 @@ grid_barrier(unsigned int *counter, unsigned int target)
   __syncthreads();
 }
 
+/* Four columns of E(k+1) from the summed partials `a` and the ring row `xin`
+   they are masked with; PLAIN is the common case (ReLU, no bottom layer),
+   kept free of branches.  Adds the squares to `sq`. */
+template <bool PLAIN>
+__device__ __forceinline__ void
+chain_chunk(const RbView &v, float4 a, float4 xin, int c, int s, float &sq, float *e_out,
+    float *hi_out, float *lo_out)
+{
+  const int H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  float av[4] = {a.x, a.y, a.z, a.w};
+  float xi[4] = {xin.x, xin.y, xin.z, xin.w};
+  float o[4], ohi[4], olo[4];
+  /* column 0 (the bias) and the padding between the hidden units and h_size
+     carry no error */
+  const bool edge = (c == 0) || (c + 4 > hs1 && c < H);
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    float e;
+    if (PLAIN) {
+      e = (xi[u] != 0.0f) ? av[u] : 0.0f;
+      sq = fmaf(e, e, sq);
+    }
+    else {
+      e = 0.0f;
+      float input = xi[u];
+      if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
+        e = av[u];
+        if (v.activation == RNN_RESQRT)
+          e /= 2.0f * (input + 1.0f);
+        sq += e * e;
+      }
+      int col = c + u;
+      if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
+        v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
+    }
+    o[u] = e;
+  }
+  if (edge) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      int col = c + u;
+      if (col == 0 || (col >= hs1 && col < H))
+        o[u] = 0.0f;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+    split_tf32(o[u], ohi[u], olo[u]);
+  __stcg((float4 *)e_out, make_float4(o[0], o[1], o[2], o[3]));
+  __stcg((float4 *)hi_out, make_float4(ohi[0], ohi[1], ohi[2], ohi[3]));
+  __stcg((float4 *)lo_out, make_float4(olo[0], olo[1], olo[2], olo[3]));
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
@@ -985,6 +1063,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   const uint32_t tmem_base = *tmem_slot;
 
   const int pos0 = v.pos[v.base]; /* the batch advances in lockstep */
+  const bool plain = (v.activation == RNN_RELU && v.CIE == NULL);
   unsigned int it = 0;       /* pipeline iterations so far (producer and MMA keep equal counts) */
   unsigned int n_gemms = 0;  /* accumulators completed by this CTA */
   unsigned int n_bar = 0;
@@ -1062,20 +1141,25 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         if (threadIdx.x == 64)
           ROLE_STAMP(3);
         float *dst = g.cpartial + (size_t)blockIdx.z * split_stride + (size_t)sidx * cpitch;
-        float acc[32];
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
-          int col0 = n0 + c;
+        float acc[2][32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        tmem_ld32_nowait(taddr, acc[0]);
+#pragma unroll
+        for (int ci = 0; ci < BN / 32; ci++) {
+          tmem_wait_ld();
+          if (ci + 1 < BN / 32)
+            tmem_ld32_nowait(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
+          const float *av = acc[ci & 1];
+          int col0 = n0 + ci * 32;
           if (!live || col0 >= I)
             continue;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             if (col0 + j + 8 <= I)
-              st_global_v8(dst + col0 + j, acc + j);
+              st_global_v8(dst + col0 + j, av + j);
             else if (col0 + j < I)
               __stcg((float4 *)(dst + col0 + j),
-                  make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
+                  make_float4(av[j], av[j + 1], av[j + 2], av[j + 3]));
           }
         }
         tc_fence_before();
@@ -1100,9 +1184,10 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           break;
         const int s = v.base + m;
         RbScalars *scp = v.sc + s;
+        /* the scalars travel with the row loads: a stopped stream's loads
+           are wasted, nothing of it is stored */
+        if (warp == 2 && lane == 0) ROLE_STAMP(10);
         RbScalars sc = load_scalars_cg(scp);
-        if (!sc.live)
-          continue;
         int p = pos0 - k;
         if (p < 0)
           p += v.depth;
@@ -1128,6 +1213,9 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
                   pz[z - 1][i] = __ldcg((const float4 *)(part + z * split_stride + c));
             }
           }
+          if (!sc.live)
+            break;
+          if (warp == 2 && lane == 0) ROLE_STAMP(11);
 #pragma unroll
           for (int z = 1; z < TC_CHAIN_SPLITS; z++) {
             if (z < (int)gridDim.z) {
@@ -1141,40 +1229,33 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
               }
             }
           }
+          if (warp == 2 && lane == 0 && a[0].x != 123.456f && a[GRP - 1].y != 123.456f) ROLE_STAMP(16);
+          if (plain) {
 #pragma unroll
-          for (int i = 0; i < GRP; i++) {
-            int c = c0 + 128 * i;
-            if (c >= I)
-              continue;
-            float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
-            float xi[4] = {xin[i].x, xin[i].y, xin[i].z, xin[i].w};
-            float o[4], ohi[4], olo[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-              float e = 0.0f;
-              float input = xi[u];
-              if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
-                e = av[u];
-                if (v.activation == RNN_RESQRT)
-                  e /= 2.0f * (input + 1.0f);
-                sq += e * e;
-              }
-              int col = c + u;
-              if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
-                v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
-              if (col == 0 || (col >= hs1 && col < H))
-                e = 0.0f;
-              o[u] = e;
-              split_tf32(e, ohi[u], olo[u]);
+            for (int i = 0; i < GRP; i++) {
+              int c = c0 + 128 * i;
+              if (c < I)
+                chain_chunk<true>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
+                    g.Elo + eoff + c);
             }
-            __stcg((float4 *)(v.E + eoff + c), make_float4(o[0], o[1], o[2], o[3]));
-            __stcg((float4 *)(g.Ehi + eoff + c), make_float4(ohi[0], ohi[1], ohi[2], ohi[3]));
-            __stcg((float4 *)(g.Elo + eoff + c), make_float4(olo[0], olo[1], olo[2], olo[3]));
+          }
+          else {
+#pragma unroll
+            for (int i = 0; i < GRP; i++) {
+              int c = c0 + 128 * i;
+              if (c < I)
+                chain_chunk<false>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
+                    g.Elo + eoff + c);
+            }
           }
         }
+        if (!sc.live)
+          continue;
+        if (warp == 2 && lane == 0) ROLE_STAMP(12);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (warp == 2 && lane == 0) ROLE_STAMP(13);
         if (lane == 0) {
           float es = sq;
           sc.err_sum = es;
@@ -1212,9 +1293,11 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           *scp = sc;
         }
       }
+      if (warp == 2 && lane == 0) ROLE_STAMP(14);
       /* E(k+1) planes were written through the generic proxy; the next step's
          TMA reads them through the async proxy */
       asm volatile("fence.proxy.async;" ::: "memory");
+      if (warp == 2 && lane == 0) ROLE_STAMP(15);
     }
     __syncthreads();
     CHAIN_STAMP(3);
@@ -1511,17 +1594,19 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     splits /= 2;
   dim3 cgrid(cdiv(v->d.i_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
   int n_ctas = cgrid.x * cgrid.y * cgrid.z;
-  if (t->persistent_ok < 0) {
-    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+  /* device facts once; the choice of kernel per call (the batch may grow) */
+  static int sms = 0, coop = 0, per_sm_single = 0;
+  if (!sms) {
+    int dev = 0;
     CUDA_OR_DIE(cudaGetDevice(&dev));
     CUDA_OR_DIE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
-    CUDA_OR_DIE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm,
+    CUDA_OR_DIE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_single,
             k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, 192, ChainCfg::SMEM_BYTES));
-    t->persistent_ok = (coop && per_sm * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
+    CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
+  t->persistent_ok = (coop && per_sm_single * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
   if (t->persistent_ok) {
     ChainArgs ca;
     ca.v = *v;
@@ -1581,6 +1666,12 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
             "last stage landed +%.2f, accumulator ready +%.2f, epilogue done +%.2f, phase end +%.2f us\n",
             (double)(q[0] - t0) * 1e-3, (double)(q[1] - t0) * 1e-3, (double)(q[2] - t0) * 1e-3,
             (double)(q[3] - t0) * 1e-3, (double)(q[4] - t0) * 1e-3, (double)(h[321] - t0) * 1e-3);
+        unsigned long long b0 = h[322];
+        fprintf(stderr, "step 5 CTA 0 warp 2 phase B (after the barrier): start +%.2f, loads landed +%.2f, "
+            "summed +%.2f, stored +%.2f, reduced +%.2f, tail done +%.2f, proxy fence done +%.2f, phase end +%.2f us\n",
+            (double)(q[10] - b0) * 1e-3, (double)(q[11] - b0) * 1e-3, (double)(q[16] - b0) * 1e-3, (double)(q[12] - b0) * 1e-3,
+            (double)(q[13] - b0) * 1e-3, (double)(q[14] - b0) * 1e-3, (double)(q[15] - b0) * 1e-3,
+            (double)(h[323] - b0) * 1e-3);
       }
     }
   }
