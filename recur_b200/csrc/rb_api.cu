@@ -768,15 +768,23 @@ rb_apply_learning_async(RecurNN *net, int method, float momentum)
   }
   if ((method == RNN_ADADELTA || method == RNN_RPROP) && !b->ih_aux)
     rb_die("recur-b200: learning method %d needs RNN_NET_FLAG_AUX_ARRAYS", method);
-  rbk_apply_learning(kernel_method, net->ho_weights, b->ho_delta, b->ho_momentum,
-      b->ho_aux, net->ho_size, b->learn_rate * b->ho_scale, momentum, mw, NULL);
-  rbk_apply_learning(kernel_method, net->ih_weights, b->ih_delta, b->ih_momentum,
-      b->ih_aux, net->ih_size, b->learn_rate, momentum, mw, NULL);
+  /* where the tensor engine holds operand planes of these weights, one kernel
+     updates both matrices and rewrites the planes */
+  RbPool *pool = rb_net_of(net)->pool;
+  int fused = rb_tc_fused_update(pool, net, kernel_method, momentum, mw);
+  if (!fused) {
+    rbk_apply_learning(kernel_method, net->ho_weights, b->ho_delta, b->ho_momentum,
+        b->ho_aux, net->ho_size, b->learn_rate * b->ho_scale, momentum, mw, NULL);
+    rbk_apply_learning(kernel_method, net->ih_weights, b->ih_delta, b->ih_momentum,
+        b->ih_aux, net->ih_size, b->learn_rate, momentum, mw, NULL);
+  }
   if (bl) {
     rbk_apply_learning(kernel_method, bl->weights, bl->delta, bl->momentums, bl->aux,
         bl->i_size * bl->o_size, b->learn_rate * bl->learn_rate_scale, momentum, mw, NULL);
   }
   rb_weights_changed(net);
+  if (fused)
+    rb_tc_planes_current(pool);
 }
 
 extern "C" void

@@ -523,7 +523,11 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
         from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
   download_rng_if_noisy(b, noise);
   rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
+  /* the update follows at once: the weight gradient may stay in its split-K
+     planes until then (single GPU; an exchange needs the finished sum) */
+  rb_tc_defer_delta_reduce(rb_comm_size() <= 1);
   calc_deltas_async(b, 0);
+  rb_tc_defer_delta_reduce(0);
   rb_apply_learning_async(proto, learning_style, momentum);
 }
 

@@ -29,6 +29,7 @@
  */
 #include "rb_kernels.h"
 #include "rb_rng.h"
+#include "rb_optim.cuh"
 #include <math.h>
 
 #define RB_WARP 32
@@ -977,8 +978,42 @@ stage_matrix(float *dst, const float *__restrict__ src, int n_floats)
   }
 }
 
+/* a5's activation (recur-nn.c:229-262) for four hidden sums starting at column col0 */
+__device__ __forceinline__ float4
+hidden_activation(const RbView &v, float4 sum, int col0, const float *noise_row)
+{
+  float h4[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int col = col0 + u;
+    float h = h4[u];
+    if (noise_row && col >= 1)
+      h += noise_row[col];
+    if (v.activation == RNN_RESQRT) {
+      h = (h > 0.0f) ? sqrtf(h + 1.0f) - 1.0f : 0.0f;
+    }
+    else if (v.activation == RNN_RECLIP20) {
+      if (col >= 1) {
+        h = h < 20.0f ? h : 20.0f;
+        h = (h > 0.0f) ? h : 0.0f;
+      }
+    }
+    else if (col >= 1) {
+      h = (h > 0.0f) ? h : 0.0f;
+    }
+    if (col == 0)
+      h = 1.0f;
+    h4[u] = h;
+  }
+  return make_float4(h4[0], h4[1], h4[2], h4[3]);
+}
+
+/* FROM_PARTIALS: the hidden rows arrive as split-K partial sums of the tensor
+   engine's forward GEMM; this kernel sums them (fixed order), applies the
+   activation, writes the hidden rows and goes on to the output layer. */
+template <bool FROM_PARTIALS>
 __global__ void __launch_bounds__(256)
-k_out_multi(RbView v)
+k_out_multi(RbView v, RbFwdPartials fp)
 {
   extern __shared__ __align__(16) float sh[]; /* Who | OS hidden rows | reduction space */
   const int H = v.d.h_size, O = v.d.o_size;
@@ -987,13 +1022,53 @@ k_out_multi(RbView v)
   float *who = sh;
   float *hid = sh + (size_t)H * O;
   float *red = hid + (size_t)OS * H;
-  stage_matrix(who, v.Who, H * O);
-  for (int q = 0; q < OS; q++) {
-    if (q < ns)
-      stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot_of(v, j0 + q) * H, H);
-    else
-      for (int i = threadIdx.x; i < H; i += blockDim.x)
-        hid[(size_t)q * H + i] = 0.0f;
+  if (FROM_PARTIALS) {
+    /* every load of the block's rows is issued before the weights are staged */
+    constexpr int MAXZ = 4;
+    for (int c = threadIdx.x * 4; c < H; c += blockDim.x * 4) {
+      float4 pz[OS][MAXZ];
+#pragma unroll
+      for (int q = 0; q < OS; q++) {
+        if (q < ns) {
+          const float *row = fp.part + (size_t)slot_of(v, j0 + q) * fp.pitch + c;
+#pragma unroll
+          for (int z = 0; z < MAXZ; z++)
+            if (z < fp.splits)
+              pz[q][z] = __ldcg((const float4 *)(row + z * fp.split_stride));
+        }
+      }
+      if (c == (int)threadIdx.x * 4)
+        stage_matrix(who, v.Who, H * O);
+#pragma unroll
+      for (int q = 0; q < OS; q++) {
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q < ns) {
+          int slot = slot_of(v, j0 + q);
+          h = pz[q][0];
+#pragma unroll
+          for (int z = 1; z < MAXZ; z++) {
+            if (z < fp.splits) {
+              h.x += pz[q][z].x; h.y += pz[q][z].y; h.z += pz[q][z].z; h.w += pz[q][z].w;
+            }
+          }
+          h = hidden_activation(v, h, c, fp.use_noise ? v.noise + (size_t)slot * H : NULL);
+          *(float4 *)(v.Hd + (size_t)slot * H + c) = h;
+        }
+        *(float4 *)(hid + (size_t)q * H + c) = h;
+      }
+    }
+    if ((int)threadIdx.x * 4 >= H)
+      stage_matrix(who, v.Who, H * O);
+  }
+  else {
+    stage_matrix(who, v.Who, H * O);
+    for (int q = 0; q < OS; q++) {
+      if (q < ns)
+        stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot_of(v, j0 + q) * H, H);
+      else
+        for (int i = threadIdx.x; i < H; i += blockDim.x)
+          hid[(size_t)q * H + i] = 0.0f;
+    }
   }
   __syncthreads();
   const int CW = (O >= 256) ? 256 : O;
@@ -1392,57 +1467,8 @@ k_apply_learning(int method, float *__restrict__ weights,
     rate *= *rate_scale;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < size;
        i += gridDim.x * blockDim.x) {
-    float d = delta[i];
-    float w = weights[i];
-    if (method == RNN_MOMENTUM_NESTEROV) {
-      float t = d * rate;
-      float m = (momentums[i] + t) * momentum;
-      w += t;
-      w += m;
-      momentums[i] = m;
-    }
-    else if (method == RNN_ADAGRAD) {
-      float a = momentums[i] + d * d;
-      w += d * rate / sqrtf(a);
-      momentums[i] = a;
-    }
-    else if (method == RNN_ADADELTA) {
-      const float decay = momentum, renewal = 1.0f - decay;
-      float gacc = momentums[i] * decay;
-      float sacc = aux[i] * decay;
-      gacc += fabsf(d) * renewal + rate;
-      float step = sacc / gacc * d;
-      sacc += fabsf(step) * renewal + rate;
-      momentums[i] = gacc;
-      aux[i] = sacc;
-      w += step;
-    }
-    else if (method == RNN_RPROP) {
-      const float max_step = 1.0f * rate;
-      const float min_step = (float)(1e-6 * (double)rate);
-      float p = momentums[i];
-      float step = aux[i];
-      if (d * p > 0.0f) {
-        step = fminf(step * 1.2f, max_step);
-      }
-      else if (d * p < 0.0f) {
-        step = fmaxf(step * 0.5f, min_step);
-        d = 0.0f;
-      }
-      if (d > 0.0f)
-        w += step;
-      else
-        w -= step;
-      aux[i] = step;
-      momentums[i] = d;
-    }
-    else { /* weighted / simplified Nesterov / classical: recur-nn.c:482-487 */
-      float t = d * rate;
-      float m = momentums[i];
-      w += t + m * momentum_weight;
-      momentums[i] = (m + t) * momentum;
-    }
-    weights[i] = w;
+    weights[i] = rb_optimiser_step(method, weights[i], delta[i], momentums, aux, i, rate,
+        momentum, momentum_weight);
   }
 }
 
@@ -1760,19 +1786,58 @@ rbk_prepare_x(const RbView *v)
   rb_prof_end(RB_PROF_SMALL);
 }
 
+static size_t
+out_multi_smem(const RbView *v)
+{
+  return ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.h_size + (size_t)OS * 256 + 8) *
+      sizeof(float);
+}
+
+static int
+out_multi_usable(const RbView *v)
+{
+  return v->n >= 4 * OS && out_multi_smem(v) <= 200 * 1024;
+}
+
+static void
+out_multi_attr(void)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_out_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    cudaFuncSetAttribute(k_out_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    attr_done = 1;
+  }
+}
+
+extern "C" int
+rbk_output_takes_partials(const RbView *v, int splits)
+{
+  return out_multi_usable(v) && splits <= 4 && (v->d.h_size % 4) == 0;
+}
+
+/* hidden activation + output layer from the split-K partial sums of the
+   tensor engine's forward GEMM */
+extern "C" void
+rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
+{
+  out_multi_attr();
+  rb_prof_begin(RB_PROF_OUT);
+  k_out_multi<true><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, *fp);
+  LAUNCH_CHECK("k_out_multi<partials>");
+  rb_prof_end(RB_PROF_OUT);
+}
+
 extern "C" void
 rbk_output(const RbView *v)
 {
-  size_t multi = ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.h_size +
-      (size_t)OS * 256 + 8) * sizeof(float);
-  if (v->n >= 4 * OS && multi <= 200 * 1024) {
-    static int attr_done = 0;
-    if (!attr_done) {
-      cudaFuncSetAttribute(k_out_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      attr_done = 1;
-    }
+  if (out_multi_usable(v)) {
+    RbFwdPartials none = {NULL, 0, 0, 0, 0};
+    out_multi_attr();
     rb_prof_begin(RB_PROF_OUT);
-    k_out_multi<<<cdiv(v->n, OS), 256, multi, rb_stream>>>(*v);
+    k_out_multi<false><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, none);
     LAUNCH_CHECK("k_out_multi");
     rb_prof_end(RB_PROF_OUT);
     return;

@@ -61,6 +61,16 @@ int rbk_step_begin_usable(const RbView *v);
 void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
     u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo);
 void rbk_output(const RbView *v);
+/* split-K partial sums of a forward GEMM: [splits][rows of `pitch` floats] */
+typedef struct RbFwdPartials {
+  const float *part;
+  size_t split_stride; /* floats between the planes of two splits */
+  int pitch;
+  int splits;
+  int use_noise;
+} RbFwdPartials;
+int rbk_output_takes_partials(const RbView *v, int splits);
+void rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp);
 void rbk_chain_decide(const RbView *v, int k);
 void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
@@ -110,6 +120,11 @@ void rb_tc_x_planes(RbPool *p, float **Xhi, float **Xlo);
 void rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     int accumulate);
 void rb_tc_pool_release(RbPool *p);
+void rb_tc_defer_delta_reduce(int on);
+void rb_tc_materialise_delta(RbPool *p, float *ih_delta);
+int rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum,
+    float momentum_weight);
+void rb_tc_planes_current(RbPool *p);
 
 /* fused split-K reduction + all-reduce over peer memory (rb_p2p.cu) */
 void *rb_p2p_new(size_t n_floats);

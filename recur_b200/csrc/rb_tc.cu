@@ -24,6 +24,7 @@
  */
 #include "rb_kernels.h"
 #include "rb_host.h"
+#include "rb_optim.cuh"
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -240,6 +241,16 @@ umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major)
     | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+/* 32 bytes per lane per instruction: whole L2 sectors even when every lane
+   writes its own row */
+__device__ __forceinline__ void
+st_global_v8(float *p, const float *a)
+{
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]),
+      "f"(a[7]) : "memory");
+}
+
 /* exact split of an FP32 number into two TF32 numbers */
 __device__ __forceinline__ void
 split_tf32(float a, float &hi, float &lo)
@@ -301,6 +312,8 @@ typedef struct RbTc {
   float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
   unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
   int persistent_ok;    /* decided per call */
+  int delta_pending;    /* the last weight gradient still sits in `partial`, unsummed */
+  int pending_accumulate;
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
@@ -308,6 +321,7 @@ typedef struct RbTc {
   CUtensorMap mEhi_k, mElo_k;   /* error rows as K-major A of CHAIN (width h_size) */
   CUtensorMap mWhi_k, mWlo_k;   /* Wih rows as K-major B of CHAIN: box 32 x 128 */
   CUtensorMap mWThi_k, mWTlo_k; /* Wih^T rows as K-major B of FWD: box 32 x 64 */
+  CUtensorMap mWThi_k128, mWTlo_k128; /* the same with 128-row boxes: split-K FWD */
   CUtensorMap mXhi_mn, mXlo_mn; /* ring rows as MN-major A of DW: box 32 x 32 */
   CUtensorMap mEhi_mn, mElo_mn; /* error rows as MN-major B of DW (width h_size) */
 } RbTc;
@@ -438,6 +452,8 @@ tc_state(RbPool *p)
   make_map(&t->mWlo_k, t->Wlo, H, I, H, TC_CHAIN_BN);
   make_map(&t->mWThi_k, t->WThi, I, H, I, TC_FWD_BN);
   make_map(&t->mWTlo_k, t->WTlo, I, H, I, TC_FWD_BN);
+  make_map(&t->mWThi_k128, t->WThi, I, H, I, TC_CHAIN_BN);
+  make_map(&t->mWTlo_k128, t->WTlo, I, H, I, TC_CHAIN_BN);
   make_map_chunked(&t->mXhi_mn, t->Xhi, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
   make_map_chunked(&t->mXlo_mn, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
   make_map_chunked(&t->mEhi_mn, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
@@ -560,7 +576,7 @@ k_compute_kmax(RbView v, unsigned int *kmax_dev)
 
 struct NtArgs {
   RbView v;
-  int mode;        /* 0 FWD, 1 CHAIN */
+  int mode;        /* 0 FWD, 1 CHAIN, 2 FWD split-K (raw partial sums) */
   int k;           /* CHAIN: step */
   int use_noise;
   float *cpartial; /* CHAIN: [splits][cap][i_size] */
@@ -592,7 +608,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int I = v.d.i_size, H = v.d.h_size;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int K = (g.mode == 0) ? I : H;
+  const int K = (g.mode == 1) ? H : I;
   const int n_kb_total = (K + TC_BK - 1) / TC_BK;
   const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
   const int kb_begin = blockIdx.z * kb_per_split;
@@ -634,7 +650,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     if (lane == 0) {
       /* row of the A operand in its ring: FWD reads the newest x row, CHAIN E[k] */
       int ring_row;
-      if (g.mode == 0)
+      if (g.mode != 1)
         ring_row = v.pos[v.base] * v.cap + v.base + m0;
       else
         ring_row = g.k * v.cap + v.base + m0;
@@ -735,8 +751,9 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     else {
       /* raw partial sums of this K split; masks and the rest happen row-wise
          in k_chain_finish_step */
-      const bool live = row_ok && v.sc[sidx].live != 0;
+      const bool live = row_ok && (g.mode == 2 || v.sc[sidx].live != 0);
       const int cpitch = (I + 31) & ~31;
+      const int n_cols = (g.mode == 2) ? H : I;
       float *dst = g.cpartial + ((size_t)blockIdx.z * v.cap + sidx) * cpitch;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
@@ -748,12 +765,15 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
             acc[j] = 0.0f;
         }
         int col0 = n0 + c;
-        if (!live || col0 >= I)
+        if (!live || col0 >= n_cols)
           continue;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (col0 + j < I)
-            *(float4 *)(dst + col0 + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+        for (int j = 0; j < 32; j += 8) {
+          if (col0 + j + 8 <= n_cols)
+            st_global_v8(dst + col0 + j, acc + j);
+          else if (col0 + j < n_cols)
+            __stcg((float4 *)(dst + col0 + j),
+                make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]));
         }
       }
     }
@@ -876,16 +896,6 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
  *   grid barrier; stop when no stream is left.
  * E(k+1)'s hi/lo planes are written with generic stores and read by the next
  * step's TMA, hence the generic->async proxy fence before the barrier.       */
-
-/* 32 bytes per lane per instruction: whole L2 sectors even when every lane
-   writes its own row */
-__device__ __forceinline__ void
-st_global_v8(float *p, const float *a)
-{
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-      ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]),
-      "f"(a[7]) : "memory");
-}
 
 __device__ __forceinline__ unsigned int
 ld_acquire_gpu(const unsigned int *p)
@@ -1482,6 +1492,96 @@ k_dw_reduce(float *__restrict__ delta, const float *__restrict__ partial, int si
   }
 }
 
+/* The end of a training step in one pass over Wih: sum the split-K partials
+   of the weight gradient (or take the finished delta), apply the optimiser
+   (a13), and write the new weights together with the four operand planes the
+   next step's GEMMs read - what k_dw_reduce, k_apply_learning and
+   k_split_weights do in three passes.  32x32 tiles because of the transposed
+   planes; the blocks past the last tile update Who elementwise.             */
+struct UpdateArgs {
+  float *W, *delta, *mom, *aux;
+  const float *partial; /* NULL: delta is final */
+  int splits, accumulate;
+  int I, H;
+  int method;
+  float rate, momentum, momentum_weight;
+  float *Whi, *Wlo, *WThi, *WTlo;
+  /* the output matrix rides along */
+  float *ho_W, *ho_mom, *ho_aux;
+  const float *ho_delta;
+  int ho_size;
+  float ho_rate;
+  int n_tiles_x, n_tiles;
+};
+
+__global__ void __launch_bounds__(256)
+k_update_split(UpdateArgs a)
+{
+  if ((int)blockIdx.x >= a.n_tiles) {
+    int i = ((int)blockIdx.x - a.n_tiles) * 256 + threadIdx.x;
+    if (i < a.ho_size)
+      a.ho_W[i] = rb_optimiser_step(a.method, a.ho_W[i], a.ho_delta[i], a.ho_mom, a.ho_aux, i,
+          a.ho_rate, a.momentum, a.momentum_weight);
+    return;
+  }
+  __shared__ float th[32][33], tl[32][33];
+  const int I = a.I, H = a.H;
+  const size_t size = (size_t)I * H;
+  const int x0 = (blockIdx.x % a.n_tiles_x) * 32, y0 = (blockIdx.x / a.n_tiles_x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + tx;
+  float d[4], w[4];
+  /* all loads of the thread's four elements first */
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int y = y0 + ty + 8 * q;
+    d[q] = 0.0f;
+    w[q] = 0.0f;
+    if (y < I && x < H) {
+      size_t i = (size_t)y * H + x;
+      w[q] = a.W[i];
+      if (a.partial) {
+        float t = a.accumulate ? a.delta[i] : 0.0f;
+#pragma unroll
+        for (int z = 0; z < TC_DW_SPLITS; z++)
+          if (z < a.splits)
+            t += __ldcg(a.partial + (size_t)z * size + i);
+        d[q] = t;
+      }
+      else
+        d[q] = a.delta[i];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int r = ty + 8 * q, y = y0 + r;
+    float hi = 0.f, lo = 0.f;
+    if (y < I && x < H) {
+      size_t i = (size_t)y * H + x;
+      if (a.partial)
+        a.delta[i] = d[q];
+      float nw = rb_optimiser_step(a.method, w[q], d[q], a.mom, a.aux, i, a.rate, a.momentum,
+          a.momentum_weight);
+      a.W[i] = nw;
+      split_tf32(nw, hi, lo);
+      a.Whi[i] = hi;
+      a.Wlo[i] = lo;
+    }
+    th[r][tx] = hi;
+    tl[r][tx] = lo;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    int r = ty + 8 * q;
+    int xx = x0 + r, y = y0 + tx;
+    if (xx < H && y < I) {
+      a.WThi[(size_t)xx * I + y] = th[tx][r];
+      a.WTlo[(size_t)xx * I + y] = tl[tx][r];
+    }
+  }
+}
+
 /* ======================================================================== */
 /* host side                                                                  */
 
@@ -1508,6 +1608,7 @@ refresh_weight_planes(RbTc *t, RbPool *p, const RbView *v)
 }
 
 static int fwd_attr_done = 0, chain_attr_done = 0, dw_attr_done = 0;
+static int defer_delta_reduce = 0;
 typedef NtCfg<TC_FWD_BN, TC_FWD_STAGES> FwdCfg;
 typedef NtCfg<TC_CHAIN_BN, TC_CHAIN_STAGES> ChainCfg;
 
@@ -1546,6 +1647,38 @@ rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise)
   if (presynaptic_noise != 0.0f) {
     rbk_gen_noise(v, presynaptic_noise, 1, v->d.h_size - 1);
     g.use_noise = 1;
+  }
+  /* Few tiles and a long K: split K so the GEMM covers the SMs, and let the
+     output-layer kernel sum the partials on its way in. */
+  {
+    int n_kb = cdiv(v->d.i_size, TC_BK);
+    int tiles = cdiv(v->d.h_size, TC_CHAIN_BN) * cdiv(v->n, TC_BM);
+    int splits = TC_CHAIN_SPLITS;
+    while (splits > 1 && (n_kb / splits < 2 || tiles * splits > 148))
+      splits /= 2;
+    if (splits > 1 && rbk_output_takes_partials(v, splits)) {
+      if (!chain_attr_done) {
+        CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
+                cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
+        chain_attr_done = 1;
+      }
+      g.mode = 2;
+      g.cpartial = t->cpartial;
+      dim3 grid(cdiv(v->d.h_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
+      rb_prof_begin(RB_PROF_FWD);
+      k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES><<<grid, 192, ChainCfg::SMEM_BYTES, rb_stream>>>(
+          t->mXhi_k, t->mXlo_k, t->mWThi_k128, t->mWTlo_k128, g);
+      LAUNCH_CHECK("k_tc_nt<FWD split-K>");
+      rb_prof_end(RB_PROF_FWD);
+      RbFwdPartials fp;
+      fp.part = t->cpartial;
+      fp.pitch = (v->d.i_size + 31) & ~31;
+      fp.split_stride = (size_t)v->cap * fp.pitch;
+      fp.splits = splits;
+      fp.use_noise = g.use_noise;
+      rbk_output_from_partials(v, &fp);
+      return;
+    }
   }
   if (!fwd_attr_done) {
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_FWD_BN, TC_FWD_STAGES>,
@@ -1714,10 +1847,98 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     rb_p2p_reduce(v->p2p, t->partial, TC_DW_SPLITS, size, v->d.h_size * v->d.o_size, ih_delta,
         accumulate);
   }
+  else if (defer_delta_reduce) {
+    /* the caller applies the update next: rb_tc_fused_update sums the
+       partials on its way through the weights */
+    t->delta_pending = 1;
+    t->pending_accumulate = accumulate;
+  }
   else {
     k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
         TC_DW_SPLITS, accumulate);
     LAUNCH_CHECK("k_dw_reduce");
   }
   rb_prof_end(RB_PROF_DW);
+}
+
+/* A caller that runs the update right after the deltas (the char step) lets
+   the weight gradient stay in its split-K planes in between. */
+extern "C" void
+rb_tc_defer_delta_reduce(int on)
+{
+  defer_delta_reduce = on;
+}
+
+/* ih_delta as the API promises it, for anyone who looks before the update */
+extern "C" void
+rb_tc_materialise_delta(RbPool *p, float *ih_delta)
+{
+  RbTc *t = (RbTc *)p->tc;
+  if (!t || !t->delta_pending)
+    return;
+  const RbDims *d = &p->group->d;
+  int size = d->i_size * d->h_size;
+  k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
+      TC_DW_SPLITS, t->pending_accumulate);
+  LAUNCH_CHECK("k_dw_reduce");
+  t->delta_pending = 0;
+}
+
+/* The ih and ho updates of rnn_apply_learning fused with the weight-gradient
+   reduction before and the operand split after.  Returns 0 (nothing done) when
+   this pool's tensor engine holds no planes of these weights. */
+extern "C" int
+rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum, float momentum_weight)
+{
+  RbTc *t = (RbTc *)p->tc;
+  if (!t)
+    return 0;
+  RecurNNBPTT *b = net->bptt;
+  if (t->w_src != net->ih_weights) {
+    rb_tc_materialise_delta(p, b->ih_delta);
+    return 0;
+  }
+  const RbDims *d = &p->group->d;
+  UpdateArgs a;
+  a.W = net->ih_weights;
+  a.delta = b->ih_delta;
+  a.mom = b->ih_momentum;
+  a.aux = b->ih_aux;
+  a.partial = t->delta_pending ? t->partial : NULL;
+  a.splits = TC_DW_SPLITS;
+  a.accumulate = t->pending_accumulate;
+  a.I = d->i_size;
+  a.H = d->h_size;
+  a.method = method;
+  a.rate = b->learn_rate;
+  a.momentum = momentum;
+  a.momentum_weight = momentum_weight;
+  a.Whi = t->Whi;
+  a.Wlo = t->Wlo;
+  a.WThi = t->WThi;
+  a.WTlo = t->WTlo;
+  a.ho_W = net->ho_weights;
+  a.ho_mom = b->ho_momentum;
+  a.ho_aux = b->ho_aux;
+  a.ho_delta = b->ho_delta;
+  a.ho_size = net->ho_size;
+  a.ho_rate = b->learn_rate * b->ho_scale;
+  a.n_tiles_x = cdiv(a.H, 32);
+  a.n_tiles = a.n_tiles_x * cdiv(a.I, 32);
+  rb_prof_begin(RB_PROF_UPDATE);
+  k_update_split<<<a.n_tiles + cdiv(a.ho_size, 256), 256, 0, rb_stream>>>(a);
+  LAUNCH_CHECK("k_update_split");
+  rb_prof_end(RB_PROF_UPDATE);
+  t->delta_pending = 0;
+  return 1;
+}
+
+/* after rb_weights_changed: the planes rb_tc_fused_update wrote are those of
+   the new weights */
+extern "C" void
+rb_tc_planes_current(RbPool *p)
+{
+  RbTc *t = (RbTc *)p->tc;
+  if (t)
+    t->w_version = p->group->weights_version;
 }
