@@ -1016,8 +1016,16 @@ chain_chunk(const RbView &v, float4 a, float4 xin, int c, int s, float &sq, floa
   __stcg((float4 *)lo_out, make_float4(olo[0], olo[1], olo[2], olo[3]));
 }
 
+#define TC_CHAIN_THREADS 256 /* TMA warp, MMA warp, four epilogue warps, two more for the rows */
+
+__device__ __forceinline__ void
+named_bar_sync(int id, int count)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_CHAIN_THREADS, 1)
 k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     const __grid_constant__ CUtensorMap mAlo, const __grid_constant__ CUtensorMap mBhi,
     const __grid_constant__ CUtensorMap mBlo, ChainArgs g)
@@ -1030,6 +1038,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   uint64_t *empty = full + STAGES;
   uint64_t *acc_ready = empty + STAGES;
   uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
+  float *pair_sq = (float *)(tmem_slot + 2); /* one sum of squares per warp */
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
@@ -1139,7 +1148,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           umma_commit(acc_ready);
         }
       }
-      else {
+      else if (warp < 6) {
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int m = m0 + row;
@@ -1185,10 +1194,13 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     grid_barrier(gsync, n_bar * grp_ctas);
     CHAIN_STAMP(2);
 
-    /* ---- phase B: rows of E(k+1), one per epilogue warp across the grid ---- */
-    if (warp >= 2) {
-      const int gw = grp_cta * 4 + (warp - 2);
-      for (int r = gw; r < TC_BM; r += grp_ctas * 4) {
+    /* ---- phase B: rows of E(k+1), one per PAIR of warps across the group
+       (all eight warps take part; each warp of a pair takes every other
+       128-column chunk) ---- */
+    {
+      const int slot = warp >> 1, half = warp & 1;
+      const int gw = grp_cta * (TC_CHAIN_THREADS / 64) + slot;
+      for (int r = gw; r < TC_BM; r += grp_ctas * (TC_CHAIN_THREADS / 64)) {
         const int m = m0 + r;
         if (m >= v.n)
           break;
@@ -1208,12 +1220,14 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         /* all loads of a group of column chunks are issued before any of
            their results is used or stored: the row costs a few L2 round
            trips instead of one per chunk */
-        constexpr int GRP = 9; /* 9 x 128 columns: a whole row at H1023 in one round of loads */
-        for (int c0 = lane * 4; c0 < I; c0 += 128 * GRP) {
+        constexpr int GRP = 5; /* 5 x 256 columns: this warp's half of a row at H1023 in one
+                                  round of loads */
+        constexpr int CSTEP = 256;
+        for (int c0 = half * 128 + lane * 4; c0 < I; c0 += CSTEP * GRP) {
           float4 a[GRP], xin[GRP], pz[TC_CHAIN_SPLITS - 1][GRP];
 #pragma unroll
           for (int i = 0; i < GRP; i++) {
-            int c = c0 + 128 * i;
+            int c = c0 + CSTEP * i;
             if (c < I) {
               a[i] = __ldcg((const float4 *)(part + c));
               xin[i] = __ldg((const float4 *)(xk + c));
@@ -1231,7 +1245,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
             if (z < (int)gridDim.z) {
 #pragma unroll
               for (int i = 0; i < GRP; i++) {
-                int c = c0 + 128 * i;
+                int c = c0 + CSTEP * i;
                 if (c < I) {
                   a[i].x += pz[z - 1][i].x; a[i].y += pz[z - 1][i].y;
                   a[i].z += pz[z - 1][i].z; a[i].w += pz[z - 1][i].w;
@@ -1243,7 +1257,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           if (plain) {
 #pragma unroll
             for (int i = 0; i < GRP; i++) {
-              int c = c0 + 128 * i;
+              int c = c0 + CSTEP * i;
               if (c < I)
                 chain_chunk<true>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
                     g.Elo + eoff + c);
@@ -1252,7 +1266,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           else {
 #pragma unroll
             for (int i = 0; i < GRP; i++) {
-              int c = c0 + 128 * i;
+              int c = c0 + CSTEP * i;
               if (c < I)
                 chain_chunk<false>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
                     g.Elo + eoff + c);
@@ -1265,9 +1279,12 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0)
+          pair_sq[warp] = sq;
+        named_bar_sync(1 + slot, 64);
         if (warp == 2 && lane == 0) ROLE_STAMP(13);
-        if (lane == 0) {
-          float es = sq;
+        if (half == 0 && lane == 0) {
+          float es = pair_sq[warp] + pair_sq[warp + 1];
           sc.err_sum = es;
           sc.cum_error += sqrtf(es);
           sc.n_steps = k + 1;
@@ -1302,6 +1319,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           }
           *scp = sc;
         }
+        named_bar_sync(1 + slot, 64); /* pair_sq may be rewritten */
       }
       if (warp == 2 && lane == 0) ROLE_STAMP(14);
       /* E(k+1) planes were written through the generic proxy; the next step's
@@ -1736,7 +1754,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
     CUDA_OR_DIE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_single,
-            k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, 192, ChainCfg::SMEM_BYTES));
+            k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, TC_CHAIN_THREADS, ChainCfg::SMEM_BYTES));
     CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   t->persistent_ok = (coop && per_sm_single * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
@@ -1765,14 +1783,14 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     rb_prof_begin(RB_PROF_CHAIN);
     if (getenv("RECUR_B200_COOP_LAUNCH")) {
       CUDA_OR_DIE(cudaLaunchCooperativeKernel(
-              (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(192),
+              (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(TC_CHAIN_THREADS),
               params, ChainCfg::SMEM_BYTES, rb_stream));
     }
     else {
       /* co-residency was established above (occupancy x SM count >= grid and
          this stream runs nothing else alongside), so a plain launch is safe
          and avoids the cooperative launch's queue drain */
-      k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, 192, ChainCfg::SMEM_BYTES,
+      k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, TC_CHAIN_THREADS, ChainCfg::SMEM_BYTES,
         rb_stream>>>(t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, ca);
     }
     LAUNCH_CHECK("k_tc_chain_persistent");
