@@ -311,6 +311,8 @@ typedef struct RbTc {
   float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
   float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
   unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
+  size_t sync_words;
+  int sync_flip;
   int persistent_ok;    /* decided per call */
   int delta_pending;    /* the last weight gradient still sits in `partial`, unsummed */
   int pending_accumulate;
@@ -440,7 +442,10 @@ tc_state(RbPool *p)
   t->WTlo = dmalloc0<float>(I * H);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
   t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * ((I + 31) & ~(size_t)31));
-  t->sync = dmalloc0<unsigned int>((size_t)(cdiv(p->cap, TC_BM) + 1) * (p->depth + 8) + 8);
+  /* two areas, used by alternate walks (see k_finalize_rows) */
+  t->sync_words = (size_t)(cdiv(p->cap, TC_BM) + 1) * (p->depth + 8) + 8;
+  t->sync = dmalloc0<unsigned int>(2 * t->sync_words);
+  t->sync_flip = 0;
   t->persistent_ok = -1;
   t->w_src = NULL;
   uint64_t ring_rows = (uint64_t)p->depth * p->cap, chain_rows = (uint64_t)(p->depth + 1) * p->cap;
@@ -521,8 +526,14 @@ k_split_rows(RbView v, int which /* 0: current x row, 1: E[0] */, float *hi_plan
    the weight gradient (zero them), and a stream whose gradient is clipped
    (ih_scale != 1, recur-nn.c:393-402) has its rows rescaled and re-split. */
 __global__ void __launch_bounds__(256)
-k_finalize_rows(RbView v, float *Ehi, float *Elo, const unsigned int *kmax_dev)
+k_finalize_rows(RbView v, float *Ehi, float *Elo, const unsigned int *kmax_dev,
+    unsigned int *zero, int zero_words)
 {
+  /* the other of the two barrier/counter areas is cleared here for the next
+     walk, which saves that walk a memset in front of its kernel */
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_words;
+       i += gridDim.x * blockDim.x)
+    zero[i] = 0u;
   const int s = v.slots[blockIdx.x];
   const RbScalars sc = v.sc[s];
   const int kmax = min((int)*kmax_dev, v.depth);
@@ -1097,6 +1108,32 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
     if (threadIdx.x == 0)
       ROLE_STAMP(0);
 
+    /* What the row phase needs and the GEMM does not produce - the stream's
+       scalars and the ring row its errors are masked with - is fetched now,
+       ahead of the barrier the partial sums have to wait for. */
+    constexpr int GRP = 5; /* 5 x 256 columns: this warp's half of a row at H1023 in one
+                              round of loads */
+    constexpr int CSTEP = 256;
+    const int slot = warp >> 1, half = warp & 1;
+    const int gw = grp_cta * (TC_CHAIN_THREADS / 64) + slot;
+    RbScalars sc_pre;
+    float4 x_pre[GRP];
+    sc_pre.live = 0;
+    if (gw < TC_BM && m0 + gw < v.n) {
+      const int s = v.base + m0 + gw;
+      sc_pre = load_scalars_cg(v.sc + s);
+      int p = pos0 - k;
+      if (p < 0)
+        p += v.depth;
+      const float *xk = v.X + ((size_t)p * v.cap + s) * I;
+#pragma unroll
+      for (int i = 0; i < GRP; i++) {
+        int c = half * 128 + lane * 4 + CSTEP * i;
+        if (c < I)
+          x_pre[i] = __ldg((const float4 *)(xk + c));
+      }
+    }
+
     if (tile_alive) {
       if (warp == 0) {
         if (lane == 0) {
@@ -1198,8 +1235,6 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
        (all eight warps take part; each warp of a pair takes every other
        128-column chunk) ---- */
     {
-      const int slot = warp >> 1, half = warp & 1;
-      const int gw = grp_cta * (TC_CHAIN_THREADS / 64) + slot;
       for (int r = gw; r < TC_BM; r += grp_ctas * (TC_CHAIN_THREADS / 64)) {
         const int m = m0 + r;
         if (m >= v.n)
@@ -1209,7 +1244,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         /* the scalars travel with the row loads: a stopped stream's loads
            are wasted, nothing of it is stored */
         if (warp == 2 && lane == 0) ROLE_STAMP(10);
-        RbScalars sc = load_scalars_cg(scp);
+        const bool pre = (r == gw);
+        RbScalars sc = pre ? sc_pre : load_scalars_cg(scp);
         int p = pos0 - k;
         if (p < 0)
           p += v.depth;
@@ -1220,17 +1256,15 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
         /* all loads of a group of column chunks are issued before any of
            their results is used or stored: the row costs a few L2 round
            trips instead of one per chunk */
-        constexpr int GRP = 5; /* 5 x 256 columns: this warp's half of a row at H1023 in one
-                                  round of loads */
-        constexpr int CSTEP = 256;
         for (int c0 = half * 128 + lane * 4; c0 < I; c0 += CSTEP * GRP) {
+          const bool x_here = pre && c0 < CSTEP; /* the first round of the first row */
           float4 a[GRP], xin[GRP], pz[TC_CHAIN_SPLITS - 1][GRP];
 #pragma unroll
           for (int i = 0; i < GRP; i++) {
             int c = c0 + CSTEP * i;
             if (c < I) {
               a[i] = __ldcg((const float4 *)(part + c));
-              xin[i] = __ldg((const float4 *)(xk + c));
+              xin[i] = x_here ? x_pre[i] : __ldg((const float4 *)(xk + c));
 #pragma unroll
               for (int z = 1; z < TC_CHAIN_SPLITS; z++)
                 if (z < (int)gridDim.z)
@@ -1758,13 +1792,16 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   t->persistent_ok = (coop && per_sm_single * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
+  unsigned int *sync_area = t->sync + (size_t)t->sync_flip * t->sync_words;
+  unsigned int *sync_next = t->sync + (size_t)(t->sync_flip ^ 1) * t->sync_words;
+  t->sync_flip ^= 1;
   if (t->persistent_ok) {
     ChainArgs ca;
     ca.v = *v;
     ca.cpartial = t->cpartial;
     ca.Ehi = t->Ehi;
     ca.Elo = t->Elo;
-    ca.sync = t->sync;
+    ca.sync = sync_area;
     ca.dbg = NULL;
     static unsigned long long *dbg_dev = NULL;
     static int dbg_calls = 0;
@@ -1775,9 +1812,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
       CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, (1280) * sizeof(unsigned long long), rb_stream));
       ca.dbg = dbg_dev;
     }
-    CUDA_OR_DIE(cudaMemsetAsync(t->sync, 0,
-            ((size_t)(cgrid.y + 1) * (v->depth + 8) + 8) * sizeof(unsigned int), rb_stream));
-    ca.kmax = t->sync + (size_t)cgrid.y * (v->depth + 8) + 4;
+    ca.kmax = sync_area + (size_t)cgrid.y * (v->depth + 8) + 4;
     void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
                       (void *)&t->mWlo_k, (void *)&ca};
     rb_prof_begin(RB_PROF_CHAIN);
@@ -1837,13 +1872,14 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     LAUNCH_CHECK("k_chain_finish_step");
     rb_prof_end(RB_PROF_CHAIN);
   }
-  unsigned int *kmax_dev = t->sync + (size_t)cdiv(v->n, TC_BM) * (v->depth + 8) + 4;
+  unsigned int *kmax_dev = sync_area + (size_t)cdiv(v->n, TC_BM) * (v->depth + 8) + 4;
   if (!t->persistent_ok) {
     k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
     LAUNCH_CHECK("k_compute_kmax");
   }
   rb_prof_begin(RB_PROF_SMALL);
-  k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo, kmax_dev);
+  k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo, kmax_dev, sync_next,
+      (int)t->sync_words);
   LAUNCH_CHECK("k_finalize_rows");
   rb_prof_end(RB_PROF_SMALL);
   if (!dw_attr_done) {
