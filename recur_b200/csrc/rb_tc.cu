@@ -165,6 +165,79 @@ umma_commit(uint64_t *bar)
       ::"r"(smem_u32(bar)) : "memory");
 }
 
+/* ---- CTA-pair (cta_group::2) variants ---------------------------------- */
+
+__device__ __forceinline__ uint32_t
+cluster_ctarank(void)
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void
+cluster_sync_all(void)
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+/* shared-window addresses of the two CTAs of a pair differ in this bit;
+   clearing it names the even (leader) CTA's copy of an object */
+#define PAIR_LEADER_MASK 0xFEFFFFFFu
+
+/* TMA load into this CTA's shared memory, completion bytes counted on the
+   LEADER CTA's mbarrier */
+__device__ __forceinline__ void
+tma_load_3d_pair(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PAIR_LEADER_MASK), "r"(c0),
+      "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void
+tmem_alloc_pair(uint32_t *dst_smem, uint32_t cols)
+{
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+      ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void
+tmem_dealloc_pair(uint32_t addr, uint32_t cols)
+{
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols)
+      : "memory");
+}
+
+/* one MMA across both SMs of the pair: M = 256 (128 rows per CTA), each CTA
+   holding half of B's N columns; issued by one thread of the leader CTA */
+__device__ __forceinline__ void
+umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+    uint32_t accumulate)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+/* arrive on the mbarrier at this shared-memory offset in BOTH CTAs of the pair
+   when all MMAs issued so far have completed */
+__device__ __forceinline__ void
+umma_commit_pair(uint64_t *bar)
+{
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 /* 32 consecutive accumulator columns of this thread's TMEM lane */
 __device__ __forceinline__ void
 tmem_ld32(uint32_t taddr, float *v)
@@ -296,6 +369,7 @@ block_sum_tc(float v, float *scratch /* >= 33 floats */)
 #define TC_FWD_STAGES 4
 #define TC_CHAIN_BN 128   /* CHAIN tile columns */
 #define TC_CHAIN_STAGES 3
+#define TC_DW2_BN 192 /* N of the CTA-pair weight-gradient tile (two halves of 96) */
 #define TC_CHAIN_SPLITS 4 /* split-K: 4 x 9 x 4 = 144 CTAs at 512 streams, H1023 */
 #define TC_DW_BN 256      /* DW tile columns */
 #define TC_DW_BK 16       /* DW ring rows per stage */
@@ -326,6 +400,9 @@ typedef struct RbTc {
   CUtensorMap mWThi_k128, mWTlo_k128; /* the same with 128-row boxes: split-K FWD */
   CUtensorMap mXhi_mn, mXlo_mn; /* ring rows as MN-major A of DW: box 32 x 32 */
   CUtensorMap mEhi_mn, mElo_mn; /* error rows as MN-major B of DW (width h_size) */
+  CUtensorMap mEhi_mn4, mElo_mn4; /* error rows as MN-major A of the pair DW: 4 chunks */
+  CUtensorMap mXhi_mn3, mXlo_mn3; /* ring rows as MN-major B half of the pair DW: 3 chunks */
+  int dw_splits;        /* split-K planes the last weight gradient wrote */
 } RbTc;
 
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
@@ -463,6 +540,11 @@ tc_state(RbPool *p)
   make_map_chunked(&t->mXlo_mn, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
   make_map_chunked(&t->mEhi_mn, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
   make_map_chunked(&t->mElo_mn, t->Elo, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
+  make_map_chunked(&t->mEhi_mn4, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_BM / 32);
+  make_map_chunked(&t->mElo_mn4, t->Elo, H, chain_rows, I, TC_DW_BK, TC_BM / 32);
+  make_map_chunked(&t->mXhi_mn3, t->Xhi, I, ring_rows, I, TC_DW_BK, TC_DW2_BN / 2 / 32);
+  make_map_chunked(&t->mXlo_mn3, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_DW2_BN / 2 / 32);
+  t->dw_splits = TC_DW_SPLITS;
   p->tc = t;
   return t;
 }
@@ -1528,6 +1610,173 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
   }
 }
 
+/* ------------------------------------------------------------------------ */
+/* DW on CTA pairs.
+ *
+ * k_tc_dw above is bound by the 64 B/clock a single SM can take in from L2:
+ * a 128 x 256 tile needs 48 KB of operands per 16 rows of K.  Two SMs of a
+ * TPC issuing ONE MMA (tcgen05 cta_group::2, M = 256) each keep half of the
+ * N operand, so per SM and 16 rows only 16 KB (its 128 M columns) + 12 KB
+ * (half of 192 N columns) arrive, and the tensor pipe, not the port, sets the
+ * pace.  The output is transposed relative to k_tc_dw: M runs over the error
+ * columns h (1024 = 4 pairs of 128, no padding), N over the input columns i
+ * (6 tiles of 192), D[h][i] = sum_rows E[row][h] X[row][i]; both operands
+ * stay MN-major.  The epilogue writes partial[z][i][h]: lanes are h, so every
+ * store is a full line.
+ *
+ * Protocol (as CUTLASS's 2-SM pipelines): both CTAs' TMA loads count their
+ * bytes on the leader's `full` barrier, on which only the leader's producer
+ * arrives (expecting both halves); the leader's MMA thread releases a stage in
+ * both CTAs with a multicast commit; the accumulator-ready commit is multicast
+ * too, and each CTA's epilogue drains its own TMEM half.                     */
+
+#define TC_DW2_STAGES 7
+#define DW2_A_BYTES ((TC_BM / 32) * DW_CHUNK_BYTES)            /* 8 KB per plane */
+#define DW2_B_BYTES ((TC_DW2_BN / 2 / 32) * DW_CHUNK_BYTES)    /* 6 KB per plane, this CTA's half */
+#define DW2_STAGE_BYTES (2 * DW2_A_BYTES + 2 * DW2_B_BYTES)
+#define DW2_SMEM_BYTES (TC_DW2_STAGES * DW2_STAGE_BYTES + 1024 + 256)
+#define DW2_TMEM_COLS 256
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ CUtensorMap mElo,
+    const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
+    DwArgs g)
+{
+  extern __shared__ uint8_t smem_raw[];
+  const RbView &v = g.v;
+  /* the dynamic shared window starts at the same offset in both CTAs, so the
+     rounded-up base does too: descriptors and barrier offsets are valid for
+     the pair */
+  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t *full = (uint64_t *)(smem + TC_DW2_STAGES * DW2_STAGE_BYTES);
+  uint64_t *empty = full + TC_DW2_STAGES;
+  uint64_t *acc_ready = empty + TC_DW2_STAGES;
+  uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int I = v.d.i_size, H = v.d.h_size;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int h0 = blockIdx.x * TC_BM;                      /* this CTA's M rows (blockIdx.x = 2 * pair + rank) */
+  const int i0 = blockIdx.y * TC_DW2_BN;                  /* the pair's N columns */
+  const int i_half = i0 + (int)rank * (TC_DW2_BN / 2);    /* the half this CTA loads */
+  const int kb_per_step = v.n / TC_DW_BK;
+  const int n_steps_max = min((int)*g.kmax, v.depth);
+  const int n_kb_total = n_steps_max * kb_per_step;
+  const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
+  const int kb_begin = blockIdx.z * kb_per_split;
+  const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_DW2_STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_ready, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&mEhi);
+    tma_prefetch_desc(&mElo);
+    tma_prefetch_desc(&mXhi);
+    tma_prefetch_desc(&mXlo);
+  }
+  if (warp == 1)
+    tmem_alloc_pair(tmem_slot, DW2_TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all(); /* both CTAs' barriers exist before anyone signals them */
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int pos = v.pos[v.base];
+      for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
+        int s = it % TC_DW2_STAGES;
+        uint32_t ph = (it / TC_DW2_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        int step = kb / kb_per_step;
+        int b0 = (kb - step * kb_per_step) * TC_DW_BK;
+        int slot = pos - step;
+        if (slot < 0)
+          slot += v.depth;
+        int xrow = slot * v.cap + v.base + b0;
+        int erow = step * v.cap + v.base + b0;
+        uint8_t *st = smem + s * DW2_STAGE_BYTES;
+        if (leader)
+          mbar_expect_tx(&full[s], 2 * DW2_STAGE_BYTES);
+        tma_load_3d_pair(&mEhi, &full[s], st, 0, erow, h0 / 32);
+        tma_load_3d_pair(&mElo, &full[s], st + DW2_A_BYTES, 0, erow, h0 / 32);
+        tma_load_3d_pair(&mXhi, &full[s], st + 2 * DW2_A_BYTES, 0, xrow, i_half / 32);
+        tma_load_3d_pair(&mXlo, &full[s], st + 2 * DW2_A_BYTES + DW2_B_BYTES, 0, xrow,
+            i_half / 32);
+      }
+    }
+  }
+  else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_tf32(2 * TC_BM, TC_DW2_BN, 1, 1);
+      for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
+        int s = it % TC_DW2_STAGES;
+        uint32_t ph = (it / TC_DW2_STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        uint32_t a_hi = smem_u32(smem + s * DW2_STAGE_BYTES);
+        uint32_t a_lo = a_hi + DW2_A_BYTES;
+        uint32_t b_hi = a_hi + 2 * DW2_A_BYTES;
+        uint32_t b_lo = b_hi + DW2_B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_DW_BK / 8; kk++) {
+          uint64_t dah = umma_desc(a_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dal = umma_desc(a_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dbh = umma_desc(b_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          uint64_t dbl = umma_desc(b_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
+          umma_tf32_pair(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
+          umma_tf32_pair(tmem_base, dah, dbl, idesc, 1u);
+          umma_tf32_pair(tmem_base, dah, dbh, idesc, 1u);
+        }
+        umma_commit_pair(&empty[s]);
+      }
+      umma_commit_pair(acc_ready);
+    }
+  }
+  else {
+    const int q = warp & 3;
+    const int h = h0 + q * 32 + lane;
+    const bool any = kb_end > kb_begin;
+    if (any) {
+      mbar_wait(acc_ready, 0);
+      tc_fence_after();
+    }
+    float *dst = g.partial + (size_t)blockIdx.z * I * H + h;
+    float acc[32];
+#pragma unroll 1
+    for (int c = 0; c < TC_DW2_BN; c += 32) {
+      if (any)
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+      else {
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+          acc[j] = 0.0f;
+      }
+      if (h < H) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          int i = i0 + c + j;
+          if (i < I)
+            dst[(size_t)i * H] = acc[j];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  /* nobody leaves (or frees tensor memory) while the other CTA may still be
+     read by the pair's MMAs or signalled by their commits */
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, DW2_TMEM_COLS);
+  }
+}
+
 /* delta (+)= sum of the split-K partials, in a fixed order */
 __global__ void __launch_bounds__(256)
 k_dw_reduce(float *__restrict__ delta, const float *__restrict__ partial, int size, int splits,
@@ -1891,14 +2140,39 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   d.v = *v;
   d.partial = t->partial;
   d.kmax = kmax_dev;
-  dim3 dgrid(cdiv(v->d.h_size, TC_DW_BN), cdiv(v->d.i_size, TC_BM), TC_DW_SPLITS);
+  static int dw_sms = 0, dw_pair_ok = 0;
+  if (!dw_sms) {
+    int dev = 0;
+    CUDA_OR_DIE(cudaGetDevice(&dev));
+    CUDA_OR_DIE(cudaDeviceGetAttribute(&dw_sms, cudaDevAttrMultiProcessorCount, dev));
+    dw_pair_ok = !getenv("RECUR_B200_NO_PAIR_DW") &&
+        cudaFuncSetAttribute(k_tc_dw_pair, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            DW2_SMEM_BYTES) == cudaSuccess;
+  }
   rb_prof_begin(RB_PROF_DW);
-  k_tc_dw<<<dgrid, 192, DW_SMEM_BYTES, rb_stream>>>(t->mXhi_mn, t->mXlo_mn, t->mEhi_mn, t->mElo_mn, d);
-  LAUNCH_CHECK("k_tc_dw");
+  int pgx = 2 * cdiv(v->d.h_size, 2 * TC_BM), pgy = cdiv(v->d.i_size, TC_DW2_BN);
+  int psplits = dw_sms / (pgx * pgy);
+  if (psplits > TC_DW_SPLITS)
+    psplits = TC_DW_SPLITS;
+  if (dw_pair_ok && psplits >= 1) {
+    /* CTA pairs: one MMA across two SMs, each holding half of the N operand */
+    dim3 dgrid(pgx, pgy, psplits);
+    k_tc_dw_pair<<<dgrid, 192, DW2_SMEM_BYTES, rb_stream>>>(t->mEhi_mn4, t->mElo_mn4,
+        t->mXhi_mn3, t->mXlo_mn3, d);
+    LAUNCH_CHECK("k_tc_dw_pair");
+    t->dw_splits = psplits;
+  }
+  else {
+    dim3 dgrid(cdiv(v->d.h_size, TC_DW_BN), cdiv(v->d.i_size, TC_BM), TC_DW_SPLITS);
+    k_tc_dw<<<dgrid, 192, DW_SMEM_BYTES, rb_stream>>>(t->mXhi_mn, t->mXlo_mn, t->mEhi_mn,
+        t->mElo_mn, d);
+    LAUNCH_CHECK("k_tc_dw");
+    t->dw_splits = TC_DW_SPLITS;
+  }
   int size = v->d.i_size * v->d.h_size;
   if (rb_p2p_ready(v->p2p)) {
     /* multi-GPU: the split-K sum is the first phase of the exchange kernel */
-    rb_p2p_reduce(v->p2p, t->partial, TC_DW_SPLITS, size, v->d.h_size * v->d.o_size, ih_delta,
+    rb_p2p_reduce(v->p2p, t->partial, t->dw_splits, size, v->d.h_size * v->d.o_size, ih_delta,
         accumulate);
   }
   else if (defer_delta_reduce) {
@@ -1909,7 +2183,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   }
   else {
     k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
-        TC_DW_SPLITS, accumulate);
+        t->dw_splits, accumulate);
     LAUNCH_CHECK("k_dw_reduce");
   }
   rb_prof_end(RB_PROF_DW);
@@ -1933,7 +2207,7 @@ rb_tc_materialise_delta(RbPool *p, float *ih_delta)
   const RbDims *d = &p->group->d;
   int size = d->i_size * d->h_size;
   k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
-      TC_DW_SPLITS, t->pending_accumulate);
+      t->dw_splits, t->pending_accumulate);
   LAUNCH_CHECK("k_dw_reduce");
   t->delta_pending = 0;
 }
@@ -1959,7 +2233,7 @@ rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum, float mo
   a.mom = b->ih_momentum;
   a.aux = b->ih_aux;
   a.partial = t->delta_pending ? t->partial : NULL;
-  a.splits = TC_DW_SPLITS;
+  a.splits = t->dw_splits;
   a.accumulate = t->pending_accumulate;
   a.I = d->i_size;
   a.H = d->h_size;
