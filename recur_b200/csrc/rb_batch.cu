@@ -518,11 +518,15 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
     rb_bottom_forward(&v, proto, NULL, noise);
     rb_forward_dispatch(&v, noise);
   }
-  else
+  else {
+    /* the output kernel may take the softmax error and its sums along */
+    rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
     rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
         from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
+  }
   download_rng_if_noisy(b, noise);
-  rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
+  if (!rbk_fused_loss_done())
+    rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
   /* the update follows at once: the weight gradient may stay in its split-K
      planes until then (single GPU; an exchange needs the finished sum) */
   rb_tc_defer_delta_reduce(rb_comm_size() <= 1);

@@ -626,13 +626,10 @@ k_out(RbView v)
    argmax; one warp per stream, warp-shuffle reductions
    (badmaths.h:71-141, charmodel-predict.c:18-27).                          */
 
-__global__ void __launch_bounds__(128)
-k_softmax_error(RbView v, const u8 *target, float *err_out, int *winner_out)
+__device__ __forceinline__ void
+softmax_error_warp(const RbView &v, int j, int lane, const u8 *target, float *err_out,
+    int *winner_out)
 {
-  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (j >= v.n)
-    return;
   int s = v.slots[j];
   const int len = v.d.output_size, O = v.d.o_size;
   const float *src = v.Y + (size_t)s * O;
@@ -697,9 +694,17 @@ k_softmax_error(RbView v, const u8 *target, float *err_out, int *winner_out)
   }
 }
 
+__global__ void __launch_bounds__(128)
+k_softmax_error(RbView v, const u8 *target, float *err_out, int *winner_out)
+{
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (j < v.n)
+    softmax_error_warp(v, j, threadIdx.x & 31, target, err_out, winner_out);
+}
+
 /* sums of charmodel-predict.c:301-303 over the batch, in a fixed order */
-__global__ void __launch_bounds__(256)
-k_char_accum(const float *err, const int *winner, const u8 *target, int n,
+__device__ __forceinline__ void
+char_accum_block(const float *err, const int *winner, const u8 *target, int n,
     RbCharAccum *acc)
 {
   __shared__ double s_err[256], s_ent[256];
@@ -707,11 +712,11 @@ k_char_accum(const float *err, const int *winner, const u8 *target, int n,
   double e = 0.0, h = 0.0;
   int c = 0;
   for (int j = threadIdx.x; j < n; j += blockDim.x) {
-    float ej = err[j];
+    float ej = __ldcg(err + j); /* written by other blocks of the same kernel in the fused case */
     e += ej;
     float x = 1.0f - ej;
     h += (x < 1e-30f) ? -100.0f : log2f(x);
-    c += (winner[j] == (int)target[j]);
+    c += (__ldcg(winner + j) == (int)target[j]);
   }
   s_err[threadIdx.x] = e;
   s_ent[threadIdx.x] = h;
@@ -731,6 +736,13 @@ k_char_accum(const float *err, const int *winner, const u8 *target, int n,
     acc->correct += s_cor[0];
     acc->count += n;
   }
+}
+
+__global__ void __launch_bounds__(256)
+k_char_accum(const float *err, const int *winner, const u8 *target, int n,
+    RbCharAccum *acc)
+{
+  char_accum_block(err, winner, target, n, acc);
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1011,9 +1023,21 @@ hidden_activation(const RbView &v, float4 sum, int col0, const float *noise_row)
 /* FROM_PARTIALS: the hidden rows arrive as split-K partial sums of the tensor
    engine's forward GEMM; this kernel sums them (fixed order), applies the
    activation, writes the hidden rows and goes on to the output layer. */
+/* optional tail of k_out_multi: the char model's softmax error against the
+   next symbol for the block's streams, and - by whichever block finishes
+   last - the sums over the batch, in the fixed order k_char_accum uses */
+struct RbLossArgs {
+  const u8 *target; /* NULL: no loss */
+  float *err;
+  int *winner;
+  RbCharAccum *accum;
+};
+
+__device__ unsigned int rb_loss_ticket;
+
 template <bool FROM_PARTIALS>
 __global__ void __launch_bounds__(256)
-k_out_multi(RbView v, RbFwdPartials fp)
+k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
 {
   extern __shared__ __align__(16) float sh[]; /* Who | OS hidden rows | reduction space */
   const int H = v.d.h_size, O = v.d.o_size;
@@ -1108,6 +1132,25 @@ k_out_multi(RbView v, RbFwdPartials fp)
     else if (c < O) {
       for (int q = 0; q < ns; q++)
         v.Y[(size_t)slot_of(v, j0 + q) * O + c] = acc[q];
+    }
+  }
+  if (loss.target) {
+    __shared__ int s_last;
+    __syncthreads(); /* the block's rows of Y are written */
+    const int w = threadIdx.x >> 5;
+    if (w < ns)
+      softmax_error_warp(v, j0 + w, threadIdx.x & 31, loss.target, loss.err, loss.winner);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_last = (atomicAdd(&rb_loss_ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      char_accum_block((const float *)loss.err, (const int *)loss.winner, loss.target, v.n,
+          loss.accum);
+      if (threadIdx.x == 0)
+        rb_loss_ticket = 0u;
     }
   }
 }
@@ -1820,12 +1863,45 @@ rbk_output_takes_partials(const RbView *v, int splits)
 
 /* hidden activation + output layer from the split-K partial sums of the
    tensor engine's forward GEMM */
+/* A caller about to run a forward pass whose outputs go straight into the
+   char model's softmax error may ask for that to happen in the output kernel;
+   rbk_fused_loss_done() afterwards says whether it did. */
+static struct {
+  RbLossArgs args;
+  int armed, done;
+} loss_request;
+
+extern "C" void
+rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
+    RbCharAccum *accum_dev)
+{
+  loss_request.args.target = target_dev;
+  loss_request.args.err = err_dev;
+  loss_request.args.winner = winner_dev;
+  loss_request.args.accum = accum_dev;
+  loss_request.armed = target_dev && err_dev && winner_dev && accum_dev;
+  loss_request.done = 0;
+}
+
+extern "C" int
+rbk_fused_loss_done(void)
+{
+  int done = loss_request.done;
+  loss_request.armed = loss_request.done = 0;
+  return done;
+}
+
 extern "C" void
 rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
 {
+  RbLossArgs loss = {NULL, NULL, NULL, NULL};
+  if (loss_request.armed && v->contiguous) {
+    loss = loss_request.args;
+    loss_request.done = 1;
+  }
   out_multi_attr();
   rb_prof_begin(RB_PROF_OUT);
-  k_out_multi<true><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, *fp);
+  k_out_multi<true><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, *fp, loss);
   LAUNCH_CHECK("k_out_multi<partials>");
   rb_prof_end(RB_PROF_OUT);
 }
@@ -1835,9 +1911,10 @@ rbk_output(const RbView *v)
 {
   if (out_multi_usable(v)) {
     RbFwdPartials none = {NULL, 0, 0, 0, 0};
+    RbLossArgs no_loss = {NULL, NULL, NULL, NULL};
     out_multi_attr();
     rb_prof_begin(RB_PROF_OUT);
-    k_out_multi<false><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, none);
+    k_out_multi<false><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, none, no_loss);
     LAUNCH_CHECK("k_out_multi");
     rb_prof_end(RB_PROF_OUT);
     return;
