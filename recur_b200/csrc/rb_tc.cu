@@ -1048,8 +1048,9 @@ grid_barrier(unsigned int *counter, unsigned int target)
 {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    /* arrive with a release reduction: nothing waits for the old value to
+       come back before the polling starts */
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
     while (ld_acquire_gpu(counter) < target)
       ;
   }
