@@ -284,48 +284,71 @@ def run_ours(args):
         L.rnn_b200_set_engine(args.engine)
     n = args.streams
     text = synthetic_text()
-    devnull_fd = os.dup(2)
-    os.dup2(os.open(os.devnull, os.O_WRONLY), 2)   # the reference-style init chatter
-    net = make_net(L, input_size=ALPHABET, hidden=args.hidden, output=ALPHABET, depth=DEPTH,
-                   seed=1, lr=LEARN_RATE / world)
-    os.dup2(devnull_fd, 2)
-    nets = L.rnn_new_training_set(net, n)
-    batch = L.rnn_batch_new(nets, n)
-    exchange = "none"
-    if world > 1:
-        exchange = "nccl all-reduce"
-        if not args.no_p2p:
-            # fused split-K reduction + all-reduce over NVLink peer memory
-            hb = (C.c_uint8 * 192)()
-            ok = L.rnn_batch_p2p_export(batch, hb) == 0
-            mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
-            allh = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(allh, mine)
-            flag = torch.tensor([1 if ok else 0], device="cuda")
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if int(flag.item()):
-                raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
-                buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
-                ok = L.rnn_batch_p2p_attach(batch, buf, rank, world) == 0
-                flag = torch.tensor([1 if ok else 0], device="cuda")
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                if int(flag.item()):
-                    exchange = "fused reduce + all-reduce kernel over NVLink peer memory"
-                else:
-                    raise SystemExit("peer attach succeeded on some ranks only")
     # each rank reads its own stretch of the text
     lo, hi = rdist.shard_bounds(len(text), rank, world)
     my_text = np.ascontiguousarray(text[lo:hi])
-    L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
+
+    def make_job():
+        """A freshly initialised net (same seed every time), its training set
+        and batch, the peer exchange attached, the text in HBM."""
+        devnull_fd = os.dup(2)
+        os.dup2(os.open(os.devnull, os.O_WRONLY), 2)   # the reference-style init chatter
+        net = make_net(L, input_size=ALPHABET, hidden=args.hidden, output=ALPHABET, depth=DEPTH,
+                       seed=1, lr=LEARN_RATE / world)
+        os.dup2(devnull_fd, 2)
+        os.close(devnull_fd)
+        nets = L.rnn_new_training_set(net, n)
+        batch = L.rnn_batch_new(nets, n)
+        exchange = attach_exchange(batch)
+        L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
+        return net, nets, batch, exchange
+
+    def drop_job(job):
+        net, nets, batch, _ = job
+        L.rnn_batch_delete(batch)
+        L.rnn_delete_training_set(nets, n, 0)   # nets[0] is the prototype: it goes too
+
+    def attach_exchange(batch):
+      exchange = "none"
+      if world > 1:
+          exchange = "nccl all-reduce"
+          if not args.no_p2p:
+              # fused split-K reduction + all-reduce over NVLink peer memory
+              hb = (C.c_uint8 * 192)()
+              ok = L.rnn_batch_p2p_export(batch, hb) == 0
+              mine = torch.tensor(list(hb), dtype=torch.uint8, device="cuda")
+              allh = [torch.zeros_like(mine) for _ in range(world)]
+              dist.all_gather(allh, mine)
+              flag = torch.tensor([1 if ok else 0], device="cuda")
+              dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+              if int(flag.item()):
+                  raw = b"".join(bytes(t.cpu().tolist()) for t in allh)
+                  buf = (C.c_uint8 * len(raw)).from_buffer_copy(raw)
+                  ok = L.rnn_batch_p2p_attach(batch, buf, rank, world) == 0
+                  flag = torch.tensor([1 if ok else 0], device="cuda")
+                  dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                  if int(flag.item()):
+                      exchange = "fused reduce + all-reduce kernel over NVLink peer memory"
+                  else:
+                      raise SystemExit("peer attach succeeded on some ranks only")
+      return exchange
+
     stream = torch.cuda.ExternalStream(L.rnn_b200_stream())
     style = abi.RNN_MOMENTUM_WEIGHTED
 
+    def warm_up(batch):
+        pos = L.rnn_batch_text_train(batch, 0, max(args.warmup, 3), style, MOMENTUM, SOFT_START,
+                                     None)
+        # fill the BPTT ring so that every timed step walks the full depth
+        if args.warmup < DEPTH and not args.cold:
+            pos = L.rnn_batch_text_train(batch, pos, DEPTH - args.warmup, style, MOMENTUM,
+                                         SOFT_START, None)
+        return pos
+
     # ---- device-resident arm (value) ---------------------------------------
-    pos = L.rnn_batch_text_train(batch, 0, max(args.warmup, 3), style, MOMENTUM, SOFT_START, None)
-    # fill the BPTT ring so that every timed step walks the full depth
-    if args.warmup < DEPTH and not args.cold:
-        pos = L.rnn_batch_text_train(batch, pos, DEPTH - args.warmup, style, MOMENTUM,
-                                     SOFT_START, None)
+    job = make_job()
+    net, nets, batch, exchange = job
+    pos = warm_up(batch)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -347,6 +370,13 @@ def run_ours(args):
     value = (args.steps * n * world) / (ms * 1e-3)
 
     # ---- end-to-end arm (host symbols in, report sums out, every step) -----
+    # the SAME job again from the same initial weights, so that both arms do
+    # the same work (the BPTT walk deepens as training goes on)
+    barrier()
+    drop_job(job)
+    job = make_job()
+    net, nets, batch, exchange = job
+    pos = warm_up(batch)
     spacing = (len(my_text) - 1) // n
     offs = (np.arange(n, dtype=np.int64) * spacing)
     est = api.RnnBatchCharStats()
@@ -423,8 +453,8 @@ def run_ours(args):
     traffic = None
     try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
-        kname = {"bptt_chain": "k_tc_chain_persistent<128, 3>", "weight_grad": "k_tc_dw",
-                 "forward": "k_tc_nt<64, 4>"}.get(dominant)
+        kname = {"bptt_chain": "k_tc_chain_persistent<128, 3>", "weight_grad": "k_tc_dw_pair",
+                 "forward": "k_tc_nt<128, 3>"}.get(dominant)
         if kname in tr:
             traffic = tr[kname]["dram_bytes_per_launch"]
     except Exception:
