@@ -1,0 +1,29 @@
+#!/bin/bash
+# One GPU-box call that produces everything profiles/ is made from (1 GPU):
+#   gpurun --timeout 1500 -- 'bash scripts/gpu_profile_run.sh r1'
+# then here: python scripts/make_profiles.py r1
+# Numbers printed under ncu are never bench values; the bench JSON lines come
+# from the un-profiled runs at the end.
+tag=${1:-r1}
+out=gpurun_out
+mkdir -p $out
+rm -f $out/*_${tag}.ncu-rep $out/launches_${tag}.csv $out/bench_${tag}_*.json
+
+# 1. launch list of the bench command, captured deep into the timed region
+#    (10 launches per training step; ncu slows every skipped launch, so only 70 steps are skipped)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 100 --csv \
+  --log-file $out/launches_${tag}.csv \
+  python bench.py --steps 100 --warmup 30 --no-cpu-baseline > $out/ncu_launches_${tag}.log 2>&1
+
+# 2. one --set full capture per hot kernel, 300 steps in
+for k in k_tc_chain_persistent k_tc_dw_pair k_tc_nt k_update_split k_out_multi; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 300 -c 1 \
+    -f -o $out/${k}_${tag} python bench.py --steps 300 --warmup 30 --no-cpu-baseline \
+    > $out/ncu_${k}_${tag}.log 2>&1
+done
+
+# 3. the bench lines themselves, un-profiled
+timeout 900 python bench.py > $out/bench_${tag}_n1.json 2> $out/bench_${tag}_n1.err
+timeout 900 python bench.py --impl reference > $out/bench_${tag}_ref.json 2> $out/bench_${tag}_ref.err
+tail -c 600 $out/bench_${tag}_n1.json
+tail -c 400 $out/bench_${tag}_ref.json
