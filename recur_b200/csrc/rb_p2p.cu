@@ -106,9 +106,12 @@ k_dw_reduce_allreduce(P2PArgs a)
     float4 s;
     if (i < a.ih_size) {
       s = a.accumulate ? *(const float4 *)(a.ih_delta + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int z = 0; z < a.splits; z++) {
-        float4 p = *(const float4 *)(a.partial + (size_t)z * a.ih_size + i);
-        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+#pragma unroll
+      for (int z = 0; z < 4; z++) {
+        if (z < a.splits) {
+          float4 p = *(const float4 *)(a.partial + (size_t)z * a.ih_size + i);
+          s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+        }
       }
     }
     else {
@@ -123,13 +126,24 @@ k_dw_reduce_allreduce(P2PArgs a)
   const int per = (n4 + a.n - 1) / a.n;
   const int lo = a.rank * per, hi = min(n4, lo + per);
   for (int i = lo + tid; i < hi; i += nthreads) {
-    float4 s = __ldcv((const float4 *)a.stage[0] + i);
-    for (int q = 1; q < a.n; q++) {
-      float4 p = __ldcv((const float4 *)a.stage[q] + i);
-      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    /* all peer loads in flight together (an NVLink round trip each), then
+       the sum in rank order */
+    float4 p[RB_P2P_MAX];
+#pragma unroll
+    for (int q = 0; q < RB_P2P_MAX; q++)
+      if (q < a.n)
+        p[q] = __ldcv((const float4 *)a.stage[q] + i);
+    float4 s = p[0];
+#pragma unroll
+    for (int q = 1; q < RB_P2P_MAX; q++) {
+      if (q < a.n) {
+        s.x += p[q].x; s.y += p[q].y; s.z += p[q].z; s.w += p[q].w;
+      }
     }
-    for (int q = 0; q < a.n; q++)
-      *((float4 *)a.result[q] + i) = s;
+#pragma unroll
+    for (int q = 0; q < RB_P2P_MAX; q++)
+      if (q < a.n)
+        *((float4 *)a.result[q] + i) = s;
   }
   publish_epoch(a, 1);
   await_epoch(a, 1);
