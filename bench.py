@@ -402,6 +402,18 @@ def run_ours(args):
     e2e_value = (e2e_steps * n * world) / (e2e_ms * 1e-3)
     sampler.stop()
 
+    # ---- forward only: rnn_opinion stream-steps/s (the metric's second half) --
+    fwd_steps = min(args.steps, 300)
+    L.rnn_batch_text_forward(batch, pos, 10)
+    barrier()
+    fev0, fev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fev0.record(stream)
+    L.rnn_batch_text_forward(batch, pos, fwd_steps)
+    fev1.record(stream)
+    barrier()
+    fwd_ms = max_over_ranks(fev0.elapsed_time(fev1))
+    opinion_rate = (fwd_steps * n * world) / (fwd_ms * 1e-3)
+
     # ---- per-kernel timing for the roofline (separate, instrumented pass) --
     prof_steps = min(args.steps, 50)
     L.rnn_b200_profile_enable(1)
@@ -495,6 +507,9 @@ def run_ours(args):
                       "accuracy": stats.correct / max(stats.count, 1)},
             "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],
             "gradient_exchange": exchange,
+            "opinion": {"value": opinion_rate, "unit": "stream-steps/s (rnn_opinion only, "
+                        "one-hot input, %d steps)" % fwd_steps,
+                        "ms_per_step": fwd_ms / fwd_steps},
         }
         if args.hidden != HIDDEN or n != STREAMS:
             line["config"]["workload"] += " [OVERRIDDEN: hidden %d streams %d]" % (args.hidden, n)

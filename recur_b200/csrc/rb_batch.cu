@@ -495,7 +495,7 @@ fetch_stats(RnnBatch *b, RnnBatchCharStats *stats)
 }
 
 extern "C" void rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos,
-    int spacing, u8 *cur_dev, u8 *next_dev, float noise);
+    int spacing, u8 *cur_dev, u8 *next_dev, float noise, int advance);
 
 /* advance .. update for one character position; the symbols come from the
    uploaded text at position `pos` (text != 0) or are already in cur/next */
@@ -522,7 +522,7 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
     /* the output kernel may take the softmax error and its sums along */
     rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
     rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
-        from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise);
+        from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise, 1);
   }
   download_rng_if_noisy(b, noise);
   if (!rbk_fused_loss_done())
@@ -595,9 +595,8 @@ rnn_batch_text_forward(RnnBatch *b, int start, int steps)
   for (int s = 0; s < steps; s++, i++) {
     if (i >= len - 1)
       i = 0;
-    rbk_text_symbols(b->text_dev, len, i, spacing, b->n, b->cur_dev, b->next_dev);
-    rbk_set_one_hot(&v, b->cur_dev);
-    rb_forward_dispatch(&v, 0.0f);
+    /* rnn_opinion without rnn_bptt_advance: the current ring row is rewritten */
+    rb_char_forward_dispatch(&v, b->text_dev, len, i, spacing, b->cur_dev, b->next_dev, 0.0f, 0);
   }
   mark_ahead(b);
   return (i >= len - 1) ? 0 : i;

@@ -50,13 +50,14 @@ rb_forward_dispatch(const RbView *v, float noise)
 /* fused start of a text step + forward (rb_batch.cu's character steps) */
 extern "C" void
 rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float noise)
+    u8 *cur_dev, u8 *next_dev, float noise, int advance)
 {
   int tensor = use_tensor_engine(v);
   if (!rbk_step_begin_usable(v)) {
     if (text_dev)
       rbk_text_symbols(text_dev, len, pos, spacing, v->n, cur_dev, next_dev);
-    rbk_advance(v);
+    if (advance)
+      rbk_advance(v);
     rbk_set_one_hot(v, cur_dev);
     rb_forward_dispatch(v, noise);
     return;
@@ -64,7 +65,7 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
   float *Xhi = NULL, *Xlo = NULL;
   if (tensor)
     rb_tc_x_planes(v->pool, &Xhi, &Xlo);
-  rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo);
+  rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo, advance);
   if (tensor)
     rb_tc_forward_core(v->pool, v, noise);
   else

@@ -1716,6 +1716,7 @@ struct StepBeginArgs {
   int len, pos, spacing;
   u8 *cur, *next;
   float *Xhi, *Xlo;
+  int advance;    /* 0: forward only, the row of the current ring position is rewritten */
 };
 
 __global__ void __launch_bounds__(256)
@@ -1727,10 +1728,11 @@ k_step_begin(StepBeginArgs a)
   const int j = blockIdx.x;
   const int s = v.contiguous ? v.base + j : v.slots[j];
   if (threadIdx.x == 0) {
-    int p = v.pos[s] + 1;
+    int p = v.pos[s] + (a.advance ? 1 : 0);
     if (p >= v.depth)
       p -= v.depth;
-    v.pos[s] = p;
+    if (a.advance)
+      v.pos[s] = p;
     s_pos = p;
     int hot;
     if (a.text) {
@@ -1802,9 +1804,10 @@ rbk_step_begin_usable(const RbView *v)
 
 extern "C" void
 rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo)
+    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance)
 {
   StepBeginArgs a;
+  a.advance = advance;
   a.v = *v;
   a.text = text_dev;
   a.len = len;

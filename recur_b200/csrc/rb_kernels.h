@@ -59,7 +59,7 @@ void rbk_prepare_x(const RbView *v);
 void rbk_forward_core(const RbView *v, float presynaptic_noise);
 int rbk_step_begin_usable(const RbView *v);
 void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo);
+    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
 void rbk_output(const RbView *v);
 /* split-K partial sums of a forward GEMM: [splits][rows of `pitch` floats] */
 typedef struct RbFwdPartials {

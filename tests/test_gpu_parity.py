@@ -395,3 +395,40 @@ def test_condition_net_matches_reference(gpu_lib, ref):
     assert rel_err(res[0][0], res[1][0]) < 1e-6
     assert rel_err(res[0][1], res[1][1]) < 1e-6
     assert res[0][2] == res[1][2]
+
+
+@pytest.mark.parametrize("n", [5, 64])
+def test_text_forward_only_matches_live_reference(gpu_lib, ref, n):
+    """rnn_batch_text_forward = rnn_opinion on one-hot symbols without
+    rnn_bptt_advance (the forward-only half of the metric), FMA engine at 5
+    streams and tensor engine at 64."""
+    lib = gpu_lib
+    steps = 12
+    text = markov_text(4000, 42, seed=9)
+    shape = dict(input_size=42, hidden=99, output=42, depth=20, seed=5, lr=1e-3)
+    r = make_net(ref, **shape)
+    g = make_net(lib, **shape)
+    rn = ref.rnn_new_training_set(r, n)
+    gn = lib.rnn_new_training_set(g, n)
+    batch = lib.rnn_batch_new(gn, n)
+    lib.rnn_batch_text_upload(batch, u8ptr(text), len(text))
+    start = 7
+    nxt = lib.rnn_batch_text_forward(batch, start, steps)
+    assert nxt == start + steps
+    lib.rnn_batch_pull(batch)
+    spacing = (len(text) - 1) // n
+    H, O = r.contents.h_size, r.contents.o_size
+    for j in range(n):
+        c = rn[j].contents
+        for i in range(start, start + steps):
+            inputs = arr(c.real_inputs, c.input_size)
+            inputs[:] = 0
+            inputs[text[(i + j * spacing) % (len(text) - 1)]] = 1.0
+            ref.rnn_opinion(rn[j], None, 0.0)
+        assert rel_err(arr(gn[j].contents.hidden_layer, H), arr(c.hidden_layer, H)) < TOL
+        assert rel_err(arr(gn[j].contents.output_layer, O), arr(c.output_layer, O)) < TOL
+        # no advance happened: the ring index is where rnn_new left it
+        assert gn[j].contents.bptt.contents.index == c.bptt.contents.index
+    lib.rnn_batch_delete(batch)
+    lib.rnn_delete_training_set(gn, n, 0)
+    ref.rnn_delete_training_set(rn, n, 0)
