@@ -567,7 +567,6 @@ rnn_batch_text_train(RnnBatch *b, int start, int steps, int learning_style,
     rb_die("recur-b200: rnn_batch_text_train before rnn_batch_text_upload");
   RecurNN *proto = &b->nets[0]->pub;
   int len = b->text_len;
-  int spacing = (len - 1) / b->n;
   int i = start;
   for (int s = 0; s < steps; s++, i++) {
     if (i >= len - 1)

@@ -1105,11 +1105,23 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
     for (int q = 0; q < OS; q++)
       acc[q] = 0.0f;
     if (grp < G && c < O) {
-      for (int r = grp; r < H; r += G) {
-        float w = who[(size_t)r * O + c];
+      /* each column group takes a contiguous run of hidden rows, four at a
+         time: one 16-byte read of each stream's hidden values per four
+         weights, sixteen multiply-adds per eight shared-memory reads */
+      const int rows_per = ((H + G - 1) / G + 3) & ~3;
+      const int r0 = grp * rows_per, r1 = min(H, r0 + rows_per);
+#pragma unroll 2
+      for (int r = r0; r < r1; r += 4) {
+        const float *wp = who + (size_t)r * O + c;
+        float w0 = wp[0], w1 = wp[O], w2 = wp[2 * O], w3 = wp[3 * O];
 #pragma unroll
-        for (int q = 0; q < OS; q++)
-          acc[q] += hid[q * H + r] * w;
+        for (int q = 0; q < OS; q++) {
+          float4 h = *(const float4 *)(hid + q * H + r);
+          acc[q] += h.x * w0;
+          acc[q] += h.y * w1;
+          acc[q] += h.z * w2;
+          acc[q] += h.w * w3;
+        }
       }
     }
     if (G > 1) {
@@ -1151,144 +1163,6 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
           loss.accum);
       if (threadIdx.x == 0)
         rb_loss_ticket = 0u;
-    }
-  }
-}
-
-/* a7/a8 for OS streams per block (dense error only); optionally also writes
-   the hi/lo planes of E[0] for the tensor engine */
-__global__ void __launch_bounds__(256)
-k_top_multi(RbView v, float *Ehi, float *Elo)
-{
-  extern __shared__ __align__(16) float sh[]; /* Who | OS errors | OS hidden | scratch | sums */
-  const int H = v.d.h_size, O = v.d.o_size, I = v.d.i_size;
-  const int j0 = blockIdx.x * OS;
-  const int ns = min(OS, v.n - j0);
-  float *who = sh;
-  float *oe = who + (size_t)H * O;
-  float *hid = oe + OS * O;
-  float *scratch = hid + (size_t)OS * H;
-  float *sums = scratch + 40;
-  int slot[OS];
-#pragma unroll
-  for (int q = 0; q < OS; q++)
-    slot[q] = slot_of(v, j0 + (q < ns ? q : 0));
-  stage_matrix(who, v.Who, H * O);
-  for (int q = 0; q < OS; q++) {
-    if (q < ns) {
-      stage_matrix(oe + q * O, v.OE + (size_t)slot[q] * O, O);
-      stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot[q] * H, H);
-    }
-    else {
-      for (int i = threadIdx.x; i < O; i += blockDim.x)
-        oe[q * O + i] = 0.0f;
-      for (int i = threadIdx.x; i < H; i += blockDim.x)
-        hid[(size_t)q * H + i] = 0.0f;
-    }
-  }
-  __syncthreads();
-  float abs_sum[OS], hsum[OS], hmag[OS], hzero[OS];
-#pragma unroll
-  for (int q = 0; q < OS; q++)
-    abs_sum[q] = hsum[q] = hmag[q] = hzero[q] = 0.0f;
-  for (int y = threadIdx.x; y < I; y += blockDim.x) {
-    float e[OS];
-#pragma unroll
-    for (int q = 0; q < OS; q++)
-      e[q] = 0.0f;
-    if (y < H) {
-      float h[OS];
-      bool any = false;
-#pragma unroll
-      for (int q = 0; q < OS; q++) {
-        h[q] = hid[(size_t)q * H + y];
-        if (q < ns) {
-          hsum[q] += h[q];
-          hmag[q] += h[q] * h[q];
-          hzero[q] += (h[q] == 0.0f);
-        }
-        any |= (h[q] != 0.0f);
-      }
-      if (y >= 1 && any) {
-        /* consecutive threads read consecutive rows of o_size floats: rotate
-           the starting column by the row so that a warp spreads over banks */
-        const float *row = who + (size_t)y * O;
-        for (int xx = 0; xx < O; xx++) {
-          int x = xx + y;
-          if (x >= O)
-            x -= O * (x / O);
-          float w = row[x];
-#pragma unroll
-          for (int q = 0; q < OS; q++)
-            e[q] += w * oe[q * O + x];
-        }
-#pragma unroll
-        for (int q = 0; q < OS; q++) {
-          if (h[q] == 0.0f)
-            e[q] = 0.0f;
-          abs_sum[q] += fabsf(e[q]);
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < OS; q++)
-      if (q < ns)
-        v.E[(size_t)slot[q] * I + y] = e[q];
-  }
-#pragma unroll
-  for (int q = 0; q < OS; q++) {
-    float a = block_sum(abs_sum[q], scratch);
-    float b = block_sum(hsum[q], scratch);
-    float c = block_sum(hmag[q], scratch);
-    float d = block_sum(hzero[q], scratch);
-    if (threadIdx.x == 0) {
-      sums[q * 4 + 0] = a;
-      sums[q * 4 + 1] = b;
-      sums[q * 4 + 2] = c;
-      sums[q * 4 + 3] = d;
-    }
-  }
-  __syncthreads();
-  const float halfmax = H * MAX_TOP_ERROR_FACTOR;
-  for (int q = 0; q < ns; q++) {
-    float total = sums[q * 4 + 0];
-    float scale = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
-    float *e0 = v.E + (size_t)slot[q] * I;
-    if (scale != 1.0f || Ehi) {
-      for (int y = threadIdx.x; y < I; y += blockDim.x) {
-        float e = e0[y];
-        if (scale != 1.0f && y < H) {
-          e *= scale;
-          e0[y] = e;
-        }
-        if (Ehi) {
-          uint32_t hb, lb;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e));
-          float hi = __uint_as_float(hb);
-          float rem = e - hi;
-          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-          Ehi[(size_t)slot[q] * I + y] = hi;
-          Elo[(size_t)slot[q] * I + y] = __uint_as_float(lb);
-        }
-      }
-    }
-    if (threadIdx.x == 0) {
-      RbScalars *sc = v.sc + slot[q];
-      float top_scaled = (total > halfmax) ? scale * total : total;
-      sc->top_raw = total;
-      sc->top_scaled = top_scaled;
-      sc->hidden_sum = sums[q * 4 + 1];
-      sc->hidden_mag = sqrtf(sums[q * 4 + 2]);
-      sc->hidden_zeros = (int)(sums[q * 4 + 3] + 0.5f);
-      float min_gain = MIN_ERROR_GAIN * top_scaled;
-      sc->min_sum = fminf(sc->mef / sc->lr, min_gain);
-      sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
-      sc->cum_error = 0.0f;
-      sc->err_sum = 0.0f;
-      sc->live = (v.depth > 0);
-      sc->n_steps = 0;
-      sc->t_left = v.depth;
-      sc->ih_scale = 1.0f;
     }
   }
 }
@@ -2002,13 +1876,6 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
 }
 
 static int ho_slab_attr_done = 0;
-
-static size_t
-top_multi_smem(const RbView *v)
-{
-  return ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.o_size +
-      (size_t)OS * v->d.h_size + 40 + OS * 4 + 8) * sizeof(float);
-}
 
 extern "C" void
 rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,

@@ -1135,9 +1135,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
   float *pair_sq = (float *)(tmem_slot + 2); /* one sum of squares per warp */
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  const int I = v.d.i_size, H = v.d.h_size;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int n_ctas = gridDim.x * gridDim.y * gridDim.z;
   const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   /* The streams of one m-tile form an independent chain: only the CTAs that
      share blockIdx.y exchange data, so they synchronise among themselves and
