@@ -1967,9 +1967,228 @@ rbk_sgd_top_apply(const RbView *v, float *ho_weights, float *ho_momentum,
   LAUNCH_CHECK("k_sgd_top_apply");
 }
 
+/* ------------------------------------------------------------------------ */
+/* a10 + a11 for ONE stream (the single-net path of config 1 and every
+ * per-net rnn_bptt_calc_deltas call): the whole truncated BPTT walk of
+ * recur-nn.c:303-450 in one launch.
+ *
+ * A single stream makes every step a matrix-vector product that depends on
+ * the previous one; launched per step the walk is ~60 launches of ~5 us for
+ * ~100 k multiply-adds each.  Here a cluster of eight CTAs stays resident for
+ * the walk with the weights in shared memory: CTA c owns input rows
+ * [c*R, (c+1)*R) of Wih (R*h_size floats) and the same rows of the gradient.
+ * Per step, one warp per owned row y: if x_k[y] is zero the row is skipped
+ * (the reference's skip of rows multiplied by zero, recur-nn.c:347; the test
+ * is warp-uniform), else   G[y,:] += x_k[y] * E_k[:]   and
+ * e = Wih[y,:] . E_k[:]   by warp shuffle.  The new error vector is pushed
+ * into every CTA's shared memory through distributed shared memory, the sum
+ * of squares likewise, one cluster barrier per step; every CTA then takes
+ * the same stop decision (recur-nn.c:383-413).  At the end each CTA writes
+ * its rows of ih_scale * G to the delta array.                              */
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define WALK_CTAS 8
+
+struct WalkArgs {
+  RbView v;
+  float *delta;
+  int accumulate;
+  int rows_per; /* R */
+};
+
+__global__ void __cluster_dims__(WALK_CTAS, 1, 1) __launch_bounds__(256, 1)
+k_walk_single(WalkArgs a)
+{
+  extern __shared__ __align__(16) float wsh[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const RbView &v = a.v;
+  const int s = v.slots[0];
+  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  const int R = a.rows_per;
+  const int rank = (int)cluster.block_rank();
+  const int y0 = min(I, rank * R), y1 = min(I, y0 + R), nr = y1 - y0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  float *W = wsh;                    /* [R][H] owned weight rows */
+  float *G = W + (size_t)R * H;      /* [R][H] their gradient */
+  float *E = G + (size_t)R * H;      /* [3][H] error vectors, rotating */
+  float *ES = E + 3 * H;             /* [3][WALK_CTAS] partial sums of squares */
+  float *xs = ES + 3 * WALK_CTAS;    /* [2][R] this CTA's slice of the ring row */
+  float *red = xs + 2 * R;           /* [8] per-warp sums */
+
+  RbScalars sc = v.sc[s];
+  const bool walk = sc.live != 0 && !(sc.adaptive & 2);
+  const int pos = v.pos[s];
+  const int depth = v.depth;
+
+  for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
+    *(float4 *)(W + i) = *(const float4 *)(v.Wih + (size_t)y0 * H + i);
+    *(float4 *)(G + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  {
+    const float *e0 = e_row(v, s, 0);
+    for (int i = threadIdx.x; i < H; i += blockDim.x)
+      E[i] = e0[i];
+    if (threadIdx.x < nr)
+      xs[threadIdx.x] = x_row(v, s, 0)[y0 + threadIdx.x];
+  }
+  cluster.sync(); /* everybody's shared memory is set up before anyone pushes into it */
+
+  if (walk) {
+    for (int k = 0; k < depth; k++) {
+      const float *cur = E + (k % 3) * H;
+      const int nb = (k + 1) % 3;
+      const float *x_now = xs + (k & 1) * R;
+      /* the next step's slice of the ring travels while this step computes */
+      float x_next = 0.0f;
+      if (k + 1 < depth && threadIdx.x < nr) {
+        int p = pos - (k + 1);
+        if (p < 0)
+          p += depth;
+        x_next = v.X[((size_t)p * v.cap + s) * I + y0 + threadIdx.x];
+      }
+      float *e_next_row = e_row(v, s, k + 1);
+      float sq = 0.0f;
+      for (int r = warp; r < nr; r += 8) {
+        const int y = y0 + r;
+        const float x = x_now[r];
+        float e = 0.0f;
+        if (x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f)) {
+          const float *w = W + (size_t)r * H;
+          float *g = G + (size_t)r * H;
+          float dot = 0.0f;
+          for (int c = lane; c < H; c += 32) {
+            float ec = cur[c];
+            dot = fmaf(w[c], ec, dot);
+            g[c] = fmaf(x, ec, g[c]);
+          }
+          dot = warp_sum(dot);
+          if (v.activation == RNN_RESQRT)
+            dot /= 2.0f * (x + 1.0f);
+          e = dot;
+        }
+        if (lane == 0) {
+          sq = fmaf(e, e, sq);
+          if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
+            v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+        }
+        const float e_store = (y == 0 || (y >= hs1 && y < H)) ? 0.0f : e;
+        if (lane == 0)
+          e_next_row[y] = e_store;
+        if (lane < WALK_CTAS && y < H)
+          cluster.map_shared_rank(E, lane)[nb * H + y] = e_store;
+      }
+      if (lane == 0)
+        red[warp] = sq;
+      __syncthreads();
+      if (threadIdx.x < WALK_CTAS) {
+        float t = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          t += red[q];
+        cluster.map_shared_rank(ES, threadIdx.x)[nb * WALK_CTAS + rank] = t;
+      }
+      if (threadIdx.x < nr)
+        xs[((k + 1) & 1) * R + threadIdx.x] = x_next;
+      cluster.sync();
+      float es = 0.0f;
+#pragma unroll
+      for (int q = 0; q < WALK_CTAS; q++)
+        es += ES[nb * WALK_CTAS + q];
+      /* recur-nn.c:383-413, identically in every thread of every CTA */
+      sc.err_sum = es;
+      sc.cum_error += sqrtf(es);
+      sc.n_steps = k + 1;
+      const int t_loop = depth - k;
+      const bool stop = (es <= sc.min_sum || es > sc.max_sum);
+      const bool last = (k == depth - 1);
+      if (stop || last) {
+        sc.live = 0;
+        const int t_left = stop ? t_loop : 0;
+        sc.t_left = t_left;
+        const float ceiling = ERROR_GAIN_CEILING * sc.top_scaled;
+        if (es > ceiling) {
+          sc.ih_scale = soft_clip_dev(es, sc.max_sum);
+        }
+        else {
+          sc.ih_scale = 1.0f;
+          if (sc.adaptive & 1) {
+            int depth_error = depth / 4 - t_left;
+            float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
+            float mef = sc.mef;
+            if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc.min_sum || depth_error < 0))
+              mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
+            sc.mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+          }
+        }
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  /* a11: ih_delta (+)= ih_scale * G on the owned rows */
+  const float scale = walk ? sc.ih_scale : 0.0f;
+  for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
+    float4 gv = *(const float4 *)(G + i);
+    float4 o = a.accumulate ? *(const float4 *)(a.delta + (size_t)y0 * H + i)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    o.x = fmaf(scale, gv.x, o.x);
+    o.y = fmaf(scale, gv.y, o.y);
+    o.z = fmaf(scale, gv.z, o.z);
+    o.w = fmaf(scale, gv.w, o.w);
+    *(float4 *)(a.delta + (size_t)y0 * H + i) = o;
+  }
+  if (walk && rank == 0 && threadIdx.x == 0)
+    v.sc[s] = sc;
+  /* nobody leaves while a neighbour might still push into its shared memory */
+  cluster.sync();
+}
+
+static size_t
+walk_smem_bytes(const RbView *v, int *rows_per)
+{
+  int R = (v->d.i_size + WALK_CTAS - 1) / WALK_CTAS;
+  *rows_per = R;
+  return ((size_t)2 * R * v->d.h_size + 3 * v->d.h_size + 3 * WALK_CTAS + 2 * R + 8 + 8) *
+      sizeof(float);
+}
+
+extern "C" int
+rbk_walk_single_usable(const RbView *v)
+{
+  int R;
+  return v->n == 1 && (v->d.h_size % 4) == 0 && walk_smem_bytes(v, &R) <= 200 * 1024 &&
+      !getenv("RECUR_B200_NO_WALK");
+}
+
+extern "C" void
+rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_walk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = 1;
+  }
+  WalkArgs a;
+  a.v = *v;
+  a.delta = ih_delta;
+  a.accumulate = accumulate;
+  size_t smem = walk_smem_bytes(v, &a.rows_per);
+  rb_prof_begin(RB_PROF_CHAIN);
+  k_walk_single<<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+  LAUNCH_CHECK("k_walk_single");
+  rb_prof_end(RB_PROF_CHAIN);
+}
+
 extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {
+  if (rbk_walk_single_usable(v)) {
+    rbk_walk_single(v, ih_delta, accumulate);
+    return;
+  }
   GemmArgs g;
   g.v = *v;
   g.delta = ih_delta;

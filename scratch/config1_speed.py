@@ -1,0 +1,34 @@
+"""config 1 (single net, H199, depth 30): chars/s through the per-net drop-in
+API on the GPU vs the compiled reference on one host core."""
+import sys, time, ctypes as C
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np
+import oracle
+from recur_b200 import api, abi
+from helpers import make_net, u8ptr, markov_text, arr
+lib = api.load_library()
+ref = oracle.load_ref(strict=False)
+text = markov_text(20000, 42, seed=6)
+shape = dict(input_size=42, hidden=199, output=42, depth=30, seed=1, lr=1e-3)
+r = make_net(ref, **shape)
+a = make_net(lib, **shape)
+steps = 2000
+t = ref.ref_single_net_train(r, u8ptr(text), len(text), 0, steps, 0.95, 2000.0, 1, None, None, None)
+print("reference CPU: %.0f chars/s" % (steps / t))
+c = a.contents
+o_err = c.bptt.contents.o_error
+def run(n0, n1):
+    for i in range(n0, n1):
+        c.bptt.contents.momentum = lib.rnn_calculate_momentum_soft_start(c.generation, 0.95, 2000.0)
+        lib.rnn_bptt_advance(a)
+        inputs = arr(c.real_inputs, c.input_size)
+        inputs[:] = 0
+        inputs[text[i]] = 1.0
+        answer = lib.rnn_opinion(a, None, 0.0)
+        ref.ref_softmax_best_guess(o_err, answer, c.output_size)
+        o_err[text[i + 1]] += 1.0
+        lib.rnn_bptt_calculate(a, 1)
+run(0, 100)
+t0 = time.perf_counter(); run(100, 600); t1 = time.perf_counter()
+print("ours per-net API: %.0f chars/s (%.1f us/char), launches/char %.1f" % (500 / (t1 - t0), (t1 - t0) / 500 * 1e6, 0))
+l0 = lib.rnn_b200_kernel_launches(); run(600, 700); print("launches per char", (lib.rnn_b200_kernel_launches() - l0) / 100)
