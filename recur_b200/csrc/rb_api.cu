@@ -580,12 +580,19 @@ rnn_opinion(RecurNN *net, const float *inputs, float presynaptic_noise)
   }
   else if (inputs)
     memcpy(net->real_inputs, inputs, net->input_size * sizeof(float));
+  RbView v;
+  rb_view_of_net(rn, &v);
+  if (!bl && presynaptic_noise == 0.0f && rbk_opinion_single_usable(&v)) {
+    /* one launch that reads and writes the pinned mirrors itself */
+    rbk_opinion_single(&v, net->hidden_layer, net->real_inputs, net->input_layer,
+        net->hidden_layer, net->output_layer);
+    sync_stream();
+    return net->output_layer;
+  }
   float *xrow = dev_x_row(rn, 0);
   h2d(p->Hd + (size_t)s * d->h_size, net->hidden_layer, d->h_size * sizeof(float));
   if (!bl)
     h2d(xrow + d->hidden_size + 1, net->real_inputs, d->input_size * sizeof(float));
-  RbView v;
-  rb_view_of_net(rn, &v);
   if (presynaptic_noise != 0.0f)
     h2d(p->rng + (size_t)s * 4, &net->rng, sizeof(rand_ctx));
   if (bl)

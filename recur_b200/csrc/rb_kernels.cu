@@ -2182,6 +2182,197 @@ rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
   rb_prof_end(RB_PROF_CHAIN);
 }
 
+/* ------------------------------------------------------------------------ */
+/* a2..a5 for ONE stream through the per-net API: rnn_opinion as a single
+ * launch.  The per-net protocol keeps the caller's vectors in pinned host
+ * mirrors; done with copies and the batch kernels that
+ * is eight dependent stream operations for 50 k multiply-adds.  Here the
+ * same cluster of eight CTAs reads hidden(t-1) and the inputs straight from
+ * the mirrors, builds the ring row (soft clip included), splits the rows of
+ * Wih between the CTAs (rows whose x is zero are skipped, the test is uniform
+ * over the block), sums the partial hidden vectors through distributed shared
+ * memory in rank order, splits the rows of Who the same way, and writes the
+ * ring row, hidden and output vectors both to the device pool and back into
+ * the mirrors.                                                              */
+
+struct OpinionArgs {
+  RbView v;
+  const float *hidden_in;  /* pinned mirrors, read and written by the kernel */
+  const float *inputs_in;
+  float *input_layer_out, *hidden_out, *output_out;
+  int rows_per;            /* rows of Wih per CTA */
+  int hrows_per;           /* rows of Who per CTA */
+};
+
+__global__ void __cluster_dims__(WALK_CTAS, 1, 1) __launch_bounds__(256, 1)
+k_opinion_single(OpinionArgs a)
+{
+  extern __shared__ __align__(16) float osh[];
+  __shared__ float scratch[33];
+  cg::cluster_group cluster = cg::this_cluster();
+  const RbView &v = a.v;
+  const int s = v.slots[0];
+  const int I = v.d.i_size, H = v.d.h_size, O = v.d.o_size, hs1 = v.d.hidden_size + 1;
+  const int rank = (int)cluster.block_rank();
+  float *x = osh;                 /* [I] the ring row */
+  float *P = x + I;               /* [WALK_CTAS][H] partial hidden sums of every CTA */
+  float *h = P + WALK_CTAS * H;   /* [H] */
+  float *PY = h + H;              /* [WALK_CTAS][O] partial outputs (used in rank 0) */
+
+  /* the row [1 | hidden(t-1) | inputs | 0..] and its emergency soft clip */
+  float sum = 0.0f;
+  for (int i = threadIdx.x; i < I; i += blockDim.x) {
+    float val = 0.0f;
+    if (i == 0)
+      val = 1.0f;
+    else if (i < hs1)
+      val = a.hidden_in[i];
+    else if (i < hs1 + v.d.input_size)
+      val = a.inputs_in[i - hs1];
+    x[i] = val;
+    sum += val;
+  }
+  sum = block_sum(sum, scratch);
+  const float softclip = I * INPUT_MEAN_SOFT_TOP;
+  if (sum > softclip) {
+    const float scale = soft_clip_dev(sum, softclip);
+    for (int i = threadIdx.x; i < I; i += blockDim.x)
+      x[i] *= scale;
+  }
+  __syncthreads();
+  if (rank == 0) {
+    float *xr = x_row(v, s, 0);
+    for (int i = threadIdx.x; i < I; i += blockDim.x) {
+      xr[i] = x[i];
+      a.input_layer_out[i] = x[i];
+    }
+  }
+
+  /* partial hidden sums over this CTA's rows of Wih */
+  const int y0 = min(I, rank * a.rows_per), y1 = min(I, y0 + a.rows_per);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float acc = 0.0f;
+    for (int yb = y0; yb < y1; yb += 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int y = yb + u;
+        w[u] = (y < y1 && x[y] != 0.0f) ? __ldg(v.Wih + (size_t)y * H + c) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int y = yb + u;
+        if (y < y1)
+          acc = fmaf(x[y], w[u], acc);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < WALK_CTAS; q++)
+      cluster.map_shared_rank(P, q)[rank * H + c] = acc;
+  }
+  cluster.sync();
+
+  /* every CTA finishes the hidden vector for itself (same order, same bits) */
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < WALK_CTAS; q++)
+      t += P[q * H + c];
+    if (v.activation == RNN_RESQRT) {
+      t = (t > 0.0f) ? sqrtf(t + 1.0f) - 1.0f : 0.0f;
+    }
+    else if (v.activation == RNN_RECLIP20) {
+      if (c >= 1) {
+        t = t < 20.0f ? t : 20.0f;
+        t = (t > 0.0f) ? t : 0.0f;
+      }
+    }
+    else if (c >= 1) {
+      t = (t > 0.0f) ? t : 0.0f;
+    }
+    if (c == 0)
+      t = 1.0f;
+    h[c] = t;
+    if (rank == 0) {
+      v.Hd[(size_t)s * H + c] = t;
+      a.hidden_out[c] = t;
+    }
+  }
+  __syncthreads();
+
+  /* partial outputs over this CTA's rows of Who */
+  const int c0 = min(H, rank * a.hrows_per), c1 = min(H, c0 + a.hrows_per);
+  float *py0 = cluster.map_shared_rank(PY, 0) + (size_t)rank * O;
+  for (int o = threadIdx.x; o < O; o += blockDim.x) {
+    float acc = 0.0f;
+    for (int cb = c0; cb < c1; cb += 8) {
+      float w[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int c = cb + u;
+        w[u] = (c < c1 && h[c] != 0.0f) ? __ldg(v.Who + (size_t)c * O + o) : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        int c = cb + u;
+        if (c < c1)
+          acc = fmaf(h[c], w[u], acc);
+      }
+    }
+    py0[o] = acc;
+  }
+  cluster.sync();
+  if (rank == 0) {
+    for (int o = threadIdx.x; o < O; o += blockDim.x) {
+      float t = 0.0f;
+#pragma unroll
+      for (int q = 0; q < WALK_CTAS; q++)
+        t += PY[(size_t)q * O + o];
+      v.Y[(size_t)s * O + o] = t;
+      a.output_out[o] = t;
+    }
+  }
+}
+
+static size_t
+opinion_smem_bytes(const RbView *v)
+{
+  return ((size_t)v->d.i_size + (size_t)(WALK_CTAS + 1) * v->d.h_size +
+      (size_t)WALK_CTAS * v->d.o_size + 16) * sizeof(float);
+}
+
+extern "C" int
+rbk_opinion_single_usable(const RbView *v)
+{
+  return v->n == 1 && opinion_smem_bytes(v) <= 200 * 1024 &&
+      (size_t)v->d.i_size * v->d.h_size <= 512 * 1024 && !getenv("RECUR_B200_NO_WALK");
+}
+
+extern "C" void
+rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_in,
+    float *input_layer_out, float *hidden_out, float *output_out)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_opinion_single, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    attr_done = 1;
+  }
+  OpinionArgs a;
+  a.v = *v;
+  a.hidden_in = hidden_in;
+  a.inputs_in = inputs_in;
+  a.input_layer_out = input_layer_out;
+  a.hidden_out = hidden_out;
+  a.output_out = output_out;
+  a.rows_per = (v->d.i_size + WALK_CTAS - 1) / WALK_CTAS;
+  a.hrows_per = (v->d.h_size + WALK_CTAS - 1) / WALK_CTAS;
+  rb_prof_begin(RB_PROF_FWD);
+  k_opinion_single<<<WALK_CTAS, 256, opinion_smem_bytes(v), rb_stream>>>(a);
+  LAUNCH_CHECK("k_opinion_single");
+  rb_prof_end(RB_PROF_FWD);
+}
+
 extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {

@@ -61,6 +61,10 @@ int rbk_step_begin_usable(const RbView *v);
 void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
     u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
 void rbk_output(const RbView *v);
+int rbk_walk_single_usable(const RbView *v);
+int rbk_opinion_single_usable(const RbView *v);
+void rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_in,
+    float *input_layer_out, float *hidden_out, float *output_out);
 /* split-K partial sums of a forward GEMM: [splits][rows of `pitch` floats] */
 typedef struct RbFwdPartials {
   const float *part;

@@ -32,3 +32,24 @@ run(0, 100)
 t0 = time.perf_counter(); run(100, 600); t1 = time.perf_counter()
 print("ours per-net API: %.0f chars/s (%.1f us/char), launches/char %.1f" % (500 / (t1 - t0), (t1 - t0) / 500 * 1e6, 0))
 l0 = lib.rnn_b200_kernel_launches(); run(600, 700); print("launches per char", (lib.rnn_b200_kernel_launches() - l0) / 100)
+import collections
+tt = collections.defaultdict(float)
+def run_timed(n0, n1):
+    for i in range(n0, n1):
+        t0 = time.perf_counter()
+        c.bptt.contents.momentum = lib.rnn_calculate_momentum_soft_start(c.generation, 0.95, 2000.0)
+        lib.rnn_bptt_advance(a)
+        inputs = arr(c.real_inputs, c.input_size)
+        inputs[:] = 0
+        inputs[text[i]] = 1.0
+        t1 = time.perf_counter()
+        answer = lib.rnn_opinion(a, None, 0.0)
+        t2 = time.perf_counter()
+        ref.ref_softmax_best_guess(o_err, answer, c.output_size)
+        o_err[text[i + 1]] += 1.0
+        t3 = time.perf_counter()
+        lib.rnn_bptt_calculate(a, 1)
+        t4 = time.perf_counter()
+        tt['prep'] += t1 - t0; tt['opinion'] += t2 - t1; tt['softmax'] += t3 - t2; tt['calculate'] += t4 - t3
+run_timed(700, 1200)
+print({k: round(v / 500 * 1e6, 1) for k, v in tt.items()})
