@@ -833,9 +833,25 @@ rnn_bptt_calculate(RecurNN *net, uint batch_size)
   const RbDims *d = &rn->group->d;
   int s = rn->slot;
   net->hidden_layer[0] = 1.0f;
-  h2d(p->OE + (size_t)s * d->o_size, b->o_error, d->o_size * sizeof(float));
   RbView v;
   rb_view_of_net(rn, &v);
+  RbScalars sc;
+  if (batch_size <= 1 && !net->bottom_layer && rbk_walk_single_usable(&v)) {
+    /* top layer, Who update, the whole walk and the Wih update in one launch;
+       o_error is read from its pinned mirror, the scalars come back the same way */
+    static RbScalars *sc_pinned = NULL;
+    if (!sc_pinned)
+      CUDA_OR_DIE(cudaHostAlloc((void **)&sc_pinned, sizeof(RbScalars), cudaHostAllocDefault));
+    rbk_calculate_single(&v, b->o_error, b->learn_rate, b->min_error_factor,
+        !!(net->flags & RNN_NET_FLAG_BPTT_ADAPTIVE_MIN_ERROR), net->ho_weights, b->ho_momentum,
+        net->ih_weights, b->ih_momentum, b->ih_delta, b->momentum, b->momentum_weight,
+        sc_pinned);
+    rb_weights_changed(net);
+    sync_stream();
+    sc = *sc_pinned;
+    goto finish;
+  }
+  h2d(p->OE + (size_t)s * d->o_size, b->o_error, d->o_size * sizeof(float));
   rbk_set_params_scalar(&v, b->learn_rate, b->min_error_factor,
       !!(net->flags & RNN_NET_FLAG_BPTT_ADAPTIVE_MIN_ERROR));
   /* apply_sgd_top_layer: error back through the old weights, then the
@@ -863,9 +879,9 @@ rnn_bptt_calculate(RecurNN *net, uint batch_size)
         b->momentum_weight, NULL);
   }
   rb_weights_changed(net);
-  RbScalars sc;
   d2h(&sc, p->sc + s, sizeof(sc));
   sync_stream();
+finish:
   b->ih_scale = sc.ih_scale;
   b->min_error_factor = sc.mef;
   log_bptt_block(net, &sc);

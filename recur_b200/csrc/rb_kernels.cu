@@ -31,6 +31,7 @@
 #include "rb_rng.h"
 #include "rb_optim.cuh"
 #include <math.h>
+#include <string.h>
 
 #define RB_WARP 32
 
@@ -1991,11 +1992,26 @@ namespace cg = cooperative_groups;
 
 #define WALK_CTAS 8
 
+/* rnn_bptt_calculate (a14, recur-nn.c:919-1019) folds more into the same
+   launch: the top layer's error (a7, a8) with the immediate update of Who in
+   front of the walk, the update of Wih behind it, o_error read from and the
+   stream's scalars written to pinned host memory. */
+struct WalkFuse {
+  int enabled;
+  const float *o_error_in;  /* pinned mirror */
+  float lr, mef;
+  int adaptive;
+  float *ho_w, *ho_mom, *ih_w, *ih_mom;
+  float momentum, momentum_weight;
+  RbScalars *sc_out;        /* pinned */
+};
+
 struct WalkArgs {
   RbView v;
   float *delta;
   int accumulate;
   int rows_per; /* R */
+  WalkFuse f;
 };
 
 __global__ void __cluster_dims__(WALK_CTAS, 1, 1) __launch_bounds__(256, 1)
@@ -2019,7 +2035,6 @@ k_walk_single(WalkArgs a)
   float *red = xs + 2 * R;           /* [8] per-warp sums */
 
   RbScalars sc = v.sc[s];
-  const bool walk = sc.live != 0 && !(sc.adaptive & 2);
   const int pos = v.pos[s];
   const int depth = v.depth;
 
@@ -2027,14 +2042,110 @@ k_walk_single(WalkArgs a)
     *(float4 *)(W + i) = *(const float4 *)(v.Wih + (size_t)y0 * H + i);
     *(float4 *)(G + i) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  {
+  if (threadIdx.x < nr)
+    xs[threadIdx.x] = x_row(v, s, 0)[y0 + threadIdx.x];
+  if (!a.f.enabled) {
     const float *e0 = e_row(v, s, 0);
     for (int i = threadIdx.x; i < H; i += blockDim.x)
       E[i] = e0[i];
-    if (threadIdx.x < nr)
-      xs[threadIdx.x] = x_row(v, s, 0)[y0 + threadIdx.x];
   }
-  cluster.sync(); /* everybody's shared memory is set up before anyone pushes into it */
+  else {
+    /* a7/a8 as k_top does them (dense error), by every CTA for itself: the
+       same operations in the same order give the same bits everywhere */
+    __shared__ float scratch[33];
+    const int O = v.d.o_size;
+    float *oe = red + 8; /* [O] */
+    for (int i = threadIdx.x; i < O; i += blockDim.x) {
+      float e = a.f.o_error_in[i];
+      oe[i] = e;
+      if (rank == 0)
+        v.OE[(size_t)s * O + i] = e;
+    }
+    __syncthreads();
+    const float *hid = v.Hd + (size_t)s * H;
+    float *e0g = e_row(v, s, 0);
+    float abs_sum = 0.0f, hsum = 0.0f, hmag = 0.0f;
+    int hzero = 0;
+    for (int y = threadIdx.x; y < I; y += blockDim.x) {
+      float e = 0.0f;
+      if (y < H) {
+        float hv = hid[y];
+        hsum += hv;
+        hmag += hv * hv;
+        hzero += (hv == 0.0f);
+        if (y >= 1 && hv != 0.0f) {
+          const float *row = v.Who + (size_t)y * O;
+          for (int x = 0; x < O; x += 4) {
+            float4 w = *(const float4 *)(row + x);
+            e += w.x * oe[x] + w.y * oe[x + 1] + w.z * oe[x + 2] + w.w * oe[x + 3];
+          }
+          abs_sum += fabsf(e);
+        }
+      }
+      if (y > v.d.hidden_size)
+        e = 0.0f;
+      if (y < H)
+        E[y] = e;
+      if (rank == 0)
+        e0g[y] = e;
+    }
+    abs_sum = block_sum(abs_sum, scratch);
+    hsum = block_sum(hsum, scratch);
+    hmag = block_sum(hmag, scratch);
+    float hz = block_sum((float)hzero, scratch);
+    const float halfmax = H * MAX_TOP_ERROR_FACTOR;
+    float top_scaled = abs_sum;
+    if (abs_sum > halfmax) {
+      const float scale = soft_clip_dev(abs_sum, halfmax);
+      for (int y = threadIdx.x; y < H; y += blockDim.x) {
+        E[y] *= scale;
+        if (rank == 0)
+          e0g[y] = E[y];
+      }
+      top_scaled = scale * abs_sum;
+    }
+    sc.lr = a.f.lr;
+    sc.mef = a.f.mef;
+    sc.adaptive = (sc.adaptive & 2) | (a.f.adaptive & 1);
+    sc.top_raw = abs_sum;
+    sc.top_scaled = top_scaled;
+    sc.hidden_sum = hsum;
+    sc.hidden_mag = sqrtf(hmag);
+    sc.hidden_zeros = (int)(hz + 0.5f);
+    sc.min_sum = fminf(sc.mef / sc.lr, MIN_ERROR_GAIN * top_scaled);
+    sc.max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
+    sc.cum_error = 0.0f;
+    sc.err_sum = 0.0f;
+    sc.live = (depth > 0) && !(sc.adaptive & 2);
+    sc.n_steps = 0;
+    sc.t_left = depth;
+    sc.ih_scale = 1.0f;
+  }
+  const bool walk = sc.live != 0 && !(sc.adaptive & 2);
+  cluster.sync(); /* everybody's shared memory is set up before anyone pushes into it
+                     (and, fused: everybody has read Who) */
+  if (a.f.enabled) {
+    /* apply_sgd_top_layer's immediate update of Who (recur-nn.c:941-964);
+       rows of silent hidden units only decay their momentum */
+    const int O = v.d.o_size;
+    const float *oe = red + 8;
+    for (int idx = rank * blockDim.x + threadIdx.x; idx < H * O; idx += WALK_CTAS * blockDim.x) {
+      int y = idx / O, xo = idx - y * O;
+      float hv = (y == 0) ? 1.0f : v.Hd[(size_t)s * H + y];
+      float mm = a.f.ho_mom[idx];
+      float w = a.f.ho_w[idx];
+      if (hv != 0.0f) {
+        float d = oe[xo] * (hv * a.f.lr);
+        w += d + mm * a.f.momentum_weight;
+        mm += d;
+      }
+      else {
+        w += mm * a.f.momentum_weight;
+      }
+      a.f.ho_w[idx] = w;
+      a.f.ho_mom[idx] = mm * a.f.momentum;
+    }
+  }
 
   if (walk) {
     for (int k = 0; k < depth; k++) {
@@ -2139,9 +2250,30 @@ k_walk_single(WalkArgs a)
     o.z = fmaf(scale, gv.z, o.z);
     o.w = fmaf(scale, gv.w, o.w);
     *(float4 *)(a.delta + (size_t)y0 * H + i) = o;
+    if (a.f.enabled) {
+      /* apply_sgd_with_bptt: the weighted-momentum step of a13 on the owned
+         rows, old weights still in shared memory */
+      const size_t gi = (size_t)y0 * H + i;
+      float4 wv = *(const float4 *)(W + i);
+      float4 mv = *(const float4 *)(a.f.ih_mom + gi);
+      float dd[4] = {o.x, o.y, o.z, o.w};
+      float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+      float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        float t = dd[u] * a.f.lr;
+        ww[u] += t + mm[u] * a.f.momentum_weight;
+        mm[u] = (mm[u] + t) * a.f.momentum;
+      }
+      *(float4 *)(a.f.ih_w + gi) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+      *(float4 *)(a.f.ih_mom + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    }
   }
-  if (walk && rank == 0 && threadIdx.x == 0)
+  if ((walk || a.f.enabled) && rank == 0 && threadIdx.x == 0) {
     v.sc[s] = sc;
+    if (a.f.enabled)
+      *a.f.sc_out = sc;
+  }
   /* nobody leaves while a neighbour might still push into its shared memory */
   cluster.sync();
 }
@@ -2151,8 +2283,8 @@ walk_smem_bytes(const RbView *v, int *rows_per)
 {
   int R = (v->d.i_size + WALK_CTAS - 1) / WALK_CTAS;
   *rows_per = R;
-  return ((size_t)2 * R * v->d.h_size + 3 * v->d.h_size + 3 * WALK_CTAS + 2 * R + 8 + 8) *
-      sizeof(float);
+  return ((size_t)2 * R * v->d.h_size + 3 * v->d.h_size + 3 * WALK_CTAS + 2 * R + 8 + 8 +
+      v->d.o_size) * sizeof(float);
 }
 
 extern "C" int
@@ -2172,6 +2304,7 @@ rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
     attr_done = 1;
   }
   WalkArgs a;
+  memset(&a, 0, sizeof(a));
   a.v = *v;
   a.delta = ih_delta;
   a.accumulate = accumulate;
@@ -2179,6 +2312,41 @@ rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
   rb_prof_begin(RB_PROF_CHAIN);
   k_walk_single<<<WALK_CTAS, 256, smem, rb_stream>>>(a);
   LAUNCH_CHECK("k_walk_single");
+  rb_prof_end(RB_PROF_CHAIN);
+}
+
+/* rnn_bptt_calculate with batch size 1 and no bottom layer, in one launch */
+extern "C" void
+rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float mef,
+    int adaptive, float *ho_w, float *ho_mom, float *ih_w, float *ih_mom, float *ih_delta,
+    float momentum, float momentum_weight, RbScalars *sc_host)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_walk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_done = 1;
+  }
+  WalkArgs a;
+  memset(&a, 0, sizeof(a));
+  a.v = *v;
+  a.delta = ih_delta;
+  a.accumulate = 0;
+  a.f.enabled = 1;
+  a.f.o_error_in = o_error_host;
+  a.f.lr = lr;
+  a.f.mef = mef;
+  a.f.adaptive = adaptive;
+  a.f.ho_w = ho_w;
+  a.f.ho_mom = ho_mom;
+  a.f.ih_w = ih_w;
+  a.f.ih_mom = ih_mom;
+  a.f.momentum = momentum;
+  a.f.momentum_weight = momentum_weight;
+  a.f.sc_out = sc_host;
+  size_t smem = walk_smem_bytes(v, &a.rows_per);
+  rb_prof_begin(RB_PROF_CHAIN);
+  k_walk_single<<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+  LAUNCH_CHECK("k_walk_single<calculate>");
   rb_prof_end(RB_PROF_CHAIN);
 }
 

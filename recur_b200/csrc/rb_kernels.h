@@ -63,6 +63,9 @@ void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int s
 void rbk_output(const RbView *v);
 int rbk_walk_single_usable(const RbView *v);
 int rbk_opinion_single_usable(const RbView *v);
+void rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float mef,
+    int adaptive, float *ho_w, float *ho_mom, float *ih_w, float *ih_mom, float *ih_delta,
+    float momentum, float momentum_weight, RbScalars *sc_host);
 void rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_in,
     float *input_layer_out, float *hidden_out, float *output_out);
 /* split-K partial sums of a forward GEMM: [splits][rows of `pitch` floats] */
