@@ -2014,6 +2014,14 @@ struct WalkArgs {
   WalkFuse f;
 };
 
+/* REG: nets of up to 256 x 256 (config 1 is 244 x 200) keep the owned weight
+   rows AND their gradient in registers - a warp owns four rows, a lane every
+   32nd column - so a step reads nothing but the error vector from shared
+   memory; larger nets keep both in shared memory. */
+#define WALK_RW 4 /* rows per warp */
+#define WALK_NC 8 /* columns per lane */
+
+template <bool REG>
 __global__ void __cluster_dims__(WALK_CTAS, 1, 1) __launch_bounds__(256, 1)
 k_walk_single(WalkArgs a)
 {
@@ -2027,23 +2035,49 @@ k_walk_single(WalkArgs a)
   const int y0 = min(I, rank * R), y1 = min(I, y0 + R), nr = y1 - y0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  float *W = wsh;                    /* [R][H] owned weight rows */
-  float *G = W + (size_t)R * H;      /* [R][H] their gradient */
-  float *E = G + (size_t)R * H;      /* [3][H] error vectors, rotating */
+  float *W = wsh;                    /* [R][H] owned weight rows (not REG) */
+  float *G = W + (REG ? 0 : (size_t)R * H); /* [R][H] their gradient (not REG) */
+  float *E = G + (REG ? 0 : (size_t)R * H); /* [3][H] error vectors, rotating */
   float *ES = E + 3 * H;             /* [3][WALK_CTAS] partial sums of squares */
-  float *xs = ES + 3 * WALK_CTAS;    /* [2][R] this CTA's slice of the ring row */
-  float *red = xs + 2 * R;           /* [8] per-warp sums */
+  float *xs = ES + 3 * WALK_CTAS;    /* [depth][R] this CTA's slice of every ring row of the walk */
+  float *red = xs + (size_t)v.depth * R; /* [32] sums of squares per (warp, row), then [o_size]
+                                            output errors */
+  float *eh = red + 32 + v.d.o_size;      /* [depth][R] the owned entries of E(1..depth): written
+                                            to the pool after the walk, so that no global store
+                                            (and the barrier's wait for it) sits inside a step */
 
   RbScalars sc = v.sc[s];
   const int pos = v.pos[s];
   const int depth = v.depth;
 
-  for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
-    *(float4 *)(W + i) = *(const float4 *)(v.Wih + (size_t)y0 * H + i);
-    *(float4 *)(G + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  float Wr[WALK_RW][WALK_NC], Gr[WALK_RW][WALK_NC];
+  if (REG) {
+#pragma unroll
+    for (int u = 0; u < WALK_RW; u++) {
+      const int r = warp + 8 * u;
+#pragma unroll
+      for (int i = 0; i < WALK_NC; i++) {
+        const int c = lane + 32 * i;
+        Wr[u][i] = (r < nr && c < H) ? v.Wih[(size_t)(y0 + r) * H + c] : 0.0f;
+        Gr[u][i] = 0.0f;
+      }
+    }
   }
-  if (threadIdx.x < nr)
-    xs[threadIdx.x] = x_row(v, s, 0)[y0 + threadIdx.x];
+  else {
+    for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
+      *(float4 *)(W + i) = *(const float4 *)(v.Wih + (size_t)y0 * H + i);
+      *(float4 *)(G + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  /* the walk's inputs do not depend on the walk: fetch them all now, one
+     round trip instead of one per step */
+  for (int idx = threadIdx.x; idx < depth * nr; idx += blockDim.x) {
+    int step = idx / nr, r = idx - step * nr;
+    int p = pos - step;
+    if (p < 0)
+      p += depth;
+    xs[step * R + r] = v.X[((size_t)p * v.cap + s) * I + y0 + r];
+  }
   if (!a.f.enabled) {
     const float *e0 = e_row(v, s, 0);
     for (int i = threadIdx.x; i < H; i += blockDim.x)
@@ -2054,7 +2088,7 @@ k_walk_single(WalkArgs a)
        same operations in the same order give the same bits everywhere */
     __shared__ float scratch[33];
     const int O = v.d.o_size;
-    float *oe = red + 8; /* [O] */
+    float *oe = red + 32; /* [O] */
     for (int i = threadIdx.x; i < O; i += blockDim.x) {
       float e = a.f.o_error_in[i];
       oe[i] = e;
@@ -2128,7 +2162,7 @@ k_walk_single(WalkArgs a)
     /* apply_sgd_top_layer's immediate update of Who (recur-nn.c:941-964);
        rows of silent hidden units only decay their momentum */
     const int O = v.d.o_size;
-    const float *oe = red + 8;
+    const float *oe = red + 32;
     for (int idx = rank * blockDim.x + threadIdx.x; idx < H * O; idx += WALK_CTAS * blockDim.x) {
       int y = idx / O, xo = idx - y * O;
       float hv = (y == 0) ? 1.0f : v.Hd[(size_t)s * H + y];
@@ -2151,58 +2185,108 @@ k_walk_single(WalkArgs a)
     for (int k = 0; k < depth; k++) {
       const float *cur = E + (k % 3) * H;
       const int nb = (k + 1) % 3;
-      const float *x_now = xs + (k & 1) * R;
-      /* the next step's slice of the ring travels while this step computes */
-      float x_next = 0.0f;
-      if (k + 1 < depth && threadIdx.x < nr) {
-        int p = pos - (k + 1);
-        if (p < 0)
-          p += depth;
-        x_next = v.X[((size_t)p * v.cap + s) * I + y0 + threadIdx.x];
-      }
-      float *e_next_row = e_row(v, s, k + 1);
-      float sq = 0.0f;
-      for (int r = warp; r < nr; r += 8) {
-        const int y = y0 + r;
-        const float x = x_now[r];
-        float e = 0.0f;
-        if (x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f)) {
-          const float *w = W + (size_t)r * H;
-          float *g = G + (size_t)r * H;
-          float dot = 0.0f;
-          for (int c = lane; c < H; c += 32) {
-            float ec = cur[c];
-            dot = fmaf(w[c], ec, dot);
-            g[c] = fmaf(x, ec, g[c]);
+      const float *x_now = xs + k * R;
+      float *e_hist = eh + (size_t)k * R;
+      float sq4 = 0.0f; /* squares of the row this lane group finishes */
+      /* four rows per warp at a time, so that their shared-memory reads and
+         shuffle reductions overlap */
+      for (int rb = warp; rb < nr; rb += 32) {
+        float xv[4], dot[4];
+        bool act[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          int r = rb + 8 * u;
+          xv[u] = (r < nr) ? x_now[r] : 0.0f;
+          act[u] = xv[u] != 0.0f && (v.activation != RNN_RECLIP20 || xv[u] < 20.0f);
+          dot[u] = 0.0f;
+        }
+        if (REG) {
+          /* rb == warp here (R <= 32): the rows are the ones in registers;
+             silent rows ride along with a zero multiplier */
+          float xa[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            xa[u] = act[u] ? xv[u] : 0.0f;
+          float ec[WALK_NC]; /* all reads of the error vector first, then the arithmetic */
+#pragma unroll
+          for (int i = 0; i < WALK_NC; i++) {
+            const int c = lane + 32 * i;
+            ec[i] = (c < H) ? cur[c] : 0.0f;
           }
-          dot = warp_sum(dot);
-          if (v.activation == RNN_RESQRT)
-            dot /= 2.0f * (x + 1.0f);
-          e = dot;
+#pragma unroll
+          for (int i = 0; i < WALK_NC; i++) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              dot[u] = fmaf(Wr[u][i], ec[i], dot[u]);
+              Gr[u][i] = fmaf(xa[u], ec[i], Gr[u][i]);
+            }
+          }
         }
-        if (lane == 0) {
-          sq = fmaf(e, e, sq);
-          if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
-            v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+        else {
+          for (int c = lane; c < H; c += 32) {
+            const float ec = cur[c];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (act[u]) { /* uniform over the warp */
+                const size_t o = (size_t)(rb + 8 * u) * H + c;
+                dot[u] = fmaf(W[o], ec, dot[u]);
+                G[o] = fmaf(xv[u], ec, G[o]);
+              }
+            }
+          }
         }
-        const float e_store = (y == 0 || (y >= hs1 && y < H)) ? 0.0f : e;
-        if (lane == 0)
-          e_next_row[y] = e_store;
-        if (lane < WALK_CTAS && y < H)
-          cluster.map_shared_rank(E, lane)[nb * H + y] = e_store;
+        /* four sums in six shuffles: after the first two exchanges the
+           eight lanes of group g = lane / 8 hold the partial sums of row g only */
+        float mine;
+        {
+          const bool hi = lane & 16;
+          float k0 = hi ? dot[2] : dot[0], k1 = hi ? dot[3] : dot[1];
+          float s0 = hi ? dot[0] : dot[2], s1 = hi ? dot[1] : dot[3];
+          k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+          k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+          const bool mid = lane & 8;
+          mine = mid ? k1 : k0;
+          const float send = mid ? k0 : k1;
+          mine += __shfl_xor_sync(0xffffffffu, send, 8);
+          mine += __shfl_xor_sync(0xffffffffu, mine, 4);
+          mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+          mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+        }
+        /* the four rows finish side by side: lane = 8 * row + target CTA */
+        {
+          const int g = lane >> 3, q = lane & 7;
+          const int r = rb + 8 * g, y = y0 + r;
+          float e = 0.0f;
+          if (r < nr) {
+            const float x = x_now[r];
+            if (x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f)) {
+              e = mine;
+              if (v.activation == RNN_RESQRT)
+                e /= 2.0f * (x + 1.0f);
+            }
+          }
+          const float e_store = (y == 0 || (y >= hs1 && y < H)) ? 0.0f : e;
+          if (q == 0 && r < nr) {
+            sq4 = fmaf(e, e, sq4);
+            e_hist[r] = e_store;
+            if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
+              v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+          }
+          /* ONE store instruction pushes the four new entries into all eight CTAs */
+          if (r < nr && y < H)
+            cluster.map_shared_rank(E, q)[nb * H + y] = e_store;
+        }
       }
-      if (lane == 0)
-        red[warp] = sq;
+      if ((lane & 7) == 0)
+        red[warp * 4 + (lane >> 3)] = sq4;
       __syncthreads();
       if (threadIdx.x < WALK_CTAS) {
         float t = 0.0f;
 #pragma unroll
-        for (int q = 0; q < 8; q++)
+        for (int q = 0; q < 32; q++)
           t += red[q];
         cluster.map_shared_rank(ES, threadIdx.x)[nb * WALK_CTAS + rank] = t;
       }
-      if (threadIdx.x < nr)
-        xs[((k + 1) & 1) * R + threadIdx.x] = x_next;
       cluster.sync();
       float es = 0.0f;
 #pragma unroll
@@ -2239,34 +2323,65 @@ k_walk_single(WalkArgs a)
     }
   }
   __syncthreads();
+  /* the error rows of the executed steps, for whoever looks at the pool later
+     (mirrors, the stale-row rule of sparse top layers) */
+  for (int idx = threadIdx.x; idx < sc.n_steps * nr && walk; idx += blockDim.x) {
+    int step = idx / nr, r = idx - step * nr;
+    e_row(v, s, step + 1)[y0 + r] = eh[(size_t)step * R + r];
+  }
   /* a11: ih_delta (+)= ih_scale * G on the owned rows */
   const float scale = walk ? sc.ih_scale : 0.0f;
-  for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
-    float4 gv = *(const float4 *)(G + i);
-    float4 o = a.accumulate ? *(const float4 *)(a.delta + (size_t)y0 * H + i)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-    o.x = fmaf(scale, gv.x, o.x);
-    o.y = fmaf(scale, gv.y, o.y);
-    o.z = fmaf(scale, gv.z, o.z);
-    o.w = fmaf(scale, gv.w, o.w);
-    *(float4 *)(a.delta + (size_t)y0 * H + i) = o;
-    if (a.f.enabled) {
-      /* apply_sgd_with_bptt: the weighted-momentum step of a13 on the owned
-         rows, old weights still in shared memory */
-      const size_t gi = (size_t)y0 * H + i;
-      float4 wv = *(const float4 *)(W + i);
-      float4 mv = *(const float4 *)(a.f.ih_mom + gi);
-      float dd[4] = {o.x, o.y, o.z, o.w};
-      float ww[4] = {wv.x, wv.y, wv.z, wv.w};
-      float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+  if (REG) {
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        float t = dd[u] * a.f.lr;
-        ww[u] += t + mm[u] * a.f.momentum_weight;
-        mm[u] = (mm[u] + t) * a.f.momentum;
+    for (int u = 0; u < WALK_RW; u++) {
+      const int r = warp + 8 * u;
+#pragma unroll
+      for (int i = 0; i < WALK_NC; i++) {
+        const int c = lane + 32 * i;
+        if (r < nr && c < H) {
+          const size_t gi = (size_t)(y0 + r) * H + c;
+          float d = fmaf(scale, Gr[u][i], a.accumulate ? a.delta[gi] : 0.0f);
+          a.delta[gi] = d;
+          if (a.f.enabled) {
+            /* apply_sgd_with_bptt: the weighted-momentum step of a13, old
+               weight still in its register */
+            float t = d * a.f.lr;
+            float m = a.f.ih_mom[gi];
+            a.f.ih_w[gi] = Wr[u][i] + (t + m * a.f.momentum_weight);
+            a.f.ih_mom[gi] = (m + t) * a.f.momentum;
+          }
+        }
       }
-      *(float4 *)(a.f.ih_w + gi) = make_float4(ww[0], ww[1], ww[2], ww[3]);
-      *(float4 *)(a.f.ih_mom + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    }
+  }
+  else {
+    for (int i = threadIdx.x * 4; i < nr * H; i += blockDim.x * 4) {
+      float4 gv = *(const float4 *)(G + i);
+      float4 o = a.accumulate ? *(const float4 *)(a.delta + (size_t)y0 * H + i)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      o.x = fmaf(scale, gv.x, o.x);
+      o.y = fmaf(scale, gv.y, o.y);
+      o.z = fmaf(scale, gv.z, o.z);
+      o.w = fmaf(scale, gv.w, o.w);
+      *(float4 *)(a.delta + (size_t)y0 * H + i) = o;
+      if (a.f.enabled) {
+        /* apply_sgd_with_bptt: the weighted-momentum step of a13 on the owned
+           rows, old weights still in shared memory */
+        const size_t gi = (size_t)y0 * H + i;
+        float4 wv = *(const float4 *)(W + i);
+        float4 mv = *(const float4 *)(a.f.ih_mom + gi);
+        float dd[4] = {o.x, o.y, o.z, o.w};
+        float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+        float mm[4] = {mv.x, mv.y, mv.z, mv.w};
+  #pragma unroll
+        for (int u = 0; u < 4; u++) {
+          float t = dd[u] * a.f.lr;
+          ww[u] += t + mm[u] * a.f.momentum_weight;
+          mm[u] = (mm[u] + t) * a.f.momentum;
+        }
+        *(float4 *)(a.f.ih_w + gi) = make_float4(ww[0], ww[1], ww[2], ww[3]);
+        *(float4 *)(a.f.ih_mom + gi) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+      }
     }
   }
   if ((walk || a.f.enabled) && rank == 0 && threadIdx.x == 0) {
@@ -2278,12 +2393,39 @@ k_walk_single(WalkArgs a)
   cluster.sync();
 }
 
+static int
+walk_in_registers(const RbView *v)
+{
+  return (v->d.i_size + WALK_CTAS - 1) / WALK_CTAS <= 8 * WALK_RW && v->d.h_size <= 32 * WALK_NC;
+}
+
+static void
+walk_launch(const WalkArgs &a, const RbView *v, size_t smem, const char *what)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_walk_single<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    cudaFuncSetAttribute(k_walk_single<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    attr_done = 1;
+  }
+  rb_prof_begin(RB_PROF_CHAIN);
+  if (walk_in_registers(v))
+    k_walk_single<true><<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+  else
+    k_walk_single<false><<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+  LAUNCH_CHECK(what);
+  rb_prof_end(RB_PROF_CHAIN);
+}
+
 static size_t
 walk_smem_bytes(const RbView *v, int *rows_per)
 {
   int R = (v->d.i_size + WALK_CTAS - 1) / WALK_CTAS;
   *rows_per = R;
-  return ((size_t)2 * R * v->d.h_size + 3 * v->d.h_size + 3 * WALK_CTAS + 2 * R + 8 + 8 +
+  size_t matrices = walk_in_registers(v) ? 0 : (size_t)2 * R * v->d.h_size;
+  return (matrices + 3 * v->d.h_size + 3 * WALK_CTAS + (size_t)2 * v->depth * R + 32 + 8 +
       v->d.o_size) * sizeof(float);
 }
 
@@ -2298,21 +2440,13 @@ rbk_walk_single_usable(const RbView *v)
 extern "C" void
 rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
 {
-  static int attr_done = 0;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_walk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = 1;
-  }
   WalkArgs a;
   memset(&a, 0, sizeof(a));
   a.v = *v;
   a.delta = ih_delta;
   a.accumulate = accumulate;
   size_t smem = walk_smem_bytes(v, &a.rows_per);
-  rb_prof_begin(RB_PROF_CHAIN);
-  k_walk_single<<<WALK_CTAS, 256, smem, rb_stream>>>(a);
-  LAUNCH_CHECK("k_walk_single");
-  rb_prof_end(RB_PROF_CHAIN);
+  walk_launch(a, v, smem, "k_walk_single");
 }
 
 /* rnn_bptt_calculate with batch size 1 and no bottom layer, in one launch */
@@ -2321,11 +2455,6 @@ rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float
     int adaptive, float *ho_w, float *ho_mom, float *ih_w, float *ih_mom, float *ih_delta,
     float momentum, float momentum_weight, RbScalars *sc_host)
 {
-  static int attr_done = 0;
-  if (!attr_done) {
-    cudaFuncSetAttribute(k_walk_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_done = 1;
-  }
   WalkArgs a;
   memset(&a, 0, sizeof(a));
   a.v = *v;
@@ -2344,10 +2473,7 @@ rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float
   a.f.momentum_weight = momentum_weight;
   a.f.sc_out = sc_host;
   size_t smem = walk_smem_bytes(v, &a.rows_per);
-  rb_prof_begin(RB_PROF_CHAIN);
-  k_walk_single<<<WALK_CTAS, 256, smem, rb_stream>>>(a);
-  LAUNCH_CHECK("k_walk_single<calculate>");
-  rb_prof_end(RB_PROF_CHAIN);
+  walk_launch(a, v, smem, "k_walk_single<calculate>");
 }
 
 /* ------------------------------------------------------------------------ */

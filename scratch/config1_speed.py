@@ -53,3 +53,11 @@ def run_timed(n0, n1):
         tt['prep'] += t1 - t0; tt['opinion'] += t2 - t1; tt['softmax'] += t3 - t2; tt['calculate'] += t4 - t3
 run_timed(700, 1200)
 print({k: round(v / 500 * 1e6, 1) for k, v in tt.items()})
+lib.rnn_b200_profile_enable(1)
+run(1200, 1700)
+pms = (C.c_double * 8)(); pln = (C.c_uint64 * 8)()
+ncls = lib.rnn_b200_profile_read(pms, pln, 8)
+lib.rnn_b200_profile_enable(0)
+for cidx in range(ncls):
+    if pln[cidx]:
+        print(lib.rnn_b200_profile_class_name(cidx).decode(), "%.1f us x %d" % (pms[cidx] / pln[cidx] * 1e3, pln[cidx]))
