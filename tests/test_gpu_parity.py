@@ -432,3 +432,52 @@ def test_text_forward_only_matches_live_reference(gpu_lib, ref, n):
     lib.rnn_batch_delete(batch)
     lib.rnn_delete_training_set(gn, n, 0)
     ref.rnn_delete_training_set(rn, n, 0)
+
+
+@pytest.mark.parametrize("hidden", [63, 299])
+def test_single_stream_kernels_both_variants(gpu_lib, ref, hidden):
+    """The single-stream cluster kernels (one launch per rnn_opinion, one per
+    rnn_bptt_calculate / walk): nets up to 256 x 256 keep their rows in
+    registers (hidden 63), larger ones in shared memory (hidden 299)."""
+    lib = gpu_lib
+    text = markov_text(400, 42, seed=8)
+    shape = dict(input_size=42, hidden=hidden, output=42, depth=12, seed=3, lr=1e-3)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    b = make_net(lib, **shape)
+    steps = 9
+    ref.ref_single_net_train(r, u8ptr(text), len(text), 0, steps, 0.95, 2000.0, 1, None, None, None)
+    # the fused path: rnn_bptt_calculate
+    for i in range(steps):
+        c = a.contents
+        c.bptt.contents.momentum = lib.rnn_calculate_momentum_soft_start(c.generation, 0.95, 2000.0)
+        lib.rnn_bptt_advance(a)
+        inputs = arr(c.real_inputs, c.input_size)
+        inputs[:] = 0
+        inputs[text[i]] = 1.0
+        answer = lib.rnn_opinion(a, None, 0.0)
+        ref.ref_softmax_best_guess(c.bptt.contents.o_error, answer, c.output_size)
+        arr(c.bptt.contents.o_error, c.o_size)[text[i + 1]] += 1.0
+        lib.rnn_bptt_calculate(a, 1)
+    for x, y in zip(weights(a), weights(r)):
+        assert rel_err(x, y) < TOL
+    H = r.contents.h_size
+    assert rel_err(arr(a.contents.hidden_layer, H), arr(r.contents.hidden_layer, H)) < TOL
+    assert abs(a.contents.bptt.contents.min_error_factor -
+               r.contents.bptt.contents.min_error_factor) <= TOL * r.contents.bptt.contents.min_error_factor
+    # the plain walk: rnn_bptt_calc_deltas + rnn_apply_learning on a second pair
+    r2 = make_net(ref, **shape)
+    for net, L in ((b, lib), (r2, ref)):
+        for i in range(steps):
+            c = net.contents
+            L.rnn_bptt_advance(net)
+            inputs = arr(c.real_inputs, c.input_size)
+            inputs[:] = 0
+            inputs[text[i]] = 1.0
+            answer = L.rnn_opinion(net, None, 0.0)
+            ref.ref_softmax_best_guess(c.bptt.contents.o_error, answer, c.output_size)
+            arr(c.bptt.contents.o_error, c.o_size)[text[i + 1]] += 1.0
+            L.rnn_bptt_calc_deltas(net, 0, None)
+            L.rnn_apply_learning(net, 0, 0.9)
+    for x, y in zip(weights(b), weights(r2)):
+        assert rel_err(x, y) < TOL
