@@ -2011,6 +2011,7 @@ struct WalkArgs {
   float *delta;
   int accumulate;
   int rows_per; /* R */
+  size_t plane_stride; /* floats between the output planes of two streams (0: one stream) */
   WalkFuse f;
 };
 
@@ -2028,7 +2029,11 @@ k_walk_single(WalkArgs a)
   extern __shared__ __align__(16) float wsh[];
   cg::cluster_group cluster = cg::this_cluster();
   const RbView &v = a.v;
-  const int s = v.slots[0];
+  /* one cluster per stream; with several streams each writes its scaled
+     gradient to its own plane and k_sum_stream_planes adds them in stream order */
+  const int stream = blockIdx.x / WALK_CTAS;
+  const int s = v.slots[stream];
+  a.delta += (size_t)stream * a.plane_stride;
   const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
   const int R = a.rows_per;
   const int rank = (int)cluster.block_rank();
@@ -2411,10 +2416,11 @@ walk_launch(const WalkArgs &a, const RbView *v, size_t smem, const char *what)
     attr_done = 1;
   }
   rb_prof_begin(RB_PROF_CHAIN);
+  const int n_streams = a.plane_stride ? v->n : 1;
   if (walk_in_registers(v))
-    k_walk_single<true><<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+    k_walk_single<true><<<WALK_CTAS * n_streams, 256, smem, rb_stream>>>(a);
   else
-    k_walk_single<false><<<WALK_CTAS, 256, smem, rb_stream>>>(a);
+    k_walk_single<false><<<WALK_CTAS * n_streams, 256, smem, rb_stream>>>(a);
   LAUNCH_CHECK(what);
   rb_prof_end(RB_PROF_CHAIN);
 }
@@ -2437,6 +2443,37 @@ rbk_walk_single_usable(const RbView *v)
       !getenv("RECUR_B200_NO_WALK");
 }
 
+/* small batches (below the tensor engine's 64 streams): one cluster per stream */
+#define WALK_MAX_STREAMS 64
+
+static int
+walk_streams_usable(const RbView *v)
+{
+  int R;
+  return v->n >= 1 && v->n <= WALK_MAX_STREAMS && (v->d.h_size % 4) == 0 &&
+      walk_smem_bytes(v, &R) <= 200 * 1024 && !getenv("RECUR_B200_NO_WALK");
+}
+
+/* delta (+)= plane_0 + plane_1 + ... in stream order (the order of the
+   reference's fold, recur-nn.c:734-748) */
+__global__ void __launch_bounds__(256)
+k_sum_stream_planes(float *__restrict__ delta, const float *__restrict__ planes, int size,
+    int n, int accumulate)
+{
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < size;
+       i += gridDim.x * blockDim.x * 4) {
+    float4 t = accumulate ? *(const float4 *)(delta + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n; j++) {
+      float4 p = *(const float4 *)(planes + (size_t)j * size + i);
+      t.x += p.x; t.y += p.y; t.z += p.z; t.w += p.w;
+    }
+    *(float4 *)(delta + i) = t;
+  }
+}
+
+static float *walk_planes = NULL;
+static size_t walk_planes_cap = 0;
+
 extern "C" void
 rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
 {
@@ -2446,6 +2483,28 @@ rbk_walk_single(const RbView *v, float *ih_delta, int accumulate)
   a.delta = ih_delta;
   a.accumulate = accumulate;
   size_t smem = walk_smem_bytes(v, &a.rows_per);
+  if (v->n > 1) {
+    size_t size = (size_t)v->d.i_size * v->d.h_size;
+    if (walk_planes_cap < size * v->n) {
+      if (walk_planes) {
+        cudaStreamSynchronize(rb_stream);
+        cudaFree(walk_planes);
+      }
+      walk_planes_cap = size * v->n;
+      if (cudaMalloc((void **)&walk_planes, walk_planes_cap * sizeof(float)) != cudaSuccess)
+        rb_die("recur-b200: out of device memory for %d gradient planes", v->n);
+    }
+    a.delta = walk_planes;
+    a.accumulate = 0;
+    a.plane_stride = size;
+    walk_launch(a, v, smem, "k_walk_single<streams>");
+    rb_prof_begin(RB_PROF_DW);
+    k_sum_stream_planes<<<grid1d((int)(size / 4), 256), 256, 0, rb_stream>>>(ih_delta,
+        walk_planes, (int)size, v->n, accumulate);
+    LAUNCH_CHECK("k_sum_stream_planes");
+    rb_prof_end(RB_PROF_DW);
+    return;
+  }
   walk_launch(a, v, smem, "k_walk_single");
 }
 
@@ -2670,7 +2729,7 @@ rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_
 extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {
-  if (rbk_walk_single_usable(v)) {
+  if (walk_streams_usable(v)) {
     rbk_walk_single(v, ih_delta, accumulate);
     return;
   }
