@@ -1,5 +1,6 @@
 """config 1 (single net, H199, depth 30): chars/s through the per-net drop-in
-API on the GPU vs the compiled reference on one host core."""
+API on the GPU vs the compiled reference on one host core.  Run from the repo
+root on a GPU box: python scripts/config1_speed.py  (numbers: DESIGN.md)."""
 import sys, time, ctypes as C
 sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
 import numpy as np
