@@ -2601,6 +2601,10 @@ k_opinion_single(OpinionArgs a)
     }
   }
 
+  /* every CTA of the cluster is running before anyone writes into a
+     neighbour's shared memory */
+  cluster.sync();
+
   /* partial hidden sums over this CTA's rows of Wih */
   const int y0 = min(I, rank * a.rows_per), y1 = min(I, y0 + a.rows_per);
   for (int c = threadIdx.x; c < H; c += blockDim.x) {
