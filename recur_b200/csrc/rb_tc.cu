@@ -1682,6 +1682,7 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ C
   if (warp == 1)
     tmem_alloc_pair(tmem_slot, DW2_TMEM_COLS);
   tc_fence_before();
+  __syncthreads();    /* the allocation's address is in shared memory for every warp */
   cluster_sync_all(); /* both CTAs' barriers exist before anyone signals them */
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
