@@ -455,6 +455,12 @@ rnn_b200_profile_class_name(int cls)
   return (cls >= 0 && cls < RB_PROF_CLASSES) ? names[cls] : NULL;
 }
 
+extern "C" int
+rb_prof_active(void)
+{
+  return prof_on;
+}
+
 extern "C" void
 rb_prof_begin(int cls)
 {

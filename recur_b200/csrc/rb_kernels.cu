@@ -1882,6 +1882,34 @@ extern "C" void
 rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo)
 {
+  /* a9 reads the hidden rows and the output errors, a7/a8 the same plus Who:
+     neither needs the other, both are too small to fill the GPU.  In a batch
+     the ho_delta kernel runs on a side stream next to the top-layer kernels
+     (not while the per-class profiler is timing them). */
+  static cudaStream_t side = NULL;
+  static cudaEvent_t ev_fork = NULL, ev_join = NULL;
+  size_t slab = ((size_t)v->n * (HO_ROWS + v->d.o_size) + 16 + (size_t)256 * 12) * sizeof(float);
+  const bool slab_ok = ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024 &&
+      v->d.o_size <= 384;
+  bool forked = false;
+  if (slab_ok && v->n >= 4 * OS && !rb_prof_active()) {
+    if (!side) {
+      cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    }
+    if (!ho_slab_attr_done) {
+      cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          200 * 1024);
+      ho_slab_attr_done = 1;
+    }
+    cudaEventRecord(ev_fork, rb_stream);
+    cudaStreamWaitEvent(side, ev_fork, 0);
+    k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, side>>>(*v, ho_delta, accumulate);
+    LAUNCH_CHECK("k_ho_delta_slab");
+    cudaEventRecord(ev_join, side);
+    forked = true;
+  }
   if (n_ranges == 0 && v->n >= 4 * OS && v->pool && v->pool->has_bptt) {
     /* a batch: E(0) = mask * (o_error . Who^T) as a tiled contraction */
     GemmArgs g;
@@ -1907,10 +1935,12 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     LAUNCH_CHECK("k_top");
     rb_prof_end(RB_PROF_TOP);
   }
+  if (forked) {
+    cudaStreamWaitEvent(rb_stream, ev_join, 0);
+    return;
+  }
   /* hidden slab + errors + slack + per-slice partial sums */
-  size_t slab = ((size_t)v->n * (HO_ROWS + v->d.o_size) + 16 +
-      (size_t)256 * 12) * sizeof(float);
-  if (ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024 && v->d.o_size <= 384) {
+  if (slab_ok) {
     if (!ho_slab_attr_done) {
       cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
           200 * 1024);

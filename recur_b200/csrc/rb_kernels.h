@@ -43,6 +43,7 @@ extern "C" {
 extern cudaStream_t rb_stream;
 void rb_view_of_net(RbNet *rn, RbView *v);
 void rb_count_launch(int n);
+int rb_prof_active(void);
 void rb_prof_begin(int cls);
 void rb_prof_end(int cls);
 enum { RB_PROF_FWD = 0, RB_PROF_CHAIN = 1, RB_PROF_DW = 2, RB_PROF_UPDATE = 3,
