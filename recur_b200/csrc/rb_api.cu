@@ -778,6 +778,7 @@ rb_apply_learning_async(RecurNN *net, int method, float momentum)
   /* where the tensor engine holds operand planes of these weights, one kernel
      updates both matrices and rewrites the planes */
   RbPool *pool = rb_net_of(net)->pool;
+  rb_mark_pre_update();
   int fused = rb_tc_fused_update(pool, net, kernel_method, momentum, mw);
   if (!fused) {
     rbk_apply_learning(kernel_method, net->ho_weights, b->ho_delta, b->ho_momentum,

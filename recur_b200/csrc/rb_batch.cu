@@ -495,12 +495,13 @@ fetch_stats(RnnBatch *b, RnnBatchCharStats *stats)
 }
 
 extern "C" void rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos,
-    int spacing, u8 *cur_dev, u8 *next_dev, float noise, int advance);
+    int spacing, u8 *cur_dev, u8 *next_dev, float noise, int advance, int continues);
 
 /* advance .. update for one character position; the symbols come from the
    uploaded text at position `pos` (text != 0) or are already in cur/next */
 static void
-char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text, int pos)
+char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text, int pos,
+    int continues = 0)
 {
   RecurNN *proto = &b->nets[0]->pub;
   advance_host_side(b);
@@ -522,7 +523,8 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
     /* the output kernel may take the softmax error and its sums along */
     rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
     rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
-        from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise, 1);
+        from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise, 1,
+        continues);
   }
   download_rng_if_noisy(b, noise);
   if (!rbk_fused_loss_done())
@@ -573,7 +575,9 @@ rnn_batch_text_train(RnnBatch *b, int start, int steps, int learning_style,
       i = 0;
     float m = rnn_calculate_momentum_soft_start(proto->generation, momentum,
         momentum_soft_start);
-    char_step_device(b, learning_style, m, 1, i);
+    /* from the second position on, the stream holds nothing behind the
+       previous position's update */
+    char_step_device(b, learning_style, m, 1, i, s > 0);
   }
   if (stats)
     fetch_stats(b, stats);
@@ -595,7 +599,8 @@ rnn_batch_text_forward(RnnBatch *b, int start, int steps)
     if (i >= len - 1)
       i = 0;
     /* rnn_opinion without rnn_bptt_advance: the current ring row is rewritten */
-    rb_char_forward_dispatch(&v, b->text_dev, len, i, spacing, b->cur_dev, b->next_dev, 0.0f, 0);
+    rb_char_forward_dispatch(&v, b->text_dev, len, i, spacing, b->cur_dev, b->next_dev, 0.0f, 0,
+        0);
   }
   mark_ahead(b);
   return (i >= len - 1) ? 0 : i;

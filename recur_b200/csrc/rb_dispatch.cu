@@ -9,6 +9,21 @@
 
 extern "C" int rb_engine(void);
 
+static cudaStream_t side_stream = NULL;
+static cudaEvent_t ev_pre_update = NULL, ev_side_done = NULL;
+static int pre_update_valid = 0;
+
+/* called in front of a weight update: the point in the stream up to which a
+   following step's input rows depend on earlier work */
+extern "C" void
+rb_mark_pre_update(void)
+{
+  if (!ev_pre_update)
+    cudaEventCreateWithFlags(&ev_pre_update, cudaEventDisableTiming);
+  cudaEventRecord(ev_pre_update, rb_stream);
+  pre_update_valid = 1;
+}
+
 extern "C" void
 rb_weights_changed(RecurNN *net)
 {
@@ -50,7 +65,7 @@ rb_forward_dispatch(const RbView *v, float noise)
 /* fused start of a text step + forward (rb_batch.cu's character steps) */
 extern "C" void
 rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float noise, int advance)
+    u8 *cur_dev, u8 *next_dev, float noise, int advance, int continues)
 {
   int tensor = use_tensor_engine(v);
   if (!rbk_step_begin_usable(v)) {
@@ -65,7 +80,25 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
   float *Xhi = NULL, *Xlo = NULL;
   if (tensor)
     rb_tc_x_planes(v->pool, &Xhi, &Xlo);
-  rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo, advance);
+  if (text_dev && advance && continues && pre_update_valid && !rb_prof_active()) {
+    /* The next position's input rows need the last forward pass and the text,
+       not the weights: with the text resident the kernel runs on a side stream
+       next to the update of the step before (everything queued up to the point
+       marked in front of that update is waited for).  `continues`: the caller
+       vouches that nothing but that update was queued since. */
+    if (!side_stream) {
+      cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming);
+    }
+    cudaStreamWaitEvent(side_stream, ev_pre_update, 0);
+    rbk_step_begin_on(side_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo,
+        advance);
+    cudaEventRecord(ev_side_done, side_stream);
+    cudaStreamWaitEvent(rb_stream, ev_side_done, 0);
+  }
+  else
+    rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo, advance);
+  pre_update_valid = 0;
   if (tensor)
     rb_tc_forward_core(v->pool, v, noise);
   else

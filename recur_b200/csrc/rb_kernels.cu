@@ -1681,6 +1681,14 @@ extern "C" void
 rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
     u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance)
 {
+  rbk_step_begin_on(rb_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo,
+      advance);
+}
+
+extern "C" void
+rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev, int len, int pos,
+    int spacing, u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance)
+{
   StepBeginArgs a;
   a.advance = advance;
   a.v = *v;
@@ -1693,7 +1701,7 @@ rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacin
   a.Xhi = Xhi;
   a.Xlo = Xlo;
   rb_prof_begin(RB_PROF_SMALL);
-  k_step_begin<<<v->n, 256, 0, rb_stream>>>(a);
+  k_step_begin<<<v->n, 256, 0, stream>>>(a);
   LAUNCH_CHECK("k_step_begin");
   rb_prof_end(RB_PROF_SMALL);
 }

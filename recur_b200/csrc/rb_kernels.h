@@ -61,6 +61,9 @@ void rbk_forward_core(const RbView *v, float presynaptic_noise);
 int rbk_step_begin_usable(const RbView *v);
 void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
     u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
+void rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev, int len, int pos,
+    int spacing, u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
+void rb_mark_pre_update(void);
 void rbk_output(const RbView *v);
 int rbk_walk_single_usable(const RbView *v);
 int rbk_opinion_single_usable(const RbView *v);

@@ -15,10 +15,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 
   --log-file $out/launches_${tag}.csv \
   python bench.py --steps 100 --warmup 30 --no-cpu-baseline > $out/ncu_launches_${tag}.log 2>&1
 
-# 2. one --set full capture per hot kernel, 300 steps in
+# 2. one --set full capture per hot kernel, 120 training steps in (ncu slows every
+#    intercepted launch, deeper captures cost minutes of box time each)
 for k in k_tc_chain_persistent k_tc_dw_pair k_tc_nt k_update_split k_out_multi; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 300 -c 1 \
-    -f -o $out/${k}_${tag} python bench.py --steps 300 --warmup 30 --no-cpu-baseline \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 120 -c 1 \
+    -f -o $out/${k}_${tag} python bench.py --steps 140 --warmup 30 --no-cpu-baseline \
     > $out/ncu_${k}_${tag}.log 2>&1
 done
 
