@@ -43,6 +43,8 @@ struct RnnBatch {
   int *i_host;           /* n */
   float *lr_host;        /* n, last uploaded learn rates */
   RbCharAccum *accum_host;
+  int accum_reset;      /* the next accumulation starts from zero (sums were fetched) */
+  int snapshot_valid;   /* accum_host holds the sums as of the last queued step */
   void *p2p;             /* fused gradient exchange (multi-GPU), or NULL */
   int masked;            /* the last calc_deltas left skip bits on the device */
 };
@@ -484,10 +486,19 @@ rnn_batch_apply_learning(RnnBatch *b, int learning_style, float momentum)
 static void
 fetch_stats(RnnBatch *b, RnnBatchCharStats *stats)
 {
-  CUDA_OR_DIE(cudaMemcpyAsync(b->accum_host, b->accum_dev, sizeof(RbCharAccum),
-          cudaMemcpyDeviceToHost, rb_stream));
-  CUDA_OR_DIE(cudaMemsetAsync(b->accum_dev, 0, sizeof(RbCharAccum), rb_stream));
-  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  if (b->snapshot_valid) {
+    /* the output kernel left the sums in pinned memory: nothing to copy, and
+       the reset rides with the next step's kernel */
+    CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+    b->snapshot_valid = 0;
+    b->accum_reset = 1;
+  }
+  else {
+    CUDA_OR_DIE(cudaMemcpyAsync(b->accum_host, b->accum_dev, sizeof(RbCharAccum),
+            cudaMemcpyDeviceToHost, rb_stream));
+    CUDA_OR_DIE(cudaMemsetAsync(b->accum_dev, 0, sizeof(RbCharAccum), rb_stream));
+    CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  }
   stats->error += b->accum_host->error;
   stats->entropy += b->accum_host->entropy;
   stats->correct += b->accum_host->correct;
@@ -521,14 +532,25 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
   }
   else {
     /* the output kernel may take the softmax error and its sums along */
-    rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
+    rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev, b->accum_host,
+        b->accum_reset);
     rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
         from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise, 1,
         continues);
   }
   download_rng_if_noisy(b, noise);
-  if (!rbk_fused_loss_done())
+  if (rbk_fused_loss_done()) {
+    b->snapshot_valid = 1;
+    b->accum_reset = 0;
+  }
+  else {
+    if (b->accum_reset) {
+      CUDA_OR_DIE(cudaMemsetAsync(b->accum_dev, 0, sizeof(RbCharAccum), rb_stream));
+      b->accum_reset = 0;
+    }
+    b->snapshot_valid = 0;
     rbk_softmax_error(&v, b->next_dev, b->err_dev, b->winner_dev, b->accum_dev);
+  }
   /* the update follows at once: the weight gradient may stay in its split-K
      planes until then (single GPU; an exchange needs the finished sum) */
   rb_tc_defer_delta_reduce(rb_comm_size() <= 1);
@@ -544,8 +566,12 @@ rnn_batch_char_step(RnnBatch *b, const u8 *cur, const u8 *next, int learning_sty
   CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
   memcpy(b->sym_host, cur, b->n);
   memcpy(b->sym_host + b->n, next, b->n);
+  /* (letting the first kernel read the symbols from the pinned buffer itself
+     was measured slower than these two small copies: 512 blocks each waiting
+     on a PCIe read) */
   CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
-  CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice, rb_stream));
+  CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice,
+          rb_stream));
   char_step_device(b, learning_style, momentum, 0, 0);
   if (stats)
     fetch_stats(b, stats);

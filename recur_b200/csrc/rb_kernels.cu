@@ -706,7 +706,7 @@ k_softmax_error(RbView v, const u8 *target, float *err_out, int *winner_out)
 /* sums of charmodel-predict.c:301-303 over the batch, in a fixed order */
 __device__ __forceinline__ void
 char_accum_block(const float *err, const int *winner, const u8 *target, int n,
-    RbCharAccum *acc)
+    RbCharAccum *acc, RbCharAccum *snapshot = NULL, int reset = 0)
 {
   __shared__ double s_err[256], s_ent[256];
   __shared__ int s_cor[256];
@@ -732,10 +732,16 @@ char_accum_block(const float *err, const int *winner, const u8 *target, int n,
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    acc->error += s_err[0];
-    acc->entropy += s_ent[0];
-    acc->correct += s_cor[0];
-    acc->count += n;
+    RbCharAccum t = *acc;
+    if (reset) /* the host has taken the sums so far */
+      t.error = t.entropy = 0.0, t.correct = t.count = 0;
+    t.error += s_err[0];
+    t.entropy += s_ent[0];
+    t.correct += s_cor[0];
+    t.count += n;
+    *acc = t;
+    if (snapshot) /* pinned host memory: the caller reads it after its next synchronise */
+      *snapshot = t;
   }
 }
 
@@ -1032,6 +1038,8 @@ struct RbLossArgs {
   float *err;
   int *winner;
   RbCharAccum *accum;
+  RbCharAccum *snapshot; /* pinned host copy of the sums, or NULL */
+  int reset;             /* start the sums from zero */
 };
 
 __device__ unsigned int rb_loss_ticket;
@@ -1161,7 +1169,7 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
     if (s_last) {
       __threadfence();
       char_accum_block((const float *)loss.err, (const int *)loss.winner, loss.target, v.n,
-          loss.accum);
+          loss.accum, loss.snapshot, loss.reset);
       if (threadIdx.x == 0)
         rb_loss_ticket = 0u;
     }
@@ -1759,8 +1767,10 @@ static struct {
 
 extern "C" void
 rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
-    RbCharAccum *accum_dev)
+    RbCharAccum *accum_dev, RbCharAccum *snapshot_host, int reset)
 {
+  loss_request.args.snapshot = snapshot_host;
+  loss_request.args.reset = reset;
   loss_request.args.target = target_dev;
   loss_request.args.err = err_dev;
   loss_request.args.winner = winner_dev;
@@ -1780,7 +1790,7 @@ rbk_fused_loss_done(void)
 extern "C" void
 rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
 {
-  RbLossArgs loss = {NULL, NULL, NULL, NULL};
+  RbLossArgs loss = {NULL, NULL, NULL, NULL, NULL, 0};
   if (loss_request.armed && v->contiguous) {
     loss = loss_request.args;
     loss_request.done = 1;
@@ -1797,7 +1807,7 @@ rbk_output(const RbView *v)
 {
   if (out_multi_usable(v)) {
     RbFwdPartials none = {NULL, 0, 0, 0, 0};
-    RbLossArgs no_loss = {NULL, NULL, NULL, NULL};
+    RbLossArgs no_loss = {NULL, NULL, NULL, NULL, NULL, 0};
     out_multi_attr();
     rb_prof_begin(RB_PROF_OUT);
     k_out_multi<false><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, none, no_loss);

@@ -83,7 +83,7 @@ typedef struct RbFwdPartials {
 int rbk_output_takes_partials(const RbView *v, int splits);
 void rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp);
 void rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
-    RbCharAccum *accum_dev);
+    RbCharAccum *accum_dev, RbCharAccum *snapshot_host, int reset);
 int rbk_fused_loss_done(void);
 void rbk_chain_decide(const RbView *v, int k);
 void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
