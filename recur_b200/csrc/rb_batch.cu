@@ -135,8 +135,10 @@ rnn_batch_new(RecurNN **nets, int n_nets)
   if ((size_t)d->o_size > widest) widest = d->o_size;
   if ((size_t)d->hidden_size + 1 > widest) widest = d->hidden_size + 1;
   b->io_floats = n * widest;
-  CUDA_OR_DIE(cudaMalloc((void **)&b->cur_dev, n));
-  CUDA_OR_DIE(cudaMalloc((void **)&b->next_dev, n));
+  /* one allocation, [current symbols | next symbols], so that a step's symbols
+     arrive in one copy */
+  CUDA_OR_DIE(cudaMalloc((void **)&b->cur_dev, 2 * (size_t)n));
+  b->next_dev = b->cur_dev + n;
   CUDA_OR_DIE(cudaMalloc((void **)&b->err_dev, n * sizeof(float)));
   CUDA_OR_DIE(cudaMalloc((void **)&b->winner_dev, n * sizeof(int)));
   CUDA_OR_DIE(cudaMalloc((void **)&b->accum_dev, sizeof(RbCharAccum)));
@@ -176,7 +178,6 @@ rnn_batch_delete(RnnBatch *b)
   CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
   cudaFree(b->slots_dev);
   cudaFree(b->cur_dev);
-  cudaFree(b->next_dev);
   cudaFree(b->err_dev);
   cudaFree(b->winner_dev);
   cudaFree(b->accum_dev);
@@ -569,8 +570,7 @@ rnn_batch_char_step(RnnBatch *b, const u8 *cur, const u8 *next, int learning_sty
   /* (letting the first kernel read the symbols from the pinned buffer itself
      was measured slower than these two small copies: 512 blocks each waiting
      on a PCIe read) */
-  CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, b->n, cudaMemcpyHostToDevice, rb_stream));
-  CUDA_OR_DIE(cudaMemcpyAsync(b->next_dev, b->sym_host + b->n, b->n, cudaMemcpyHostToDevice,
+  CUDA_OR_DIE(cudaMemcpyAsync(b->cur_dev, b->sym_host, 2 * (size_t)b->n, cudaMemcpyHostToDevice,
           rb_stream));
   char_step_device(b, learning_style, momentum, 0, 0);
   if (stats)
