@@ -1,0 +1,32 @@
+"""config 5 at the reference's own size: 144 x 96 = 13,824 forward-only cells
+(gstrnnca.h:13-51), one clone per cell sharing the trainers' weights; frames/s
+of set_inputs -> opinion -> get_outputs through the batch API."""
+import sys, time, ctypes as C
+sys.path.insert(0, 'tests'); sys.path.insert(0, '.')
+import numpy as np
+from recur_b200 import api, abi
+from helpers import make_net, fptr
+lib = api.load_library()
+W, Hh = 144, 96
+n = W * Hh
+a = make_net(lib, input_size=35, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
+fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+t0 = time.perf_counter()
+cells = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+t1 = time.perf_counter()
+batch = lib.rnn_batch_new((abi.RecurNN_p * n)(*cells), n)
+t2 = time.perf_counter()
+print("%d clones in %.2f s, batch in %.2f s" % (n, t1 - t0, t2 - t1))
+rs = np.random.RandomState(5)
+inputs = rs.random_sample((n, 35)).astype(np.float32)
+outs = np.zeros((n, 3), dtype=np.float32)
+for f in range(5):
+    lib.rnn_batch_set_inputs(batch, fptr(inputs)); lib.rnn_batch_opinion(batch, 0.0); lib.rnn_batch_get_outputs(batch, fptr(outs))
+frames = 200
+t0 = time.perf_counter()
+for f in range(frames):
+    lib.rnn_batch_set_inputs(batch, fptr(inputs))
+    lib.rnn_batch_opinion(batch, 0.0)
+    lib.rnn_batch_get_outputs(batch, fptr(outs))
+t1 = time.perf_counter()
+print("%.0f frames/s (%.1f us per frame of %d cells, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, n, frames * n / (t1 - t0) / 1e6))
