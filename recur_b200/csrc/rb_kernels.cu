@@ -594,14 +594,24 @@ k_out(RbView v)
   const int G = 256 / CW;
   const int col = threadIdx.x % CW, grp = threadIdx.x / CW;
   float *y = v.Y + (size_t)s * O;
-  for (int c0 = 0; c0 < O; c0 += CW) {
+  /* wide output layers (config 4: 3650 outputs) spread their 256-column
+     chunks over blockIdx.y */
+  for (int c0 = blockIdx.y * CW; c0 < O; c0 += gridDim.y * CW) {
     int c = c0 + col;
     float acc = 0.0f;
     if (grp < G && c < O) {
-      for (int r = grp; r < H; r += G) {
-        float h = hid[r];
-        if (h != 0.0f)
-          acc += h * v.Who[(size_t)r * O + c];
+      /* eight rows' loads in flight together; silent rows load nothing */
+      for (int rb = grp; rb < H; rb += 8 * G) {
+        float w[8], hv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int r = rb + u * G;
+          hv[u] = (r < H) ? hid[r] : 0.0f;
+          w[u] = (hv[u] != 0.0f) ? __ldg(v.Who + (size_t)r * O + c) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          acc = fmaf(hv[u], w[u], acc);
       }
     }
     if (G > 1) {
@@ -1816,8 +1826,11 @@ rbk_output(const RbView *v)
     return;
   }
   size_t sh = (size_t)(v->d.h_size + 256 + 8) * sizeof(float);
+  int col_chunks = (v->d.o_size > 256) ? cdiv(v->d.o_size, 256) : 1;
+  if (col_chunks > 64)
+    col_chunks = 64;
   rb_prof_begin(RB_PROF_OUT);
-  k_out<<<v->n, 256, sh, rb_stream>>>(*v);
+  k_out<<<dim3(v->n, col_chunks), 256, sh, rb_stream>>>(*v);
   LAUNCH_CHECK("k_out");
   rb_prof_end(RB_PROF_OUT);
 }
