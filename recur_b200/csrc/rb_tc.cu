@@ -1195,9 +1195,14 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
        ahead of the barrier the partial sums have to wait for. */
     constexpr int GRP = 5; /* 5 x 256 columns: this warp's half of a row at H1023 in one
                               round of loads */
-    constexpr int CSTEP = 256;
-    const int slot = warp >> 1, half = warp & 1;
-    const int gw = grp_cta * (TC_CHAIN_THREADS / 64) + slot;
+    /* wide rows (H1023: 1068 columns) take a pair of warps each; rows that one
+       warp covers in a single round of loads (small nets: few CTAs per group,
+       several rows per slot) take one warp each, twice as many at a time */
+    const int wpr = (I <= 128 * GRP) ? 1 : 2;
+    const int CSTEP = 128 * wpr;
+    const int slot = warp / wpr, half = warp % wpr;
+    const int slots_per_cta = (TC_CHAIN_THREADS / 32) / wpr;
+    const int gw = grp_cta * slots_per_cta + slot;
     RbScalars sc_pre;
     float4 x_pre[GRP];
     sc_pre.live = 0;
@@ -1317,7 +1322,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
        (all eight warps take part; each warp of a pair takes every other
        128-column chunk) ---- */
     {
-      for (int r = gw; r < TC_BM; r += grp_ctas * (TC_CHAIN_THREADS / 64)) {
+      for (int r = gw; r < TC_BM; r += grp_ctas * slots_per_cta) {
         const int m = m0 + r;
         if (m >= v.n)
           break;
@@ -1395,12 +1400,14 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0)
-          pair_sq[warp] = sq;
-        named_bar_sync(1 + slot, 64);
+        if (wpr == 2) {
+          if (lane == 0)
+            pair_sq[warp] = sq;
+          named_bar_sync(1 + slot, 64);
+        }
         if (warp == 2 && lane == 0) ROLE_STAMP(13);
         if (half == 0 && lane == 0) {
-          float es = pair_sq[warp] + pair_sq[warp + 1];
+          float es = (wpr == 2) ? pair_sq[warp] + pair_sq[warp + 1] : sq;
           sc.err_sum = es;
           sc.cum_error += sqrtf(es);
           sc.n_steps = k + 1;
@@ -1435,7 +1442,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
           }
           *scp = sc;
         }
-        named_bar_sync(1 + slot, 64); /* pair_sq may be rewritten */
+        if (wpr == 2)
+          named_bar_sync(1 + slot, 64); /* pair_sq may be rewritten */
       }
       if (warp == 2 && lane == 0) ROLE_STAMP(14);
       /* E(k+1) planes were written through the generic proxy; the next step's
