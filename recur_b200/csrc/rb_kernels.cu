@@ -2791,6 +2791,270 @@ rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_
   rb_prof_end(RB_PROF_FWD);
 }
 
+/* ------------------------------------------------------------------------ */
+/* a10 for a batch of SMALL nets: the whole of Wih resident in one SM's shared
+ * memory (up to ~50 k weights: H199 nets are 46 k), one CTA per stream, no
+ * synchronisation between CTAs at all.
+ *
+ * For such nets a BPTT step of the whole batch is a few MFLOP: the persistent
+ * tensor kernel spends its 8-11 us per step on barriers and phases, not on
+ * MMAs, and only a handful of its CTAs have work.  Streams are independent
+ * given the weights, so here each CTA walks its stream alone at the speed of
+ * shared memory: per step a warp takes four rows at a time, skips the rows
+ * whose x_k is zero (recur-nn.c:347), reduces the four dot products in six
+ * shuffles, and the block sums the squares for the stop rule
+ * (recur-nn.c:383-413).  E(k+1) goes to the pool (and, for the tensor
+ * engine's weight-gradient kernel, as hi/lo planes); the gradient itself is
+ * left to that kernel.                                                      */
+
+struct ResidentArgs {
+  RbView v;
+  float *Ehi, *Elo; /* optional planes of the error chain */
+};
+
+#define RES_THREADS 512
+#define RES_WARPS (RES_THREADS / 32)
+
+__global__ void __launch_bounds__(RES_THREADS, 1)
+k_walk_resident(ResidentArgs a)
+{
+  extern __shared__ __align__(16) float rsh[];
+  const RbView &v = a.v;
+  const int s = slot_of(v, blockIdx.x);
+  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *W = rsh;                      /* [I][H] */
+  float *E = W + (size_t)I * H;        /* [2][H] */
+  float *xs = E + 2 * H;               /* [2][I] ring rows, this step's and the next */
+  float *red = xs + 2 * I;             /* [4 * RES_WARPS] */
+  int *rows = (int *)(red + 4 * RES_WARPS); /* [I] indices of the rows with a nonzero x_k */
+  int *cnt = rows + I;                 /* [32 + 1] active rows per 32-row segment */
+
+  RbScalars sc = v.sc[s];
+  if (!sc.live || (sc.adaptive & 2))
+    return; /* uniform over the block */
+  const int pos = v.pos[s];
+  const int depth = v.depth;
+  for (int i = threadIdx.x * 4; i < I * H; i += RES_THREADS * 4)
+    *(float4 *)(W + i) = __ldg((const float4 *)(v.Wih + i));
+  {
+    const float *e0 = e_row(v, s, 0);
+    for (int i = threadIdx.x; i < H; i += RES_THREADS)
+      E[i] = e0[i];
+    const float *x0 = x_row(v, s, 0);
+    for (int i = threadIdx.x; i < I; i += RES_THREADS)
+      xs[i] = x0[i];
+  }
+  __syncthreads();
+  const int n_seg = (I + 31) >> 5; /* <= 32 */
+
+  for (int k = 0; k < depth; k++) {
+    const float *cur = E + (k & 1) * H;
+    float *nxt = E + ((k + 1) & 1) * H;
+    const float *x_now = xs + (k & 1) * I;
+    /* the next step's ring row travels while this one computes */
+    float x_next[2] = {0.f, 0.f};
+    if (k + 1 < depth) {
+      int p = pos - (k + 1);
+      if (p < 0)
+        p += depth;
+      const float *xr = v.X + ((size_t)p * v.cap + s) * I;
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        int i = threadIdx.x + u * RES_THREADS;
+        if (i < I)
+          x_next[u] = xr[i];
+      }
+    }
+    float *e_next_row = e_row(v, s, k + 1);
+    const size_t plane_off = ((size_t)(k + 1) * v.cap + s) * I;
+
+    /* the rows that were multiplied by zero have no error and cost nothing
+       (recur-nn.c:347): list the others, 32-row segments by ballot */
+    unsigned int seg_mask[2] = {0u, 0u};
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int seg = warp + u * RES_WARPS;
+      if (seg < n_seg) {
+        const int y = seg * 32 + lane;
+        const float x = (y < I) ? x_now[y] : 0.0f;
+        const bool act = x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f);
+        seg_mask[u] = __ballot_sync(0xffffffffu, act);
+        if (lane == 0)
+          cnt[seg] = __popc(seg_mask[u]);
+        if (!act && y < I) {
+          e_next_row[y] = 0.0f;
+          if (y < H)
+            nxt[y] = 0.0f;
+          if (a.Ehi) {
+            a.Ehi[plane_off + y] = 0.0f;
+            a.Elo[plane_off + y] = 0.0f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    int n_act = 0;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int seg = warp + u * RES_WARPS;
+      if (seg < n_seg) {
+        int off = 0;
+        for (int q = 0; q < seg; q++)
+          off += cnt[q];
+        if (seg_mask[u] & (1u << lane))
+          rows[off + __popc(seg_mask[u] & ((1u << lane) - 1u))] = seg * 32 + lane;
+      }
+    }
+    for (int q = 0; q < n_seg; q++)
+      n_act += cnt[q];
+    __syncthreads();
+
+    float sq4 = 0.0f;
+    for (int ib = warp * 4; ib < n_act; ib += RES_WARPS * 4) {
+      int yr[4];
+      float dot[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        yr[u] = (ib + u < n_act) ? rows[ib + u] : -1;
+        dot[u] = 0.0f;
+      }
+      for (int c = lane; c < H; c += 32) {
+        const float ec = cur[c];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+          if (yr[u] >= 0) /* uniform over the warp */
+            dot[u] = fmaf(W[(size_t)yr[u] * H + c], ec, dot[u]);
+      }
+      float mine;
+      {
+        const bool hi = lane & 16;
+        float k0 = hi ? dot[2] : dot[0], k1 = hi ? dot[3] : dot[1];
+        float s0 = hi ? dot[0] : dot[2], s1 = hi ? dot[1] : dot[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        const bool mid = lane & 8;
+        mine = mid ? k1 : k0;
+        const float send = mid ? k0 : k1;
+        mine += __shfl_xor_sync(0xffffffffu, send, 8);
+        mine += __shfl_xor_sync(0xffffffffu, mine, 4);
+        mine += __shfl_xor_sync(0xffffffffu, mine, 2);
+        mine += __shfl_xor_sync(0xffffffffu, mine, 1);
+      }
+      /* lanes 8g .. 8g+7 hold row g's sum; the first of them finishes the row */
+      if ((lane & 7) == 0) {
+        const int g = lane >> 3;
+        const int y = (g == 0) ? yr[0] : (g == 1) ? yr[1] : (g == 2) ? yr[2] : yr[3];
+        if (y >= 0) {
+          float e = mine;
+          if (v.activation == RNN_RESQRT)
+            e /= 2.0f * (x_now[y] + 1.0f);
+          sq4 = fmaf(e, e, sq4);
+          if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
+            v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+          const float e_store = (y == 0 || (y >= hs1 && y < H)) ? 0.0f : e;
+          e_next_row[y] = e_store;
+          if (y < H)
+            nxt[y] = e_store;
+          if (a.Ehi) {
+            uint32_t hb, lb;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e_store));
+            float hiv = __uint_as_float(hb);
+            float rem = e_store - hiv;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+            a.Ehi[plane_off + y] = hiv;
+            a.Elo[plane_off + y] = __uint_as_float(lb);
+          }
+        }
+      }
+    }
+    {
+      /* the warp's four row groups first (fixed order), then one value per warp */
+      float w = ((lane & 7) == 0) ? sq4 : 0.0f;
+      w += __shfl_xor_sync(0xffffffffu, w, 8);
+      w += __shfl_xor_sync(0xffffffffu, w, 16);
+      if (lane == 0)
+        red[warp] = w;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      int i = threadIdx.x + u * RES_THREADS;
+      if (i < I)
+        xs[((k + 1) & 1) * I + i] = x_next[u];
+    }
+    __syncthreads();
+    float es = 0.0f;
+#pragma unroll
+    for (int q = 0; q < RES_WARPS; q++)
+      es += red[q];
+    __syncthreads(); /* red, rows and cnt are rewritten next step */
+    /* recur-nn.c:383-413, the same in every thread */
+    sc.err_sum = es;
+    sc.cum_error += sqrtf(es);
+    sc.n_steps = k + 1;
+    const int t_loop = depth - k;
+    const bool stop = (es <= sc.min_sum || es > sc.max_sum);
+    const bool last = (k == depth - 1);
+    if (stop || last) {
+      sc.live = 0;
+      const int t_left = stop ? t_loop : 0;
+      sc.t_left = t_left;
+      const float ceiling = ERROR_GAIN_CEILING * sc.top_scaled;
+      if (es > ceiling) {
+        sc.ih_scale = soft_clip_dev(es, sc.max_sum);
+      }
+      else {
+        sc.ih_scale = 1.0f;
+        if (sc.adaptive & 1) {
+          int depth_error = depth / 4 - t_left;
+          float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
+          float mef = sc.mef;
+          if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc.min_sum || depth_error < 0))
+            mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
+          sc.mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+        }
+      }
+      break;
+    }
+  }
+  if (threadIdx.x == 0)
+    v.sc[s] = sc;
+}
+
+static size_t
+resident_smem_bytes(const RbView *v)
+{
+  return ((size_t)v->d.i_size * v->d.h_size + 2 * v->d.h_size + 2 * v->d.i_size +
+      4 * RES_WARPS + v->d.i_size + 40) * sizeof(float);
+}
+
+extern "C" int
+rbk_walk_resident_usable(const RbView *v)
+{
+  return (v->d.h_size % 4) == 0 && v->d.i_size <= 1024 &&
+      resident_smem_bytes(v) <= 224 * 1024 && !getenv("RECUR_B200_NO_RESIDENT");
+}
+
+/* the walk of every stream of the batch; E(1..) to the pool (and planes) */
+extern "C" void
+rbk_walk_resident(const RbView *v, float *Ehi, float *Elo)
+{
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_walk_resident, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        224 * 1024);
+    attr_done = 1;
+  }
+  ResidentArgs a;
+  a.v = *v;
+  a.Ehi = Ehi;
+  a.Elo = Elo;
+  rb_prof_begin(RB_PROF_CHAIN);
+  k_walk_resident<<<v->n, RES_THREADS, resident_smem_bytes(v), rb_stream>>>(a);
+  LAUNCH_CHECK("k_walk_resident");
+  rb_prof_end(RB_PROF_CHAIN);
+}
+
 extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {

@@ -66,6 +66,8 @@ void rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev,
 void rb_mark_pre_update(void);
 void rbk_output(const RbView *v);
 int rbk_walk_single_usable(const RbView *v);
+int rbk_walk_resident_usable(const RbView *v);
+void rbk_walk_resident(const RbView *v, float *Ehi, float *Elo);
 int rbk_opinion_single_usable(const RbView *v);
 void rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float mef,
     int adaptive, float *ho_w, float *ho_mom, float *ih_w, float *ih_mom, float *ih_delta,

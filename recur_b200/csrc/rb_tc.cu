@@ -2050,6 +2050,10 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
   t->persistent_ok = (coop && per_sm_single * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
+  /* small nets: every stream walks alone with the weights resident in its SM */
+  const bool resident = rbk_walk_resident_usable(v);
+  if (resident)
+    t->persistent_ok = 0;
   unsigned int *sync_area = t->sync + (size_t)t->sync_flip * t->sync_words;
   unsigned int *sync_next = t->sync + (size_t)(t->sync_flip ^ 1) * t->sync_words;
   t->sync_flip ^= 1;
@@ -2118,6 +2122,9 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
             (double)(h[323] - b0) * 1e-3);
       }
     }
+  }
+  else if (resident) {
+    rbk_walk_resident(v, t->Ehi, t->Elo);
   }
   else
   for (int k = 0; k < v->depth; k++) {
