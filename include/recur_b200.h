@@ -173,6 +173,18 @@ int rnn_batch_text_train(RnnBatch *batch, int start, int steps,
    stream over the uploaded text, no training. */
 int rnn_batch_text_forward(RnnBatch *batch, int start, int steps);
 
+/* One frame of gstrnnca's cellular automaton (reference gstrnnca.c:805-830, fill_frame, with
+   fill_net_inputs :670-691 and get_offset_point :644-667): `cells` holds one forward-only net
+   per pixel, row-major, width * height of them.  frame_in / frame_out are three planes (Y, Cb,
+   Cr) of width * height bytes in host memory.  Every cell reads len_y luma and len_c chroma
+   neighbours of frame_in at the (dx, dy) pairs in offsets_y / offsets_c (clamped when `edges`,
+   else wrapped once), scaled by 1/255, then x/width, y/height (and with len_pos 3 the radial
+   term), runs rnn_opinion, and its three outputs go through fast_sigmoid and UNIT_TO_BYTE into
+   frame_out.  Nothing but the two frames crosses PCIe. */
+void rnn_batch_rnnca_frame(RnnBatch *cells, const unsigned char *frame_in,
+    unsigned char *frame_out, int width, int height, const int *offsets_y, int len_y,
+    const int *offsets_c, int len_c, int len_pos, int edges);
+
 /* Number of BPTT steps each stream executed in the most recent
    rnn_batch_calc_deltas / training step (the value the reference logs as
    "depth", plus one when the walk stopped early; recur-nn.c:387,416): n

@@ -131,6 +131,12 @@ def load_port():
     lib.oracle_apply_learning.argtypes = [C.c_int, c_float_p, c_float_p, c_float_p,
                                           c_float_p, C.c_int, C.c_float, C.c_float,
                                           C.c_float]
+    lib.oracle_rnnca_fill_inputs.restype = None
+    lib.oracle_rnnca_fill_inputs.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,
+                                             c_int_p, C.c_int, c_int_p, C.c_int, C.c_int,
+                                             C.c_int, c_float_p]
+    lib.oracle_rnnca_unit_to_byte.restype = C.c_uint8
+    lib.oracle_rnnca_unit_to_byte.argtypes = [C.c_float]
     lib.oracle_momentum_soft_start.restype = C.c_float
     lib.oracle_momentum_soft_start.argtypes = [C.c_float, C.c_float, C.c_float]
     lib.oracle_set_new.restype = vp

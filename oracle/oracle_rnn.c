@@ -498,3 +498,66 @@ oracle_set_text_train(OracleSet *s, const uint8_t *text, int len, int start, int
   free(next);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+
+/* ---- f4: gstrnnca's neighbourhood gather ------------------------------------
+ * Restated from reference gstrnnca.c:644-667 (get_offset_point) and :670-691
+ * (fill_net_inputs).  gstrnnca.c itself needs GStreamer and cannot be compiled
+ * here, so for these forty lines parity is UNPINNED by the live reference: the
+ * arithmetic is index clamping / wrapping and a scale by 1/255.  The sigmoid
+ * that follows IS the reference's (oracle/_ref exports badmaths.h's
+ * fast_sigmoid as ref_fast_sigmoid). */
+
+static int
+rnnca_offset_point(const int *offset, int cx, int cy, int w, int h, int edges)
+{
+  int x = cx + offset[0];
+  int y = cy + offset[1];
+  if (edges) {
+    y = y < 0 ? 0 : (y > h - 1 ? h - 1 : y);
+    x = x < 0 ? 0 : (x > w - 1 ? w - 1 : x);
+  }
+  else {
+    if (y < 0)
+      y += h;
+    else if (y >= h)
+      y -= h;
+    if (x < 0)
+      x += w;
+    else if (x >= w)
+      x -= w;
+  }
+  return y * w + x;
+}
+
+void
+oracle_rnnca_fill_inputs(const uint8_t *frame, int w, int h, int cx, int cy,
+    const int *offsets_y, int len_y, const int *offsets_c, int len_c, int len_pos, int edges,
+    float *inputs)
+{
+  const uint8_t *Y = frame, *Cb = frame + w * h, *Cr = frame + 2 * w * h;
+  int i = 0;
+  for (int j = 0; j < len_y; j++) {
+    int off = rnnca_offset_point(offsets_y + j * 2, cx, cy, w, h, edges);
+    inputs[i++] = Y[off] * (1.0f / 255.0f);
+  }
+  for (int j = 0; j < len_c; j++) {
+    int off = rnnca_offset_point(offsets_c + j * 2, cx, cy, w, h, edges);
+    inputs[i] = Cb[off] * (1.0f / 255.0f);
+    inputs[i + 1] = Cr[off] * (1.0f / 255.0f);
+    i += 2;
+  }
+  float xx = cx * 1.0f / w;
+  float yy = cy * 1.0f / h;
+  inputs[i] = xx;
+  inputs[i + 1] = yy;
+  if (len_pos == 3)
+    inputs[i + 2] = 0.5 - ((yy - 0.5) * (yy - 0.5) + (xx - 0.5) * (xx - 0.5));
+}
+
+/* UNIT_TO_BYTE, gstrnnca.c:642 */
+uint8_t
+oracle_rnnca_unit_to_byte(float x)
+{
+  return (uint8_t)(x * 255.9f);
+}

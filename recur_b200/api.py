@@ -31,7 +31,7 @@ B200_API_SYMBOLS = [
     "rnn_batch_set_errors", "rnn_batch_calc_deltas", "rnn_batch_calc_deltas_masked",
     "rnn_batch_apply_learning",
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
-    "rnn_batch_text_forward", "rnn_batch_pull", "rnn_batch_bptt_depths",
+    "rnn_batch_text_forward", "rnn_batch_rnnca_frame", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
     "rnn_b200_comm_size", "rnn_batch_p2p_export", "rnn_batch_p2p_attach",
 ]
@@ -104,6 +104,10 @@ def _declare_b200(lib):
                                          C.POINTER(RnnBatchCharStats)]
     lib.rnn_batch_text_forward.restype = C.c_int
     lib.rnn_batch_text_forward.argtypes = [vp, C.c_int, C.c_int]
+    lib.rnn_batch_rnnca_frame.restype = None
+    lib.rnn_batch_rnnca_frame.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int,
+                                          C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                          C.c_int, C.c_int, C.c_int]
     lib.rnn_batch_bptt_depths.restype = None
     lib.rnn_batch_bptt_depths.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.rnn_batch_pull.restype = None

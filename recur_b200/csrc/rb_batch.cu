@@ -43,6 +43,8 @@ struct RnnBatch {
   int *i_host;           /* n */
   float *lr_host;        /* n, last uploaded learn rates */
   RbCharAccum *accum_host;
+  u8 *rnnca_dev, *rnnca_host; /* rnn_batch_rnnca_frame: offsets, frame in, frame out */
+  size_t rnnca_cap;
   int accum_reset;      /* the next accumulation starts from zero (sums were fetched) */
   int snapshot_valid;   /* accum_host holds the sums as of the last queued step */
   void *p2p;             /* fused gradient exchange (multi-GPU), or NULL */
@@ -191,6 +193,8 @@ rnn_batch_delete(RnnBatch *b)
   cudaFreeHost(b->i_host);
   cudaFreeHost(b->lr_host);
   cudaFreeHost(b->accum_host);
+  cudaFree(b->rnnca_dev);
+  cudaFreeHost(b->rnnca_host);
   free(b->nets);
   free(b);
 }
@@ -265,6 +269,58 @@ rnn_batch_set_inputs(RnnBatch *b, const float *inputs)
     rb_bottom_set_inputs(&v, b->io_dev, width);
   else
     rbk_set_inputs(&v, b->io_dev);
+  mark_ahead(b);
+}
+
+extern "C" void rb_forward_dispatch(const RbView *v, float noise);
+
+/* f4, gstrnnca.c:805-830 (fill_frame): one frame of the cellular automaton.
+   The three planes go to the device once, every cell gathers its inputs
+   there (fill_net_inputs, :670-691), runs forward, and the next frame comes
+   back as bytes.  `cells` is one forward-only net per pixel, row-major. */
+extern "C" void
+rnn_batch_rnnca_frame(RnnBatch *b, const u8 *frame_in, u8 *frame_out, int width, int height,
+    const int *offsets_y, int len_y, const int *offsets_c, int len_c, int len_pos, int edges)
+{
+  const RbDims *d = &b->group->d;
+  if (width * height != b->n || d->input_size != len_y + 2 * len_c + len_pos ||
+      d->output_size < 3 || b->nets[0]->pub.bottom_layer)
+    rb_die("recur-b200: rnn_batch_rnnca_frame: %d cells of %d inputs do not match a %d x %d "
+        "frame with %d + 2*%d + %d inputs", b->n, d->input_size, width, height, len_y, len_c,
+        len_pos);
+  const size_t frame_bytes = 3 * (size_t)b->n;
+  const size_t off_ints = 2 * (size_t)(len_y + len_c);
+  if (b->rnnca_cap < frame_bytes + off_ints * sizeof(int)) {
+    CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+    cudaFree(b->rnnca_dev);
+    cudaFreeHost(b->rnnca_host);
+    b->rnnca_cap = frame_bytes + off_ints * sizeof(int);
+    CUDA_OR_DIE(cudaMalloc((void **)&b->rnnca_dev, 2 * frame_bytes + off_ints * sizeof(int) + 64));
+    CUDA_OR_DIE(cudaHostAlloc((void **)&b->rnnca_host, frame_bytes + off_ints * sizeof(int) + 64,
+            cudaHostAllocDefault));
+  }
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream)); /* staging buffer reuse */
+  /* [offsets | frame] in one copy; the outgoing frame sits behind them */
+  int *off_host = (int *)b->rnnca_host;
+  memcpy(off_host, offsets_y, 2 * (size_t)len_y * sizeof(int));
+  memcpy(off_host + 2 * len_y, offsets_c, 2 * (size_t)len_c * sizeof(int));
+  memcpy(b->rnnca_host + off_ints * sizeof(int), frame_in, frame_bytes);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->rnnca_dev, b->rnnca_host, off_ints * sizeof(int) + frame_bytes,
+          cudaMemcpyHostToDevice, rb_stream));
+  const int *off_dev = (const int *)b->rnnca_dev;
+  const u8 *frame_dev = b->rnnca_dev + off_ints * sizeof(int);
+  u8 *out_dev = b->rnnca_dev + ((off_ints * sizeof(int) + frame_bytes + 15) & ~(size_t)15);
+  RbView v;
+  batch_view(b, &v);
+  rb_matrices_to_device(&b->nets[0]->pub);
+  rbk_rnnca_gather(&v, frame_dev, width, height, off_dev, len_y, off_dev + 2 * len_y, len_c,
+      len_pos, edges);
+  rb_forward_dispatch(&v, 0.0f);
+  rbk_rnnca_emit(&v, out_dev, width, height);
+  CUDA_OR_DIE(cudaMemcpyAsync(b->rnnca_host, out_dev, frame_bytes, cudaMemcpyDeviceToHost,
+          rb_stream));
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  memcpy(frame_out, b->rnnca_host, frame_bytes);
   mark_ahead(b);
 }
 

@@ -3055,6 +3055,130 @@ rbk_walk_resident(const RbView *v, float *Ehi, float *Elo)
   rb_prof_end(RB_PROF_CHAIN);
 }
 
+/* ------------------------------------------------------------------------ */
+/* f4: the feature front end of gstrnnca (gstrnnca.c:644-691, 805-830), so
+   that a frame of the cellular automaton never leaves the device between
+   its planes coming in and going out.
+   k_rnnca_gather: cell (cx, cy) reads len_Y luma and len_C chroma neighbours
+   of the previous frame at the given offsets (clamped at the edges or wrapped
+   once, get_offset_point), scaled to the unit interval, then its position
+   (and optionally the radial term) - straight into the input part of its
+   ring row.  k_rnnca_emit: fast_sigmoid of the three outputs, UNIT_TO_BYTE. */
+
+struct RnncaArgs {
+  RbView v;
+  const u8 *frame;      /* [3][height][width]: Y, Cb, Cr */
+  u8 *frame_out;
+  int width, height;
+  const int *off_y, *off_c; /* (dx, dy) pairs */
+  int len_y, len_c, len_pos, edges;
+};
+
+__device__ __forceinline__ int
+rnnca_offset_point(const int *off, int cx, int cy, int w, int h, int edges)
+{
+  int x = cx + off[0], y = cy + off[1];
+  if (edges) {
+    y = max(0, min(h - 1, y));
+    x = max(0, min(w - 1, x));
+  }
+  else {
+    if (y < 0)
+      y += h;
+    else if (y >= h)
+      y -= h;
+    if (x < 0)
+      x += w;
+    else if (x >= w)
+      x -= w;
+  }
+  return y * w + x;
+}
+
+__global__ void __launch_bounds__(128)
+k_rnnca_gather(RnncaArgs a)
+{
+  const RbView &v = a.v;
+  const int cell = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (cell >= v.n)
+    return;
+  const int s = slot_of(v, cell);
+  const int cx = cell % a.width, cy = cell / a.width;
+  const int plane = a.width * a.height;
+  float *in = x_row(v, s, 0) + v.d.hidden_size + 1;
+  const float unit = 1.0f / 255.0f;
+  for (int j = lane; j < a.len_y; j += 32)
+    in[j] = a.frame[rnnca_offset_point(a.off_y + 2 * j, cx, cy, a.width, a.height, a.edges)] * unit;
+  for (int j = lane; j < a.len_c; j += 32) {
+    int o = rnnca_offset_point(a.off_c + 2 * j, cx, cy, a.width, a.height, a.edges);
+    in[a.len_y + 2 * j] = a.frame[plane + o] * unit;
+    in[a.len_y + 2 * j + 1] = a.frame[2 * plane + o] * unit;
+  }
+  if (lane == 0) {
+    const int i = a.len_y + 2 * a.len_c;
+    const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+    in[i] = xx;
+    in[i + 1] = yy;
+    if (a.len_pos == 3)
+      in[i + 2] = (float)(0.5 - (double)((yy - 0.5f) * (yy - 0.5f) + (xx - 0.5f) * (xx - 0.5f)));
+  }
+}
+
+__global__ void
+k_rnnca_emit(RnncaArgs a)
+{
+  const RbView &v = a.v;
+  const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cell >= v.n)
+    return;
+  const int s = slot_of(v, cell);
+  const int plane = a.width * a.height;
+  const float *y = v.Y + (size_t)s * v.d.o_size;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float sg = 1.0f / (1.0f + fast_expf_dev(-y[i] * 1.0f)); /* badmaths.h:31-44, SIGMOID_SCALE 1 */
+    a.frame_out[i * plane + cell] = (u8)(sg * 255.9f);       /* UNIT_TO_BYTE */
+  }
+}
+
+extern "C" void
+rbk_rnnca_gather(const RbView *v, const u8 *frame_dev, int width, int height,
+    const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos, int edges)
+{
+  RnncaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.v = *v;
+  a.frame = frame_dev;
+  a.width = width;
+  a.height = height;
+  a.off_y = off_y_dev;
+  a.off_c = off_c_dev;
+  a.len_y = len_y;
+  a.len_c = len_c;
+  a.len_pos = len_pos;
+  a.edges = edges;
+  rb_prof_begin(RB_PROF_SMALL);
+  k_rnnca_gather<<<cdiv(v->n, 4), 128, 0, rb_stream>>>(a);
+  LAUNCH_CHECK("k_rnnca_gather");
+  rb_prof_end(RB_PROF_SMALL);
+}
+
+extern "C" void
+rbk_rnnca_emit(const RbView *v, u8 *frame_out_dev, int width, int height)
+{
+  RnncaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.v = *v;
+  a.frame_out = frame_out_dev;
+  a.width = width;
+  a.height = height;
+  rb_prof_begin(RB_PROF_SMALL);
+  k_rnnca_emit<<<cdiv(v->n, 256), 256, 0, rb_stream>>>(a);
+  LAUNCH_CHECK("k_rnnca_emit");
+  rb_prof_end(RB_PROF_SMALL);
+}
+
 extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {

@@ -65,6 +65,9 @@ void rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev,
     int spacing, u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
 void rb_mark_pre_update(void);
 void rbk_output(const RbView *v);
+void rbk_rnnca_gather(const RbView *v, const u8 *frame_dev, int width, int height,
+    const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos, int edges);
+void rbk_rnnca_emit(const RbView *v, u8 *frame_out_dev, int width, int height);
 int rbk_walk_single_usable(const RbView *v);
 int rbk_walk_resident_usable(const RbView *v);
 void rbk_walk_resident(const RbView *v, float *Ehi, float *Elo);

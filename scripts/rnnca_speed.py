@@ -30,3 +30,20 @@ for f in range(frames):
     lib.rnn_batch_get_outputs(batch, fptr(outs))
 t1 = time.perf_counter()
 print("%.0f frames/s (%.1f us per frame of %d cells, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, n, frames * n / (t1 - t0) / 1e6))
+
+# the same frame loop with the gather and the byte conversion on the device
+# (rnn_batch_rnnca_frame): only the two 3-plane frames cross PCIe
+off_y = np.array([(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)
+                  if abs(dx) + abs(dy) <= 2 or (abs(dx), abs(dy)) == (2, 2)][:17], dtype=np.int32)
+off_c = np.array([(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)], dtype=np.int32)
+frame = rs.randint(0, 256, size=3 * n).astype(np.uint8)
+out = np.zeros(3 * n, dtype=np.uint8)
+u8p = C.POINTER(C.c_uint8); ip = C.POINTER(C.c_int)
+def frame_step():
+    lib.rnn_batch_rnnca_frame(batch, frame.ctypes.data_as(u8p), out.ctypes.data_as(u8p), W, Hh,
+                              off_y.ctypes.data_as(ip), 17, off_c.ctypes.data_as(ip), 8, 2, 0)
+for f in range(5): frame_step()
+t0 = time.perf_counter()
+for f in range(frames): frame_step()
+t1 = time.perf_counter()
+print("rnn_batch_rnnca_frame: %.0f frames/s (%.1f us per frame, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, frames * n / (t1 - t0) / 1e6))

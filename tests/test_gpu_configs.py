@@ -326,3 +326,58 @@ def test_training_with_presynaptic_noise_matches_reference(gpu_lib, ref, n):
         ca, cr = an[j].contents, rn[j].contents
         assert (ca.rng.a, ca.rng.d) == (cr.rng.a, cr.rng.d)
     lib.rnn_batch_delete(batch)
+
+
+@pytest.mark.parametrize("edges,len_pos", [(1, 2), (0, 3)])
+def test_f4_rnnca_frame_on_device(gpu_lib, ref, port, edges, len_pos):
+    """SURVEY.md §8 f4, gstrnnca.c:805-830: a whole frame of the cellular
+    automaton through rnn_batch_rnnca_frame (gather, forward, fast_sigmoid,
+    bytes, all on the device) against the CPU: the oracle's restatement of
+    fill_net_inputs (gstrnnca.c cannot be compiled, see oracle_rnn.c), the
+    live reference's rnn_opinion and fast_sigmoid, UNIT_TO_BYTE."""
+    lib = gpu_lib
+    W, Hh = 24, 16
+    n = W * Hh
+    # 17 luma and 8 chroma neighbours like the default pattern (gstrnnca.h:49-51)
+    off_y = np.array([(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)
+                      if abs(dx) + abs(dy) <= 2 or (abs(dx), abs(dy)) == (2, 2)][:17],
+                     dtype=np.int32)
+    off_c = np.array([(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)],
+                     dtype=np.int32)
+    len_y, len_c = len(off_y), len(off_c)
+    n_in = len_y + 2 * len_c + len_pos
+    shape = dict(input_size=n_in, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    ac = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+    rc = [ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+    batch = lib.rnn_batch_new((abi.RecurNN_p * n)(*ac), n)
+    rs = np.random.RandomState(9)
+    frame = rs.randint(0, 256, size=3 * n).astype(np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    ip = C.POINTER(C.c_int)
+    n_off = 0
+    for f in range(3):
+        got = np.zeros(3 * n, dtype=np.uint8)
+        lib.rnn_batch_rnnca_frame(batch, frame.ctypes.data_as(u8p), got.ctypes.data_as(u8p), W, Hh,
+                                  off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                                  len_pos, edges)
+        want = np.zeros(3 * n, dtype=np.uint8)
+        inputs = np.zeros(n_in, dtype=np.float32)
+        for cell in range(n):
+            port.oracle_rnnca_fill_inputs(frame.ctypes.data_as(u8p), W, Hh, cell % W, cell // W,
+                                          off_y.ctypes.data_as(ip), len_y,
+                                          off_c.ctypes.data_as(ip), len_c, len_pos, edges,
+                                          fptr(inputs))
+            out = arr(ref.rnn_opinion(rc[cell], fptr(inputs), 0.0), 3)
+            for i in range(3):
+                want[i * n + cell] = port.oracle_rnnca_unit_to_byte(ref.ref_fast_sigmoid(float(out[i])))
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        # bytes are truncations of sigmoid * 255.9: a last-bit difference in the
+        # float can move a value across an integer boundary, never further
+        assert diff.max() <= 1, (f, diff.max())
+        n_off += int((diff != 0).sum())
+        frame = want  # both sides continue from the reference's frame
+    assert n_off <= 0.01 * 3 * 3 * n, n_off
+    lib.rnn_batch_delete(batch)
