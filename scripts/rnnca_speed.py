@@ -8,6 +8,9 @@ from recur_b200 import api, abi
 from helpers import make_net, fptr
 lib = api.load_library()
 W, Hh = 144, 96
+if len(sys.argv) > 1:   # WxH; a 1920x1080 grid does not work this way: making 2 M host nets with
+    # their pinned mirrors takes longer than 13 minutes (measured), see DESIGN.md
+    W, Hh = (int(x) for x in sys.argv[1].split('x'))
 n = W * Hh
 a = make_net(lib, input_size=35, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
 fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
@@ -22,7 +25,7 @@ inputs = rs.random_sample((n, 35)).astype(np.float32)
 outs = np.zeros((n, 3), dtype=np.float32)
 for f in range(5):
     lib.rnn_batch_set_inputs(batch, fptr(inputs)); lib.rnn_batch_opinion(batch, 0.0); lib.rnn_batch_get_outputs(batch, fptr(outs))
-frames = 200
+frames = 200 if n < 100000 else 20
 t0 = time.perf_counter()
 for f in range(frames):
     lib.rnn_batch_set_inputs(batch, fptr(inputs))
