@@ -168,6 +168,38 @@ rb_free_matrix(float *p)
     free(p);
 }
 
+/* Pinned host mirrors come out of slabs: one cudaHostAlloc per net costs tens
+   of microseconds (and seconds once there are thousands of nets - an rnnca
+   grid has one net per pixel); a slab is pinned once and carved up.  Each
+   block carries its slab in a 64-byte header; a slab is returned to the driver
+   when its last block is freed. */
+#define MIRROR_SLAB_BYTES ((size_t)4 << 20)
+#define MIRROR_HEADER 64
+
+typedef struct RbSlab {
+  char *base;
+  size_t used, cap;
+  long live;
+  struct RbSlab *next, *prev;
+} RbSlab;
+
+static RbSlab *mirror_slabs = NULL; /* the head is the one being carved */
+
+static RbSlab *
+slab_new(size_t cap)
+{
+  RbSlab *sl = (RbSlab *)calloc(1, sizeof(RbSlab));
+  if (!sl)
+    rb_die("recur-b200: out of memory");
+  CUDA_OR_DIE(cudaHostAlloc((void **)&sl->base, cap, cudaHostAllocDefault));
+  sl->cap = cap;
+  sl->next = mirror_slabs;
+  if (mirror_slabs)
+    mirror_slabs->prev = sl;
+  mirror_slabs = sl;
+  return sl;
+}
+
 extern "C" void *
 rb_alloc_mirror(size_t bytes)
 {
@@ -175,7 +207,30 @@ rb_alloc_mirror(size_t bytes)
     bytes = 16;
   void *p = NULL;
   if (rb_have_device()) {
-    CUDA_OR_DIE(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    size_t need = ((bytes + 63) & ~(size_t)63) + MIRROR_HEADER;
+    RbSlab *sl = mirror_slabs;
+    if (need > MIRROR_SLAB_BYTES / 4) {
+      /* big blocks (history rings of deep nets) get a slab of their own,
+         linked behind the head so that carving goes on where it was */
+      RbSlab *head = mirror_slabs;
+      sl = slab_new(need);
+      if (head) { /* move the new slab behind the old head */
+        mirror_slabs = head;
+        sl->next = head->next;
+        if (head->next)
+          head->next->prev = sl;
+        head->next = sl;
+        sl->prev = head;
+        head->prev = NULL;
+      }
+    }
+    else if (!sl || sl->cap - sl->used < need || sl->cap != MIRROR_SLAB_BYTES)
+      sl = slab_new(MIRROR_SLAB_BYTES);
+    char *blk = sl->base + sl->used;
+    sl->used += need;
+    sl->live++;
+    *(RbSlab **)blk = sl;
+    p = blk + MIRROR_HEADER;
     memset(p, 0, bytes);
   }
   else {
@@ -191,10 +246,27 @@ rb_free_mirror(void *p)
 {
   if (!p)
     return;
-  if (rb_have_device())
-    CUDA_OR_DIE(cudaFreeHost(p));
-  else
+  if (!rb_have_device()) {
     free(p);
+    return;
+  }
+  RbSlab *sl = *(RbSlab **)((char *)p - MIRROR_HEADER);
+  if (--sl->live > 0)
+    return;
+  if (sl == mirror_slabs && sl->cap == MIRROR_SLAB_BYTES) {
+    sl->used = 0; /* the slab being carved: start over */
+    return;
+  }
+  if (sl->prev)
+    sl->prev->next = sl->next;
+  else
+    mirror_slabs = sl->next;
+  if (sl->next)
+    sl->next->prev = sl->prev;
+  /* kernels may still be reading or writing the mirrors through the stream */
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  CUDA_OR_DIE(cudaFreeHost(sl->base));
+  free(sl);
 }
 
 static void
