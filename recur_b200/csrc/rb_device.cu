@@ -463,19 +463,25 @@ rb_pool_reserve(RbPool *p, int n_slots)
 extern "C" int
 rb_pool_take_slot(RbPool *p)
 {
-  if (p->n_live == p->cap)
-    rb_pool_reserve(p, p->cap + 1);
+  if (p->n_live == p->cap) {
+    /* one more slot: grow by half, not by one block, or a grid of thousands
+       of clones (one rnnca cell per pixel) copies the pool thousands of times */
+    int want = p->cap + p->cap / 2;
+    rb_pool_reserve(p, want > p->cap + 1 ? want : p->cap + 1);
+  }
   int slot = -1;
-  for (int i = 0; i < p->cap; i++) {
-    if (!p->used[i]) {
+  for (int i = p->free_hint; i < p->cap; i++) {
+    if (!(p->used[i] & 1)) {
       slot = i;
       break;
     }
   }
-  p->used[slot] = 1;
+  p->free_hint = slot + 1;
+  const bool recycled = (p->used[slot] & 2) != 0;
+  p->used[slot] = 3;
   p->n_live++;
   p->pos_shadow[slot] = 0;
-  if (rb_have_device()) {
+  if (rb_have_device() && recycled) {
     /* a recycled slot starts from zeroed state, like a calloc'ed net */
     const RbDims *d = &p->group->d;
     for (int r = 0; r < p->depth; r++)
@@ -496,9 +502,11 @@ rb_pool_take_slot(RbPool *p)
 extern "C" void
 rb_pool_release_slot(RbPool *p, int slot)
 {
-  if (slot >= 0 && slot < p->cap && p->used[slot]) {
-    p->used[slot] = 0;
+  if (slot >= 0 && slot < p->cap && (p->used[slot] & 1)) {
+    p->used[slot] &= ~1;
     p->n_live--;
+    if (slot < p->free_hint)
+      p->free_hint = slot;
   }
 }
 

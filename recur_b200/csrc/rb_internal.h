@@ -56,7 +56,9 @@ typedef struct RbPool {
   int has_bptt;
   int cap;        /* slots allocated */
   int n_live;     /* slots in use */
-  uint8_t *used;  /* host: cap flags */
+  uint8_t *used;  /* host: cap flags; bit 0 in use, bit 1 has been used since the arrays were
+                     (re)allocated zeroed */
+  int free_hint;  /* no free slot below this index */
   int *pos_shadow;/* host copy of pos[] */
   /* device arrays (slot-major) */
   float *X;       /* [depth][cap][i_size]   history ring of input rows */
