@@ -15,6 +15,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+unsigned long long rb_ahead_epoch = 0;
+
 #define CUDA_OR_DIE(call) do {                                          \
     cudaError_t e_ = (call);                                            \
     if (e_ != cudaSuccess)                                              \
@@ -150,6 +152,7 @@ rb_net_pull(RbNet *rn)
   }
   sync_stream();
   rn->dev_ahead = 0;
+  rb_ahead_epoch++; /* batches re-flag their nets on their next call */
 }
 
 /* host -> device */
@@ -178,6 +181,7 @@ rb_net_push(RbNet *rn)
   }
   sync_stream();
   rn->dev_ahead = 0;
+  rb_ahead_epoch++; /* batches re-flag their nets on their next call */
 }
 
 extern "C" void

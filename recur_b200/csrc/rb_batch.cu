@@ -45,6 +45,8 @@ struct RnnBatch {
   RbCharAccum *accum_host;
   u8 *rnnca_dev, *rnnca_host; /* rnn_batch_rnnca_frame: offsets, frame in, frame out */
   size_t rnnca_cap;
+  int all_marked;       /* every net carries dev_ahead (see mark_ahead) ... */
+  unsigned long long marked_epoch; /* ... as of this value of rb_ahead_epoch */
   int accum_reset;      /* the next accumulation starts from zero (sums were fetched) */
   int snapshot_valid;   /* accum_host holds the sums as of the last queued step */
   void *p2p;             /* fused gradient exchange (multi-GPU), or NULL */
@@ -84,8 +86,16 @@ batch_view(RnnBatch *b, RbView *v)
 static void
 mark_ahead(RnnBatch *b)
 {
+  /* one pass per run of batch calls, not one per call: with a net per pixel
+     (rnnca) the loop alone costs tens of milliseconds a frame.  Whoever clears
+     any net's flag bumps rb_ahead_epoch (rb_net_pull / rb_net_push), and the
+     next batch call flags again. */
+  if (b->all_marked && b->marked_epoch == rb_ahead_epoch)
+    return;
   for (int j = 0; j < b->n; j++)
     b->nets[j]->dev_ahead = 1;
+  b->all_marked = 1;
+  b->marked_epoch = rb_ahead_epoch;
 }
 
 extern "C" RnnBatch *
@@ -111,9 +121,10 @@ rnn_batch_new(RecurNN **nets, int n_nets)
     }
   }
   /* a previous batch may have left the structs behind the device */
-  for (int j = 0; j < n_nets; j++)
+  for (int j = 0; j < n_nets; j++) {
     if (b->nets[j]->dev_ahead)
       rb_net_pull(b->nets[j]);
+  }
   b->pool = b->nets[0]->pool;
   b->group = b->nets[0]->group;
   b->base = b->nets[0]->slot;

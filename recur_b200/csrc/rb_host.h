@@ -9,6 +9,8 @@ extern "C" {
 #endif
 
 void rb_net_pull(RbNet *rn);
+/* bumped whenever a net's dev_ahead flag is cleared (pull / push) */
+extern unsigned long long rb_ahead_epoch;
 void rb_net_push(RbNet *rn);
 void rb_apply_learning_async(RecurNN *net, int method, float momentum);
 void rb_weights_changed(RecurNN *net);

@@ -8,8 +8,7 @@ from recur_b200 import api, abi
 from helpers import make_net, fptr
 lib = api.load_library()
 W, Hh = 144, 96
-if len(sys.argv) > 1:   # WxH; a 1920x1080 grid does not work this way: making 2 M host nets with
-    # their pinned mirrors takes longer than 13 minutes (measured), see DESIGN.md
+if len(sys.argv) > 1:   # WxH, e.g. 1920x1080 (about a minute to make 2 M cells)
     W, Hh = (int(x) for x in sys.argv[1].split('x'))
 n = W * Hh
 a = make_net(lib, input_size=35, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
@@ -19,20 +18,21 @@ cells = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
 t1 = time.perf_counter()
 batch = lib.rnn_batch_new((abi.RecurNN_p * n)(*cells), n)
 t2 = time.perf_counter()
-print("%d clones in %.2f s, batch in %.2f s" % (n, t1 - t0, t2 - t1))
+print("%d clones in %.2f s, batch in %.2f s" % (n, t1 - t0, t2 - t1), flush=True)
+big = n > 100000
 rs = np.random.RandomState(5)
 inputs = rs.random_sample((n, 35)).astype(np.float32)
 outs = np.zeros((n, 3), dtype=np.float32)
-for f in range(5):
+frames = 200 if not big else 10
+for f in range(5 if not big else 1):
     lib.rnn_batch_set_inputs(batch, fptr(inputs)); lib.rnn_batch_opinion(batch, 0.0); lib.rnn_batch_get_outputs(batch, fptr(outs))
-frames = 200 if n < 100000 else 20
 t0 = time.perf_counter()
 for f in range(frames):
     lib.rnn_batch_set_inputs(batch, fptr(inputs))
     lib.rnn_batch_opinion(batch, 0.0)
     lib.rnn_batch_get_outputs(batch, fptr(outs))
 t1 = time.perf_counter()
-print("%.0f frames/s (%.1f us per frame of %d cells, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, n, frames * n / (t1 - t0) / 1e6))
+print("%.1f frames/s (%.1f us per frame of %d cells, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, n, frames * n / (t1 - t0) / 1e6), flush=True)
 
 # the same frame loop with the gather and the byte conversion on the device
 # (rnn_batch_rnnca_frame): only the two 3-plane frames cross PCIe
@@ -45,8 +45,8 @@ u8p = C.POINTER(C.c_uint8); ip = C.POINTER(C.c_int)
 def frame_step():
     lib.rnn_batch_rnnca_frame(batch, frame.ctypes.data_as(u8p), out.ctypes.data_as(u8p), W, Hh,
                               off_y.ctypes.data_as(ip), 17, off_c.ctypes.data_as(ip), 8, 2, 0)
-for f in range(5): frame_step()
+for f in range(5 if not big else 1): frame_step()
 t0 = time.perf_counter()
 for f in range(frames): frame_step()
 t1 = time.perf_counter()
-print("rnn_batch_rnnca_frame: %.0f frames/s (%.1f us per frame, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, frames * n / (t1 - t0) / 1e6))
+print("rnn_batch_rnnca_frame: %.1f frames/s (%.1f us per frame, %.1f M cell-steps/s)" % (frames / (t1 - t0), (t1 - t0) / frames * 1e6, frames * n / (t1 - t0) / 1e6))
