@@ -324,10 +324,17 @@ rnn_batch_rnnca_frame(RnnBatch *b, const u8 *frame_in, u8 *frame_out, int width,
   RbView v;
   batch_view(b, &v);
   rb_matrices_to_device(&b->nets[0]->pub);
-  rbk_rnnca_gather(&v, frame_dev, width, height, off_dev, len_y, off_dev + 2 * len_y, len_c,
-      len_pos, edges);
-  rb_forward_dispatch(&v, 0.0f);
-  rbk_rnnca_emit(&v, out_dev, width, height);
+  if (rbk_rnnca_cells_usable(&v)) {
+    /* tiny nets: a warp per cell, frame bytes in, frame bytes out */
+    rbk_rnnca_cells(&v, frame_dev, out_dev, width, height, off_dev, len_y, off_dev + 2 * len_y,
+        len_c, len_pos, edges);
+  }
+  else {
+    rbk_rnnca_gather(&v, frame_dev, width, height, off_dev, len_y, off_dev + 2 * len_y, len_c,
+        len_pos, edges);
+    rb_forward_dispatch(&v, 0.0f);
+    rbk_rnnca_emit(&v, out_dev, width, height);
+  }
   CUDA_OR_DIE(cudaMemcpyAsync(b->rnnca_host, out_dev, frame_bytes, cudaMemcpyDeviceToHost,
           rb_stream));
   CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));

@@ -3142,6 +3142,171 @@ k_rnnca_emit(RnncaArgs a)
   }
 }
 
+/* The whole frame step for TINY nets (rnnca's cells are 35 / 51 / 3): the
+   batch kernels give every cell a thread block for its input row and tile the
+   forward pass as a GEMM - at two million cells of a 52-unit net that is
+   eleven milliseconds of mostly empty blocks.  Here the weights (18 KB) sit in
+   shared memory and ONE WARP does a cell from the frame bytes to the frame
+   bytes: gather (gstrnnca.c:670-691), the row [1 | hidden(t-1) | inputs] with
+   its soft clip, hidden = act(x . Wih) two units per lane, output = hidden .
+   Who by shuffle, fast_sigmoid, UNIT_TO_BYTE; hidden state, ring row and
+   outputs are also written to the pool, so every other call still sees the
+   state it expects.  Warps walk the cells in a grid-stride loop. */
+__global__ void __launch_bounds__(256)
+k_rnnca_cells(RnncaArgs a)
+{
+  extern __shared__ __align__(16) float csh[];
+  const RbView &v = a.v;
+  const int I = v.d.i_size, H = v.d.h_size, O = v.d.o_size, hs1 = v.d.hidden_size + 1;
+  float *W = csh;               /* [I][H] */
+  float *Wo = W + I * H;        /* [H][O] */
+  float *xw = Wo + H * O;       /* [8 warps][I] */
+  for (int i = threadIdx.x; i < I * H; i += blockDim.x)
+    W[i] = v.Wih[i];
+  for (int i = threadIdx.x; i < H * O; i += blockDim.x)
+    Wo[i] = v.Who[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float *x = xw + warp * I;
+  const int plane = a.width * a.height;
+  const float unit = 1.0f / 255.0f;
+  const int n_in = a.len_y + 2 * a.len_c;
+  for (int cell = blockIdx.x * 8 + warp; cell < v.n; cell += gridDim.x * 8) {
+    const int s = v.base + cell;
+    const int cx = cell % a.width, cy = cell / a.width;
+    const float *hprev = v.Hd + (size_t)s * H;
+    float sum = 0.0f;
+    for (int i = lane; i < I; i += 32) {
+      float val = 0.0f;
+      if (i == 0)
+        val = 1.0f;
+      else if (i < hs1)
+        val = hprev[i];
+      else if (i < hs1 + a.len_y)
+        val = a.frame[rnnca_offset_point(a.off_y + 2 * (i - hs1), cx, cy, a.width, a.height,
+                a.edges)] * unit;
+      else if (i < hs1 + n_in) {
+        const int j = (i - hs1 - a.len_y) >> 1, which = (i - hs1 - a.len_y) & 1;
+        const int o = rnnca_offset_point(a.off_c + 2 * j, cx, cy, a.width, a.height, a.edges);
+        val = a.frame[(1 + which) * plane + o] * unit;
+      }
+      else if (i < hs1 + n_in + a.len_pos) {
+        const int k = i - hs1 - n_in;
+        const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+        val = (k == 0) ? xx : (k == 1) ? yy
+            : (float)(0.5 - (double)((yy - 0.5f) * (yy - 0.5f) + (xx - 0.5f) * (xx - 0.5f)));
+      }
+      x[i] = val;
+      sum += val;
+    }
+    sum = warp_sum(sum);
+    const float softclip = I * INPUT_MEAN_SOFT_TOP;
+    const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
+    __syncwarp();
+    float *xr = x_row(v, s, 0);
+    for (int i = lane; i < I; i += 32) {
+      float val = x[i] * scale;
+      if (scale != 1.0f)
+        x[i] = val;
+      xr[i] = val;
+    }
+    __syncwarp();
+    /* hidden units lane and lane + 32 */
+    float h0 = 0.0f, h1 = 0.0f;
+    const int c0 = lane, c1 = lane + 32;
+    for (int y = 0; y < I; y++) {
+      const float xv = x[y];
+      if (xv != 0.0f) { /* uniform over the warp: the reference's row skip */
+        h0 = fmaf(xv, W[y * H + c0], h0);
+        if (c1 < H)
+          h1 = fmaf(xv, W[y * H + c1], h1);
+      }
+    }
+    float hv[2] = {h0, h1};
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const int c = lane + 32 * u;
+      float t = hv[u];
+      if (v.activation == RNN_RESQRT) {
+        t = (t > 0.0f) ? sqrtf(t + 1.0f) - 1.0f : 0.0f;
+      }
+      else if (v.activation == RNN_RECLIP20) {
+        if (c >= 1) {
+          t = t < 20.0f ? t : 20.0f;
+          t = (t > 0.0f) ? t : 0.0f;
+        }
+      }
+      else if (c >= 1) {
+        t = (t > 0.0f) ? t : 0.0f;
+      }
+      if (c == 0)
+        t = 1.0f;
+      if (c >= H)
+        t = 0.0f;
+      hv[u] = t;
+      if (c < H)
+        v.Hd[(size_t)s * H + c] = t;
+    }
+    /* outputs by shuffle; lane o keeps output o */
+    float mine = 0.0f;
+    for (int o = 0; o < O; o++) {
+      float p = hv[0] * Wo[c0 * O + o] + ((c1 < H) ? hv[1] * Wo[c1 * O + o] : 0.0f);
+      p = warp_sum(p);
+      if (lane == o)
+        mine = p;
+    }
+    if (lane < O)
+      v.Y[(size_t)s * O + lane] = mine;
+    if (lane < 3) {
+      float sg = 1.0f / (1.0f + fast_expf_dev(-mine * 1.0f));
+      a.frame_out[lane * plane + cell] = (u8)(sg * 255.9f);
+    }
+    __syncwarp();
+  }
+}
+
+extern "C" int
+rbk_rnnca_cells_usable(const RbView *v)
+{
+  return v->contiguous && v->d.h_size <= 64 && v->d.i_size <= 256 && v->d.o_size <= 32 &&
+      v->d.output_size >= 3 && !getenv("RECUR_B200_NO_CELLS");
+}
+
+extern "C" void
+rbk_rnnca_cells(const RbView *v, const u8 *frame_dev, u8 *frame_out_dev, int width, int height,
+    const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos, int edges)
+{
+  RnncaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.v = *v;
+  a.frame = frame_dev;
+  a.frame_out = frame_out_dev;
+  a.width = width;
+  a.height = height;
+  a.off_y = off_y_dev;
+  a.off_c = off_c_dev;
+  a.len_y = len_y;
+  a.len_c = len_c;
+  a.len_pos = len_pos;
+  a.edges = edges;
+  size_t smem = ((size_t)v->d.i_size * v->d.h_size + (size_t)v->d.h_size * v->d.o_size +
+      8 * (size_t)v->d.i_size) * sizeof(float);
+  static int attr_done = 0;
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_rnnca_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = 1;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int blocks = sms * 8;
+  if (blocks > cdiv(v->n, 8))
+    blocks = cdiv(v->n, 8);
+  rb_prof_begin(RB_PROF_FWD);
+  k_rnnca_cells<<<blocks, 256, smem, rb_stream>>>(a);
+  LAUNCH_CHECK("k_rnnca_cells");
+  rb_prof_end(RB_PROF_FWD);
+}
+
 extern "C" void
 rbk_rnnca_gather(const RbView *v, const u8 *frame_dev, int width, int height,
     const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos, int edges)

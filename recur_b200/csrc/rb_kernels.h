@@ -68,6 +68,10 @@ void rbk_output(const RbView *v);
 void rbk_rnnca_gather(const RbView *v, const u8 *frame_dev, int width, int height,
     const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos, int edges);
 void rbk_rnnca_emit(const RbView *v, u8 *frame_out_dev, int width, int height);
+int rbk_rnnca_cells_usable(const RbView *v);
+void rbk_rnnca_cells(const RbView *v, const u8 *frame_dev, u8 *frame_out_dev, int width,
+    int height, const int *off_y_dev, int len_y, const int *off_c_dev, int len_c, int len_pos,
+    int edges);
 int rbk_walk_single_usable(const RbView *v);
 int rbk_walk_resident_usable(const RbView *v);
 void rbk_walk_resident(const RbView *v, float *Ehi, float *Elo);

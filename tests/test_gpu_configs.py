@@ -328,14 +328,19 @@ def test_training_with_presynaptic_noise_matches_reference(gpu_lib, ref, n):
     lib.rnn_batch_delete(batch)
 
 
+@pytest.mark.parametrize("cells_kernel", [True, False])
 @pytest.mark.parametrize("edges,len_pos", [(1, 2), (0, 3)])
-def test_f4_rnnca_frame_on_device(gpu_lib, ref, port, edges, len_pos):
+def test_f4_rnnca_frame_on_device(gpu_lib, ref, port, edges, len_pos, cells_kernel, monkeypatch):
     """SURVEY.md §8 f4, gstrnnca.c:805-830: a whole frame of the cellular
     automaton through rnn_batch_rnnca_frame (gather, forward, fast_sigmoid,
     bytes, all on the device) against the CPU: the oracle's restatement of
     fill_net_inputs (gstrnnca.c cannot be compiled, see oracle_rnn.c), the
-    live reference's rnn_opinion and fast_sigmoid, UNIT_TO_BYTE."""
+    live reference's rnn_opinion and fast_sigmoid, UNIT_TO_BYTE.  Both device
+    paths: the warp-per-cell kernel for tiny nets and gather + batch forward +
+    emit."""
     lib = gpu_lib
+    if not cells_kernel:
+        monkeypatch.setenv("RECUR_B200_NO_CELLS", "1")
     W, Hh = 24, 16
     n = W * Hh
     # 17 luma and 8 chroma neighbours like the default pattern (gstrnnca.h:49-51)
