@@ -227,3 +227,38 @@ def test_reference_fixture_loads_identically(lib, ref):
     assert rng_tuple(a) == rng_tuple(b)
     keys = [k for k, v in cdb_items(FIXTURE)]
     assert keys[0] == b"save_format_version" and b"net.ih_weights" in keys
+
+
+def test_stream_slots_are_recycled_and_sets_stay_contiguous(lib):
+    """Host-side bookkeeping of the stream pools (rb_device.cu): slots freed
+    by deleted clones are found again (next-fit hint), a training set made
+    afterwards still works, and hundreds of clones taken one at a time (an
+    rnnca grid makes one per pixel) do not disturb the nets made before."""
+    net = make_net(lib, input_size=8, hidden=13, output=4, depth=5, seed=3)
+    first = lib.rnn_new_training_set(net, 6)
+    marks = []
+    for j in range(6):
+        c = first[j].contents
+        arr(c.hidden_layer, c.h_size)[1] = 10.0 + j      # something to recognise the net by
+        marks.append(C.addressof(c))
+    # clones taken one by one: the pool grows several times underneath
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    cells = [lib.rnn_clone(net, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(300)]
+    assert all(cells)
+    for j in range(6):
+        c = first[j].contents
+        assert arr(c.hidden_layer, c.h_size)[1] == 10.0 + j
+        assert c.ih_weights and C.addressof(c) == marks[j]
+    for cell in cells[::2]:
+        lib.rnn_delete_net(cell)
+    more = [lib.rnn_clone(net, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(200)]
+    assert all(more)
+    for cell in cells[1::2] + more:
+        assert arr(cell.contents.hidden_layer, cell.contents.h_size)[1] == 0.0
+        lib.rnn_delete_net(cell)
+    second = lib.rnn_new_training_set(first[1], 4)       # clones of a clone share the same weights
+    assert C.addressof(second[1].contents.ih_weights.contents) == \
+        C.addressof(net.contents.ih_weights.contents)
+    for j in range(1, 4):
+        lib.rnn_delete_net(second[j])
+    lib.rnn_delete_training_set(first, 6, 0)
