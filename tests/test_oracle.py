@@ -123,3 +123,44 @@ def test_reference_builds_agree_within_noise_floor(ref, ref_fast):
         res.append([w.copy() for w in weights(net)])
     for a, b in zip(*res):
         assert np.abs(a - b).max() / np.abs(a).max() < 1e-5
+
+
+def test_rnnca_gather_restatement_against_numpy(port):
+    """f4: the restated fill_net_inputs / get_offset_point (gstrnnca.c:644-691,
+    oracle_rnn.c) against an independent numpy statement of the same rule -
+    clamp at the edges or wrap once, 1/255, position, radial term.  (The
+    GStreamer element itself cannot be compiled; this pins the restatement to
+    a second reading, not to the reference binary.)"""
+    import ctypes as C
+    rs = np.random.RandomState(4)
+    W, H = 13, 9
+    frame = rs.randint(0, 256, size=3 * W * H).astype(np.uint8)
+    Y, Cb, Cr = frame.reshape(3, H, W)
+    off_y = rs.randint(-2, 3, size=(17, 2)).astype(np.int32)
+    off_c = rs.randint(-2, 3, size=(8, 2)).astype(np.int32)
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    for edges, len_pos in ((1, 2), (0, 3), (0, 2)):
+        for cx, cy in ((0, 0), (W - 1, H - 1), (5, 4), (0, H - 1), (W - 1, 0)):
+            got = np.zeros(17 + 16 + len_pos, dtype=np.float32)
+            port.oracle_rnnca_fill_inputs(frame.ctypes.data_as(u8p), W, H, cx, cy,
+                                          off_y.ctypes.data_as(ip), 17, off_c.ctypes.data_as(ip), 8,
+                                          len_pos, edges, fptr(got))
+
+            def at(plane, dx, dy):
+                x, y = cx + dx, cy + dy
+                if edges:
+                    x, y = min(max(x, 0), W - 1), min(max(y, 0), H - 1)
+                else:
+                    x, y = x % W, y % H     # offsets are smaller than the frame: one wrap
+                return np.float32(plane[y, x]) * np.float32(1.0 / 255.0)
+            want = [at(Y, dx, dy) for dx, dy in off_y]
+            for dx, dy in off_c:
+                want += [at(Cb, dx, dy), at(Cr, dx, dy)]
+            xx, yy = np.float32(cx) / np.float32(W), np.float32(cy) / np.float32(H)
+            want += [xx, yy]
+            if len_pos == 3:
+                want.append(np.float32(0.5 - ((float(yy) - 0.5) ** 2 + (float(xx) - 0.5) ** 2)))
+            np.testing.assert_allclose(got, np.array(want, dtype=np.float32), rtol=1e-6, atol=1e-7)
+    assert port.oracle_rnnca_unit_to_byte(0.0) == 0
+    assert port.oracle_rnnca_unit_to_byte(0.5) == 127
+    assert port.oracle_rnnca_unit_to_byte(0.99999) == 255
