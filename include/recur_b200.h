@@ -54,6 +54,12 @@ const char *rnn_b200_version(void);
 /* Count of kernels launched by this library since load (monotonic). */
 uint64_t rnn_b200_kernel_launches(void);
 
+/* Name of the kernel that walked the history ring in the most recent BPTT
+   call ("k_tc_chain_persistent", "k_walk_resident", "k_tc_nt<CHAIN>",
+   "k_walk_single", "k_gemm<CHAIN>"; "" before the first).  Diagnostic: tests
+   use it to prove which path they compared with the oracle. */
+const char *rnn_b200_last_walk_kernel(void);
+
 /* Choose the matrix engine for batches: 0 = automatic (tensor cores when the
    batch has >= 64 streams and the sizes allow, FP32 FMA otherwise),
    1 = force FP32 FMA kernels, 2 = force tensor-core kernels (aborts if the
@@ -144,7 +150,9 @@ void rnn_batch_calc_deltas(RnnBatch *batch, int accumulate);
    stream j's rnn_bptt_calc_deltas call is skipped altogether, as
    rnn_char_classify_epoch does for characters without a class
    (charmodel-classify.c:124-148); its generation, min_error_factor and
-   contribution to the deltas stay untouched.  active == NULL: all train. */
+   contribution to the deltas stay untouched; its o_error row on the device
+   is consumed (zeroed) by the call, so set the errors again before training
+   that stream on them.  active == NULL: all train. */
 void rnn_batch_calc_deltas_masked(RnnBatch *batch, int accumulate, const u8 *active);
 
 /* rnn_apply_learning(nets[0], ...) (recur-nn.c:601-678). */
@@ -203,7 +211,10 @@ void rnn_batch_pull(RnnBatch *batch);
    rnn_batch_char_step / rnn_batch_text_train all-reduce (sum) the
    concatenated [ih_delta | ho_delta] over the ranks before the update, so
    every rank applies the identical update to its weight replica
-   (SURVEY.md §8e).  Returns 0 on success, -1 if NCCL cannot be loaded. */
+   (SURVEY.md §8e).  With more than one rank the deltas of a step are
+   exchanged whole: accumulate != 0 would add an already exchanged sum into
+   the next exchange, so the library aborts on it.
+   Returns 0 on success, -1 if NCCL cannot be loaded. */
 int rnn_b200_comm_unique_id(void *id128);
 int rnn_b200_comm_join(const void *id128, int rank, int n_ranks);
 void rnn_b200_comm_leave(void);

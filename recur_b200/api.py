@@ -23,7 +23,7 @@ class RnnBatchCharStats(C.Structure):
 B200_API_SYMBOLS = [
     "rnn_b200_device_count", "rnn_b200_set_device", "rnn_b200_synchronize",
     "rnn_b200_stream", "rnn_b200_version", "rnn_b200_kernel_launches",
-    "rnn_b200_set_engine", "rnn_b200_pull", "rnn_b200_push",
+    "rnn_b200_set_engine", "rnn_b200_last_walk_kernel", "rnn_b200_pull", "rnn_b200_push",
     "rnn_b200_profile_enable", "rnn_b200_profile_read", "rnn_b200_profile_class_name",
     "rnn_batch_new", "rnn_batch_delete", "rnn_batch_size", "rnn_batch_advance",
     "rnn_batch_set_inputs", "rnn_batch_set_one_hot", "rnn_batch_opinion",
@@ -54,6 +54,8 @@ def _declare_b200(lib):
     lib.rnn_b200_kernel_launches.argtypes = []
     lib.rnn_b200_set_engine.restype = C.c_int
     lib.rnn_b200_set_engine.argtypes = [C.c_int]
+    lib.rnn_b200_last_walk_kernel.restype = C.c_char_p
+    lib.rnn_b200_last_walk_kernel.argtypes = []
     lib.rnn_b200_profile_enable.restype = None
     lib.rnn_b200_profile_enable.argtypes = [C.c_int]
     lib.rnn_b200_profile_read.restype = C.c_int

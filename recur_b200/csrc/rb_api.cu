@@ -179,6 +179,7 @@ rb_net_push(RbNet *rn)
   else {
     h2d(dev_x_row(rn, 0), net->input_layer, d->i_size * sizeof(float));
   }
+  p->x_planes_stale = 2;
   sync_stream();
   rn->dev_ahead = 0;
   rb_ahead_epoch++; /* batches re-flag their nets on their next call */
@@ -586,6 +587,7 @@ rnn_opinion(RecurNN *net, const float *inputs, float presynaptic_noise)
     memcpy(net->real_inputs, inputs, net->input_size * sizeof(float));
   RbView v;
   rb_view_of_net(rn, &v);
+  p->x_planes_stale = 2; /* the per-net forward writes no operand planes */
   if (!bl && presynaptic_noise == 0.0f && rbk_opinion_single_usable(&v)) {
     /* one launch that reads and writes the pinned mirrors itself */
     rbk_opinion_single(&v, net->hidden_layer, net->real_inputs, net->input_layer,
@@ -624,6 +626,7 @@ rnn_forget_history(RecurNN *net, int bptt_too)
   if (rb_have_device()) {
     RbPool *p = rn->pool;
     const RbDims *d = &rn->group->d;
+    p->x_planes_stale = 2;
     CUDA_OR_DIE(cudaMemsetAsync(p->Hd + (size_t)rn->slot * d->h_size, 0,
             d->h_size * sizeof(float), rb_stream));
     CUDA_OR_DIE(cudaMemsetAsync(dev_x_row(rn, 0), 0,

@@ -278,8 +278,11 @@ rnn_batch_set_inputs(RnnBatch *b, const float *inputs)
   batch_view(b, &v);
   if (bl)
     rb_bottom_set_inputs(&v, b->io_dev, width);
-  else
+  else {
     rbk_set_inputs(&v, b->io_dev);
+    if (b->pool->x_planes_stale < 1)
+      b->pool->x_planes_stale = 1;
+  }
   mark_ahead(b);
 }
 
@@ -352,8 +355,11 @@ rnn_batch_set_one_hot(RnnBatch *b, const u8 *hot)
   batch_view(b, &v);
   if (b->nets[0]->pub.bottom_layer)
     rb_bottom_one_hot(&v, b->cur_dev);
-  else
+  else {
     rbk_set_one_hot(&v, b->cur_dev);
+    if (b->pool->x_planes_stale < 1)
+      b->pool->x_planes_stale = 1;
+  }
   mark_ahead(b);
 }
 
@@ -505,6 +511,9 @@ calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
   RecurNNBPTT *bp = proto->bptt;
   if (proto->bottom_layer && rb_comm_size() > 1)
     rb_die("recur-b200: the bottom layer's deltas are not exchanged between GPUs yet");
+  if (accumulate && rb_comm_size() > 1)
+    rb_die("recur-b200: accumulate != 0 across GPUs would exchange the previous sum again "
+        "(see recur_b200.h)");
   rb_matrices_to_device(proto);
   RbView v;
   batch_view(b, &v);

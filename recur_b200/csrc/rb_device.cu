@@ -458,6 +458,7 @@ rb_pool_reserve(RbPool *p, int n_slots)
     CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
   }
   p->cap = new_cap;
+  p->x_planes_stale = 2;
 }
 
 extern "C" int
@@ -482,6 +483,7 @@ rb_pool_take_slot(RbPool *p)
   p->n_live++;
   p->pos_shadow[slot] = 0;
   if (rb_have_device() && recycled) {
+    p->x_planes_stale = 2;
     /* a recycled slot starts from zeroed state, like a calloc'ed net */
     const RbDims *d = &p->group->d;
     for (int r = 0; r < p->depth; r++)

@@ -58,8 +58,10 @@ rb_forward_dispatch(const RbView *v, float noise)
 {
   if (use_tensor_engine(v))
     rb_tc_forward(v->pool, v, noise);
-  else
+  else {
+    v->pool->x_planes_stale = 2;
     rbk_forward(v, noise);
+  }
 }
 
 /* fused start of a text step + forward (rb_batch.cu's character steps) */
@@ -80,6 +82,8 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
   float *Xhi = NULL, *Xlo = NULL;
   if (tensor)
     rb_tc_x_planes(v->pool, &Xhi, &Xlo);
+  else
+    v->pool->x_planes_stale = 2;
   if (text_dev && advance && continues && pre_update_valid && !rb_prof_active()) {
     /* The next position's input rows need the last forward pass and the text,
        not the weights: with the text resident the kernel runs on a side stream
@@ -106,6 +110,21 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
 }
 
 static int last_bptt_tensor = 0;
+static const char *last_walk_kernel = "";
+
+/* which kernel walked the ring in the most recent BPTT call (tests and
+   smoke() assert that the path they mean to check is the one that ran) */
+extern "C" void
+rb_note_walk_kernel(const char *name)
+{
+  last_walk_kernel = name;
+}
+
+extern "C" const char *
+rnn_b200_last_walk_kernel(void)
+{
+  return last_walk_kernel;
+}
 
 extern "C" int
 rb_last_bptt_used_tensor_engine(void)

@@ -74,6 +74,13 @@ typedef struct RbPool {
   uint64_t *rng;  /* [cap][4] per-stream PRNG state when noise runs on device */
   int n_part;
   void *tc;        /* tensor-core engine state (rb_tc.cu), made on first use */
+  /* The tensor engine reads the ring through operand planes written next to X
+     by its own forward pass.  Anything else that rewrites ring rows marks
+     them stale: 1 = the current row only (inputs set, forward not yet run:
+     rb_tc_forward re-splits that row anyway), 2 = any row (push, forget,
+     FMA / per-net forward, recycled slot, regrown pool).  rb_tc_top_and_bptt
+     re-splits the whole ring before the weight gradient when it finds 2. */
+  int x_planes_stale;
   /* bottom layer (recur-nn.c:88-103,377-382,751-764), made on first use */
   float *BI;      /* [cap][bl_i] bottom inputs [1 | inputs] per stream */
   float *BO;      /* [cap][bl_o] bottom outputs (pre-ReLU) */

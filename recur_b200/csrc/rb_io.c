@@ -4,7 +4,7 @@
  * recur-nn-io.c:149-357: a constant database (rb_cdb.h) whose values are the
  * raw host-endian C objects, keyed "net.<field>", "bptt.<field>" and
  * "bottom_layer.<field>".  Keys and their order are kept so that files made
- * here and files made by the reference are interchangeable (tests/test_io.py
+ * here and files made by the reference are interchangeable (tests/test_host_logic.py
  * checks both directions and the reference's own fixture
  * test/multi-text-6c34c563i73-h99-o3650.net).
  *
@@ -299,7 +299,9 @@ rnn_load_net(const char *filename)
         fprintf(stderr, "cannot load 'bottom_layer.weights'\n");
         goto error;
       }
-      bl->learn_rate_scale = tl.learn_rate_scale;
+      /* like the reference (recur-nn-io.c:225,292-299: read, never
+         installed), the saved learn_rate_scale does not override the
+         constructor's default */
     }
   }
   close(fd);

@@ -369,6 +369,14 @@ k_gemm(GemmArgs g)
           int ca = m0 + fcq, cb = n0 + fcq;
           if (ca < M) {
             ra = *(const float4 *)(x_row(v, s, step) + ca);
+            if (v.activation == RNN_RECLIP20) {
+              /* recur-nn.c:347: a row whose input sits at the clip (>= 20)
+                 is skipped altogether, its delta row included */
+              if (!(ra.x < 20.0f)) ra.x = 0.0f;
+              if (!(ra.y < 20.0f)) ra.y = 0.0f;
+              if (!(ra.z < 20.0f)) ra.z = 0.0f;
+              if (!(ra.w < 20.0f)) ra.w = 0.0f;
+            }
             ra.x *= scale; ra.y *= scale; ra.z *= scale; ra.w *= scale;
           }
           if (cb < N)
@@ -3348,9 +3356,11 @@ extern "C" void
 rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
 {
   if (walk_streams_usable(v)) {
+    rb_note_walk_kernel("k_walk_single");
     rbk_walk_single(v, ih_delta, accumulate);
     return;
   }
+  rb_note_walk_kernel("k_gemm<CHAIN>");
   GemmArgs g;
   g.v = *v;
   g.delta = ih_delta;

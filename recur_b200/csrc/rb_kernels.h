@@ -43,6 +43,7 @@ extern "C" {
 extern cudaStream_t rb_stream;
 void rb_view_of_net(RbNet *rn, RbView *v);
 void rb_count_launch(int n);
+void rb_note_walk_kernel(const char *name);
 int rb_prof_active(void);
 void rb_prof_begin(int cls);
 void rb_prof_end(int cls);

@@ -546,6 +546,7 @@ tc_state(RbPool *p)
   make_map_chunked(&t->mXlo_mn3, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_DW2_BN / 2 / 32);
   t->dw_splits = TC_DW_SPLITS;
   p->tc = t;
+  p->x_planes_stale = 2; /* the ring may hold rows from before the planes existed */
   return t;
 }
 
@@ -601,6 +602,24 @@ k_split_rows(RbView v, int which /* 0: current x row, 1: E[0] */, float *hi_plan
     split_tf32(src[i], hi, lo);
     hi_plane[off + i] = hi;
     lo_plane[off + i] = lo;
+  }
+}
+
+/* every row of the ring -> its planes (after something other than the tensor
+   engine's own forward pass rewrote ring rows: RbPool.x_planes_stale) */
+__global__ void __launch_bounds__(256)
+k_split_ring(const float *__restrict__ X, size_t n, float *hi_plane, float *lo_plane)
+{
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
+       i += (size_t)gridDim.x * blockDim.x * 4) {
+    float4 x = *(const float4 *)(X + i);
+    float4 h, l;
+    split_tf32(x.x, h.x, l.x);
+    split_tf32(x.y, h.y, l.y);
+    split_tf32(x.z, h.z, l.z);
+    split_tf32(x.w, h.w, l.w);
+    *(float4 *)(hi_plane + i) = h;
+    *(float4 *)(lo_plane + i) = l;
   }
 }
 
@@ -1051,8 +1070,15 @@ grid_barrier(unsigned int *counter, unsigned int target)
     /* arrive with a release reduction: nothing waits for the old value to
        come back before the polling starts */
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-    while (ld_acquire_gpu(counter) < target)
-      ;
+    /* a poll is an L2 round trip (~0.7 us): 2^22 of them are seconds, against
+       the microseconds a healthy barrier takes.  A grid that is not fully
+       resident can never complete the barrier; trap (the host then aborts
+       with the launch failure) rather than hang the device. */
+    unsigned int spins = 0;
+    while (ld_acquire_gpu(counter) < target) {
+      if (++spins > (1u << 22))
+        __trap();
+    }
   }
   __syncthreads();
 }
@@ -1374,7 +1400,6 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
               }
             }
           }
-          if (warp == 2 && lane == 0 && a[0].x != 123.456f && a[GRP - 1].y != 123.456f) ROLE_STAMP(16);
           if (plain) {
 #pragma unroll
             for (int i = 0; i < GRP; i++) {
@@ -1898,7 +1923,11 @@ k_update_split(UpdateArgs a)
 extern "C" int
 rb_tc_usable(const RbView *v)
 {
-  return v->contiguous && v->n >= 64 && (v->n % TC_BK) == 0 && v->d.h_size >= 64;
+  /* ReCLIP20 nets stay on the FMA engine: the reference leaves saturated rows
+     (x >= 20) out of the weight gradient (recur-nn.c:347), and the operand
+     planes of the ring, shared with the forward pass, hold them unmasked */
+  return v->contiguous && v->n >= 64 && (v->n % TC_BK) == 0 && v->d.h_size >= 64 &&
+      v->activation != RNN_RECLIP20;
 }
 
 static void
@@ -1939,6 +1968,8 @@ rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
   k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 0, t->Xhi, t->Xlo);
   LAUNCH_CHECK("k_split_rows");
   rb_prof_end(RB_PROF_SMALL);
+  if (p->x_planes_stale == 1)
+    p->x_planes_stale = 0; /* the row whose inputs were set is the one just split */
   rb_tc_forward_core(p, v, presynaptic_noise);
 }
 
@@ -2009,6 +2040,17 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
 {
   RbTc *t = tc_state(p);
   refresh_weight_planes(t, p, v);
+  if (p->x_planes_stale) {
+    /* ring rows were rewritten behind the planes' back (rnn_forget_history,
+       rnn_b200_push, a per-net or FMA forward, a regrown pool): the weight
+       gradient reads the ring only through the planes */
+    size_t n = (size_t)p->depth * p->cap * v->d.i_size;
+    rb_prof_begin(RB_PROF_SMALL);
+    k_split_ring<<<148 * 4, 256, 0, rb_stream>>>(p->X, n, t->Xhi, t->Xlo);
+    LAUNCH_CHECK("k_split_ring");
+    rb_prof_end(RB_PROF_SMALL);
+    p->x_planes_stale = 0;
+  }
   /* top layer: E[0] and, where the batch kernel applies, its planes too */
   if (rbk_top_layer_can_write_planes(v)) {
     rbk_top_layer_planes(v, ho_delta, accumulate, NULL, 0, t->Ehi, t->Elo);
@@ -2057,6 +2099,8 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   unsigned int *sync_area = t->sync + (size_t)t->sync_flip * t->sync_words;
   unsigned int *sync_next = t->sync + (size_t)(t->sync_flip ^ 1) * t->sync_words;
   t->sync_flip ^= 1;
+  rb_note_walk_kernel(t->persistent_ok ? "k_tc_chain_persistent"
+      : resident ? "k_walk_resident" : "k_tc_nt<CHAIN>");
   if (t->persistent_ok) {
     ChainArgs ca;
     ca.v = *v;
@@ -2078,15 +2122,16 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
                       (void *)&t->mWlo_k, (void *)&ca};
     rb_prof_begin(RB_PROF_CHAIN);
-    if (getenv("RECUR_B200_COOP_LAUNCH")) {
+    if (!getenv("RECUR_B200_PLAIN_LAUNCH")) {
+      /* cooperative by default: the driver guarantees all CTAs are resident
+         together or fails the launch, whatever else shares the device */
       CUDA_OR_DIE(cudaLaunchCooperativeKernel(
               (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(TC_CHAIN_THREADS),
               params, ChainCfg::SMEM_BYTES, rb_stream));
     }
     else {
-      /* co-residency was established above (occupancy x SM count >= grid and
-         this stream runs nothing else alongside), so a plain launch is safe
-         and avoids the cooperative launch's queue drain */
+      /* opt-out for measurements: co-residency then rests on the occupancy
+         check above and on nothing else using the device */
       k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, TC_CHAIN_THREADS, ChainCfg::SMEM_BYTES,
         rb_stream>>>(t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, ca);
     }

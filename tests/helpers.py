@@ -76,3 +76,52 @@ def rel_err(a, b):
     b = np.asarray(b, dtype=np.float64)
     scale = max(np.abs(b).max(), 1e-30)
     return float(np.abs(a - b).max() / scale)
+
+
+def transplant_training_set(src_nets, dst_lib, dst_nets, n):
+    """Copy everything a training step reads - weights, momentums, and every
+    stream's ring, hidden layer, ring index, min_error_factor, generation -
+    from the nets of one library (mirrors already pulled) into the nets of
+    another with the same shapes.  This is the 'teacher forcing' of SURVEY.md
+    §8c: both sides then take the next steps from bit-identical state, so a
+    per-step comparison is not blurred by earlier rounding drift."""
+    s0, d0 = src_nets[0].contents, dst_nets[0].contents
+    sb, db = s0.bptt.contents, d0.bptt.contents
+    for name, size in (("ih_weights", s0.ih_size), ("ho_weights", s0.ho_size)):
+        arr(getattr(d0, name), size)[:] = arr(getattr(s0, name), size)
+    for name, size in (("ih_momentum", s0.ih_size), ("ho_momentum", s0.ho_size)):
+        arr(getattr(db, name), size)[:] = arr(getattr(sb, name), size)
+    for j in range(n):
+        s, d = src_nets[j].contents, dst_nets[j].contents
+        sb, db = s.bptt.contents, d.bptt.contents
+        assert sb.depth == db.depth and s.i_size == d.i_size
+        arr(d.hidden_layer, d.h_size)[:] = arr(s.hidden_layer, s.h_size)
+        arr(db.history, db.depth * d.i_size)[:] = arr(sb.history, sb.depth * s.i_size)
+        # rnn_bptt_advance repoints input_layer / real_inputs into the ring
+        # (recur-nn.c:696-704): step the destination onto the source's index
+        db.index = (sb.index - 1) % sb.depth
+        dst_lib.rnn_bptt_advance(dst_nets[j])
+        assert db.index == sb.index
+        db.min_error_factor = sb.min_error_factor
+        db.ih_scale = sb.ih_scale
+        db.learn_rate = sb.learn_rate
+        d.generation = s.generation
+
+
+def reference_walk_depths(ref, nets, n, depth, run_step, tmpdir):
+    """Executed BPTT depth of every stream for ONE training step of the
+    reference, read from its own log (recur-nn.c:416 logs depth - t, which is
+    one less than the steps executed when the walk broke off early)."""
+    import os
+    import re
+    paths = [os.path.join(str(tmpdir), "walk%d.log" % j) for j in range(n)]
+    for j in range(n):
+        ref.rnn_set_log_file(nets[j], paths[j].encode(), 0)
+    run_step()
+    out = []
+    for j in range(n):
+        ref.rnn_set_log_file(nets[j], None, 0)
+        logged = [int(x) for x in re.findall(r"^depth (\d+)", open(paths[j]).read(), re.M)]
+        assert len(logged) == 1, (j, logged)
+        out.append(min(logged[0] + 1, depth))
+    return out

@@ -481,3 +481,35 @@ def test_single_stream_kernels_both_variants(gpu_lib, ref, hidden):
             L.rnn_apply_learning(net, 0, 0.9)
     for x, y in zip(weights(b), weights(r2)):
         assert rel_err(x, y) < TOL
+
+
+def test_input_soft_clip_per_net_matches_reference(gpu_lib, ref):
+    """maybe_scale_inputs (recur-nn.c:68-81) through rnn_opinion itself: with
+    Wih x 10 the sum of the input row passes 16 * i_size after a few steps
+    and the row is scaled in place in the ring."""
+    lib = gpu_lib
+    text = markov_text(400, 12, seed=8)
+    res, clipped = [], False
+    for L in (lib, ref):
+        net = make_net(L, input_size=12, hidden=40, output=12, depth=6, seed=4, lr=1e-3)
+        ih, ho = weights(net)
+        ih *= 10.0
+        c = net.contents
+        rows = []
+        for i in range(8):
+            before = 2.0 + arr(c.hidden_layer, c.h_size)[1:41].sum()
+            L.rnn_bptt_advance(net)
+            x = arr(c.real_inputs, c.input_size)
+            x[:] = 0
+            x[text[i]] = 1.0
+            L.rnn_opinion(net, None, 0.0)
+            row = arr(c.input_layer, c.i_size).copy()
+            if L is ref and before > 16 * c.i_size:
+                clipped = True
+                assert row.sum() < 0.5 * before       # scaled down, not copied
+            rows.append(np.concatenate([row, arr(c.hidden_layer, c.h_size),
+                                        arr(c.output_layer, c.o_size)]))
+        res.append(rows)
+    assert clipped
+    for a, b in zip(*res):
+        assert rel_err(a, b) < TOL

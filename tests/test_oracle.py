@@ -8,7 +8,7 @@ import numpy as np
 
 import oracle
 from recur_b200 import abi
-from helpers import fptr, u8ptr, arr, weights, make_net
+from helpers import fptr, u8ptr, arr, weights, make_net, markov_text
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "recur_golden.npz")
 
@@ -164,3 +164,30 @@ def test_rnnca_gather_restatement_against_numpy(port):
     assert port.oracle_rnnca_unit_to_byte(0.0) == 0
     assert port.oracle_rnnca_unit_to_byte(0.5) == 127
     assert port.oracle_rnnca_unit_to_byte(0.99999) == 255
+
+
+def test_transplanted_training_state_continues_bit_for_bit(ref):
+    """helpers.transplant_training_set (used by the GPU parity tests to start
+    the reference from a state trained on the GPU) moves everything a
+    training step reads: a reference training set continued in place and its
+    transplanted copy take bit-identical steps."""
+    from helpers import transplant_training_set
+    n, shape = 3, dict(input_size=12, hidden=31, output=12, depth=7, seed=4, lr=3e-3)
+    text = markov_text(900, 12, seed=4)
+    a = make_net(ref, **shape)
+    b = make_net(ref, **shape)
+    for w in weights(b):
+        w[:] = 0
+    an = ref.rnn_new_training_set(a, n)
+    bn = ref.rnn_new_training_set(b, n)
+    ref.ref_multi_tap_train(an, n, u8ptr(text), len(text), 0, 11, 0, 0.95, 20.0, None, None, None)
+    transplant_training_set(an, ref, bn, n)
+    for nets in (an, bn):
+        ref.ref_multi_tap_train(nets, n, u8ptr(text), len(text), 11, 4, 0, 0.95, 20.0,
+                                None, None, None)
+    for x, y in zip(weights(a), weights(b)):
+        assert np.array_equal(x, y)
+    for j in range(n):
+        ca, cb = an[j].contents, bn[j].contents
+        assert np.array_equal(arr(ca.hidden_layer, ca.h_size), arr(cb.hidden_layer, cb.h_size))
+        assert ca.bptt.contents.min_error_factor == cb.bptt.contents.min_error_factor
