@@ -199,6 +199,23 @@ void rnn_batch_rnnca_frame(RnnBatch *cells, const unsigned char *frame_in,
    int32 values.  Synchronises. */
 void rnn_batch_bptt_depths(RnnBatch *batch, int32_t *depths);
 
+/* What bptt_and_accumulate_error and rnn_bptt_calc_deltas write to net->log
+   for one stream (recur-nn.c:415-421,766-770), for every stream of the batch
+   after its most recent walk: n records.  Synchronises. */
+typedef struct RnnBatchBpttLog {
+  int32_t depth;              /* "depth": bptt->depth - t at the exit */
+  int32_t n_steps;            /* BPTT steps executed (as rnn_batch_bptt_depths) */
+  float scaled_error;         /* "scaled_error": ih_scale * error_sum */
+  float ih_scale;             /* "ih_scale" */
+  float min_error_threshold;  /* "min_error_threshold" */
+  float min_error_factor;     /* "min_error_factor" (after adaptation) */
+  float cum_error;            /* "cum_error" */
+  float error_sum;            /* error_sum of the last executed step */
+  float top_error_scaled;     /* "top_error_scaled" */
+  float top_error_raw;        /* "top_error_raw" */
+} RnnBatchBpttLog;
+void rnn_batch_bptt_log(RnnBatch *batch, RnnBatchBpttLog *log);
+
 /* Refresh host mirrors and struct scalars (generation, ih_scale,
    min_error_factor, bptt->index) of every net in the batch. */
 void rnn_batch_pull(RnnBatch *batch);

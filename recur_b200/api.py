@@ -20,6 +20,14 @@ class RnnBatchCharStats(C.Structure):
                 ("correct", C.c_int64), ("count", C.c_int64)]
 
 
+class RnnBatchBpttLog(C.Structure):
+    _fields_ = [("depth", C.c_int32), ("n_steps", C.c_int32),
+                ("scaled_error", C.c_float), ("ih_scale", C.c_float),
+                ("min_error_threshold", C.c_float), ("min_error_factor", C.c_float),
+                ("cum_error", C.c_float), ("error_sum", C.c_float),
+                ("top_error_scaled", C.c_float), ("top_error_raw", C.c_float)]
+
+
 B200_API_SYMBOLS = [
     "rnn_b200_device_count", "rnn_b200_set_device", "rnn_b200_synchronize",
     "rnn_b200_stream", "rnn_b200_version", "rnn_b200_kernel_launches",
@@ -32,6 +40,7 @@ B200_API_SYMBOLS = [
     "rnn_batch_apply_learning",
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
     "rnn_batch_text_forward", "rnn_batch_rnnca_frame", "rnn_batch_pull", "rnn_batch_bptt_depths",
+    "rnn_batch_bptt_log",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
     "rnn_b200_comm_size", "rnn_batch_p2p_export", "rnn_batch_p2p_attach",
 ]
@@ -112,6 +121,8 @@ def _declare_b200(lib):
                                           C.c_int, C.c_int, C.c_int]
     lib.rnn_batch_bptt_depths.restype = None
     lib.rnn_batch_bptt_depths.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.rnn_batch_bptt_log.restype = None
+    lib.rnn_batch_bptt_log.argtypes = [vp, C.POINTER(RnnBatchBpttLog)]
     lib.rnn_batch_pull.restype = None
     lib.rnn_batch_pull.argtypes = [vp]
     lib.rnn_b200_comm_unique_id.restype = C.c_int

@@ -728,6 +728,30 @@ rnn_batch_bptt_depths(RnnBatch *b, int32_t *depths)
 }
 
 extern "C" void
+rnn_batch_bptt_log(RnnBatch *b, RnnBatchBpttLog *log)
+{
+  RbScalars *sc = (RbScalars *)malloc(sizeof(RbScalars) * b->pool->cap);
+  CUDA_OR_DIE(cudaMemcpyAsync(sc, b->pool->sc, sizeof(RbScalars) * b->pool->cap,
+          cudaMemcpyDeviceToHost, rb_stream));
+  CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+  for (int j = 0; j < b->n; j++) {
+    const RbScalars *s = sc + b->nets[j]->slot;
+    RnnBatchBpttLog *l = log + j;
+    l->depth = b->pool->depth - s->t_left;
+    l->n_steps = s->n_steps;
+    l->scaled_error = s->ih_scale * s->err_sum;
+    l->ih_scale = s->ih_scale;
+    l->min_error_threshold = s->min_sum;
+    l->min_error_factor = s->mef;
+    l->cum_error = s->cum_error;
+    l->error_sum = s->err_sum;
+    l->top_error_scaled = s->top_scaled;
+    l->top_error_raw = s->top_raw;
+  }
+  free(sc);
+}
+
+extern "C" void
 rnn_batch_pull(RnnBatch *b)
 {
   for (int j = 0; j < b->n; j++) {

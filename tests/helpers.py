@@ -108,12 +108,11 @@ def transplant_training_set(src_nets, dst_lib, dst_nets, n):
         d.generation = s.generation
 
 
-def reference_walk_depths(ref, nets, n, depth, run_step, tmpdir):
-    """Executed BPTT depth of every stream for ONE training step of the
-    reference, read from its own log (recur-nn.c:416 logs depth - t, which is
-    one less than the steps executed when the walk broke off early)."""
+def reference_walk_logs(ref, nets, n, run_step, tmpdir):
+    """What the reference logs for ONE training step of every stream
+    (recur-nn.c:415-421, 766-770): a list of dicts keyed by the log names.
+    The log prints floats with %.5g: five significant digits."""
     import os
-    import re
     paths = [os.path.join(str(tmpdir), "walk%d.log" % j) for j in range(n)]
     for j in range(n):
         ref.rnn_set_log_file(nets[j], paths[j].encode(), 0)
@@ -121,7 +120,17 @@ def reference_walk_depths(ref, nets, n, depth, run_step, tmpdir):
     out = []
     for j in range(n):
         ref.rnn_set_log_file(nets[j], None, 0)
-        logged = [int(x) for x in re.findall(r"^depth (\d+)", open(paths[j]).read(), re.M)]
-        assert len(logged) == 1, (j, logged)
-        out.append(min(logged[0] + 1, depth))
+        rec = {}
+        for line in open(paths[j]).read().splitlines():
+            key, _, val = line.partition(" ")
+            if key != "generation":
+                assert key not in rec, (j, key)     # exactly one walk was logged
+            rec[key] = float(val)
+        out.append(rec)
     return out
+
+
+def executed_depth(logged_depth, depth):
+    """recur-nn.c:416 logs depth - t, one less than the steps executed when the
+    walk broke off early."""
+    return min(int(logged_depth) + 1, depth)
