@@ -79,9 +79,11 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
     rb_forward_dispatch(v, noise);
     return;
   }
-  float *Xhi = NULL, *Xlo = NULL;
-  if (tensor)
-    rb_tc_x_planes(v->pool, &Xhi, &Xlo);
+  RbPlanes xp, *X = NULL;
+  if (tensor) {
+    rb_tc_x_planes(v->pool, &xp);
+    X = &xp;
+  }
   else
     v->pool->x_planes_stale = 2;
   if (text_dev && advance && continues && pre_update_valid && !rb_prof_active()) {
@@ -95,13 +97,13 @@ rb_char_forward_dispatch(const RbView *v, const u8 *text_dev, int len, int pos, 
       cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming);
     }
     cudaStreamWaitEvent(side_stream, ev_pre_update, 0);
-    rbk_step_begin_on(side_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo,
+    rbk_step_begin_on(side_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, X,
         advance);
     cudaEventRecord(ev_side_done, side_stream);
     cudaStreamWaitEvent(rb_stream, ev_side_done, 0);
   }
   else
-    rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo, advance);
+    rbk_step_begin(v, text_dev, len, pos, spacing, cur_dev, next_dev, X, advance);
   pre_update_valid = 0;
   if (tensor)
     rb_tc_forward_core(v->pool, v, noise);

@@ -28,6 +28,7 @@
  *   a16 rnn_bptt_clear_deltas       k_fill
  */
 #include "rb_kernels.h"
+#include "rb_split.cuh"
 #include "rb_rng.h"
 #include "rb_optim.cuh"
 #include <math.h>
@@ -867,14 +868,14 @@ k_top(RbView v, const RecurErrorRange *ranges, int n_ranges)
 
 /* a8 and the set-up of the BPTT walk after k_gemm<TOP>: per stream, total
    |e| from the column-block partials, the hidden statistics the log wants,
-   the soft clip (recur-nn.c:720-721), optional hi/lo planes of E[0] for the
-   tensor engine, and the walk's thresholds (recur-nn.c:318-322).            */
+   the soft clip (recur-nn.c:720-721) and the walk's thresholds
+   (recur-nn.c:318-322).                                                     */
 __global__ void __launch_bounds__(256)
-k_top_finish(RbView v, int n_col_blocks, float *Ehi, float *Elo)
+k_top_finish(RbView v, int n_col_blocks)
 {
   __shared__ float scratch[33];
   const int s = v.slots[blockIdx.x];
-  const int H = v.d.h_size, I = v.d.i_size;
+  const int H = v.d.h_size;
   const float *hid = v.Hd + (size_t)s * H;
   float hsum = 0.0f, hmag = 0.0f, hzero = 0.0f;
   for (int y = threadIdx.x; y < H; y += blockDim.x) {
@@ -894,23 +895,9 @@ k_top_finish(RbView v, int n_col_blocks, float *Ehi, float *Elo)
   const float halfmax = H * MAX_TOP_ERROR_FACTOR;
   const float scale = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
   float *e0 = e_row(v, s, 0);
-  if (scale != 1.0f || Ehi) {
-    for (int y = threadIdx.x; y < H; y += blockDim.x) {
-      float e = e0[y];
-      if (scale != 1.0f) {
-        e *= scale;
-        e0[y] = e;
-      }
-      if (Ehi) {
-        uint32_t hb, lb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e));
-        float hi = __uint_as_float(hb);
-        float rem = e - hi;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-        Ehi[(size_t)s * I + y] = hi;
-        Elo[(size_t)s * I + y] = __uint_as_float(lb);
-      }
-    }
+  if (scale != 1.0f) {
+    for (int y = threadIdx.x; y < H; y += blockDim.x)
+      e0[y] *= scale;
   }
   if (v.CIE)
     for (int i = threadIdx.x; i < v.bl_o; i += blockDim.x)
@@ -1616,7 +1603,7 @@ struct StepBeginArgs {
   const u8 *text; /* NULL: symbols are already in cur/next */
   int len, pos, spacing;
   u8 *cur, *next;
-  float *Xhi, *Xlo;
+  RbPlanes X;     /* hi == NULL: no planes wanted */
   int advance;    /* 0: forward only, the row of the current ring position is rewritten */
 };
 
@@ -1652,6 +1639,7 @@ k_step_begin(StepBeginArgs a)
   __syncthreads();
   const int I = v.d.i_size, hs1 = v.d.hidden_size + 1;
   const size_t off = ((size_t)s_pos * v.cap + s) * I;
+  const size_t prow = ((size_t)s_pos * v.cap + s) * a.X.pitch;
   float *x = v.X + off;
   const float *h = v.Hd + (size_t)s * v.d.h_size;
   const int hot_col = hs1 + s_hot;
@@ -1684,14 +1672,11 @@ k_step_begin(StepBeginArgs a)
       if (scale != 1.0f)
         val *= scale;
       x[i] = val;
-      if (a.Xhi) {
-        uint32_t hb, lb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(val));
-        float hi = __uint_as_float(hb);
-        float rem = val - hi;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-        a.Xhi[off + i] = hi;
-        a.Xlo[off + i] = __uint_as_float(lb);
+      if (a.X.hi) {
+        rb_h16 hi, lo;
+        rb_split_f16(val * a.X.scale, hi, lo);
+        a.X.hi[prow + i] = hi;
+        a.X.lo[prow + i] = lo;
       }
     }
   }
@@ -1705,15 +1690,14 @@ rbk_step_begin_usable(const RbView *v)
 
 extern "C" void
 rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance)
+    u8 *cur_dev, u8 *next_dev, const RbPlanes *X, int advance)
 {
-  rbk_step_begin_on(rb_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, Xhi, Xlo,
-      advance);
+  rbk_step_begin_on(rb_stream, v, text_dev, len, pos, spacing, cur_dev, next_dev, X, advance);
 }
 
 extern "C" void
 rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev, int len, int pos,
-    int spacing, u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance)
+    int spacing, u8 *cur_dev, u8 *next_dev, const RbPlanes *X, int advance)
 {
   StepBeginArgs a;
   a.advance = advance;
@@ -1724,8 +1708,10 @@ rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev, int 
   a.spacing = spacing;
   a.cur = cur_dev;
   a.next = next_dev;
-  a.Xhi = Xhi;
-  a.Xlo = Xlo;
+  if (X)
+    a.X = *X;
+  else
+    memset(&a.X, 0, sizeof(a.X));
   rb_prof_begin(RB_PROF_SMALL);
   k_step_begin<<<v->n, 256, 0, stream>>>(a);
   LAUNCH_CHECK("k_step_begin");
@@ -1918,8 +1904,8 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
 static int ho_slab_attr_done = 0;
 
 extern "C" void
-rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
-    const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo)
+rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges)
 {
   /* a9 reads the hidden rows and the output errors, a7/a8 the same plus Who:
      neither needs the other, both are too small to fill the GPU.  In a batch
@@ -1961,13 +1947,11 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     rb_prof_begin(RB_PROF_TOP);
     k_gemm<G_TOP><<<grid, 256, 0, rb_stream>>>(g);
     LAUNCH_CHECK("k_gemm<TOP>");
-    k_top_finish<<<v->n, 256, 0, rb_stream>>>(*v, (int)grid.x, Ehi, Elo);
+    k_top_finish<<<v->n, 256, 0, rb_stream>>>(*v, (int)grid.x);
     LAUNCH_CHECK("k_top_finish");
     rb_prof_end(RB_PROF_TOP);
   }
   else {
-    if (Ehi)
-      rb_die("recur-b200: internal: E[0] planes requested from the per-stream top kernel");
     size_t sh = (size_t)(v->d.o_size + 40) * sizeof(float);
     rb_prof_begin(RB_PROF_TOP);
     k_top<<<v->n, 256, sh, rb_stream>>>(*v, ranges_dev, n_ranges);
@@ -2012,19 +1996,6 @@ rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
     LAUNCH_CHECK("k_ho_delta");
     rb_prof_end(RB_PROF_HO);
   }
-}
-
-extern "C" int
-rbk_top_layer_can_write_planes(const RbView *v)
-{
-  return v->n >= 4 * OS && v->pool && v->pool->has_bptt;
-}
-
-extern "C" void
-rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
-    const RecurErrorRange *ranges_dev, int n_ranges)
-{
-  rbk_top_layer_planes(v, ho_delta, accumulate, ranges_dev, n_ranges, NULL, NULL);
 }
 
 extern "C" void
@@ -2817,7 +2788,7 @@ rbk_opinion_single(const RbView *v, const float *hidden_in, const float *inputs_
 
 struct ResidentArgs {
   RbView v;
-  float *Ehi, *Elo; /* optional planes of the error chain */
+  RbPlanes E; /* optional planes of the error chain (hi == NULL: none) */
 };
 
 #define RES_THREADS 512
@@ -2843,6 +2814,7 @@ k_walk_resident(ResidentArgs a)
     return; /* uniform over the block */
   const int pos = v.pos[s];
   const int depth = v.depth;
+  const float e_scale = a.E.scale_dev ? *a.E.scale_dev : a.E.scale;
   for (int i = threadIdx.x * 4; i < I * H; i += RES_THREADS * 4)
     *(float4 *)(W + i) = __ldg((const float4 *)(v.Wih + i));
   {
@@ -2875,7 +2847,7 @@ k_walk_resident(ResidentArgs a)
       }
     }
     float *e_next_row = e_row(v, s, k + 1);
-    const size_t plane_off = ((size_t)(k + 1) * v.cap + s) * I;
+    const size_t plane_off = ((size_t)(k + 1) * v.cap + s) * a.E.pitch;
 
     /* the rows that were multiplied by zero have no error and cost nothing
        (recur-nn.c:347): list the others, 32-row segments by ballot */
@@ -2894,9 +2866,9 @@ k_walk_resident(ResidentArgs a)
           e_next_row[y] = 0.0f;
           if (y < H)
             nxt[y] = 0.0f;
-          if (a.Ehi) {
-            a.Ehi[plane_off + y] = 0.0f;
-            a.Elo[plane_off + y] = 0.0f;
+          if (a.E.hi) {
+            a.E.hi[plane_off + y] = 0;
+            a.E.lo[plane_off + y] = 0;
           }
         }
       }
@@ -2964,14 +2936,11 @@ k_walk_resident(ResidentArgs a)
           e_next_row[y] = e_store;
           if (y < H)
             nxt[y] = e_store;
-          if (a.Ehi) {
-            uint32_t hb, lb;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(e_store));
-            float hiv = __uint_as_float(hb);
-            float rem = e_store - hiv;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
-            a.Ehi[plane_off + y] = hiv;
-            a.Elo[plane_off + y] = __uint_as_float(lb);
+          if (a.E.hi) {
+            rb_h16 hiv, lov;
+            rb_split_f16(e_store * e_scale, hiv, lov);
+            a.E.hi[plane_off + y] = hiv;
+            a.E.lo[plane_off + y] = lov;
           }
         }
       }
@@ -3045,7 +3014,7 @@ rbk_walk_resident_usable(const RbView *v)
 
 /* the walk of every stream of the batch; E(1..) to the pool (and planes) */
 extern "C" void
-rbk_walk_resident(const RbView *v, float *Ehi, float *Elo)
+rbk_walk_resident(const RbView *v, const RbPlanes *E)
 {
   static int attr_done = 0;
   if (!attr_done) {
@@ -3055,8 +3024,10 @@ rbk_walk_resident(const RbView *v, float *Ehi, float *Elo)
   }
   ResidentArgs a;
   a.v = *v;
-  a.Ehi = Ehi;
-  a.Elo = Elo;
+  if (E)
+    a.E = *E;
+  else
+    memset(&a.E, 0, sizeof(a.E));
   rb_prof_begin(RB_PROF_CHAIN);
   k_walk_resident<<<v->n, RES_THREADS, resident_smem_bytes(v), rb_stream>>>(a);
   LAUNCH_CHECK("k_walk_resident");
@@ -3380,6 +3351,22 @@ rbk_bptt(const RbView *v, float *ih_delta, int accumulate)
   k_gemm<G_DW><<<dgrid, 256, 0, rb_stream>>>(g);
   LAUNCH_CHECK("k_gemm<DW>");
   rb_prof_end(RB_PROF_DW);
+}
+
+/* the weight gradient alone on the FMA engine (the tensor engine's fallback
+   for shapes its pair kernel has no grid for) */
+extern "C" void
+rbk_dw_fma(const RbView *v, float *ih_delta, int accumulate)
+{
+  GemmArgs g;
+  g.v = *v;
+  g.k = 0;
+  g.delta = ih_delta;
+  g.accumulate = accumulate;
+  g.use_noise = 0;
+  dim3 dgrid(cdiv(v->d.h_size, TN), cdiv(v->d.i_size, TM));
+  k_gemm<G_DW><<<dgrid, 256, 0, rb_stream>>>(g);
+  LAUNCH_CHECK("k_gemm<DW>");
 }
 
 extern "C" void

@@ -28,6 +28,18 @@ typedef struct RbView {
   int bl_i, bl_o;
 } RbView;
 
+/* One operand of the tensor engine as FP16 hi/lo planes (rb_split.cuh): row r
+   of the operand starts at r * pitch halves.  The values were multiplied by
+   `scale` before the split; for the error chain that scale is chosen per walk
+   and lives on the device (`scale_dev`, written by the kernel that makes the
+   planes of E(0)), otherwise scale_dev is NULL and `scale` holds it. */
+typedef struct RbPlanes {
+  unsigned short *hi, *lo;
+  int pitch;
+  float scale;
+  const float *scale_dev;
+} RbPlanes;
+
 /* device accumulators of the text-predict report sums */
 typedef struct RbCharAccum {
   double error;
@@ -61,9 +73,9 @@ void rbk_prepare_x(const RbView *v);
 void rbk_forward_core(const RbView *v, float presynaptic_noise);
 int rbk_step_begin_usable(const RbView *v);
 void rbk_step_begin(const RbView *v, const u8 *text_dev, int len, int pos, int spacing,
-    u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
+    u8 *cur_dev, u8 *next_dev, const RbPlanes *X, int advance);
 void rbk_step_begin_on(cudaStream_t stream, const RbView *v, const u8 *text_dev, int len, int pos,
-    int spacing, u8 *cur_dev, u8 *next_dev, float *Xhi, float *Xlo, int advance);
+    int spacing, u8 *cur_dev, u8 *next_dev, const RbPlanes *X, int advance);
 void rb_mark_pre_update(void);
 void rbk_output(const RbView *v);
 void rbk_rnnca_gather(const RbView *v, const u8 *frame_dev, int width, int height,
@@ -75,7 +87,8 @@ void rbk_rnnca_cells(const RbView *v, const u8 *frame_dev, u8 *frame_out_dev, in
     int edges);
 int rbk_walk_single_usable(const RbView *v);
 int rbk_walk_resident_usable(const RbView *v);
-void rbk_walk_resident(const RbView *v, float *Ehi, float *Elo);
+void rbk_walk_resident(const RbView *v, const RbPlanes *E);
+void rbk_dw_fma(const RbView *v, float *ih_delta, int accumulate);
 int rbk_opinion_single_usable(const RbView *v);
 void rbk_calculate_single(const RbView *v, const float *o_error_host, float lr, float mef,
     int adaptive, float *ho_w, float *ho_mom, float *ih_w, float *ih_mom, float *ih_delta,
@@ -100,9 +113,6 @@ void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
 void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges);       /* a7..a9 */
-void rbk_top_layer_planes(const RbView *v, float *ho_delta, int accumulate,
-    const RecurErrorRange *ranges_dev, int n_ranges, float *Ehi, float *Elo);
-int rbk_top_layer_can_write_planes(const RbView *v);
 void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */
 void rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive);
 void rbk_mask_streams(const RbView *v, const u8 *active_dev);
@@ -140,7 +150,7 @@ void rb_bottom_pool_release(RbPool *p);
 int rb_tc_usable(const RbView *v);
 void rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise);
 void rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise);
-void rb_tc_x_planes(RbPool *p, float **Xhi, float **Xlo);
+void rb_tc_x_planes(RbPool *p, RbPlanes *X);
 void rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     int accumulate);
 void rb_tc_pool_release(RbPool *p);

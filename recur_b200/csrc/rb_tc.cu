@@ -6,25 +6,25 @@
  *   CHAIN  E(k+1)[b, y]   = mask * sum_x E(k)[b, x] * Wih[y, x]    (recur-nn.c:338-376)
  *   DW     delta[y, x]   += sum_{k,b} x_k[b, y] * E(k)[b, x]       (recur-nn.c:353-356)
  *
- * Numerics: "3xTF32".  Every FP32 operand a is split exactly into
- * hi = tf32(a) and lo = tf32(a - hi); a product a*b is issued as three
- * kind::tf32 MMAs hi*hi + hi*lo + lo*hi accumulated in FP32 in tensor
- * memory, which keeps ~21 mantissa bits per product (the dropped lo*lo term
- * is 2^-22 relative) — FP32-faithful within the 1e-4 parity tolerance.
- * The hi/lo planes of the operands are materialised once where each operand
- * is produced (weights: after an update; input rows: when the row enters the
- * ring; error rows: in the CHAIN epilogue), so the GEMM mainloops are pure
+ * Numerics: every FP32 operand is kept as two FP16 planes (rb_split.cuh); a
+ * product is three kind::f16 MMAs into two FP32 accumulators in tensor
+ * memory, 22 significant bits per operand - FP32-faithful within the 1e-4
+ * parity tolerance at half the bytes and twice the MMA rate of TF32 planes.
+ * The planes are materialised once where each operand is produced (weights:
+ * in the update kernel; ring rows: when the row enters the ring; error rows:
+ * by the kernel that computes them), so the GEMM main loops are pure
  * TMA -> shared memory -> tcgen05.mma pipelines.
  *
- * Kernel anatomy (both kernels): 192 threads = warp 0 TMA producer (one
- * elected lane), warp 1 TMEM allocator + MMA issuer (one elected lane),
- * warps 2..5 epilogue (one TMEM lane quarter each).  Operand tiles are
- * 128B-swizzled; FWD/CHAIN read both operands K-major, DW reads both
- * MN-major (the contraction runs over ring rows).
+ * Kernel anatomy: warp 0 TMA producer (one lane), warp 1 TMEM allocator + MMA
+ * issuer (one lane), warps 2..5 epilogue (one TMEM lane quarter each); the
+ * persistent chain kernel adds two warps.  Operand tiles are swizzled; FWD and
+ * CHAIN read both operands K-major, DW reads both MN-major (the contraction
+ * runs over ring rows).
  */
 #include "rb_kernels.h"
 #include "rb_host.h"
 #include "rb_optim.cuh"
+#include "rb_split.cuh"
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -87,6 +87,12 @@ mbar_wait(uint64_t *bar, uint32_t parity)
 }
 
 __device__ __forceinline__ void
+mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void
 fence_barrier_init(void)
 {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -145,15 +151,15 @@ tc_fence_after(void)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
-/* D[tmem] (+)= A[smem] . B[smem], kind::tf32, issued by one thread */
+/* D[tmem] (+)= A[smem] . B[smem], kind::f16, issued by one thread */
 __device__ __forceinline__ void
-umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
 {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
@@ -180,6 +186,25 @@ cluster_sync_all(void)
 {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+/* the address of a shared-memory object of this CTA as it appears in the
+   shared window of the cluster's CTA `rank` (distributed shared memory) */
+__device__ __forceinline__ uint32_t
+dsmem_addr(const void *p, uint32_t rank)
+{
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(smem_u32(p)), "r"(rank));
+  return a;
+}
+
+__device__ __forceinline__ float4
+ld_dsmem_v4(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 
 /* shared-window addresses of the two CTAs of a pair differ in this bit;
@@ -217,14 +242,14 @@ tmem_dealloc_pair(uint32_t addr, uint32_t cols)
 /* one MMA across both SMs of the pair: M = 256 (128 rows per CTA), each CTA
    holding half of B's N columns; issued by one thread of the leader CTA */
 __device__ __forceinline__ void
-umma_tf32_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
     uint32_t accumulate)
 {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
@@ -285,9 +310,8 @@ tmem_wait_ld(void)
 /* Shared-memory matrix descriptor for a 128B-swizzled operand tile
    (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start address, leading and
    stride byte offsets in 16-byte units, version 1, layout SWIZZLE_128B. */
-#define UMMA_SW128 2u        /* 16-byte chunks swizzled over 8 rows */
-#define UMMA_SW128_BASE32 1u /* 32-byte chunks swizzled over 4 rows: the only
-                                layout for MN-major 32-bit operands */
+#define UMMA_SW128 2u /* 128-byte rows, 16-byte chunks swizzled over 8 rows */
+#define UMMA_SW64 4u  /* 64-byte rows, swizzled over 4 rows */
 
 __device__ __forceinline__ uint64_t
 umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
@@ -303,13 +327,11 @@ umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
 }
 
 /* Instruction descriptor (mma_sm100_desc.hpp InstrDescriptor) for
-   kind::tf32, FP32 accumulate. */
+   kind::f16 with FP16 operands (a_format = b_format = 0), FP32 accumulate. */
 __host__ __device__ constexpr uint32_t
-umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major)
+umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major)
 {
   return (1u << 4)      /* c_format  F32 */
-    | (2u << 7)         /* a_format  TF32 */
-    | (2u << 10)        /* b_format  TF32 */
     | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16)
     | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
@@ -322,19 +344,6 @@ st_global_v8(float *p, const float *a)
   asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
       ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(a[4]), "f"(a[5]), "f"(a[6]),
       "f"(a[7]) : "memory");
-}
-
-/* exact split of an FP32 number into two TF32 numbers */
-__device__ __forceinline__ void
-split_tf32(float a, float &hi, float &lo)
-{
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(a));
-  hi = __uint_as_float(h);
-  float r = a - hi;
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
 }
 
 __device__ __forceinline__ float
@@ -364,44 +373,45 @@ block_sum_tc(float v, float *scratch /* >= 33 floats */)
 /* the engine's extra state per pool                                          */
 
 #define TC_BM 128      /* tile rows (TMEM lanes) */
-#define TC_BK 32       /* K per stage: 32 floats = one 128-byte swizzle row */
-#define TC_FWD_BN 64      /* FWD tile columns */
+#define TC_KB 64       /* K per stage: 64 halves = one 128-byte swizzle row */
+#define TC_FWD_BN 64      /* FWD tile columns (unsplit variant) */
 #define TC_FWD_STAGES 4
-#define TC_CHAIN_BN 128   /* CHAIN tile columns */
-#define TC_CHAIN_STAGES 3
-#define TC_DW2_BN 192 /* N of the CTA-pair weight-gradient tile (two halves of 96) */
-#define TC_CHAIN_SPLITS 4 /* split-K: 4 x 9 x 4 = 144 CTAs at 512 streams, H1023 */
-#define TC_DW_BN 256      /* DW tile columns */
-#define TC_DW_BK 16       /* DW ring rows per stage */
-#define TC_DW_STAGES 4
-#define TC_DW_SPLITS 4
+#define TC_NT_BN 128      /* split-K FWD and per-step CHAIN tile columns */
+#define TC_NT_STAGES 3
+#define TC_NT_SPLITS 4    /* split-K of those */
+#define TC_DW_BK 32       /* DW ring rows per stage (two MMAs of K = 16) */
+#define TC_DW2_BN 192     /* N of the CTA-pair weight-gradient tile (two halves of 96) */
+#define TC_DW_SPLITS 4    /* most split-K planes the weight gradient writes */
+#define CH_SQ_SLOTS 64    /* floats per stream in the chain's sum-of-squares exchange */
+#define CH_SYNC_STRIDE 32 /* words between the barrier counters of two stream groups */
 
 typedef struct RbTc {
   int cap, depth;
-  float *Xhi, *Xlo;     /* [depth][cap][i_size]   planes of the ring */
-  float *Ehi, *Elo;     /* [depth+1][cap][i_size] planes of the error chain */
-  float *Whi, *Wlo;     /* [i_size][h_size] */
-  float *WThi, *WTlo;   /* [h_size][i_size] */
-  float *partial;       /* [TC_DW_SPLITS][i_size][h_size] */
-  float *cpartial;      /* [TC_CHAIN_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
-  unsigned int *sync;   /* grid barrier counter + per-step live counts of the persistent chain */
+  int pitch;            /* halves per ring / chain plane row: i_size rounded up to 64 */
+  int wpitch;           /* halves per Wih plane row: h_size rounded up to 64 */
+  rb_h16 *Xhi, *Xlo;    /* [depth][cap][pitch]     planes of the ring */
+  rb_h16 *Ehi, *Elo;    /* [depth+1][cap][pitch]   planes of the error chain */
+  rb_h16 *Whi, *Wlo;    /* [i_size][wpitch]        Wih, K-major B of CHAIN */
+  rb_h16 *WThi, *WTlo;  /* [h_size][pitch]         Wih^T, K-major B of FWD */
+  float *escale;        /* device: the chain planes' scale of the current walk */
+  float *partial;       /* [TC_DW_SPLITS][i_size][h_size] split-K planes of the weight gradient */
+  float *cpartial;      /* [TC_NT_SPLITS][cap][i_size rounded up to 32] split-K partial sums */
+  float *sqpart;        /* [2][m tiles][128][CH_SQ_SLOTS] per-CTA sums of squares of the chain */
+  unsigned int *sync;   /* barrier counters of the persistent chain + kmax, two areas */
   size_t sync_words;
   int sync_flip;
-  int persistent_ok;    /* decided per call */
   int delta_pending;    /* the last weight gradient still sits in `partial`, unsummed */
   int pending_accumulate;
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
-  CUtensorMap mXhi_k, mXlo_k;   /* ring rows as K-major A of FWD: box 32 x 128 */
+  CUtensorMap mXhi_k, mXlo_k;   /* ring rows as K-major A of FWD: box 64 x 128 */
   CUtensorMap mEhi_k, mElo_k;   /* error rows as K-major A of CHAIN (width h_size) */
-  CUtensorMap mWhi_k, mWlo_k;   /* Wih rows as K-major B of CHAIN: box 32 x 128 */
-  CUtensorMap mWThi_k, mWTlo_k; /* Wih^T rows as K-major B of FWD: box 32 x 64 */
+  CUtensorMap mWhi_k, mWlo_k;   /* Wih rows as K-major B of CHAIN: box 64 x 128 */
+  CUtensorMap mWThi_k, mWTlo_k; /* Wih^T rows as K-major B of FWD: box 64 x 64 */
   CUtensorMap mWThi_k128, mWTlo_k128; /* the same with 128-row boxes: split-K FWD */
-  CUtensorMap mXhi_mn, mXlo_mn; /* ring rows as MN-major A of DW: box 32 x 32 */
-  CUtensorMap mEhi_mn, mElo_mn; /* error rows as MN-major B of DW (width h_size) */
-  CUtensorMap mEhi_mn4, mElo_mn4; /* error rows as MN-major A of the pair DW: 4 chunks */
-  CUtensorMap mXhi_mn3, mXlo_mn3; /* ring rows as MN-major B half of the pair DW: 3 chunks */
+  CUtensorMap mEhi_mn, mElo_mn; /* error rows as MN-major A of DW: 2 chunks of 64 columns */
+  CUtensorMap mXhi_mn, mXlo_mn; /* ring rows as MN-major B half of DW: 3 chunks of 32 columns */
   int dw_splits;        /* split-K planes the last weight gradient wrote */
 } RbTc;
 
@@ -424,38 +434,40 @@ get_encode(void)
   return fn;
 }
 
-/* rows x width floats with a row pitch of pitch floats, boxes of 32 x box_rows */
+/* rows x width halves with a row pitch of pitch halves, boxes of 64 x box_rows
+   (K-major operand tiles, 128-byte swizzle); reads past `width` or `rows`
+   return zeros */
 static void
-make_map(CUtensorMap *m, float *base, uint64_t width, uint64_t rows, uint64_t pitch,
-    uint32_t box_rows, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
+make_map(CUtensorMap *m, rb_h16 *base, uint64_t width, uint64_t rows, uint64_t pitch,
+    uint32_t box_rows)
 {
   cuuint64_t dims[2] = {width, rows};
-  cuuint64_t strides[1] = {pitch * sizeof(float)};
-  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint64_t strides[1] = {pitch * sizeof(rb_h16)};
+  cuuint32_t box[2] = {TC_KB, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box,
-      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     rb_die("recur-b200: cuTensorMapEncodeTiled failed (%d) for %llu x %llu pitch %llu", (int)r,
         (unsigned long long)width, (unsigned long long)rows, (unsigned long long)pitch);
 }
 
-/* The same rows seen as [chunk of 32 columns][row][32 floats], so that one
-   TMA fetches n_chunks column chunks of box_rows rows into consecutive
-   (chunk-major) shared memory: the MN-major operand layout of DW.  A chunk
-   that straddles the end of a row reads on into the next row; those columns
-   only ever feed output rows/columns that are discarded. */
+/* The same rows seen as [chunk of `chunk` columns][row][chunk halves], so
+   that one TMA fetches n_chunks column chunks of box_rows rows into
+   consecutive (chunk-major) shared memory: the MN-major operand layout of DW
+   (chunk 64: 128-byte swizzle, chunk 32: 64-byte swizzle). */
 static void
-make_map_chunked(CUtensorMap *m, float *base, uint64_t width, uint64_t rows, uint64_t pitch,
-    uint32_t box_rows, uint32_t n_chunks)
+make_map_chunked(CUtensorMap *m, rb_h16 *base, uint64_t width, uint64_t rows, uint64_t pitch,
+    uint32_t box_rows, uint32_t chunk, uint32_t n_chunks)
 {
-  cuuint64_t dims[3] = {32, rows, (width + 31) / 32};
-  cuuint64_t strides[2] = {pitch * sizeof(float), 32 * sizeof(float)};
-  cuuint32_t box[3] = {32, box_rows, n_chunks};
+  cuuint64_t dims[3] = {chunk, rows, (width + chunk - 1) / chunk};
+  cuuint64_t strides[2] = {pitch * sizeof(rb_h16), chunk * sizeof(rb_h16)};
+  cuuint32_t box[3] = {chunk, box_rows, n_chunks};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box,
-      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, base, dims, strides, box,
+      estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      chunk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     rb_die("recur-b200: cuTensorMapEncodeTiled (chunked) failed (%d)", (int)r);
@@ -480,8 +492,10 @@ tc_free(RbTc *t)
     return;
   cudaFree(t->Xhi); cudaFree(t->Xlo); cudaFree(t->Ehi); cudaFree(t->Elo);
   cudaFree(t->Whi); cudaFree(t->Wlo); cudaFree(t->WThi); cudaFree(t->WTlo);
+  cudaFree(t->escale);
   cudaFree(t->partial);
   cudaFree(t->cpartial);
+  cudaFree(t->sqpart);
   cudaFree(t->sync);
   free(t);
 }
@@ -508,46 +522,58 @@ tc_state(RbPool *p)
   t = (RbTc *)calloc(1, sizeof(RbTc));
   t->cap = p->cap;
   t->depth = p->depth;
-  size_t ring = (size_t)p->depth * p->cap * I, chain = (size_t)(p->depth + 1) * p->cap * I;
-  t->Xhi = dmalloc0<float>(ring + 64);
-  t->Xlo = dmalloc0<float>(ring + 64);
-  t->Ehi = dmalloc0<float>(chain + 64);
-  t->Elo = dmalloc0<float>(chain + 64);
-  t->Whi = dmalloc0<float>(I * H);
-  t->Wlo = dmalloc0<float>(I * H);
-  t->WThi = dmalloc0<float>(I * H);
-  t->WTlo = dmalloc0<float>(I * H);
+  t->pitch = (int)((I + 63) & ~(size_t)63);
+  t->wpitch = (int)((H + 63) & ~(size_t)63);
+  const size_t P = t->pitch, WP = t->wpitch;
+  size_t ring_rows = (size_t)p->depth * p->cap, chain_rows = (size_t)(p->depth + 1) * p->cap;
+  t->Xhi = dmalloc0<rb_h16>(ring_rows * P);
+  t->Xlo = dmalloc0<rb_h16>(ring_rows * P);
+  t->Ehi = dmalloc0<rb_h16>(chain_rows * P);
+  t->Elo = dmalloc0<rb_h16>(chain_rows * P);
+  t->Whi = dmalloc0<rb_h16>(I * WP);
+  t->Wlo = dmalloc0<rb_h16>(I * WP);
+  t->WThi = dmalloc0<rb_h16>(H * P);
+  t->WTlo = dmalloc0<rb_h16>(H * P);
+  t->escale = dmalloc0<float>(4);
   t->partial = dmalloc0<float>((size_t)TC_DW_SPLITS * I * H);
-  t->cpartial = dmalloc0<float>((size_t)TC_CHAIN_SPLITS * p->cap * ((I + 31) & ~(size_t)31));
+  t->cpartial = dmalloc0<float>((size_t)TC_NT_SPLITS * p->cap * ((I + 31) & ~(size_t)31));
+  const size_t m_tiles = cdiv(p->cap, TC_BM) + 1;
+  t->sqpart = dmalloc0<float>(2 * m_tiles * TC_BM * CH_SQ_SLOTS);
   /* two areas, used by alternate walks (see k_finalize_rows) */
-  t->sync_words = (size_t)(cdiv(p->cap, TC_BM) + 1) * (p->depth + 8) + 8;
+  t->sync_words = m_tiles * CH_SYNC_STRIDE + 8;
   t->sync = dmalloc0<unsigned int>(2 * t->sync_words);
   t->sync_flip = 0;
-  t->persistent_ok = -1;
   t->w_src = NULL;
-  uint64_t ring_rows = (uint64_t)p->depth * p->cap, chain_rows = (uint64_t)(p->depth + 1) * p->cap;
-  make_map(&t->mXhi_k, t->Xhi, I, ring_rows, I, TC_BM);
-  make_map(&t->mXlo_k, t->Xlo, I, ring_rows, I, TC_BM);
-  make_map(&t->mEhi_k, t->Ehi, H, chain_rows, I, TC_BM);
-  make_map(&t->mElo_k, t->Elo, H, chain_rows, I, TC_BM);
-  make_map(&t->mWhi_k, t->Whi, H, I, H, TC_CHAIN_BN);
-  make_map(&t->mWlo_k, t->Wlo, H, I, H, TC_CHAIN_BN);
-  make_map(&t->mWThi_k, t->WThi, I, H, I, TC_FWD_BN);
-  make_map(&t->mWTlo_k, t->WTlo, I, H, I, TC_FWD_BN);
-  make_map(&t->mWThi_k128, t->WThi, I, H, I, TC_CHAIN_BN);
-  make_map(&t->mWTlo_k128, t->WTlo, I, H, I, TC_CHAIN_BN);
-  make_map_chunked(&t->mXhi_mn, t->Xhi, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
-  make_map_chunked(&t->mXlo_mn, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_BM / 32);
-  make_map_chunked(&t->mEhi_mn, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
-  make_map_chunked(&t->mElo_mn, t->Elo, H, chain_rows, I, TC_DW_BK, TC_DW_BN / 32);
-  make_map_chunked(&t->mEhi_mn4, t->Ehi, H, chain_rows, I, TC_DW_BK, TC_BM / 32);
-  make_map_chunked(&t->mElo_mn4, t->Elo, H, chain_rows, I, TC_DW_BK, TC_BM / 32);
-  make_map_chunked(&t->mXhi_mn3, t->Xhi, I, ring_rows, I, TC_DW_BK, TC_DW2_BN / 2 / 32);
-  make_map_chunked(&t->mXlo_mn3, t->Xlo, I, ring_rows, I, TC_DW_BK, TC_DW2_BN / 2 / 32);
+  make_map(&t->mXhi_k, t->Xhi, I, ring_rows, P, TC_BM);
+  make_map(&t->mXlo_k, t->Xlo, I, ring_rows, P, TC_BM);
+  make_map(&t->mEhi_k, t->Ehi, H, chain_rows, P, TC_BM);
+  make_map(&t->mElo_k, t->Elo, H, chain_rows, P, TC_BM);
+  make_map(&t->mWhi_k, t->Whi, H, I, WP, TC_NT_BN);
+  make_map(&t->mWlo_k, t->Wlo, H, I, WP, TC_NT_BN);
+  make_map(&t->mWThi_k, t->WThi, I, H, P, TC_FWD_BN);
+  make_map(&t->mWTlo_k, t->WTlo, I, H, P, TC_FWD_BN);
+  make_map(&t->mWThi_k128, t->WThi, I, H, P, TC_NT_BN);
+  make_map(&t->mWTlo_k128, t->WTlo, I, H, P, TC_NT_BN);
+  make_map_chunked(&t->mEhi_mn, t->Ehi, H, chain_rows, P, TC_DW_BK, 64, TC_BM / 64);
+  make_map_chunked(&t->mElo_mn, t->Elo, H, chain_rows, P, TC_DW_BK, 64, TC_BM / 64);
+  make_map_chunked(&t->mXhi_mn, t->Xhi, I, ring_rows, P, TC_DW_BK, 32, TC_DW2_BN / 2 / 32);
+  make_map_chunked(&t->mXlo_mn, t->Xlo, I, ring_rows, P, TC_DW_BK, 32, TC_DW2_BN / 2 / 32);
   t->dw_splits = TC_DW_SPLITS;
   p->tc = t;
   p->x_planes_stale = 2; /* the ring may hold rows from before the planes existed */
   return t;
+}
+
+static RbPlanes
+planes_of(rb_h16 *hi, rb_h16 *lo, int pitch, float scale, const float *scale_dev)
+{
+  RbPlanes pl;
+  pl.hi = hi;
+  pl.lo = lo;
+  pl.pitch = pitch;
+  pl.scale = scale;
+  pl.scale_dev = scale_dev;
+  return pl;
 }
 
 /* ======================================================================== */
@@ -555,19 +581,19 @@ tc_state(RbPool *p)
 
 /* Wih -> hi/lo planes, plain and transposed (32x32 tiles through smem) */
 __global__ void __launch_bounds__(256)
-k_split_weights(const float *__restrict__ W, int I, int H, float *Whi, float *Wlo,
-    float *WThi, float *WTlo)
+k_split_weights(const float *__restrict__ W, int I, int H, rb_h16 *Whi, rb_h16 *Wlo, int wpitch,
+    rb_h16 *WThi, rb_h16 *WTlo, int tpitch)
 {
-  __shared__ float th[32][33], tl[32][33];
+  __shared__ rb_h16 th[32][34], tl[32][34];
   int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int r = ty; r < 32; r += 8) {
     int y = y0 + r, x = x0 + tx;
-    float hi = 0.f, lo = 0.f;
+    rb_h16 hi = 0, lo = 0;
     if (y < I && x < H) {
-      split_tf32(W[(size_t)y * H + x], hi, lo);
-      Whi[(size_t)y * H + x] = hi;
-      Wlo[(size_t)y * H + x] = lo;
+      rb_split_f16(W[(size_t)y * H + x] * RB_W_SCALE, hi, lo);
+      Whi[(size_t)y * wpitch + x] = hi;
+      Wlo[(size_t)y * wpitch + x] = lo;
     }
     th[r][tx] = hi;
     tl[r][tx] = lo;
@@ -576,50 +602,88 @@ k_split_weights(const float *__restrict__ W, int I, int H, float *Whi, float *Wl
   for (int r = ty; r < 32; r += 8) {
     int x = x0 + r, y = y0 + tx;
     if (x < H && y < I) {
-      WThi[(size_t)x * I + y] = th[tx][r];
-      WTlo[(size_t)x * I + y] = tl[tx][r];
+      WThi[(size_t)x * tpitch + y] = th[tx][r];
+      WTlo[(size_t)x * tpitch + y] = tl[tx][r];
     }
   }
 }
 
-/* one ring / chain row per block -> its hi/lo planes */
+/* the current ring row of every stream of the batch -> its planes */
 __global__ void __launch_bounds__(256)
-k_split_rows(RbView v, int which /* 0: current x row, 1: E[0] */, float *hi_plane, float *lo_plane)
+k_split_rows(RbView v, RbPlanes X)
 {
   int s = v.slots[blockIdx.x];
-  size_t off;
-  const float *src;
-  if (which == 0) {
-    off = ((size_t)v.pos[s] * v.cap + s) * v.d.i_size;
-    src = v.X + off;
-  }
-  else {
-    off = (size_t)s * v.d.i_size;
-    src = v.E + off;
-  }
+  size_t row = (size_t)v.pos[s] * v.cap + s;
+  const float *src = v.X + row * v.d.i_size;
   for (int i = threadIdx.x; i < v.d.i_size; i += blockDim.x) {
-    float hi, lo;
-    split_tf32(src[i], hi, lo);
-    hi_plane[off + i] = hi;
-    lo_plane[off + i] = lo;
+    rb_h16 hi, lo;
+    rb_split_f16(src[i] * X.scale, hi, lo);
+    X.hi[row * X.pitch + i] = hi;
+    X.lo[row * X.pitch + i] = lo;
   }
 }
 
 /* every row of the ring -> its planes (after something other than the tensor
    engine's own forward pass rewrote ring rows: RbPool.x_planes_stale) */
 __global__ void __launch_bounds__(256)
-k_split_ring(const float *__restrict__ X, size_t n, float *hi_plane, float *lo_plane)
+k_split_ring(const float *__restrict__ X, int I, size_t n_rows, RbPlanes P)
 {
-  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
-       i += (size_t)gridDim.x * blockDim.x * 4) {
-    float4 x = *(const float4 *)(X + i);
-    float4 h, l;
-    split_tf32(x.x, h.x, l.x);
-    split_tf32(x.y, h.y, l.y);
-    split_tf32(x.z, h.z, l.z);
-    split_tf32(x.w, h.w, l.w);
-    *(float4 *)(hi_plane + i) = h;
-    *(float4 *)(lo_plane + i) = l;
+  const int per_row = I / 4;
+  const size_t n = n_rows * per_row;
+  for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+       q += (size_t)gridDim.x * blockDim.x) {
+    size_t row = q / per_row;
+    int c = (int)(q - row * per_row) * 4;
+    float4 x = *(const float4 *)(X + row * I + c);
+    uint2 h, l;
+    rb_split4(x, P.scale, h, l);
+    *(uint2 *)(P.hi + row * P.pitch + c) = h;
+    *(uint2 *)(P.lo + row * P.pitch + c) = l;
+  }
+}
+
+/* Planes of E(0) for the whole batch, and the scale of this walk's error
+   planes.  The top layer's soft clip bounds what the walk can hold: elements
+   of E(0) are at most top_scaled (the sum of their magnitudes), and a later
+   row's elements at most sqrt(max_sum) = sqrt(2 top + 1) as long as the walk
+   goes on (recur-nn.c:318,387).  The largest bound over the batch's streams,
+   rounded up to a power of two, is put just inside FP16's range; every block
+   computes it from the streams' scalars by itself (same loads, same order,
+   same result), block 0 publishes it for the kernels that read the planes. */
+__global__ void __launch_bounds__(256)
+k_e0_planes(RbView v, RbPlanes E, float *scale_out)
+{
+  __shared__ float s_max[8];
+  float m = 0.0f;
+  for (int j = threadIdx.x; j < v.n; j += blockDim.x) {
+    const RbScalars *sc = v.sc + v.slots[j];
+    if (sc->live)
+      m = fmaxf(m, sc->top_scaled);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0)
+    s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = s_max[0];
+#pragma unroll
+  for (int w = 1; w < 8; w++)
+    m = fmaxf(m, s_max[w]);
+  const float bound = fmaxf(m, sqrtf(2.0f * m + 1.0f));
+  int e;
+  frexpf(bound, &e);                       /* bound < 2^e */
+  const float scale = (bound < 3.0e38f) ? ldexpf(1.0f, 15 - e) : 1.0f;   /* NaN or inf: anything */
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    *scale_out = scale;
+  const int s = v.slots[blockIdx.x];
+  const float *e0 = v.E + (size_t)s * v.d.i_size;
+  rb_h16 *hi = E.hi + (size_t)s * E.pitch, *lo = E.lo + (size_t)s * E.pitch;
+  for (int i = threadIdx.x * 4; i < v.d.h_size; i += blockDim.x * 4) {
+    uint2 h, l;
+    rb_split4(*(const float4 *)(e0 + i), scale, h, l);
+    *(uint2 *)(hi + i) = h;
+    *(uint2 *)(lo + i) = l;
   }
 }
 
@@ -627,8 +691,8 @@ k_split_ring(const float *__restrict__ X, size_t n, float *hi_plane, float *lo_p
    the weight gradient (zero them), and a stream whose gradient is clipped
    (ih_scale != 1, recur-nn.c:393-402) has its rows rescaled and re-split. */
 __global__ void __launch_bounds__(256)
-k_finalize_rows(RbView v, float *Ehi, float *Elo, const unsigned int *kmax_dev,
-    unsigned int *zero, int zero_words)
+k_finalize_rows(RbView v, RbPlanes E, const unsigned int *kmax_dev, unsigned int *zero,
+    int zero_words)
 {
   /* the other of the two barrier/counter areas is cleared here for the next
      walk, which saves that walk a memset in front of its kernel */
@@ -638,23 +702,26 @@ k_finalize_rows(RbView v, float *Ehi, float *Elo, const unsigned int *kmax_dev,
   const int s = v.slots[blockIdx.x];
   const RbScalars sc = v.sc[s];
   const int kmax = min((int)*kmax_dev, v.depth);
+  const float scale = *E.scale_dev;
   /* rows this stream never reached, up to the deepest step any stream took
      (the weight gradient stops there) */
   for (int step = sc.n_steps; step < kmax; step++) {
-    size_t off = ((size_t)step * v.cap + s) * v.d.i_size;
-    for (int i = threadIdx.x * 4; i < v.d.h_size; i += blockDim.x * 4) {
-      *(float4 *)(Ehi + off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *(float4 *)(Elo + off + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t off = ((size_t)step * v.cap + s) * E.pitch;
+    for (int i = threadIdx.x * 8; i < v.d.h_size; i += blockDim.x * 8) {
+      *(uint4 *)(E.hi + off + i) = make_uint4(0u, 0u, 0u, 0u);
+      *(uint4 *)(E.lo + off + i) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   if (sc.ih_scale != 1.0f) {
+    const float f = sc.ih_scale * scale;
     for (int step = 0; step < sc.n_steps; step++) {
-      size_t off = ((size_t)step * v.cap + s) * v.d.i_size;
-      for (int i = threadIdx.x; i < v.d.h_size; i += blockDim.x) {
-        float hi, lo;
-        split_tf32(v.E[off + i] * sc.ih_scale, hi, lo);
-        Ehi[off + i] = hi;
-        Elo[off + i] = lo;
+      size_t off = ((size_t)step * v.cap + s) * E.pitch;
+      const float *src = v.E + ((size_t)step * v.cap + s) * v.d.i_size;
+      for (int i = threadIdx.x * 4; i < v.d.h_size; i += blockDim.x * 4) {
+        uint2 h, l;
+        rb_split4(*(const float4 *)(src + i), f, h, l);
+        *(uint2 *)(E.hi + off + i) = h;
+        *(uint2 *)(E.lo + off + i) = l;
       }
     }
   }
@@ -678,29 +745,54 @@ k_compute_kmax(RbView v, unsigned int *kmax_dev)
 }
 
 /* ======================================================================== */
-/* FWD and CHAIN: C[128 x BN] tiles, both operands K-major.
+/* FWD and per-step CHAIN: C[128 x BN] tiles, both operands K-major.
  *
  * FWD  (BN 64): activation epilogue straight from tensor memory.
- * CHAIN (BN 128, split-K over blockIdx.z): one BPTT step is too small to
- * fill 148 SMs with tiles the tensor pipe likes, so K is split four ways and
- * each CTA writes its raw partial tile; k_chain_finish_step sums the
- * partials and does the row-wise part of the step.                          */
+ * FWD split-K / per-step CHAIN (BN 128, split-K over blockIdx.z): few tiles
+ * and a long K, so K is split and each CTA writes its raw partial tile; the
+ * output kernel (FWD) or k_chain_finish_step (CHAIN) sums the partials on its
+ * way in.  The per-step CHAIN is the fallback for shapes the persistent
+ * kernel below does not take.                                               */
 
 struct NtArgs {
   RbView v;
   int mode;        /* 0 FWD, 1 CHAIN, 2 FWD split-K (raw partial sums) */
   int k;           /* CHAIN: step */
   int use_noise;
-  float *cpartial; /* CHAIN: [splits][cap][i_size] */
+  float *cpartial; /* split-K: [splits][cap][i_size rounded up to 32] */
+  float inv_scale; /* 1 / (scale of A's planes * scale of B's planes) ... */
+  const float *a_scale_dev; /* ... CHAIN: A's scale lives on the device */
 };
 
 template <int BN, int STAGES>
 struct NtCfg {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int A_BYTES = TC_BM * TC_KB * 2;   /* one plane of the A tile */
+  static constexpr int B_BYTES = BN * TC_KB * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 2 * BN; /* main and correction accumulators */
 };
+
+/* the three MMAs of one 64-wide K block of split operands: `main` takes
+   hi*hi, `corr` the two cross terms (rb_split.cuh) */
+__device__ __forceinline__ void
+issue_block_f16(uint32_t tmem_main, uint32_t tmem_corr, uint32_t a_hi, uint32_t a_lo,
+    uint32_t b_hi, uint32_t b_lo, uint32_t idesc, bool first)
+{
+#pragma unroll
+  for (int kk = 0; kk < TC_KB / 16; kk++) {
+    /* K-major, 128B swizzle: 8-row groups 1024 B apart; a K step of 16
+       halves moves the start address by 32 bytes inside the swizzle row */
+    uint64_t dah = umma_desc(a_hi + kk * 32, 16, 1024);
+    uint64_t dal = umma_desc(a_lo + kk * 32, 16, 1024);
+    uint64_t dbh = umma_desc(b_hi + kk * 32, 16, 1024);
+    uint64_t dbl = umma_desc(b_lo + kk * 32, 16, 1024);
+    const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+    umma_f16(tmem_main, dah, dbh, idesc, acc);
+    umma_f16(tmem_corr, dah, dbl, idesc, acc);
+    umma_f16(tmem_corr, dal, dbh, idesc, 1u);
+  }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
@@ -721,7 +813,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
   const int I = v.d.i_size, H = v.d.h_size;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int K = (g.mode == 1) ? H : I;
-  const int n_kb_total = (K + TC_BK - 1) / TC_BK;
+  const int n_kb_total = (K + TC_KB - 1) / TC_KB;
   const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
@@ -752,7 +844,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     tma_prefetch_desc(&mBlo);
   }
   if (warp == 1)
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -773,16 +865,16 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t *st = smem + s * Cfg::STAGE_BYTES;
         mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-        tma_load_2d(&mAhi, &full[s], st, kb * TC_BK, ring_row);
-        tma_load_2d(&mAlo, &full[s], st + Cfg::A_BYTES, kb * TC_BK, ring_row);
-        tma_load_2d(&mBhi, &full[s], st + 2 * Cfg::A_BYTES, kb * TC_BK, n0);
-        tma_load_2d(&mBlo, &full[s], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * TC_BK, n0);
+        tma_load_2d(&mAhi, &full[s], st, kb * TC_KB, ring_row);
+        tma_load_2d(&mAlo, &full[s], st + Cfg::A_BYTES, kb * TC_KB, ring_row);
+        tma_load_2d(&mBhi, &full[s], st + 2 * Cfg::A_BYTES, kb * TC_KB, n0);
+        tma_load_2d(&mBlo, &full[s], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * TC_KB, n0);
       }
     }
   }
   else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(TC_BM, BN, 0, 0);
       for (int it = 0; it < n_kb; it++) {
         int s = it % STAGES;
         uint32_t ph = (it / STAGES) & 1;
@@ -792,18 +884,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
         uint32_t a_lo = a_hi + Cfg::A_BYTES;
         uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
         uint32_t b_lo = b_hi + Cfg::B_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; kk++) {
-          /* K-major, 128B swizzle: 8-row groups 1024 B apart; a K step of 8
-             floats moves the start address by 32 bytes inside the swizzle row */
-          uint64_t dah = umma_desc(a_hi + kk * 32, 16, 1024);
-          uint64_t dal = umma_desc(a_lo + kk * 32, 16, 1024);
-          uint64_t dbh = umma_desc(b_hi + kk * 32, 16, 1024);
-          uint64_t dbl = umma_desc(b_lo + kk * 32, 16, 1024);
-          umma_tf32(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
-        }
+        issue_block_f16(tmem_base, tmem_base + BN, a_hi, a_lo, b_hi, b_lo, idesc, it == 0);
         umma_commit(&empty[s]);
       }
       umma_commit(acc_ready);
@@ -820,11 +901,14 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
       mbar_wait(acc_ready, 0);
       tc_fence_after();
     }
-    float acc[32];
+    const float inv = g.a_scale_dev ? g.inv_scale / *g.a_scale_dev : g.inv_scale;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float acc[32], cor[32];
     if (g.mode == 0) {
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+        tmem_ld32_nowait(taddr + c, acc);
+        tmem_ld32(taddr + BN + c, cor);
         int col0 = n0 + c;
         if (!row_ok || col0 >= H)
           continue;
@@ -836,7 +920,7 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             int col = col0 + j + u;
-            float h = acc[j + u];
+            float h = fmaf(cor[j + u], RB_LO_UNGAIN, acc[j + u]) * inv;
             if (g.use_noise && col >= 1 && col < H)
               h += nz[j + u];
             if (v.activation == RNN_RESQRT) {
@@ -862,15 +946,20 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
     }
     else {
       /* raw partial sums of this K split; masks and the rest happen row-wise
-         in k_chain_finish_step */
+         in the kernel that sums the splits */
       const bool live = row_ok && (g.mode == 2 || v.sc[sidx].live != 0);
       const int cpitch = (I + 31) & ~31;
       const int n_cols = (g.mode == 2) ? H : I;
       float *dst = g.cpartial + ((size_t)blockIdx.z * v.cap + sidx) * cpitch;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
-        if (n_kb > 0)
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+        if (n_kb > 0) {
+          tmem_ld32_nowait(taddr + c, acc);
+          tmem_ld32(taddr + BN + c, cor);
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            acc[j] = fmaf(cor[j], RB_LO_UNGAIN, acc[j]) * inv;
+        }
         else {
 #pragma unroll
           for (int j = 0; j < 32; j++)
@@ -894,210 +983,61 @@ k_tc_nt(const __grid_constant__ CUtensorMap mAhi, const __grid_constant__ CUtens
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-/* The row-wise half of a BPTT step (recur-nn.c:338-389, 393-413), one block
-   per stream: sum the split-K partials in a fixed order, mask by the input
-   that fed each row, ReSQRT derivative, write E(k+1) with its hi/lo planes,
-   sum the squares, and decide whether this stream walks further.           */
-__global__ void __launch_bounds__(256)
-k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int splits,
-    float *__restrict__ Ehi, float *__restrict__ Elo)
+/* What the reference does with one stream's error row once its sum of
+   squares is known (recur-nn.c:383-413): count the step, stop the walk on
+   either threshold, and on the way out clip the gradient or adapt
+   min_error_factor.  k is the step just executed. */
+__device__ __forceinline__ void
+chain_decide(RbScalars &sc, float es, int k, int depth)
 {
-  __shared__ float scratch[33];
-  const int s = v.slots[blockIdx.x];
-  RbScalars *scp = v.sc + s;
-  RbScalars scv = *scp; /* one read up front; thread 0 writes the changes back */
-  RbScalars *sc = &scv;
-  if (!sc->live)
+  sc.err_sum = es;
+  sc.cum_error += sqrtf(es);
+  sc.n_steps = k + 1;
+  const int t = depth - k;
+  const bool stop = (es <= sc.min_sum || es > sc.max_sum);
+  const bool last = (k == depth - 1);
+  if (!stop && !last)
     return;
-  const int I = v.d.i_size, H = v.d.h_size, hs1 = v.d.hidden_size + 1;
-  int p = v.pos[s] - k;
-  if (p < 0)
-    p += v.depth;
-  const float *xk = v.X + ((size_t)p * v.cap + s) * I;
-  const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
-  const int cpitch = (I + 31) & ~31;
-  const size_t split_stride = (size_t)v.cap * cpitch;
-  const float *part = cpartial + (size_t)s * cpitch;
-  float sq = 0.0f;
-  for (int c = threadIdx.x * 4; c < I; c += blockDim.x * 4) {
-    float4 a = *(const float4 *)(part + c);
-    for (int z = 1; z < splits; z++) {
-      float4 b = *(const float4 *)(part + z * split_stride + c);
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-    }
-    float4 xin = *(const float4 *)(xk + c);
-    float acc[4] = {a.x, a.y, a.z, a.w};
-    float xi[4] = {xin.x, xin.y, xin.z, xin.w};
-    float o[4], ohi[4], olo[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      float e = 0.0f;
-      float input = xi[u];
-      if (input != 0.0f && (v.activation != RNN_RECLIP20 || input < 20.0f)) {
-        e = acc[u];
-        if (v.activation == RNN_RESQRT)
-          e /= 2.0f * (input + 1.0f);
-        sq += e * e;
-      }
-      int col = c + u;
-      if (v.CIE && col >= hs1 && col < hs1 + v.d.input_size)
-        v.CIE[(size_t)s * v.bl_o + col - hs1] += e;
-      if (col == 0 || (col >= hs1 && col < H))
-        e = 0.0f;
-      o[u] = e;
-      split_tf32(e, ohi[u], olo[u]);
-    }
-    *(float4 *)(v.E + eoff + c) = make_float4(o[0], o[1], o[2], o[3]);
-    *(float4 *)(Ehi + eoff + c) = make_float4(ohi[0], ohi[1], ohi[2], ohi[3]);
-    *(float4 *)(Elo + eoff + c) = make_float4(olo[0], olo[1], olo[2], olo[3]);
-  }
-  float es = block_sum_tc(sq, scratch);
-  if (threadIdx.x != 0)
-    return;
-  sc->err_sum = es;
-  sc->cum_error += sqrtf(es);
-  sc->n_steps = k + 1;
-  int t = v.depth - k;
-  bool stop = (es <= sc->min_sum || es > sc->max_sum);
-  bool last = (k == v.depth - 1);
-  if (!stop && !last) {
-    *scp = scv;
-    return;
-  }
-  sc->live = 0;
-  int t_left = stop ? t : 0;
-  sc->t_left = t_left;
-  float ceiling = ERROR_GAIN_CEILING * sc->top_scaled;
+  sc.live = 0;
+  const int t_left = stop ? t : 0;
+  sc.t_left = t_left;
+  const float ceiling = ERROR_GAIN_CEILING * sc.top_scaled;
   if (es > ceiling) {
-    float halfmax = sc->max_sum;
+    float halfmax = sc.max_sum;
     float x = es / halfmax;
     float fudge = (float)(0.99 + (double)(x * x / 100.0f));
-    sc->ih_scale = (halfmax == 0.0f) ? es : 2.0f * x / (1.0f + x * x * fudge);
+    sc.ih_scale = (halfmax == 0.0f) ? es : 2.0f * x / (1.0f + x * x * fudge);
   }
   else {
-    sc->ih_scale = 1.0f;
-    if (sc->adaptive & 1) {
-      int depth_error = v.depth / 4 - t_left;
-      float min_gain = MIN_ERROR_GAIN * sc->top_scaled;
-      float mef = sc->mef;
-      if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc->min_sum || depth_error < 0))
+    sc.ih_scale = 1.0f;
+    if (sc.adaptive & 1) {
+      int depth_error = depth / 4 - t_left;
+      float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
+      float mef = sc.mef;
+      if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc.min_sum || depth_error < 0))
         mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
-      sc->mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
+      sc.mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
     }
   }
-  *scp = scv;
 }
 
-/* ======================================================================== */
-/* The whole BPTT walk as ONE persistent, grid-synchronised kernel.
- *
- * A BPTT step is a small dependent GEMM; launched per step it spends more
- * time on launch gaps, pipeline prologues and cold tensor-map fetches than on
- * MMAs.  Here 144 CTAs (n-tiles x m-tiles x K-splits, one per SM, co-resident
- * through a cooperative launch) stay alive for all `depth` steps.  Per step:
- *   phase A  the split-K tcgen05 GEMM of k_tc_nt (TMEM allocated once, mbarrier
- *            pipeline state carried across steps), partial tiles to L2;
- *   grid barrier;
- *   phase B  the row-wise half (k_chain_finish_step's body), one row per
- *            epilogue warp across the grid, which also counts the streams
- *            that walk on;
- *   grid barrier; stop when no stream is left.
- * E(k+1)'s hi/lo planes are written with generic stores and read by the next
- * step's TMA, hence the generic->async proxy fence before the barrier.       */
-
-__device__ __forceinline__ unsigned int
-ld_acquire_gpu(const unsigned int *p)
-{
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-/* per-stream scalars change between steps inside one launch: read them past L1 */
-__device__ __forceinline__ RbScalars
-load_scalars_cg(const RbScalars *p)
-{
-  static_assert(sizeof(RbScalars) == 64, "RbScalars is read as four 16-byte words");
-  union { RbScalars s; int4 w[4]; } u;
-  const int4 *src = (const int4 *)p;
-#pragma unroll
-  for (int i = 0; i < 4; i++)
-    u.w[i] = __ldcg(src + i);
-  return u.s;
-}
-
-struct ChainArgs {
-  RbView v;
-  float *cpartial;
-  float *Ehi, *Elo;
-  unsigned int *sync;   /* [0] barrier counter, [1 + k] streams alive at step k */
-  unsigned long long *dbg; /* optional: 5 globaltimer stamps per step from CTA 0 */
-  unsigned int *kmax;   /* out: steps executed before every stream had stopped */
-};
-
-__device__ __forceinline__ unsigned long long
-globaltimer_ns(void)
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
-
-#define ROLE_STAMP(slot) do {                                           \
-    if (g.dbg && cta == 0 && k == 5)                                    \
-      g.dbg[1200 + (slot)] = globaltimer_ns();                          \
-  } while (0)
-
-#define CHAIN_STAMP(slot) do {                                          \
-    if (g.dbg && threadIdx.x == 0) {                                    \
-      unsigned long long now_ = globaltimer_ns();                       \
-      if (cta == 0)                                                     \
-        g.dbg[k * 5 + (slot)] = now_;                                   \
-      if (k == 5)                                                       \
-        g.dbg[320 + cta * 5 + (slot)] = now_;                           \
-    }                                                                   \
-  } while (0)
-
-__device__ __forceinline__ void
-grid_barrier(unsigned int *counter, unsigned int target)
-{
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    /* arrive with a release reduction: nothing waits for the old value to
-       come back before the polling starts */
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
-    /* a poll is an L2 round trip (~0.7 us): 2^22 of them are seconds, against
-       the microseconds a healthy barrier takes.  A grid that is not fully
-       resident can never complete the barrier; trap (the host then aborts
-       with the launch failure) rather than hang the device. */
-    unsigned int spins = 0;
-    while (ld_acquire_gpu(counter) < target) {
-      if (++spins > (1u << 22))
-        __trap();
-    }
-  }
-  __syncthreads();
-}
-
-/* Four columns of E(k+1) from the summed partials `a` and the ring row `xin`
-   they are masked with; PLAIN is the common case (ReLU, no bottom layer),
-   kept free of branches.  Adds the squares to `sq`. */
+/* Four columns of E(k+1) from the summed products `a` and the ring row `xin`
+   they are masked with (recur-nn.c:338-376): the value that enters the sum
+   of squares, the bottom layer's accumulator, and what is stored as the next
+   step's operand (bias and padding columns carry no error).  PLAIN is the
+   common case (ReLU, no bottom layer), kept free of branches. */
 template <bool PLAIN>
-__device__ __forceinline__ void
-chain_chunk(const RbView &v, float4 a, float4 xin, int c, int s, float &sq, float *e_out,
-    float *hi_out, float *lo_out)
+__device__ __forceinline__ float4
+chain_mask4(const RbView &v, float4 a, float4 xin, int c, int s, float &sq)
 {
   const int H = v.d.h_size, hs1 = v.d.hidden_size + 1;
   float av[4] = {a.x, a.y, a.z, a.w};
   float xi[4] = {xin.x, xin.y, xin.z, xin.w};
-  float o[4], ohi[4], olo[4];
-  /* column 0 (the bias) and the padding between the hidden units and h_size
-     carry no error */
-  const bool edge = (c == 0) || (c + 4 > hs1 && c < H);
+  float o[4];
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     float e;
@@ -1120,7 +1060,7 @@ chain_chunk(const RbView &v, float4 a, float4 xin, int c, int s, float &sq, floa
     }
     o[u] = e;
   }
-  if (edge) {
+  if ((c == 0) || (c + 4 > hs1 && c < H)) {
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       int col = c + u;
@@ -1128,534 +1068,542 @@ chain_chunk(const RbView &v, float4 a, float4 xin, int c, int s, float &sq, floa
         o[u] = 0.0f;
     }
   }
-#pragma unroll
-  for (int u = 0; u < 4; u++)
-    split_tf32(o[u], ohi[u], olo[u]);
-  __stcg((float4 *)e_out, make_float4(o[0], o[1], o[2], o[3]));
-  __stcg((float4 *)hi_out, make_float4(ohi[0], ohi[1], ohi[2], ohi[3]));
-  __stcg((float4 *)lo_out, make_float4(olo[0], olo[1], olo[2], olo[3]));
+  return make_float4(o[0], o[1], o[2], o[3]);
 }
 
-#define TC_CHAIN_THREADS 256 /* TMA warp, MMA warp, four epilogue warps, two more for the rows */
+/* The row-wise half of a BPTT step (recur-nn.c:338-389, 393-413), one block
+   per stream: sum the split-K partials in a fixed order, mask by the input
+   that fed each row, ReSQRT derivative, write E(k+1) with its planes,
+   sum the squares, and decide whether this stream walks further.           */
+__global__ void __launch_bounds__(256)
+k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int splits, RbPlanes E)
+{
+  __shared__ float scratch[33];
+  const int s = v.slots[blockIdx.x];
+  RbScalars *scp = v.sc + s;
+  RbScalars sc = *scp; /* one read up front; thread 0 writes the changes back */
+  if (!sc.live)
+    return;
+  const int I = v.d.i_size;
+  const float scale = *E.scale_dev;
+  int p = v.pos[s] - k;
+  if (p < 0)
+    p += v.depth;
+  const float *xk = v.X + ((size_t)p * v.cap + s) * I;
+  const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
+  const size_t poff = ((size_t)(k + 1) * v.cap + s) * E.pitch;
+  const int cpitch = (I + 31) & ~31;
+  const size_t split_stride = (size_t)v.cap * cpitch;
+  const float *part = cpartial + (size_t)s * cpitch;
+  float sq = 0.0f;
+  for (int c = threadIdx.x * 4; c < I; c += blockDim.x * 4) {
+    float4 a = *(const float4 *)(part + c);
+    for (int z = 1; z < splits; z++) {
+      float4 b = *(const float4 *)(part + z * split_stride + c);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 o = chain_mask4<false>(v, a, *(const float4 *)(xk + c), c, s, sq);
+    *(float4 *)(v.E + eoff + c) = o;
+    uint2 h, l;
+    rb_split4(o, scale, h, l);
+    *(uint2 *)(E.hi + poff + c) = h;
+    *(uint2 *)(E.lo + poff + c) = l;
+  }
+  float es = block_sum_tc(sq, scratch);
+  if (threadIdx.x != 0)
+    return;
+  chain_decide(sc, es, k, v.depth);
+  *scp = sc;
+}
 
+/* ======================================================================== */
+/* The whole BPTT walk as ONE persistent kernel on thread-block clusters.
+ *
+ * A BPTT step is a small dependent GEMM, E(k+1) = mask * (E(k) . Wih^T): at
+ * 512 streams of a 1023-unit net a [512 x 1024] x [1024 x 1068] product that
+ * the next step cannot start without.  The grid is (column tiles x K splits)
+ * x stream tiles of 128, one CTA per SM, alive for all `depth` steps:
+ *
+ *  * the K splits of one output tile form a CLUSTER.  Each CTA's slice of
+ *    Wih (128 rows x its K range, both planes: 128 KB at H1023) is loaded
+ *    into shared memory ONCE and stays there for the whole walk; only the
+ *    error rows stream through the TMA ring each step;
+ *  * the split-K reduction never leaves the cluster: every CTA parks its
+ *    partial tile in its own shared memory, one cluster barrier, then each
+ *    CTA sums ITS quarter of the tile's columns out of its peers' shared
+ *    memory (distributed shared memory loads, fixed order), masks, writes
+ *    E(k+1) with its planes, and the row's partial sum of squares;
+ *  * the streams of a tile of 128 are an independent chain, so only the CTAs
+ *    that share blockIdx.y synchronise, ONCE per step (monotonic counter,
+ *    arrive = red.release.gpu, wait = ld.acquire.gpu by the TMA thread, which
+ *    issues the next step's loads the moment the counter is there);
+ *  * the stop rule (recur-nn.c:383-413) needs a row's sum of squares over
+ *    ALL columns, which no CTA has: every CTA of the group sums the per-CTA
+ *    parts of the PREVIOUS step for all 128 streams (same loads, same order,
+ *    same result everywhere) while that step's successor is already in the
+ *    tensor pipe, so the decision costs the critical path nothing; the group
+ *    leaves one (speculative) K loop after its last stream stopped.  Rows of
+ *    a stream beyond its own stop are computed but never stored;
+ *  * columns past the last tile (the input rows of a one-hot text net: 44 of
+ *    1068) would cost a whole extra tile per stream group and more clusters
+ *    than fit the GPU's GPCs; their few nonzero rows are dot products on two
+ *    spare warps instead (recur-nn.c:347 skips the zero rows just so).
+ *
+ * Shared memory: W slice 128 KB | TMA ring 3 x 32 KB (its first 66 KB double
+ * as the partial-tile parking area between the K loop and the next step's
+ * loads) | barriers.  Tensor memory: two 128-column accumulators.           */
+
+#define CH_THREADS 256
+#define CH_BN 128
+#define CH_WKB 4      /* K blocks of Wih resident per CTA */
+#define CH_STAGES 3
+#define CH_PLANE_BYTES (TC_BM * TC_KB * 2)        /* 16 KB: 128 rows x 64 halves */
+#define CH_STAGE_BYTES (2 * CH_PLANE_BYTES)       /* hi and lo planes of one K block */
+#define CH_W_BYTES (CH_WKB * 2 * CH_PLANE_BYTES)  /* 128 KB */
+#define CH_PARK_PITCH 132                          /* floats: 16-byte rows, conflict-free */
+#define CH_SMEM_BYTES (CH_W_BYTES + CH_STAGES * CH_STAGE_BYTES + 1024 + 1024)
+static_assert(TC_BM * CH_PARK_PITCH * 4 <= CH_STAGES * CH_STAGE_BYTES, "parking area fits the ring");
+
+__device__ __forceinline__ unsigned int
+ld_acquire_gpu(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+/* A poll is an L2 round trip (~0.7 us): 2^22 of them are seconds, against the
+   microseconds a healthy barrier takes.  A grid that is not fully resident
+   can never complete the barrier; trap (the host then aborts with the launch
+   failure) rather than hang the device. */
 __device__ __forceinline__ void
-named_bar_sync(int id, int count)
+wait_counter(const unsigned int *counter, unsigned int target)
 {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+  unsigned int spins = 0;
+  while (ld_acquire_gpu(counter) < target) {
+    if (++spins > (1u << 22))
+      __trap();
+  }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(TC_CHAIN_THREADS, 1)
-k_tc_chain_persistent(const __grid_constant__ CUtensorMap mAhi,
-    const __grid_constant__ CUtensorMap mAlo, const __grid_constant__ CUtensorMap mBhi,
-    const __grid_constant__ CUtensorMap mBlo, ChainArgs g)
+struct ChainArgs {
+  RbView v;
+  RbPlanes E;           /* planes of the chain; scale on the device */
+  float *sqpart;        /* [2][m tiles][128][CH_SQ_SLOTS] */
+  unsigned int *sync;   /* [m tiles][CH_SYNC_STRIDE] barrier counters */
+  unsigned int *kmax;   /* out: deepest step any stream executed */
+  int splits;           /* K splits == cluster size */
+  int nkb_total, kb_per;/* 64-wide K blocks in all, per split */
+  int tail0;            /* first column left to the CUDA-core tail (i_size: none) */
+};
+
+template <int SPLITS>
+__global__ void __launch_bounds__(CH_THREADS, 1)
+k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
+    const __grid_constant__ CUtensorMap mElo, const __grid_constant__ CUtensorMap mWhi,
+    const __grid_constant__ CUtensorMap mWlo, ChainArgs g)
 {
-  using Cfg = NtCfg<BN, STAGES>;
+  constexpr int CPR = CH_BN / SPLITS; /* columns of the tile this CTA finishes */
+  constexpr int CPT = CPR / 2;        /* per thread: two threads share a row */
+  constexpr int NG = CPT / 4;         /* float4 groups per thread */
   extern __shared__ uint8_t smem_raw[];
   const RbView &v = g.v;
+  /* the dynamic shared window starts at the same offset in every CTA, so the
+     rounded-up base does too: the parking area has one address cluster-wide */
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = (uint64_t *)(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t *empty = full + STAGES;
-  uint64_t *acc_ready = empty + STAGES;
-  uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
-  float *pair_sq = (float *)(tmem_slot + 2); /* one sum of squares per warp */
+  uint8_t *w_smem = smem;
+  uint8_t *a_smem = smem + CH_W_BYTES;
+  float *park = (float *)a_smem;
+  uint64_t *full = (uint64_t *)(a_smem + CH_STAGES * CH_STAGE_BYTES);
+  uint64_t *empty = full + CH_STAGES;
+  uint64_t *acc_ready = empty + CH_STAGES;
+  uint64_t *w_ready = acc_ready + 1;
+  uint64_t *step_go = w_ready + 1;
+  uint32_t *tmem_slot = (uint32_t *)(step_go + 1);
+  int *s_any = (int *)(tmem_slot + 1);      /* [2] a stream walks on, by step parity */
+  int *s_kmax = s_any + 2;
+  uint8_t *s_live = (uint8_t *)(s_kmax + 1); /* [128] */
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int I = v.d.i_size, H = v.d.h_size;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  /* The streams of one m-tile form an independent chain: only the CTAs that
-     share blockIdx.y exchange data, so they synchronise among themselves and
-     the four groups drift apart, one group's latency-bound row phase hiding
-     under another group's loads. */
+  const uint32_t rank = cluster_ctarank();
+  const int n0 = ((int)blockIdx.x / SPLITS) * CH_BN, m0 = blockIdx.y * TC_BM;
   const int grp = blockIdx.y;
-  const int grp_ctas = gridDim.x * gridDim.z;
-  const int grp_cta = blockIdx.z * gridDim.x + blockIdx.x;
-  const int sync_stride = v.depth + 8;
-  unsigned int *gsync = g.sync + (size_t)grp * sync_stride;
-  const int n_kb_total = (H + TC_BK - 1) / TC_BK;
-  const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
-  const int n_kb = max(0, kb_end - kb_begin);
-  const int cpitch = (I + 31) & ~31; /* rows of the partial planes start on 128-byte lines */
-  const size_t split_stride = (size_t)v.cap * cpitch;
+  const int grp_ctas = gridDim.x, grp_cta = blockIdx.x;
+  unsigned int *gsync = g.sync + (size_t)grp * CH_SYNC_STRIDE;
+  const int kb_begin = (int)rank * g.kb_per;
+  const int n_kb = min(g.kb_per, g.nkb_total - kb_begin);
+  const bool has_tail = g.tail0 < I;
+  const int n_slots = grp_ctas + (has_tail ? 1 : 0);
+  float *sq_grp = g.sqpart + (size_t)grp * TC_BM * CH_SQ_SLOTS;
+  const size_t sq_par = (size_t)gridDim.y * TC_BM * CH_SQ_SLOTS; /* floats between the two parities */
+  const int depth = v.depth;
+  const int pos0 = v.pos[v.base]; /* the batch advances in lockstep */
+  const bool plain = (v.activation == RNN_RELU && v.CIE == NULL);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) {
+    for (int s = 0; s < CH_STAGES; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     mbar_init(acc_ready, 1);
+    mbar_init(w_ready, 1);
+    mbar_init(step_go, 1);
     fence_barrier_init();
-    tma_prefetch_desc(&mAhi);
-    tma_prefetch_desc(&mAlo);
-    tma_prefetch_desc(&mBhi);
-    tma_prefetch_desc(&mBlo);
+    tma_prefetch_desc(&mEhi);
+    tma_prefetch_desc(&mElo);
+    tma_prefetch_desc(&mWhi);
+    tma_prefetch_desc(&mWlo);
+    s_any[0] = 0;
+    s_any[1] = 0;
+    *s_kmax = 0;
   }
   if (warp == 1)
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * CH_BN);
+
+  /* the decision threads (warps 2..5) keep one stream's scalars each */
+  const int di = threadIdx.x - 64;
+  const bool decider = di >= 0 && di < TC_BM;
+  const bool d_valid = decider && m0 + di < v.n;
+  RbScalars dsc;
+  dsc.live = 0;
+  dsc.n_steps = 0;
+  if (d_valid)
+    dsc = v.sc[v.base + m0 + di];
+  if (decider)
+    s_live[di] = d_valid && dsc.live;
+  const bool owner = grp_cta == 0; /* this CTA writes the group's scalars back */
+
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const float e_scale = *g.E.scale_dev;
+  const float inv_scale = 1.0f / (e_scale * RB_W_SCALE);
 
-  const int pos0 = v.pos[v.base]; /* the batch advances in lockstep */
-  const bool plain = (v.activation == RNN_RELU && v.CIE == NULL);
-  unsigned int it = 0;       /* pipeline iterations so far (producer and MMA keep equal counts) */
-  unsigned int n_gemms = 0;  /* accumulators completed by this CTA */
-  unsigned int n_bar = 0;
+  /* the part of the output tile this thread finishes: row, 16-column run */
+  const int r_row = threadIdx.x >> 1;
+  const int r_c = (int)rank * CPR + (threadIdx.x & 1) * CPT; /* tile-local first column */
+  const bool r_ok = m0 + r_row < v.n;
+  const int r_s = v.base + (r_ok ? m0 + r_row : 0);
 
-  for (int k = 0; k < v.depth; k++) {
-    /* ---- phase A: partial tile of E(k) . Wih^T over this CTA's K range ---- */
-    CHAIN_STAMP(0);
-    /* no per-tile liveness test here: it would put an L2 round trip in front
-       of the first TMA; dead rows are simply not stored, and the walk ends
-       for the whole grid once no stream is left */
-    const bool tile_alive = n_kb > 0;
-    if (threadIdx.x == 0)
-      ROLE_STAMP(0);
+  unsigned int it = 0; /* ring iterations so far (producer and MMA keep equal counts) */
+  bool finished = false;
 
-    /* What the row phase needs and the GEMM does not produce - the stream's
-       scalars and the ring row its errors are masked with - is fetched now,
-       ahead of the barrier the partial sums have to wait for. */
-    constexpr int GRP = 5; /* 5 x 256 columns: this warp's half of a row at H1023 in one
-                              round of loads */
-    /* wide rows (H1023: 1068 columns) take a pair of warps each; rows that one
-       warp covers in a single round of loads (small nets: few CTAs per group,
-       several rows per slot) take one warp each, twice as many at a time */
-    const int wpr = (I <= 128 * GRP) ? 1 : 2;
-    const int CSTEP = 128 * wpr;
-    const int slot = warp / wpr, half = warp % wpr;
-    const int slots_per_cta = (TC_CHAIN_THREADS / 32) / wpr;
-    const int gw = grp_cta * slots_per_cta + slot;
-    RbScalars sc_pre;
-    float4 x_pre[GRP];
-    sc_pre.live = 0;
-    if (gw < TC_BM && m0 + gw < v.n) {
-      const int s = v.base + m0 + gw;
-      sc_pre = load_scalars_cg(v.sc + s);
+  for (int k = 0; k < depth; k++) {
+    const int par = k & 1;
+    /* the ring row that masks this step's errors travels while the GEMM runs */
+    float4 xq[NG];
+    {
       int p = pos0 - k;
       if (p < 0)
-        p += v.depth;
-      const float *xk = v.X + ((size_t)p * v.cap + s) * I;
+        p += depth;
+      const float *xk = v.X + ((size_t)p * v.cap + r_s) * I + n0 + r_c;
 #pragma unroll
-      for (int i = 0; i < GRP; i++) {
-        int c = half * 128 + lane * 4 + CSTEP * i;
-        if (c < I)
-          x_pre[i] = __ldg((const float4 *)(xk + c));
+      for (int q = 0; q < NG; q++) {
+        xq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r_ok && n0 + r_c + 4 * q < I)
+          xq[q] = __ldg((const float4 *)(xk + 4 * q));
       }
     }
 
-    if (tile_alive) {
-      if (warp == 0) {
-        if (lane == 0) {
-          const int ring_row = k * v.cap + v.base + m0;
+    if (warp == 0) {
+      if (lane == 0) {
+        if (k == 0) {
+          mbar_expect_tx(w_ready, (uint32_t)n_kb * CH_STAGE_BYTES);
           for (int j = 0; j < n_kb; j++) {
-            unsigned int i2 = it + j;
-            int s = i2 % STAGES;
-            uint32_t ph = (i2 / STAGES) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
-            uint8_t *st = smem + s * Cfg::STAGE_BYTES;
-            int kb = kb_begin + j;
-            mbar_expect_tx(&full[s], Cfg::STAGE_BYTES);
-            tma_load_2d(&mAhi, &full[s], st, kb * TC_BK, ring_row);
-            tma_load_2d(&mAlo, &full[s], st + Cfg::A_BYTES, kb * TC_BK, ring_row);
-            tma_load_2d(&mBhi, &full[s], st + 2 * Cfg::A_BYTES, kb * TC_BK, n0);
-            tma_load_2d(&mBlo, &full[s], st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, kb * TC_BK, n0);
+            tma_load_2d(&mWhi, w_ready, w_smem + j * CH_STAGE_BYTES, (kb_begin + j) * TC_KB, n0);
+            tma_load_2d(&mWlo, w_ready, w_smem + j * CH_STAGE_BYTES + CH_PLANE_BYTES,
+                (kb_begin + j) * TC_KB, n0);
           }
         }
-      }
-      else if (warp == 1) {
-        if (lane == 0) {
-          const uint32_t idesc = umma_idesc_tf32(TC_BM, BN, 0, 0);
-          for (int j = 0; j < n_kb; j++) {
-            unsigned int i2 = it + j;
-            int s = i2 % STAGES;
-            uint32_t ph = (i2 / STAGES) & 1;
-            mbar_wait(&full[s], ph);
-            tc_fence_after();
-            if (j == 0)
-              ROLE_STAMP(1);
-            if (j == n_kb - 1)
-              ROLE_STAMP(2);
-            uint32_t a_hi = smem_u32(smem + s * Cfg::STAGE_BYTES);
-            uint32_t a_lo = a_hi + Cfg::A_BYTES;
-            uint32_t b_hi = a_hi + 2 * Cfg::A_BYTES;
-            uint32_t b_lo = b_hi + Cfg::B_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < TC_BK / 8; kk++) {
-              uint64_t dah = umma_desc(a_hi + kk * 32, 16, 1024);
-              uint64_t dal = umma_desc(a_lo + kk * 32, 16, 1024);
-              uint64_t dbh = umma_desc(b_hi + kk * 32, 16, 1024);
-              uint64_t dbl = umma_desc(b_lo + kk * 32, 16, 1024);
-              umma_tf32(tmem_base, dal, dbh, idesc, (j | kk) ? 1u : 0u);
-              umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_base, dah, dbh, idesc, 1u);
-            }
-            umma_commit(&empty[s]);
-          }
-          umma_commit(acc_ready);
+        else {
+          /* every CTA of the group has written its part of E(k) and has read
+             what it needed from its cluster peers' parking areas */
+          wait_counter(gsync, (unsigned int)k * grp_ctas);
+          mbar_arrive(step_go);
+        }
+        const int erow = k * v.cap + v.base + m0;
+        for (int j = 0; j < n_kb; j++, it++) {
+          int s = it % CH_STAGES;
+          uint32_t ph = (it / CH_STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t *st = a_smem + s * CH_STAGE_BYTES;
+          mbar_expect_tx(&full[s], CH_STAGE_BYTES);
+          tma_load_2d(&mEhi, &full[s], st, (kb_begin + j) * TC_KB, erow);
+          tma_load_2d(&mElo, &full[s], st + CH_PLANE_BYTES, (kb_begin + j) * TC_KB, erow);
         }
       }
-      else if (warp < 6) {
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int m = m0 + row;
-        const bool row_ok = m < v.n;
-        const int sidx = v.base + (row_ok ? m : 0);
-        const bool live = row_ok && __ldcg(&v.sc[sidx].live) != 0;
-        mbar_wait(acc_ready, n_gemms & 1);
-        tc_fence_after();
-        if (threadIdx.x == 64)
-          ROLE_STAMP(3);
-        float *dst = g.cpartial + (size_t)blockIdx.z * split_stride + (size_t)sidx * cpitch;
-        float acc[2][32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        tmem_ld32_nowait(taddr, acc[0]);
-#pragma unroll
-        for (int ci = 0; ci < BN / 32; ci++) {
-          tmem_wait_ld();
-          if (ci + 1 < BN / 32)
-            tmem_ld32_nowait(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
-          const float *av = acc[ci & 1];
-          int col0 = n0 + ci * 32;
-          if (!live || col0 >= I)
-            continue;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j + 8 <= I)
-              st_global_v8(dst + col0 + j, av + j);
-            else if (col0 + j < I)
-              __stcg((float4 *)(dst + col0 + j),
-                  make_float4(av[j], av[j + 1], av[j + 2], av[j + 3]));
-          }
-        }
-        tc_fence_before();
-        if (threadIdx.x == 64)
-          ROLE_STAMP(4);
-      }
-      it += n_kb;
-      n_gemms++;
     }
-    __syncthreads();
-    CHAIN_STAMP(1);
-    n_bar++;
-    grid_barrier(gsync, n_bar * grp_ctas);
-    CHAIN_STAMP(2);
-
-    /* ---- phase B: rows of E(k+1), one per PAIR of warps across the group
-       (all eight warps take part; each warp of a pair takes every other
-       128-column chunk) ---- */
-    {
-      for (int r = gw; r < TC_BM; r += grp_ctas * slots_per_cta) {
-        const int m = m0 + r;
-        if (m >= v.n)
-          break;
-        const int s = v.base + m;
-        RbScalars *scp = v.sc + s;
-        /* the scalars travel with the row loads: a stopped stream's loads
-           are wasted, nothing of it is stored */
-        if (warp == 2 && lane == 0) ROLE_STAMP(10);
-        const bool pre = (r == gw);
-        RbScalars sc = pre ? sc_pre : load_scalars_cg(scp);
+    else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = umma_idesc_f16(TC_BM, CH_BN, 0, 0);
+        if (k == 0)
+          mbar_wait(w_ready, 0);
+        for (int j = 0; j < n_kb; j++, it++) {
+          int s = it % CH_STAGES;
+          uint32_t ph = (it / CH_STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint32_t a_hi = smem_u32(a_smem + s * CH_STAGE_BYTES);
+          uint32_t b_hi = smem_u32(w_smem + j * CH_STAGE_BYTES);
+          issue_block_f16(tmem_base, tmem_base + CH_BN, a_hi, a_hi + CH_PLANE_BYTES, b_hi,
+              b_hi + CH_PLANE_BYTES, idesc, j == 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(acc_ready);
+      }
+    }
+    else if (warp < 6) {
+      /* ---- the previous step's verdict, for every stream of the group ---- */
+      if (k > 0) {
+        mbar_wait(step_go, (k - 1) & 1);
+        bool on = false;
+        if (d_valid && dsc.live) {
+          const float *sp = sq_grp + (size_t)((k - 1) & 1) * sq_par + (size_t)di * CH_SQ_SLOTS;
+          float es = 0.0f;
+          for (int q = 0; q < n_slots; q += 4) {
+            float4 t = __ldcg((const float4 *)(sp + q));
+            es += t.x;
+            if (q + 1 < n_slots) es += t.y;
+            if (q + 2 < n_slots) es += t.z;
+            if (q + 3 < n_slots) es += t.w;
+          }
+          chain_decide(dsc, es, k - 1, depth);
+          on = dsc.live != 0;
+          if (!on) {
+            s_live[di] = 0;
+            if (owner)
+              v.sc[v.base + m0 + di] = dsc;
+          }
+        }
+        if (__any_sync(0xffffffffu, on) && lane == 0)
+          s_any[par] = 1;
+      }
+      /* ---- this step's partial tile: tensor memory -> parking area ---- */
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      mbar_wait(acc_ready, par);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      float *dst = park + (size_t)row * CH_PARK_PITCH;
+      float acc[2][32], cor[2][32];
+      tmem_ld32_nowait(taddr, acc[0]);
+      tmem_ld32_nowait(taddr + CH_BN, cor[0]);
+#pragma unroll
+      for (int ci = 0; ci < CH_BN / 32; ci++) {
+        tmem_wait_ld();
+        if (ci + 1 < CH_BN / 32) {
+          tmem_ld32_nowait(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
+          tmem_ld32_nowait(taddr + CH_BN + (ci + 1) * 32, cor[(ci + 1) & 1]);
+        }
+        const float *av = acc[ci & 1], *cv = cor[ci & 1];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *(float4 *)(dst + ci * 32 + j) = make_float4(fmaf(cv[j], RB_LO_UNGAIN, av[j]),
+              fmaf(cv[j + 1], RB_LO_UNGAIN, av[j + 1]), fmaf(cv[j + 2], RB_LO_UNGAIN, av[j + 2]),
+              fmaf(cv[j + 3], RB_LO_UNGAIN, av[j + 3]));
+      }
+      tc_fence_before();
+    }
+    else if (has_tail) {
+      /* ---- columns past the last tile: the nonzero rows among them as dot
+         products over E(k) in FP32, two warps, this CTA's share of the
+         group's streams ---- */
+      if (k > 0)
+        mbar_wait(step_go, (k - 1) & 1);
+      const int spc = (TC_BM + grp_ctas - 1) / grp_ctas;
+      for (int t = warp - 6; t < spc; t += 2) {
+        const int i = grp_cta * spc + t;
+        if (i >= TC_BM || m0 + i >= v.n || !s_live[i])
+          continue; /* uniform over the warp */
+        const int s = v.base + m0 + i;
         int p = pos0 - k;
         if (p < 0)
-          p += v.depth;
+          p += depth;
         const float *xk = v.X + ((size_t)p * v.cap + s) * I;
-        const size_t eoff = ((size_t)(k + 1) * v.cap + s) * I;
-        const float *part = g.cpartial + (size_t)s * cpitch;
+        const float *ek = v.E + ((size_t)k * v.cap + s) * I;
+        float *en = v.E + ((size_t)(k + 1) * v.cap + s) * I;
+        const int hs1 = v.d.hidden_size + 1;
         float sq = 0.0f;
-        /* all loads of a group of column chunks are issued before any of
-           their results is used or stored: the row costs a few L2 round
-           trips instead of one per chunk */
-        for (int c0 = half * 128 + lane * 4; c0 < I; c0 += CSTEP * GRP) {
-          const bool x_here = pre && c0 < CSTEP; /* the first round of the first row */
-          float4 a[GRP], xin[GRP], pz[TC_CHAIN_SPLITS - 1][GRP];
-#pragma unroll
-          for (int i = 0; i < GRP; i++) {
-            int c = c0 + CSTEP * i;
-            if (c < I) {
-              a[i] = __ldcg((const float4 *)(part + c));
-              xin[i] = x_here ? x_pre[i] : __ldg((const float4 *)(xk + c));
-#pragma unroll
-              for (int z = 1; z < TC_CHAIN_SPLITS; z++)
-                if (z < (int)gridDim.z)
-                  pz[z - 1][i] = __ldcg((const float4 *)(part + z * split_stride + c));
+        for (int c0 = g.tail0; c0 < I; c0 += 32) {
+          const int y = c0 + lane;
+          const float x = (y < I) ? __ldg(xk + y) : 0.0f;
+          const bool act = x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f);
+          unsigned int todo = __ballot_sync(0xffffffffu, act);
+          float mine = 0.0f;
+          while (todo) {
+            const int b = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float *wrow = v.Wih + (size_t)(c0 + b) * H;
+            float dot = 0.0f;
+            for (int c = lane * 4; c < H; c += 128) {
+              float4 w4 = __ldg((const float4 *)(wrow + c));
+              float4 e4 = __ldcg((const float4 *)(ek + c));
+              dot = fmaf(w4.x, e4.x, dot);
+              dot = fmaf(w4.y, e4.y, dot);
+              dot = fmaf(w4.z, e4.z, dot);
+              dot = fmaf(w4.w, e4.w, dot);
             }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+              dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            if (lane == b)
+              mine = dot;
           }
-          if (!sc.live)
-            break;
-          if (warp == 2 && lane == 0) ROLE_STAMP(11);
-#pragma unroll
-          for (int z = 1; z < TC_CHAIN_SPLITS; z++) {
-            if (z < (int)gridDim.z) {
-#pragma unroll
-              for (int i = 0; i < GRP; i++) {
-                int c = c0 + CSTEP * i;
-                if (c < I) {
-                  a[i].x += pz[z - 1][i].x; a[i].y += pz[z - 1][i].y;
-                  a[i].z += pz[z - 1][i].z; a[i].w += pz[z - 1][i].w;
-                }
-              }
+          if (y < I) {
+            float e = mine;
+            if (act) {
+              if (v.activation == RNN_RESQRT)
+                e /= 2.0f * (x + 1.0f);
+              sq = fmaf(e, e, sq);
+              if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
+                v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
             }
-          }
-          if (plain) {
-#pragma unroll
-            for (int i = 0; i < GRP; i++) {
-              int c = c0 + CSTEP * i;
-              if (c < I)
-                chain_chunk<true>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
-                    g.Elo + eoff + c);
-            }
-          }
-          else {
-#pragma unroll
-            for (int i = 0; i < GRP; i++) {
-              int c = c0 + CSTEP * i;
-              if (c < I)
-                chain_chunk<false>(v, a[i], xin[i], c, s, sq, v.E + eoff + c, g.Ehi + eoff + c,
-                    g.Elo + eoff + c);
-            }
+            __stcg(en + y, (y >= hs1 && y < H) ? 0.0f : e);
           }
         }
-        if (!sc.live)
-          continue;
-        if (warp == 2 && lane == 0) ROLE_STAMP(12);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (wpr == 2) {
-          if (lane == 0)
-            pair_sq[warp] = sq;
-          named_bar_sync(1 + slot, 64);
-        }
-        if (warp == 2 && lane == 0) ROLE_STAMP(13);
-        if (half == 0 && lane == 0) {
-          float es = (wpr == 2) ? pair_sq[warp] + pair_sq[warp + 1] : sq;
-          sc.err_sum = es;
-          sc.cum_error += sqrtf(es);
-          sc.n_steps = k + 1;
-          int t = v.depth - k;
-          bool stop = (es <= sc.min_sum || es > sc.max_sum);
-          bool last = (k == v.depth - 1);
-          if (stop || last) {
-            sc.live = 0;
-            int t_left = stop ? t : 0;
-            sc.t_left = t_left;
-            float ceiling = ERROR_GAIN_CEILING * sc.top_scaled;
-            if (es > ceiling) {
-              float halfmax = sc.max_sum;
-              float x = es / halfmax;
-              float fudge = (float)(0.99 + (double)(x * x / 100.0f));
-              sc.ih_scale = (halfmax == 0.0f) ? es : 2.0f * x / (1.0f + x * x * fudge);
-            }
-            else {
-              sc.ih_scale = 1.0f;
-              if (sc.adaptive & 1) {
-                int depth_error = v.depth / 4 - t_left;
-                float min_gain = MIN_ERROR_GAIN * sc.top_scaled;
-                float mef = sc.mef;
-                if (mef < MAX_MIN_ERROR_FACTOR && (min_gain != sc.min_sum || depth_error < 0))
-                  mef = (float)((double)mef * (1.0 + depth_error * 1e-3));
-                sc.mef = fmaxf(mef, ABS_MIN_ERROR_FACTOR);
-              }
-            }
+        if (lane == 0)
+          __stcg(sq_grp + (size_t)par * sq_par + (size_t)i * CH_SQ_SLOTS + grp_ctas, sq);
+      }
+    }
+    __syncthreads();    /* the tile is parked, the verdicts are in */
+    __syncwarp();
+    cluster_sync_all(); /* ... in every CTA of the cluster */
+    if (k > 0 && !s_any[par]) {
+      finished = true;  /* no stream of the group walks on (the same in all its CTAs) */
+      break;
+    }
+
+    /* ---- E(k+1): this CTA's columns of the tile, summed over the K splits ---- */
+    {
+      float4 a[NG];
+      {
+        float4 pz[SPLITS][NG];
+#pragma unroll
+        for (int z = 0; z < SPLITS; z++) {
+          const float *src = park + (size_t)r_row * CH_PARK_PITCH + r_c;
+          if (z == (int)rank) {
+#pragma unroll
+            for (int q = 0; q < NG; q++)
+              pz[z][q] = *(const float4 *)(src + 4 * q);
           }
           else {
-            atomicAdd(&gsync[1 + k], 1u);
+            const uint32_t ra = dsmem_addr(src, (uint32_t)z);
+#pragma unroll
+            for (int q = 0; q < NG; q++)
+              pz[z][q] = ld_dsmem_v4(ra + 16 * q);
           }
-          *scp = sc;
         }
-        if (wpr == 2)
-          named_bar_sync(1 + slot, 64); /* pair_sq may be rewritten */
+#pragma unroll
+        for (int q = 0; q < NG; q++) {
+          a[q] = pz[0][q];
+#pragma unroll
+          for (int z = 1; z < SPLITS; z++) {
+            a[q].x += pz[z][q].x; a[q].y += pz[z][q].y;
+            a[q].z += pz[z][q].z; a[q].w += pz[z][q].w;
+          }
+          a[q].x *= inv_scale; a[q].y *= inv_scale; a[q].z *= inv_scale; a[q].w *= inv_scale;
+        }
       }
-      if (warp == 2 && lane == 0) ROLE_STAMP(14);
-      /* E(k+1) planes were written through the generic proxy; the next step's
-         TMA reads them through the async proxy */
-      asm volatile("fence.proxy.async;" ::: "memory");
-      if (warp == 2 && lane == 0) ROLE_STAMP(15);
+      const bool live = r_ok && s_live[r_row];
+      float sq = 0.0f;
+      const size_t eoff = ((size_t)(k + 1) * v.cap + r_s) * I;
+      const size_t poff = ((size_t)(k + 1) * v.cap + r_s) * g.E.pitch;
+      if (live) {
+#pragma unroll
+        for (int q = 0; q < NG; q += 2) {
+          const int c = n0 + r_c + 4 * q;
+          if (c >= I)
+            break;
+          float4 o0 = plain ? chain_mask4<true>(v, a[q], xq[q], c, r_s, sq)
+                            : chain_mask4<false>(v, a[q], xq[q], c, r_s, sq);
+          uint2 h0, l0;
+          rb_split4(o0, e_scale, h0, l0);
+          __stcg((float4 *)(v.E + eoff + c), o0);
+          if (c + 4 < I) {
+            float4 o1 = plain ? chain_mask4<true>(v, a[q + 1], xq[q + 1], c + 4, r_s, sq)
+                              : chain_mask4<false>(v, a[q + 1], xq[q + 1], c + 4, r_s, sq);
+            uint2 h1, l1;
+            rb_split4(o1, e_scale, h1, l1);
+            __stcg((float4 *)(v.E + eoff + c + 4), o1);
+            __stcg((uint4 *)(g.E.hi + poff + c), make_uint4(h0.x, h0.y, h1.x, h1.y));
+            __stcg((uint4 *)(g.E.lo + poff + c), make_uint4(l0.x, l0.y, l1.x, l1.y));
+          }
+          else {
+            __stcg((uint2 *)(g.E.hi + poff + c), h0);
+            __stcg((uint2 *)(g.E.lo + poff + c), l0);
+          }
+        }
+      }
+      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+      if (live && (threadIdx.x & 1) == 0)
+        __stcg(sq_grp + (size_t)par * sq_par + (size_t)r_row * CH_SQ_SLOTS + grp_cta, sq);
     }
+    if (threadIdx.x == 0)
+      s_any[par ^ 1] = 0; /* the next step's verdicts start from "nobody" */
+    /* E(k+1)'s planes were written through the generic proxy; the next step's
+       TMA reads them through the async proxy */
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
-    CHAIN_STAMP(3);
-    n_bar++;
-    grid_barrier(gsync, n_bar * grp_ctas);
-    CHAIN_STAMP(4);
-    if (__ldcg(&gsync[1 + k]) == 0) {
-      if (grp_cta == 0 && threadIdx.x == 0)
-        atomicMax(g.kmax, (unsigned int)(k + 1));
-      break; /* every stream of this group has stopped (uniform across the group) */
-    }
+    if (threadIdx.x == 0)
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(gsync), "r"(1u) : "memory");
   }
 
+  if (!finished) {
+    /* all `depth` steps ran: the last step's verdicts are still out */
+    if (threadIdx.x == 0)
+      wait_counter(gsync, (unsigned int)depth * grp_ctas);
+    __syncthreads();
+    if (d_valid && dsc.live) {
+      const float *sp = sq_grp + (size_t)((depth - 1) & 1) * sq_par + (size_t)di * CH_SQ_SLOTS;
+      float es = 0.0f;
+      for (int q = 0; q < n_slots; q += 4) {
+        float4 t = __ldcg((const float4 *)(sp + q));
+        es += t.x;
+        if (q + 1 < n_slots) es += t.y;
+        if (q + 2 < n_slots) es += t.z;
+        if (q + 3 < n_slots) es += t.w;
+      }
+      chain_decide(dsc, es, depth - 1, depth);
+      if (owner)
+        v.sc[v.base + m0 + di] = dsc;
+    }
+  }
+  /* (on the early exit the speculative K loop's accumulator was drained like
+     any other before the verdict was looked at: no MMA is in flight) */
+  if (owner && d_valid)
+    atomicMax(s_kmax, dsc.n_steps);
+  tc_fence_before();
   __syncthreads();
+  if (owner && threadIdx.x == 0)
+    atomicMax(g.kmax, (unsigned int)*s_kmax);
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, 2 * CH_BN);
   }
 }
 
 /* ======================================================================== */
-/* DW: delta tile [128 y x 256 x] += X^T . E over (step, stream) rows;
-   both operands MN-major, 16 ring rows per stage, split-K across blockIdx.z  */
-
-struct DwArgs {
-  RbView v;
-  float *partial; /* [splits][i_size][h_size] */
-  const unsigned int *kmax; /* deepest step any stream executed: rows beyond contribute nothing */
-};
-
-#define DW_CHUNK_BYTES (32 * TC_DW_BK * 4)          /* one TMA box: 32 floats x 16 rows */
-#define DW_A_BYTES ((TC_BM / 32) * DW_CHUNK_BYTES)    /* 8 KB */
-#define DW_B_BYTES ((TC_DW_BN / 32) * DW_CHUNK_BYTES) /* 16 KB */
-#define DW_STAGE_BYTES (2 * DW_A_BYTES + 2 * DW_B_BYTES)
-#define DW_SMEM_BYTES (TC_DW_STAGES * DW_STAGE_BYTES + 1024 + 256)
-
-__global__ void __launch_bounds__(192, 1)
-k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtensorMap mXlo,
-    const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ CUtensorMap mElo,
-    DwArgs g)
-{
-  extern __shared__ uint8_t smem_raw[];
-  const RbView &v = g.v;
-  uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = (uint64_t *)(smem + TC_DW_STAGES * DW_STAGE_BYTES);
-  uint64_t *empty = full + TC_DW_STAGES;
-  uint64_t *acc_ready = empty + TC_DW_STAGES;
-  uint32_t *tmem_slot = (uint32_t *)(acc_ready + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int I = v.d.i_size, H = v.d.h_size;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_DW_BN;
-  const int kb_per_step = v.n / TC_DW_BK;
-  const int n_steps_max = min((int)*g.kmax, v.depth);
-  const int n_kb_total = n_steps_max * kb_per_step;
-  const int kb_per_split = (n_kb_total + gridDim.z - 1) / gridDim.z;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(n_kb_total, kb_begin + kb_per_split);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_DW_STAGES; s++) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    mbar_init(acc_ready, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&mXhi);
-    tma_prefetch_desc(&mXlo);
-    tma_prefetch_desc(&mEhi);
-    tma_prefetch_desc(&mElo);
-  }
-  if (warp == 1)
-    tmem_alloc(tmem_slot, TC_DW_BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      const int pos = v.pos[v.base];
-      for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
-        int s = it % TC_DW_STAGES;
-        uint32_t ph = (it / TC_DW_STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        int step = kb / kb_per_step;
-        int b0 = (kb - step * kb_per_step) * TC_DW_BK;
-        int slot = pos - step;
-        if (slot < 0)
-          slot += v.depth;
-        int xrow = slot * v.cap + v.base + b0;
-        int erow = step * v.cap + v.base + b0;
-        uint8_t *st = smem + s * DW_STAGE_BYTES;
-        mbar_expect_tx(&full[s], DW_STAGE_BYTES);
-        tma_load_3d(&mXhi, &full[s], st, 0, xrow, m0 / 32);
-        tma_load_3d(&mXlo, &full[s], st + DW_A_BYTES, 0, xrow, m0 / 32);
-        tma_load_3d(&mEhi, &full[s], st + 2 * DW_A_BYTES, 0, erow, n0 / 32);
-        tma_load_3d(&mElo, &full[s], st + 2 * DW_A_BYTES + DW_B_BYTES, 0, erow, n0 / 32);
-      }
-    }
-  }
-  else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TC_BM, TC_DW_BN, 1, 1);
-      for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
-        int s = it % TC_DW_STAGES;
-        uint32_t ph = (it / TC_DW_STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        uint32_t a_hi = smem_u32(smem + s * DW_STAGE_BYTES);
-        uint32_t a_lo = a_hi + DW_A_BYTES;
-        uint32_t b_hi = a_hi + 2 * DW_A_BYTES;
-        uint32_t b_lo = b_hi + DW_B_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < TC_DW_BK / 8; kk++) {
-          /* MN-major 32-bit operands (SWIZZLE_128B_BASE32B): each K row is one
-             128-byte line of 32 floats along M/N; 32-float chunks along M/N
-             are one TMA box apart (leading offset), groups of 4 K rows 512 B
-             apart (stride offset); one MMA consumes 8 K rows = 1024 B */
-          uint64_t dah = umma_desc(a_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dal = umma_desc(a_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dbh = umma_desc(b_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dbl = umma_desc(b_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          umma_tf32(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
-          umma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32(tmem_base, dah, dbh, idesc, 1u);
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(acc_ready);
-    }
-  }
-  else {
-    const int q = warp & 3;
-    const int y = m0 + q * 32 + lane;
-    float acc[32];
-    const bool any = kb_end > kb_begin;
-    if (any) {
-      mbar_wait(acc_ready, 0);
-      tc_fence_after();
-    }
-    float *dst = g.partial + ((size_t)blockIdx.z * I + (y < I ? y : 0)) * H + n0;
-#pragma unroll 1
-    for (int c = 0; c < TC_DW_BN; c += 32) {
-      if (any)
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
-      else {
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-          acc[j] = 0.0f;
-      }
-      if (y < I) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + c + j < H)
-            *(float4 *)(dst + c + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-        }
-      }
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TC_DW_BN);
-  }
-}
-
-/* ------------------------------------------------------------------------ */
-/* DW on CTA pairs.
+/* DW on CTA pairs: delta^T tile [256 h x 192 i] += E^T . X over (step, stream)
+ * rows, both operands MN-major, 32 ring rows per stage, split-K across
+ * blockIdx.z.
  *
- * k_tc_dw above is bound by the 64 B/clock a single SM can take in from L2:
- * a 128 x 256 tile needs 48 KB of operands per 16 rows of K.  Two SMs of a
- * TPC issuing ONE MMA (tcgen05 cta_group::2, M = 256) each keep half of the
- * N operand, so per SM and 16 rows only 16 KB (its 128 M columns) + 12 KB
- * (half of 192 N columns) arrive, and the tensor pipe, not the port, sets the
- * pace.  The output is transposed relative to k_tc_dw: M runs over the error
- * columns h (1024 = 4 pairs of 128, no padding), N over the input columns i
- * (6 tiles of 192), D[h][i] = sum_rows E[row][h] X[row][i]; both operands
- * stay MN-major.  The epilogue writes partial[z][i][h]: lanes are h, so every
- * store is a full line.
+ * A single SM takes in 64 B per clock from L2; a 128-row tile of this
+ * contraction wants more than that per MMA cycle.  Two SMs of a TPC issuing
+ * ONE MMA (tcgen05 cta_group::2, M = 256) each keep half of the N operand, so
+ * per SM and 32 rows only 16 KB (its 128 M columns, both planes) + 12 KB (half
+ * of 192 N columns) arrive and the tensor pipe, not the port, sets the pace.
+ * M runs over the error columns h (1024 = 4 pairs of 128, no padding), N over
+ * the input columns i (tiles of 192), D[h][i] = sum_rows E[row][h] X[row][i].
+ * MN-major FP16 operands: the error planes come in 64-column chunks (128-byte
+ * swizzle), the ring planes in 32-column chunks (64-byte swizzle: 96 = 3
+ * chunks per CTA); one 3-D TMA per plane fetches all chunks of 32 ring rows.
+ * The epilogue writes partial[z][i][h]: lanes are h, so every store is a full
+ * line.
  *
  * Protocol (as CUTLASS's 2-SM pipelines): both CTAs' TMA loads count their
  * bytes on the leader's `full` barrier, on which only the leader's producer
@@ -1663,12 +1611,22 @@ k_tc_dw(const __grid_constant__ CUtensorMap mXhi, const __grid_constant__ CUtens
  * both CTAs with a multicast commit; the accumulator-ready commit is multicast
  * too, and each CTA's epilogue drains its own TMEM half.                     */
 
+struct DwArgs {
+  RbView v;
+  float *partial; /* [splits][i_size][h_size] */
+  const unsigned int *kmax; /* deepest step any stream executed: rows beyond contribute nothing */
+  const float *e_scale_dev; /* scale of the error planes */
+};
+
 #define TC_DW2_STAGES 7
-#define DW2_A_BYTES ((TC_BM / 32) * DW_CHUNK_BYTES)            /* 8 KB per plane */
-#define DW2_B_BYTES ((TC_DW2_BN / 2 / 32) * DW_CHUNK_BYTES)    /* 6 KB per plane, this CTA's half */
-#define DW2_STAGE_BYTES (2 * DW2_A_BYTES + 2 * DW2_B_BYTES)
+#define DW2_A_CHUNK (TC_DW_BK * 128)                         /* 64 columns x 32 rows: 4 KB */
+#define DW2_B_CHUNK (TC_DW_BK * 64)                          /* 32 columns x 32 rows: 2 KB */
+#define DW2_A_BYTES ((TC_BM / 64) * DW2_A_CHUNK)             /* 8 KB per plane */
+#define DW2_B_BYTES ((TC_DW2_BN / 2 / 32) * DW2_B_CHUNK)     /* 6 KB per plane, this CTA's half */
+#define DW2_STAGE_BYTES (2 * DW2_A_BYTES + 2 * DW2_B_BYTES)  /* 28 KB */
 #define DW2_SMEM_BYTES (TC_DW2_STAGES * DW2_STAGE_BYTES + 1024 + 256)
-#define DW2_TMEM_COLS 256
+#define DW2_TMEM_COLS 512
+#define DW2_CORR_COL 256
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ CUtensorMap mElo,
@@ -1737,8 +1695,8 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ C
         uint8_t *st = smem + s * DW2_STAGE_BYTES;
         if (leader)
           mbar_expect_tx(&full[s], 2 * DW2_STAGE_BYTES);
-        tma_load_3d_pair(&mEhi, &full[s], st, 0, erow, h0 / 32);
-        tma_load_3d_pair(&mElo, &full[s], st + DW2_A_BYTES, 0, erow, h0 / 32);
+        tma_load_3d_pair(&mEhi, &full[s], st, 0, erow, h0 / 64);
+        tma_load_3d_pair(&mElo, &full[s], st + DW2_A_BYTES, 0, erow, h0 / 64);
         tma_load_3d_pair(&mXhi, &full[s], st + 2 * DW2_A_BYTES, 0, xrow, i_half / 32);
         tma_load_3d_pair(&mXlo, &full[s], st + 2 * DW2_A_BYTES + DW2_B_BYTES, 0, xrow,
             i_half / 32);
@@ -1747,7 +1705,8 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ C
   }
   else if (warp == 1) {
     if (lane == 0 && leader) {
-      const uint32_t idesc = umma_idesc_tf32(2 * TC_BM, TC_DW2_BN, 1, 1);
+      const uint32_t idesc = umma_idesc_f16(2 * TC_BM, TC_DW2_BN, 1, 1);
+      const uint32_t t_main = tmem_base, t_corr = tmem_base + DW2_CORR_COL;
       for (int kb = kb_begin, it = 0; kb < kb_end; kb++, it++) {
         int s = it % TC_DW2_STAGES;
         uint32_t ph = (it / TC_DW2_STAGES) & 1;
@@ -1758,14 +1717,19 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ C
         uint32_t b_hi = a_hi + 2 * DW2_A_BYTES;
         uint32_t b_lo = b_hi + DW2_B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TC_DW_BK / 8; kk++) {
-          uint64_t dah = umma_desc(a_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dal = umma_desc(a_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dbh = umma_desc(b_hi + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          uint64_t dbl = umma_desc(b_lo + kk * 1024, DW_CHUNK_BYTES, 512, UMMA_SW128_BASE32);
-          umma_tf32_pair(tmem_base, dal, dbh, idesc, (it | kk) ? 1u : 0u);
-          umma_tf32_pair(tmem_base, dah, dbl, idesc, 1u);
-          umma_tf32_pair(tmem_base, dah, dbh, idesc, 1u);
+        for (int kk = 0; kk < TC_DW_BK / 16; kk++) {
+          /* MN-major: each K row is one swizzle row of 64 (A) or 32 (B) halves
+             along M/N; chunks along M/N are one TMA box apart (leading
+             offset), groups of 8 K rows 1024 B (A) / 512 B (B) apart (stride
+             offset); one MMA consumes 16 K rows */
+          uint64_t dah = umma_desc(a_hi + kk * 2048, DW2_A_CHUNK, 1024, UMMA_SW128);
+          uint64_t dal = umma_desc(a_lo + kk * 2048, DW2_A_CHUNK, 1024, UMMA_SW128);
+          uint64_t dbh = umma_desc(b_hi + kk * 1024, DW2_B_CHUNK, 512, UMMA_SW64);
+          uint64_t dbl = umma_desc(b_lo + kk * 1024, DW2_B_CHUNK, 512, UMMA_SW64);
+          const uint32_t acc = (it | kk) ? 1u : 0u;
+          umma_f16_pair(t_main, dah, dbh, idesc, acc);
+          umma_f16_pair(t_corr, dah, dbl, idesc, acc);
+          umma_f16_pair(t_corr, dal, dbh, idesc, 1u);
         }
         umma_commit_pair(&empty[s]);
       }
@@ -1780,23 +1744,27 @@ k_tc_dw_pair(const __grid_constant__ CUtensorMap mEhi, const __grid_constant__ C
       mbar_wait(acc_ready, 0);
       tc_fence_after();
     }
+    const float inv = 1.0f / *g.e_scale_dev; /* the ring planes carry no scale */
     float *dst = g.partial + (size_t)blockIdx.z * I * H + h;
-    float acc[32];
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float acc[32], cor[32];
 #pragma unroll 1
     for (int c = 0; c < TC_DW2_BN; c += 32) {
-      if (any)
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c, acc);
+      if (any) {
+        tmem_ld32_nowait(taddr + c, acc);
+        tmem_ld32(taddr + DW2_CORR_COL + c, cor);
+      }
       else {
 #pragma unroll
         for (int j = 0; j < 32; j++)
-          acc[j] = 0.0f;
+          acc[j] = cor[j] = 0.0f;
       }
       if (h < H) {
 #pragma unroll
         for (int j = 0; j < 32; j++) {
           int i = i0 + c + j;
           if (i < I)
-            dst[(size_t)i * H] = acc[j];
+            dst[(size_t)i * H] = fmaf(cor[j], RB_LO_UNGAIN, acc[j]) * inv;
         }
       }
     }
@@ -1840,7 +1808,8 @@ struct UpdateArgs {
   int I, H;
   int method;
   float rate, momentum, momentum_weight;
-  float *Whi, *Wlo, *WThi, *WTlo;
+  rb_h16 *Whi, *Wlo, *WThi, *WTlo;
+  int wpitch, tpitch;
   /* the output matrix rides along */
   float *ho_W, *ho_mom, *ho_aux;
   const float *ho_delta;
@@ -1859,7 +1828,7 @@ k_update_split(UpdateArgs a)
           a.ho_rate, a.momentum, a.momentum_weight);
     return;
   }
-  __shared__ float th[32][33], tl[32][33];
+  __shared__ rb_h16 th[32][34], tl[32][34];
   const int I = a.I, H = a.H;
   const size_t size = (size_t)I * H;
   const int x0 = (blockIdx.x % a.n_tiles_x) * 32, y0 = (blockIdx.x / a.n_tiles_x) * 32;
@@ -1890,7 +1859,7 @@ k_update_split(UpdateArgs a)
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     int r = ty + 8 * q, y = y0 + r;
-    float hi = 0.f, lo = 0.f;
+    rb_h16 hi = 0, lo = 0;
     if (y < I && x < H) {
       size_t i = (size_t)y * H + x;
       if (a.partial)
@@ -1898,9 +1867,9 @@ k_update_split(UpdateArgs a)
       float nw = rb_optimiser_step(a.method, w[q], d[q], a.mom, a.aux, i, a.rate, a.momentum,
           a.momentum_weight);
       a.W[i] = nw;
-      split_tf32(nw, hi, lo);
-      a.Whi[i] = hi;
-      a.Wlo[i] = lo;
+      rb_split_f16(nw * RB_W_SCALE, hi, lo);
+      a.Whi[(size_t)y * a.wpitch + x] = hi;
+      a.Wlo[(size_t)y * a.wpitch + x] = lo;
     }
     th[r][tx] = hi;
     tl[r][tx] = lo;
@@ -1911,8 +1880,8 @@ k_update_split(UpdateArgs a)
     int r = ty + 8 * q;
     int xx = x0 + r, y = y0 + tx;
     if (xx < H && y < I) {
-      a.WThi[(size_t)xx * I + y] = th[tx][r];
-      a.WTlo[(size_t)xx * I + y] = tl[tx][r];
+      a.WThi[(size_t)xx * a.tpitch + y] = th[tx][r];
+      a.WTlo[(size_t)xx * a.tpitch + y] = tl[tx][r];
     }
   }
 }
@@ -1925,9 +1894,11 @@ rb_tc_usable(const RbView *v)
 {
   /* ReCLIP20 nets stay on the FMA engine: the reference leaves saturated rows
      (x >= 20) out of the weight gradient (recur-nn.c:347), and the operand
-     planes of the ring, shared with the forward pass, hold them unmasked */
-  return v->contiguous && v->n >= 64 && (v->n % TC_BK) == 0 && v->d.h_size >= 64 &&
-      v->activation != RNN_RECLIP20;
+     planes of the ring, shared with the forward pass, hold them unmasked.
+     i_size: a ring row's entries are bounded by the input soft clip at about
+     27 * i_size (recur-nn.c:68-81), which must stay inside FP16. */
+  return v->contiguous && v->n >= 64 && (v->n % TC_DW_BK) == 0 && v->d.h_size >= 64 &&
+      v->d.i_size <= 2400 && v->activation != RNN_RECLIP20;
 }
 
 static void
@@ -1939,24 +1910,34 @@ refresh_weight_planes(RbTc *t, RbPool *p, const RbView *v)
   const int I = v->d.i_size, H = v->d.h_size;
   dim3 grid(cdiv(H, 32), cdiv(I, 32));
   rb_prof_begin(RB_PROF_SMALL);
-  k_split_weights<<<grid, 256, 0, rb_stream>>>(v->Wih, I, H, t->Whi, t->Wlo, t->WThi, t->WTlo);
+  k_split_weights<<<grid, 256, 0, rb_stream>>>(v->Wih, I, H, t->Whi, t->Wlo, t->wpitch, t->WThi,
+      t->WTlo, t->pitch);
   LAUNCH_CHECK("k_split_weights");
   rb_prof_end(RB_PROF_SMALL);
   t->w_src = v->Wih;
   t->w_version = g->weights_version;
 }
 
-static int fwd_attr_done = 0, chain_attr_done = 0, dw_attr_done = 0;
+static int fwd_attr_done = 0, nt_attr_done = 0;
 static int defer_delta_reduce = 0;
 typedef NtCfg<TC_FWD_BN, TC_FWD_STAGES> FwdCfg;
-typedef NtCfg<TC_CHAIN_BN, TC_CHAIN_STAGES> ChainCfg;
+typedef NtCfg<TC_NT_BN, TC_NT_STAGES> NtBigCfg;
+
+static void
+nt_big_attr(void)
+{
+  if (!nt_attr_done) {
+    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_NT_BN, TC_NT_STAGES>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, NtBigCfg::SMEM_BYTES));
+    nt_attr_done = 1;
+  }
+}
 
 extern "C" void
-rb_tc_x_planes(RbPool *p, float **Xhi, float **Xlo)
+rb_tc_x_planes(RbPool *p, RbPlanes *X)
 {
   RbTc *t = tc_state(p);
-  *Xhi = t->Xhi;
-  *Xlo = t->Xlo;
+  *X = planes_of(t->Xhi, t->Xlo, t->pitch, 1.0f, NULL);
 }
 
 extern "C" void
@@ -1965,7 +1946,7 @@ rb_tc_forward(RbPool *p, const RbView *v, float presynaptic_noise)
   RbTc *t = tc_state(p);
   rbk_prepare_x(v);
   rb_prof_begin(RB_PROF_SMALL);
-  k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 0, t->Xhi, t->Xlo);
+  k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, planes_of(t->Xhi, t->Xlo, t->pitch, 1.0f, NULL));
   LAUNCH_CHECK("k_split_rows");
   rb_prof_end(RB_PROF_SMALL);
   if (p->x_planes_stale == 1)
@@ -1985,6 +1966,8 @@ rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise)
   g.k = 0;
   g.use_noise = 0;
   g.cpartial = NULL;
+  g.inv_scale = 1.0f / RB_W_SCALE; /* ring planes: scale 1 */
+  g.a_scale_dev = NULL;
   if (presynaptic_noise != 0.0f) {
     rbk_gen_noise(v, presynaptic_noise, 1, v->d.h_size - 1);
     g.use_noise = 1;
@@ -1992,22 +1975,18 @@ rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise)
   /* Few tiles and a long K: split K so the GEMM covers the SMs, and let the
      output-layer kernel sum the partials on its way in. */
   {
-    int n_kb = cdiv(v->d.i_size, TC_BK);
-    int tiles = cdiv(v->d.h_size, TC_CHAIN_BN) * cdiv(v->n, TC_BM);
-    int splits = TC_CHAIN_SPLITS;
+    int n_kb = cdiv(v->d.i_size, TC_KB);
+    int tiles = cdiv(v->d.h_size, TC_NT_BN) * cdiv(v->n, TC_BM);
+    int splits = TC_NT_SPLITS;
     while (splits > 1 && (n_kb / splits < 2 || tiles * splits > 148))
       splits /= 2;
     if (splits > 1 && rbk_output_takes_partials(v, splits)) {
-      if (!chain_attr_done) {
-        CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
-                cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
-        chain_attr_done = 1;
-      }
+      nt_big_attr();
       g.mode = 2;
       g.cpartial = t->cpartial;
-      dim3 grid(cdiv(v->d.h_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
+      dim3 grid(cdiv(v->d.h_size, TC_NT_BN), cdiv(v->n, TC_BM), splits);
       rb_prof_begin(RB_PROF_FWD);
-      k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES><<<grid, 192, ChainCfg::SMEM_BYTES, rb_stream>>>(
+      k_tc_nt<TC_NT_BN, TC_NT_STAGES><<<grid, 192, NtBigCfg::SMEM_BYTES, rb_stream>>>(
           t->mXhi_k, t->mXlo_k, t->mWThi_k128, t->mWTlo_k128, g);
       LAUNCH_CHECK("k_tc_nt<FWD split-K>");
       rb_prof_end(RB_PROF_FWD);
@@ -2035,172 +2014,230 @@ rb_tc_forward_core(RbPool *p, const RbView *v, float presynaptic_noise)
   rbk_output(v);
 }
 
+/* ---- the persistent chain's launch plan ---------------------------------- */
+
+typedef struct ChainPlan {
+  int ok;
+  int splits, n_tiles, m_tiles, nkb_total, kb_per, tail0;
+} ChainPlan;
+
+template <int SPLITS>
+static int
+chain_clusters_fit(int n_clusters, dim3 grid)
+{
+  static int attr_done = 0, coop = -1;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(k_tc_chain_persistent<SPLITS>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    int dev = 0;
+    CUDA_OR_DIE(cudaGetDevice(&dev));
+    CUDA_OR_DIE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    attr_done = 1;
+  }
+  if (!coop)
+    return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLITS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, k_tc_chain_persistent<SPLITS>, &cfg) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return max_clusters >= n_clusters;
+}
+
+/* Column tiles x K splits x stream tiles, every cluster resident at once.
+   All i_size columns on the tensor cores if that many clusters fit the GPU,
+   else the h_size columns there and the rest on the CUDA-core tail. */
+static ChainPlan
+chain_plan(const RbView *v)
+{
+  ChainPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (getenv("RECUR_B200_NO_PERSISTENT"))
+    return pl;
+  const int I = v->d.i_size, H = v->d.h_size;
+  pl.nkb_total = cdiv(H, TC_KB);
+  pl.m_tiles = cdiv(v->n, TC_BM);
+  for (int splits = 4; splits >= 2 && !pl.ok; splits /= 2) {
+    int kb_per = cdiv(pl.nkb_total, splits);
+    if (kb_per > CH_WKB || (splits - 1) * kb_per >= pl.nkb_total)
+      continue; /* the slice of Wih must fit, and every split must have work */
+    int candidates[2] = {cdiv(I, CH_BN), cdiv(H, CH_BN)};
+    for (int c = 0; c < 2 && !pl.ok; c++) {
+      int n_tiles = candidates[c];
+      if (c == 1 && n_tiles == candidates[0])
+        break;
+      if (n_tiles * splits + 1 > CH_SQ_SLOTS)
+        continue;
+      dim3 grid(n_tiles * splits, pl.m_tiles, 1);
+      int fit = (splits == 4) ? chain_clusters_fit<4>(n_tiles * pl.m_tiles, grid)
+                              : chain_clusters_fit<2>(n_tiles * pl.m_tiles, grid);
+      if (fit) {
+        pl.ok = 1;
+        pl.splits = splits;
+        pl.kb_per = kb_per;
+        pl.n_tiles = n_tiles;
+        pl.tail0 = (n_tiles * CH_BN < I) ? n_tiles * CH_BN : I;
+      }
+    }
+  }
+  return pl;
+}
+
+template <int SPLITS>
+static void
+launch_chain(RbTc *t, const ChainPlan *pl, ChainArgs *ca)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pl->n_tiles * pl->splits, pl->m_tiles, 1);
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM_BYTES;
+  cfg.stream = rb_stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = SPLITS;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  /* cooperative: the driver guarantees that all CTAs are resident together
+     or fails the launch, whatever else shares the device (the kernel spins
+     on barriers between CTAs) */
+  static int cooperative = -1;
+  if (cooperative < 0)
+    cooperative = getenv("RECUR_B200_PLAIN_LAUNCH") ? 0 : 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = cooperative;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_tc_chain_persistent<SPLITS>, t->mEhi_k, t->mElo_k,
+      t->mWhi_k, t->mWlo_k, *ca);
+  if (e != cudaSuccess && cooperative) {
+    /* a driver that does not combine cooperative launches with clusters:
+       co-residency then rests on cudaOccupancyMaxActiveClusters (chain_plan)
+       and on nothing else using the device; say so once */
+    cudaGetLastError();
+    fprintf(stderr, "recur-b200: cooperative cluster launch refused (%s); launching the "
+        "persistent chain kernel plainly\n", cudaGetErrorString(e));
+    cooperative = 0;
+    at[1].val.cooperative = 0;
+    e = cudaLaunchKernelEx(&cfg, k_tc_chain_persistent<SPLITS>, t->mEhi_k, t->mElo_k,
+        t->mWhi_k, t->mWlo_k, *ca);
+  }
+  if (e != cudaSuccess)
+    rb_die("recur-b200: launch of k_tc_chain_persistent failed: %s", cudaGetErrorString(e));
+}
+
 extern "C" void
 rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta, int accumulate)
 {
   RbTc *t = tc_state(p);
   refresh_weight_planes(t, p, v);
+  const RbPlanes Xp = planes_of(t->Xhi, t->Xlo, t->pitch, 1.0f, NULL);
+  const RbPlanes Ep = planes_of(t->Ehi, t->Elo, t->pitch, 0.0f, t->escale);
   if (p->x_planes_stale) {
     /* ring rows were rewritten behind the planes' back (rnn_forget_history,
        rnn_b200_push, a per-net or FMA forward, a regrown pool): the weight
        gradient reads the ring only through the planes */
-    size_t n = (size_t)p->depth * p->cap * v->d.i_size;
     rb_prof_begin(RB_PROF_SMALL);
-    k_split_ring<<<148 * 4, 256, 0, rb_stream>>>(p->X, n, t->Xhi, t->Xlo);
+    k_split_ring<<<148 * 4, 256, 0, rb_stream>>>(p->X, v->d.i_size, (size_t)p->depth * p->cap, Xp);
     LAUNCH_CHECK("k_split_ring");
     rb_prof_end(RB_PROF_SMALL);
     p->x_planes_stale = 0;
   }
-  /* top layer: E[0] and, where the batch kernel applies, its planes too */
-  if (rbk_top_layer_can_write_planes(v)) {
-    rbk_top_layer_planes(v, ho_delta, accumulate, NULL, 0, t->Ehi, t->Elo);
-  }
-  else {
-    rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
-    rb_prof_begin(RB_PROF_SMALL);
-    k_split_rows<<<v->n, 256, 0, rb_stream>>>(*v, 1, t->Ehi, t->Elo);
-    LAUNCH_CHECK("k_split_rows");
-    rb_prof_end(RB_PROF_SMALL);
-  }
-  if (!chain_attr_done) {
-    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
-    chain_attr_done = 1;
-  }
-  NtArgs g;
-  g.v = *v;
-  g.mode = 1;
-  g.use_noise = 0;
-  g.cpartial = t->cpartial;
-  /* split K only as far as there are K blocks to share out */
-  int n_kb = cdiv(v->d.h_size, TC_BK);
-  int splits = TC_CHAIN_SPLITS;
-  while (splits > 1 && n_kb / splits < 2)
-    splits /= 2;
-  dim3 cgrid(cdiv(v->d.i_size, TC_CHAIN_BN), cdiv(v->n, TC_BM), splits);
-  int n_ctas = cgrid.x * cgrid.y * cgrid.z;
-  /* device facts once; the choice of kernel per call (the batch may grow) */
-  static int sms = 0, coop = 0, per_sm_single = 0;
-  if (!sms) {
-    int dev = 0;
-    CUDA_OR_DIE(cudaGetDevice(&dev));
-    CUDA_OR_DIE(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>,
-            cudaFuncAttributeMaxDynamicSharedMemorySize, ChainCfg::SMEM_BYTES));
-    CUDA_OR_DIE(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_single,
-            k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, TC_CHAIN_THREADS, ChainCfg::SMEM_BYTES));
-    CUDA_OR_DIE(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  t->persistent_ok = (coop && per_sm_single * sms >= n_ctas && !getenv("RECUR_B200_NO_PERSISTENT"));
+  /* top layer: E(0), then its planes and the scale of this walk's planes */
+  rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
+  rb_prof_begin(RB_PROF_TOP);
+  k_e0_planes<<<v->n, 256, 0, rb_stream>>>(*v, Ep, t->escale);
+  LAUNCH_CHECK("k_e0_planes");
+  rb_prof_end(RB_PROF_TOP);
+
   /* small nets: every stream walks alone with the weights resident in its SM */
   const bool resident = rbk_walk_resident_usable(v);
-  if (resident)
-    t->persistent_ok = 0;
+  ChainPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  if (!resident)
+    pl = chain_plan(v);
   unsigned int *sync_area = t->sync + (size_t)t->sync_flip * t->sync_words;
   unsigned int *sync_next = t->sync + (size_t)(t->sync_flip ^ 1) * t->sync_words;
   t->sync_flip ^= 1;
-  rb_note_walk_kernel(t->persistent_ok ? "k_tc_chain_persistent"
+  unsigned int *kmax_dev = sync_area + (size_t)cdiv(v->n, TC_BM) * CH_SYNC_STRIDE + 4;
+  rb_note_walk_kernel(pl.ok ? "k_tc_chain_persistent"
       : resident ? "k_walk_resident" : "k_tc_nt<CHAIN>");
-  if (t->persistent_ok) {
+  if (pl.ok) {
     ChainArgs ca;
     ca.v = *v;
-    ca.cpartial = t->cpartial;
-    ca.Ehi = t->Ehi;
-    ca.Elo = t->Elo;
+    ca.E = Ep;
+    ca.sqpart = t->sqpart;
     ca.sync = sync_area;
-    ca.dbg = NULL;
-    static unsigned long long *dbg_dev = NULL;
-    static int dbg_calls = 0;
-    const bool timing = getenv("RECUR_B200_CHAIN_TIMING") != NULL;
-    if (timing) {
-      if (!dbg_dev)
-        CUDA_OR_DIE(cudaMalloc((void **)&dbg_dev, (1280) * sizeof(unsigned long long)));
-      CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, (1280) * sizeof(unsigned long long), rb_stream));
-      ca.dbg = dbg_dev;
-    }
-    ca.kmax = sync_area + (size_t)cgrid.y * (v->depth + 8) + 4;
-    void *params[] = {(void *)&t->mEhi_k, (void *)&t->mElo_k, (void *)&t->mWhi_k,
-                      (void *)&t->mWlo_k, (void *)&ca};
+    ca.kmax = kmax_dev;
+    ca.splits = pl.splits;
+    ca.nkb_total = pl.nkb_total;
+    ca.kb_per = pl.kb_per;
+    ca.tail0 = pl.tail0;
     rb_prof_begin(RB_PROF_CHAIN);
-    if (!getenv("RECUR_B200_PLAIN_LAUNCH")) {
-      /* cooperative by default: the driver guarantees all CTAs are resident
-         together or fails the launch, whatever else shares the device */
-      CUDA_OR_DIE(cudaLaunchCooperativeKernel(
-              (void *)k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES>, cgrid, dim3(TC_CHAIN_THREADS),
-              params, ChainCfg::SMEM_BYTES, rb_stream));
-    }
-    else {
-      /* opt-out for measurements: co-residency then rests on the occupancy
-         check above and on nothing else using the device */
-      k_tc_chain_persistent<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, TC_CHAIN_THREADS, ChainCfg::SMEM_BYTES,
-        rb_stream>>>(t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, ca);
-    }
+    if (pl.splits == 4)
+      launch_chain<4>(t, &pl, &ca);
+    else
+      launch_chain<2>(t, &pl, &ca);
     LAUNCH_CHECK("k_tc_chain_persistent");
     rb_prof_end(RB_PROF_CHAIN);
-    if (timing && (++dbg_calls % 100) == 60) {
-      static unsigned long long h[1280];
-      CUDA_OR_DIE(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, rb_stream));
-      CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
-      double a = 0, b1 = 0, b = 0, b2 = 0;
-      int steps = 0;
-      for (int k = 0; k < v->depth && k < 64 && h[k * 5 + 4]; k++, steps++) {
-        a += (double)(h[k * 5 + 1] - h[k * 5 + 0]);
-        b1 += (double)(h[k * 5 + 2] - h[k * 5 + 1]);
-        b += (double)(h[k * 5 + 3] - h[k * 5 + 2]);
-        b2 += (double)(h[k * 5 + 4] - h[k * 5 + 3]);
-      }
-      if (steps)
-        fprintf(stderr, "chain timing (CTA 0, %d steps): phase A %.2f us, barrier %.2f us, "
-            "phase B %.2f us, barrier %.2f us per step\n", steps, a / steps * 1e-3,
-            b1 / steps * 1e-3, b / steps * 1e-3, b2 / steps * 1e-3);
-      {
-        const unsigned long long *q = h + 1200, t0 = h[320];
-        fprintf(stderr, "step 5 CTA 0 phase A: alive check done +%.2f, first stage landed +%.2f, "
-            "last stage landed +%.2f, accumulator ready +%.2f, epilogue done +%.2f, phase end +%.2f us\n",
-            (double)(q[0] - t0) * 1e-3, (double)(q[1] - t0) * 1e-3, (double)(q[2] - t0) * 1e-3,
-            (double)(q[3] - t0) * 1e-3, (double)(q[4] - t0) * 1e-3, (double)(h[321] - t0) * 1e-3);
-        unsigned long long b0 = h[322];
-        fprintf(stderr, "step 5 CTA 0 warp 2 phase B (after the barrier): start +%.2f, loads landed +%.2f, "
-            "summed +%.2f, stored +%.2f, reduced +%.2f, tail done +%.2f, proxy fence done +%.2f, phase end +%.2f us\n",
-            (double)(q[10] - b0) * 1e-3, (double)(q[11] - b0) * 1e-3, (double)(q[16] - b0) * 1e-3, (double)(q[12] - b0) * 1e-3,
-            (double)(q[13] - b0) * 1e-3, (double)(q[14] - b0) * 1e-3, (double)(q[15] - b0) * 1e-3,
-            (double)(h[323] - b0) * 1e-3);
-      }
-    }
   }
   else if (resident) {
-    rbk_walk_resident(v, t->Ehi, t->Elo);
+    rbk_walk_resident(v, &Ep);
   }
-  else
-  for (int k = 0; k < v->depth; k++) {
-    g.k = k;
-    rb_prof_begin(RB_PROF_CHAIN);
-    k_tc_nt<TC_CHAIN_BN, TC_CHAIN_STAGES><<<cgrid, 192, ChainCfg::SMEM_BYTES, rb_stream>>>(
-        t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, g);
-    LAUNCH_CHECK("k_tc_nt<CHAIN>");
-    k_chain_finish_step<<<v->n, 256, 0, rb_stream>>>(*v, k, t->cpartial, splits, t->Ehi, t->Elo);
-    LAUNCH_CHECK("k_chain_finish_step");
-    rb_prof_end(RB_PROF_CHAIN);
+  else {
+    nt_big_attr();
+    NtArgs g;
+    g.v = *v;
+    g.mode = 1;
+    g.use_noise = 0;
+    g.cpartial = t->cpartial;
+    g.inv_scale = 1.0f / RB_W_SCALE;
+    g.a_scale_dev = t->escale;
+    /* split K only as far as there are K blocks to share out */
+    int n_kb = cdiv(v->d.h_size, TC_KB);
+    int splits = TC_NT_SPLITS;
+    while (splits > 1 && n_kb / splits < 2)
+      splits /= 2;
+    dim3 cgrid(cdiv(v->d.i_size, TC_NT_BN), cdiv(v->n, TC_BM), splits);
+    for (int k = 0; k < v->depth; k++) {
+      g.k = k;
+      rb_prof_begin(RB_PROF_CHAIN);
+      k_tc_nt<TC_NT_BN, TC_NT_STAGES><<<cgrid, 192, NtBigCfg::SMEM_BYTES, rb_stream>>>(
+          t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, g);
+      LAUNCH_CHECK("k_tc_nt<CHAIN>");
+      k_chain_finish_step<<<v->n, 256, 0, rb_stream>>>(*v, k, t->cpartial, splits, Ep);
+      LAUNCH_CHECK("k_chain_finish_step");
+      rb_prof_end(RB_PROF_CHAIN);
+    }
   }
-  unsigned int *kmax_dev = sync_area + (size_t)cdiv(v->n, TC_BM) * (v->depth + 8) + 4;
-  if (!t->persistent_ok) {
+  if (!pl.ok) {
     k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
     LAUNCH_CHECK("k_compute_kmax");
   }
   rb_prof_begin(RB_PROF_SMALL);
-  k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, t->Ehi, t->Elo, kmax_dev, sync_next,
-      (int)t->sync_words);
+  k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, Ep, kmax_dev, sync_next, (int)t->sync_words);
   LAUNCH_CHECK("k_finalize_rows");
   rb_prof_end(RB_PROF_SMALL);
-  if (!dw_attr_done) {
-    CUDA_OR_DIE(cudaFuncSetAttribute(k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            DW_SMEM_BYTES));
-    dw_attr_done = 1;
-  }
+
   DwArgs d;
   d.v = *v;
   d.partial = t->partial;
   d.kmax = kmax_dev;
+  d.e_scale_dev = t->escale;
   static int dw_sms = 0, dw_pair_ok = 0;
   if (!dw_sms) {
     int dev = 0;
@@ -2215,22 +2252,21 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   int psplits = dw_sms / (pgx * pgy);
   if (psplits > TC_DW_SPLITS)
     psplits = TC_DW_SPLITS;
+  int size = v->d.i_size * v->d.h_size;
   if (dw_pair_ok && psplits >= 1) {
     /* CTA pairs: one MMA across two SMs, each holding half of the N operand */
     dim3 dgrid(pgx, pgy, psplits);
-    k_tc_dw_pair<<<dgrid, 192, DW2_SMEM_BYTES, rb_stream>>>(t->mEhi_mn4, t->mElo_mn4,
-        t->mXhi_mn3, t->mXlo_mn3, d);
+    k_tc_dw_pair<<<dgrid, 192, DW2_SMEM_BYTES, rb_stream>>>(t->mEhi_mn, t->mElo_mn, t->mXhi_mn,
+        t->mXlo_mn, d);
     LAUNCH_CHECK("k_tc_dw_pair");
     t->dw_splits = psplits;
   }
   else {
-    dim3 dgrid(cdiv(v->d.h_size, TC_DW_BN), cdiv(v->d.i_size, TC_BM), TC_DW_SPLITS);
-    k_tc_dw<<<dgrid, 192, DW_SMEM_BYTES, rb_stream>>>(t->mXhi_mn, t->mXlo_mn, t->mEhi_mn,
-        t->mElo_mn, d);
-    LAUNCH_CHECK("k_tc_dw");
-    t->dw_splits = TC_DW_SPLITS;
+    /* no pair grid for this shape: the FMA engine's weight gradient, parked
+       as a single "split" */
+    rbk_dw_fma(v, t->partial, 0);
+    t->dw_splits = 1;
   }
-  int size = v->d.i_size * v->d.h_size;
   if (rb_p2p_ready(v->p2p)) {
     /* multi-GPU: the split-K sum is the first phase of the exchange kernel */
     rb_p2p_reduce(v->p2p, t->partial, t->dw_splits, size, v->d.h_size * v->d.o_size, ih_delta,
@@ -2306,6 +2342,8 @@ rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum, float mo
   a.Wlo = t->Wlo;
   a.WThi = t->WThi;
   a.WTlo = t->WTlo;
+  a.wpitch = t->wpitch;
+  a.tpitch = t->pitch;
   a.ho_W = net->ho_weights;
   a.ho_mom = b->ho_momentum;
   a.ho_aux = b->ho_aux;
