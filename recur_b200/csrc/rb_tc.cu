@@ -1128,11 +1128,16 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
  *    Wih (128 rows x its K range, both planes: 128 KB at H1023) is loaded
  *    into shared memory ONCE and stays there for the whole walk; only the
  *    error rows stream through the TMA ring each step;
- *  * the split-K reduction never leaves the cluster: every CTA parks its
- *    partial tile in its own shared memory, one cluster barrier, then each
- *    CTA sums ITS quarter of the tile's columns out of its peers' shared
- *    memory (distributed shared memory loads, fixed order), masks, writes
- *    E(k+1) with its planes, and the row's partial sum of squares;
+ *  * the split-K reduction never leaves the cluster, and nobody waits for a
+ *    load from another SM: each CTA finishes one column slice of the tile.
+ *    From tensor memory it keeps its own slice in registers and parks the
+ *    slices of its peers in shared memory; once every CTA of the cluster has
+ *    signalled (remote mbarrier arrive) that its K loop is over - the ring is
+ *    free to be written - one bulk copy per peer (cp.async.bulk shared::cta ->
+ *    shared::cluster) drops each parked slice into the peer's ring memory and
+ *    counts its bytes on the peer's mbarrier.  The receiver sums the slices
+ *    in rank order out of its OWN shared memory, masks, writes E(k+1) with
+ *    its planes, and the row's partial sum of squares;
  *  * the streams of a tile of 128 are an independent chain, so only the CTAs
  *    that share blockIdx.y synchronise, ONCE per step (monotonic counter,
  *    arrive = red.release.gpu, wait = ld.acquire.gpu by the TMA thread, which
@@ -1149,9 +1154,10 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
  *    than fit the GPU's GPCs; their few nonzero rows are dot products on two
  *    spare warps instead (recur-nn.c:347 skips the zero rows just so).
  *
- * Shared memory: W slice 128 KB | TMA ring 3 x 32 KB (its first 66 KB double
- * as the partial-tile parking area between the K loop and the next step's
- * loads) | barriers.  Tensor memory: two 128-column accumulators.           */
+ * Shared memory: W slice 128 KB | TMA ring 3 x 32 KB, which between a step's
+ * K loop and the next step's loads holds the outgoing (48 KB) and incoming
+ * (48 KB) slices of the exchange | barriers.  Tensor memory: two 128-column
+ * accumulators.                                                             */
 
 #define CH_THREADS 256
 #define CH_BN 128
@@ -1160,9 +1166,8 @@ k_chain_finish_step(RbView v, int k, const float *__restrict__ cpartial, int spl
 #define CH_PLANE_BYTES (TC_BM * TC_KB * 2)        /* 16 KB: 128 rows x 64 halves */
 #define CH_STAGE_BYTES (2 * CH_PLANE_BYTES)       /* hi and lo planes of one K block */
 #define CH_W_BYTES (CH_WKB * 2 * CH_PLANE_BYTES)  /* 128 KB */
-#define CH_PARK_PITCH 132                          /* floats: 16-byte rows, conflict-free */
-#define CH_SMEM_BYTES (CH_W_BYTES + CH_STAGES * CH_STAGE_BYTES + 1024 + 1024)
-static_assert(TC_BM * CH_PARK_PITCH * 4 <= CH_STAGES * CH_STAGE_BYTES, "parking area fits the ring");
+#define CH_RING_BYTES (CH_STAGES * CH_STAGE_BYTES)
+#define CH_SMEM_BYTES (CH_W_BYTES + CH_RING_BYTES + 1024 + 1024)
 
 __device__ __forceinline__ unsigned int
 ld_acquire_gpu(const unsigned int *p)
@@ -1186,6 +1191,40 @@ wait_counter(const unsigned int *counter, unsigned int target)
   }
 }
 
+/* arrive on the mbarrier at the same shared-memory offset in CTA `rank` of
+   the cluster (a pure signal: relaxed, nothing is published with it) */
+__device__ __forceinline__ void
+mbar_arrive_cluster(uint64_t *bar, uint32_t rank)
+{
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];"
+      ::"r"(dsmem_addr(bar, rank)) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+/* `bytes` of this CTA's shared memory -> the same-layout buffer `dst` in CTA
+   `rank`, completion counted on that CTA's mbarrier */
+__device__ __forceinline__ void
+bulk_copy_to_peer(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint32_t rank)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dsmem_addr(dst, rank)), "r"(smem_u32(src)), "r"(bytes), "r"(dsmem_addr(bar, rank))
+      : "memory");
+}
+
 struct ChainArgs {
   RbView v;
   RbPlanes E;           /* planes of the chain; scale on the device */
@@ -1195,31 +1234,109 @@ struct ChainArgs {
   int splits;           /* K splits == cluster size */
   int nkb_total, kb_per;/* 64-wide K blocks in all, per split */
   int tail0;            /* first column left to the CUDA-core tail (i_size: none) */
+  unsigned long long *dbg; /* TIMING instantiation only: [step][16] globaltimer stamps of CTA 0 */
 };
 
-template <int SPLITS>
+__device__ __forceinline__ unsigned long long
+globaltimer_ns(void)
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+/* measurement build of the kernel only (RECUR_B200_CHAIN_TIMING): the
+   production instantiation compiles these away */
+#define CH_STAMP(slot) do {                                             \
+    if (TIMING && blockIdx.x == 0 && blockIdx.y == 0 && k < 64)         \
+      g.dbg[k * 32 + (slot)] = globaltimer_ns();                        \
+  } while (0)
+
+__device__ __forceinline__ void
+named_bar_sync(int id, int count)
+{
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+/* one stream's sum of squares of the step decided on: the per-CTA parts in
+   slot order (the same in every CTA of the group) */
+__device__ __forceinline__ float
+sum_sq_parts(const float *sp, int n_slots)
+{
+  /* eight loads in flight at a time: summed one after the other they would
+     each wait out an L2 round trip */
+  float es = 0.0f;
+#pragma unroll 1
+  for (int q0 = 0; 4 * q0 < n_slots; q0 += 8) {
+    float4 t[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (4 * (q0 + q) < n_slots)
+        t[q] = __ldcg((const float4 *)(sp + 4 * (q0 + q)));
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int c = 4 * (q0 + q);
+      if (c < n_slots) es += t[q].x;
+      if (c + 1 < n_slots) es += t[q].y;
+      if (c + 2 < n_slots) es += t[q].z;
+      if (c + 3 < n_slots) es += t[q].w;
+    }
+  }
+  return es;
+}
+
+/* 16 consecutive accumulator columns of this thread's TMEM lane */
+__device__ __forceinline__ void
+tmem_ld16_nowait(uint32_t taddr, float *v)
+{
+  uint32_t *r = (uint32_t *)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+template <int SPLITS, bool TIMING>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
     const __grid_constant__ CUtensorMap mElo, const __grid_constant__ CUtensorMap mWhi,
     const __grid_constant__ CUtensorMap mWlo, ChainArgs g)
 {
-  constexpr int CPR = CH_BN / SPLITS; /* columns of the tile this CTA finishes */
-  constexpr int CPT = CPR / 2;        /* per thread: two threads share a row */
-  constexpr int NG = CPT / 4;         /* float4 groups per thread */
+  constexpr int CPR = CH_BN / SPLITS;     /* columns of the tile this CTA finishes: its slice */
+  constexpr int SEG = CPR / 32;           /* 128-byte segments per slice row */
+  constexpr int SLICE_BYTES = TC_BM * CPR * 4;
+  constexpr int LPR = CPR / 4;            /* row phase: threads per row, one float4 each */
+  constexpr int RPI = CH_THREADS / LPR;   /* rows per pass over the slice */
+  constexpr int NG = TC_BM / RPI;         /* passes == float4 groups per thread */
+  static_assert(2 * (SPLITS - 1) * SLICE_BYTES <= CH_RING_BYTES, "exchange buffers fit the ring");
+  static_assert(SLICE_BYTES <= CH_STAGE_BYTES, "the own slice fits the last Wih slot");
   extern __shared__ uint8_t smem_raw[];
   const RbView &v = g.v;
   /* the dynamic shared window starts at the same offset in every CTA, so the
-     rounded-up base does too: the parking area has one address cluster-wide */
+     rounded-up base does too: buffers and barriers have one address cluster-wide */
   uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *w_smem = smem;
   uint8_t *a_smem = smem + CH_W_BYTES;
-  float *park = (float *)a_smem;
-  uint64_t *full = (uint64_t *)(a_smem + CH_STAGES * CH_STAGE_BYTES);
+  uint8_t *out_buf = a_smem;                                  /* [SPLITS-1] slices for the peers */
+  uint8_t *in_buf = a_smem + (SPLITS - 1) * SLICE_BYTES;      /* [SPLITS-1] slices from the peers */
+  /* This CTA's own slice is parked at the end of the Wih area.  When all
+     CH_WKB slots hold weights, the planes under it (the last block's lo
+     plane, at two splits the whole block) are fetched again at the start of
+     the next step - 16 KB with no dependence on anything, long there before
+     the last block's MMAs want them. */
+  uint8_t *own_buf = w_smem + CH_W_BYTES - SLICE_BYTES;
+  uint64_t *full = (uint64_t *)(a_smem + CH_RING_BYTES);
   uint64_t *empty = full + CH_STAGES;
   uint64_t *acc_ready = empty + CH_STAGES;
   uint64_t *w_ready = acc_ready + 1;
   uint64_t *step_go = w_ready + 1;
-  uint32_t *tmem_slot = (uint32_t *)(step_go + 1);
+  uint64_t *k_done = step_go + 1;   /* every CTA of the cluster is through its K loop */
+  uint64_t *data_in = k_done + 1;   /* the peers' slices have landed */
+  uint64_t *w_again = data_in + 1;  /* the weights the own slice sat on are back */
+  uint32_t *tmem_slot = (uint32_t *)(w_again + 1);
   int *s_any = (int *)(tmem_slot + 1);      /* [2] a stream walks on, by step parity */
   int *s_kmax = s_any + 2;
   uint8_t *s_live = (uint8_t *)(s_kmax + 1); /* [128] */
@@ -1235,6 +1352,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
   const int n_kb = min(g.kb_per, g.nkb_total - kb_begin);
   const bool has_tail = g.tail0 < I;
   const int n_slots = grp_ctas + (has_tail ? 1 : 0);
+  const bool w_refetch = n_kb == CH_WKB; /* the own slice's parking place holds weights */
   float *sq_grp = g.sqpart + (size_t)grp * TC_BM * CH_SQ_SLOTS;
   const size_t sq_par = (size_t)gridDim.y * TC_BM * CH_SQ_SLOTS; /* floats between the two parities */
   const int depth = v.depth;
@@ -1249,6 +1367,9 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
     mbar_init(acc_ready, 1);
     mbar_init(w_ready, 1);
     mbar_init(step_go, 1);
+    mbar_init(k_done, SPLITS);
+    mbar_init(data_in, 1);
+    mbar_init(w_again, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mEhi);
     tma_prefetch_desc(&mElo);
@@ -1276,34 +1397,37 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all(); /* every CTA's barriers exist before a peer signals them */
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const float e_scale = *g.E.scale_dev;
   const float inv_scale = 1.0f / (e_scale * RB_W_SCALE);
 
-  /* the part of the output tile this thread finishes: row, 16-column run */
-  const int r_row = threadIdx.x >> 1;
-  const int r_c = (int)rank * CPR + (threadIdx.x & 1) * CPT; /* tile-local first column */
-  const bool r_ok = m0 + r_row < v.n;
-  const int r_s = v.base + (r_ok ? m0 + r_row : 0);
+  /* row phase: one float4 of this CTA's slice in every RPI-th row, a row's
+     threads side by side (whole 128-byte runs to global memory) */
+  const int r_row0 = threadIdx.x / LPR;
+  const int r_j = threadIdx.x % LPR;               /* float4 index within the slice row */
+  const int r_col = n0 + (int)rank * CPR + r_j * 4;
 
   unsigned int it = 0; /* ring iterations so far (producer and MMA keep equal counts) */
   bool finished = false;
 
   for (int k = 0; k < depth; k++) {
     const int par = k & 1;
-    /* the ring row that masks this step's errors travels while the GEMM runs */
+    if (threadIdx.x == 0)
+      CH_STAMP(0);
+    /* the ring rows that mask this step's errors travel while the GEMM runs */
     float4 xq[NG];
     {
       int p = pos0 - k;
       if (p < 0)
         p += depth;
-      const float *xk = v.X + ((size_t)p * v.cap + r_s) * I + n0 + r_c;
 #pragma unroll
       for (int q = 0; q < NG; q++) {
+        const int row = r_row0 + q * RPI;
         xq[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r_ok && n0 + r_c + 4 * q < I)
-          xq[q] = __ldg((const float4 *)(xk + 4 * q));
+        if (m0 + row < v.n && r_col < I)
+          xq[q] = __ldg((const float4 *)(v.X + ((size_t)p * v.cap + v.base + m0 + row) * I + r_col));
       }
     }
 
@@ -1318,11 +1442,24 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           }
         }
         else {
-          /* every CTA of the group has written its part of E(k) and has read
-             what it needed from its cluster peers' parking areas */
+          if (w_refetch) {
+            /* the weights under the own slice's parking place */
+            const int j = CH_WKB - 1;
+            if (SLICE_BYTES > CH_PLANE_BYTES) {
+              mbar_expect_tx(w_again, CH_STAGE_BYTES);
+              tma_load_2d(&mWhi, w_again, w_smem + j * CH_STAGE_BYTES, (kb_begin + j) * TC_KB, n0);
+            }
+            else
+              mbar_expect_tx(w_again, CH_PLANE_BYTES);
+            tma_load_2d(&mWlo, w_again, w_smem + j * CH_STAGE_BYTES + CH_PLANE_BYTES,
+                (kb_begin + j) * TC_KB, n0);
+          }
+          /* every CTA of the group has written its part of E(k) - and, being
+             there, has taken delivery of the slices this CTA sent it */
           wait_counter(gsync, (unsigned int)k * grp_ctas);
           mbar_arrive(step_go);
         }
+        CH_STAMP(1);
         const int erow = k * v.cap + v.base + m0;
         for (int j = 0; j < n_kb; j++, it++) {
           int s = it % CH_STAGES;
@@ -1345,6 +1482,12 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           uint32_t ph = (it / CH_STAGES) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
+          if (j == 0)
+            CH_STAMP(2);
+          if (w_refetch && k > 0 && j == CH_WKB - 1) {
+            mbar_wait(w_again, (k - 1) & 1);
+            tc_fence_after();
+          }
           uint32_t a_hi = smem_u32(a_smem + s * CH_STAGE_BYTES);
           uint32_t b_hi = smem_u32(w_smem + j * CH_STAGE_BYTES);
           issue_block_f16(tmem_base, tmem_base + CH_BN, a_hi, a_hi + CH_PLANE_BYTES, b_hi,
@@ -1352,6 +1495,14 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           umma_commit(&empty[s]);
         }
         umma_commit(acc_ready);
+        CH_STAMP(3);
+        /* when the MMAs are through, this CTA's ring is free: tell the
+           cluster (itself included).  Nothing of this thread's own needs
+           publishing with it, hence relaxed. */
+        mbar_wait(acc_ready, par);
+#pragma unroll
+        for (int z = 0; z < SPLITS; z++)
+          mbar_arrive_cluster(k_done, (uint32_t)z);
       }
     }
     else if (warp < 6) {
@@ -1360,15 +1511,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
         mbar_wait(step_go, (k - 1) & 1);
         bool on = false;
         if (d_valid && dsc.live) {
-          const float *sp = sq_grp + (size_t)((k - 1) & 1) * sq_par + (size_t)di * CH_SQ_SLOTS;
-          float es = 0.0f;
-          for (int q = 0; q < n_slots; q += 4) {
-            float4 t = __ldcg((const float4 *)(sp + q));
-            es += t.x;
-            if (q + 1 < n_slots) es += t.y;
-            if (q + 2 < n_slots) es += t.z;
-            if (q + 3 < n_slots) es += t.w;
-          }
+          float es = sum_sq_parts(sq_grp + (size_t)((k - 1) & 1) * sq_par +
+              (size_t)di * CH_SQ_SLOTS, n_slots);
           chain_decide(dsc, es, k - 1, depth);
           on = dsc.live != 0;
           if (!on) {
@@ -1379,32 +1523,75 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
         }
         if (__any_sync(0xffffffffu, on) && lane == 0)
           s_any[par] = 1;
+        if (threadIdx.x == 64)
+          CH_STAMP(7);
       }
-      /* ---- this step's partial tile: tensor memory -> parking area ---- */
+      /* ---- this step's partial tile: the peers' slices leave tensor memory ---- */
       const int q = warp & 3;
       const int row = q * 32 + lane;
       mbar_wait(acc_ready, par);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-      float *dst = park + (size_t)row * CH_PARK_PITCH;
-      float acc[2][32], cor[2][32];
-      tmem_ld32_nowait(taddr, acc[0]);
-      tmem_ld32_nowait(taddr + CH_BN, cor[0]);
+      named_bar_sync(1, 128); /* the four warps' verdicts are in s_any */
+      const bool go_on = !(k > 0 && !s_any[par]);
+      if (go_on) {
+        if (threadIdx.x == 64)
+          CH_STAMP(4);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float acc[2][16], cor[2][16];
+        tmem_ld16_nowait(taddr, acc[0]);
+        tmem_ld16_nowait(taddr + CH_BN, cor[0]);
 #pragma unroll
-      for (int ci = 0; ci < CH_BN / 32; ci++) {
-        tmem_wait_ld();
-        if (ci + 1 < CH_BN / 32) {
-          tmem_ld32_nowait(taddr + (ci + 1) * 32, acc[(ci + 1) & 1]);
-          tmem_ld32_nowait(taddr + CH_BN + (ci + 1) * 32, cor[(ci + 1) & 1]);
+        for (int ci = 0; ci < CH_BN / 16; ci++) {
+          tmem_wait_ld();
+          if (ci + 1 < CH_BN / 16) {
+            tmem_ld16_nowait(taddr + (ci + 1) * 16, acc[(ci + 1) & 1]);
+            tmem_ld16_nowait(taddr + CH_BN + (ci + 1) * 16, cor[(ci + 1) & 1]);
+          }
+          const float *av = acc[ci & 1], *cv = cor[ci & 1];
+          const int z = ci / (2 * SEG); /* the rank that finishes these 16 columns */
+          /* a slice: rows of CPR floats, the eight float4 of a 128-byte
+             segment XOR-swizzled by the row so that a warp's stores (one row
+             per lane) spread over the banks.  Outgoing slots: peers in rank
+             order, this CTA left out. */
+          uint8_t *dst = (z == (int)rank ? own_buf
+                  : out_buf + (z - (z > (int)rank ? 1 : 0)) * SLICE_BYTES) +
+              (size_t)row * (CPR * 4);
+          const int jb = (ci % (2 * SEG)) * 4; /* first float4 index within the slice row */
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int jj = jb + j;
+            *(float4 *)(dst + (jj >> 3) * 128 + (((jj & 7) ^ (row & 7)) << 4)) = make_float4(
+                fmaf(cv[4 * j], RB_LO_UNGAIN, av[4 * j]),
+                fmaf(cv[4 * j + 1], RB_LO_UNGAIN, av[4 * j + 1]),
+                fmaf(cv[4 * j + 2], RB_LO_UNGAIN, av[4 * j + 2]),
+                fmaf(cv[4 * j + 3], RB_LO_UNGAIN, av[4 * j + 3]));
+          }
         }
-        const float *av = acc[ci & 1], *cv = cor[ci & 1];
+        tc_fence_before();
+        if (threadIdx.x == 64)
+          CH_STAMP(14);
+        /* the outgoing slices were written through the generic proxy, the bulk
+           copies read them through the async proxy */
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        named_bar_sync(1, 128);
+        if (threadIdx.x == 64) {
+          CH_STAMP(5);
+          mbar_expect_tx(data_in, (SPLITS - 1) * SLICE_BYTES);
+          /* no peer may still be reading its ring with the tensor core */
+          mbar_wait_cluster(k_done, par);
+          CH_STAMP(8);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *(float4 *)(dst + ci * 32 + j) = make_float4(fmaf(cv[j], RB_LO_UNGAIN, av[j]),
-              fmaf(cv[j + 1], RB_LO_UNGAIN, av[j + 1]), fmaf(cv[j + 2], RB_LO_UNGAIN, av[j + 2]),
-              fmaf(cv[j + 3], RB_LO_UNGAIN, av[j + 3]));
+          for (int z = 0; z < SPLITS; z++) {
+            if (z == (int)rank)
+              continue;
+            /* at the receiver: senders in rank order, the receiver left out */
+            const int out_slot = z - (z > (int)rank ? 1 : 0);
+            const int in_slot = (int)rank - ((int)rank > z ? 1 : 0);
+            bulk_copy_to_peer(in_buf + in_slot * SLICE_BYTES, out_buf + out_slot * SLICE_BYTES,
+                SLICE_BYTES, data_in, (uint32_t)z);
+          }
+        }
       }
-      tc_fence_before();
     }
     else if (has_tail) {
       /* ---- columns past the last tile: the nonzero rows among them as dot
@@ -1412,11 +1599,16 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
          group's streams ---- */
       if (k > 0)
         mbar_wait(step_go, (k - 1) & 1);
+      /* half a warp per stream, so that this CTA's (usually four) streams
+         wait for their loads together, not one after the other */
       const int spc = (TC_BM + grp_ctas - 1) / grp_ctas;
-      for (int t = warp - 6; t < spc; t += 2) {
+      const int hl = lane & 15;
+      const unsigned int hmask = (lane & 16) ? 0xffff0000u : 0x0000ffffu;
+      const int hs1 = v.d.hidden_size + 1;
+      for (int t = (warp - 6) * 2 + (lane >> 4); t < spc; t += 4) {
         const int i = grp_cta * spc + t;
         if (i >= TC_BM || m0 + i >= v.n || !s_live[i])
-          continue; /* uniform over the warp */
+          continue; /* uniform over the half warp */
         const int s = v.base + m0 + i;
         int p = pos0 - k;
         if (p < 0)
@@ -1424,78 +1616,104 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
         const float *xk = v.X + ((size_t)p * v.cap + s) * I;
         const float *ek = v.E + ((size_t)k * v.cap + s) * I;
         float *en = v.E + ((size_t)(k + 1) * v.cap + s) * I;
-        const int hs1 = v.d.hidden_size + 1;
         float sq = 0.0f;
-        for (int c0 = g.tail0; c0 < I; c0 += 32) {
-          const int y = c0 + lane;
-          const float x = (y < I) ? __ldg(xk + y) : 0.0f;
-          const bool act = x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f);
-          unsigned int todo = __ballot_sync(0xffffffffu, act);
-          float mine = 0.0f;
-          while (todo) {
-            const int b = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const float *wrow = v.Wih + (size_t)(c0 + b) * H;
-            float dot = 0.0f;
-            for (int c = lane * 4; c < H; c += 128) {
-              float4 w4 = __ldg((const float4 *)(wrow + c));
-              float4 e4 = __ldcg((const float4 *)(ek + c));
-              dot = fmaf(w4.x, e4.x, dot);
-              dot = fmaf(w4.y, e4.y, dot);
-              dot = fmaf(w4.z, e4.z, dot);
-              dot = fmaf(w4.w, e4.w, dot);
-            }
+        for (int c00 = g.tail0; c00 < I; c00 += 64) {
+          /* the ring row's entries of up to 64 columns first, in one go */
+          float xs[4];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-              dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            if (lane == b)
-              mine = dot;
+          for (int u = 0; u < 4; u++) {
+            const int y = c00 + 16 * u + hl;
+            xs[u] = (y < I) ? __ldg(xk + y) : 0.0f;
           }
-          if (y < I) {
-            float e = mine;
-            if (act) {
-              if (v.activation == RNN_RESQRT)
-                e /= 2.0f * (x + 1.0f);
-              sq = fmaf(e, e, sq);
-              if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
-                v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int c0 = c00 + 16 * u;
+            if (c0 >= I)
+              break;
+            const int y = c0 + hl;
+            const float x = xs[u];
+            const bool act = x != 0.0f && (v.activation != RNN_RECLIP20 || x < 20.0f);
+            unsigned int todo = (__ballot_sync(hmask, act) >> (lane & 16)) & 0xffffu;
+            float mine = 0.0f;
+            while (todo) {
+              const int b = __ffs(todo) - 1;
+              todo &= todo - 1;
+              const float *wrow = v.Wih + (size_t)(c0 + b) * H;
+              /* eight loads of each operand in flight before the first is
+                 used (h_size <= 1024 here: two rounds) */
+              float dot = 0.0f;
+              for (int cb = hl * 4; cb < H; cb += 512) {
+                float4 w4[8], e4[8];
+#pragma unroll
+                for (int u2 = 0; u2 < 8; u2++) {
+                  const int c = cb + 64 * u2;
+                  if (c < H) {
+                    w4[u2] = __ldg((const float4 *)(wrow + c));
+                    e4[u2] = __ldcg((const float4 *)(ek + c));
+                  }
+                }
+#pragma unroll
+                for (int u2 = 0; u2 < 8; u2++) {
+                  if (cb + 64 * u2 < H) {
+                    dot = fmaf(w4[u2].x, e4[u2].x, dot);
+                    dot = fmaf(w4[u2].y, e4[u2].y, dot);
+                    dot = fmaf(w4[u2].z, e4[u2].z, dot);
+                    dot = fmaf(w4[u2].w, e4[u2].w, dot);
+                  }
+                }
+              }
+#pragma unroll
+              for (int o = 8; o > 0; o >>= 1)
+                dot += __shfl_xor_sync(hmask, dot, o);
+              if (hl == b)
+                mine = dot;
             }
-            __stcg(en + y, (y >= hs1 && y < H) ? 0.0f : e);
+            if (y < I) {
+              float e = mine;
+              if (act) {
+                if (v.activation == RNN_RESQRT)
+                  e /= 2.0f * (x + 1.0f);
+                sq = fmaf(e, e, sq);
+                if (v.CIE && y >= hs1 && y < hs1 + v.d.input_size)
+                  v.CIE[(size_t)s * v.bl_o + y - hs1] += e;
+              }
+              __stcg(en + y, (y >= hs1 && y < H) ? 0.0f : e);
+            }
           }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-          sq += __shfl_xor_sync(0xffffffffu, sq, o);
-        if (lane == 0)
+        for (int o = 8; o > 0; o >>= 1)
+          sq += __shfl_xor_sync(hmask, sq, o);
+        if (hl == 0)
           __stcg(sq_grp + (size_t)par * sq_par + (size_t)i * CH_SQ_SLOTS + grp_ctas, sq);
       }
+      if (threadIdx.x == 192)
+        CH_STAMP(6);
     }
-    __syncthreads();    /* the tile is parked, the verdicts are in */
-    __syncwarp();
-    cluster_sync_all(); /* ... in every CTA of the cluster */
+    __syncthreads(); /* the verdicts are in for every warp */
     if (k > 0 && !s_any[par]) {
-      finished = true;  /* no stream of the group walks on (the same in all its CTAs) */
+      finished = true; /* no stream of the group walks on (the same in all its CTAs) */
       break;
     }
 
-    /* ---- E(k+1): this CTA's columns of the tile, summed over the K splits ---- */
+    /* ---- E(k+1): this CTA's slice of the tile, summed over the K splits:
+       the peers' parts have landed in this CTA's own shared memory ---- */
     {
+      mbar_wait(data_in, par);
+      if (threadIdx.x == 0)
+        CH_STAMP(10);
       float4 a[NG];
       {
         float4 pz[SPLITS][NG];
 #pragma unroll
         for (int z = 0; z < SPLITS; z++) {
-          const float *src = park + (size_t)r_row * CH_PARK_PITCH + r_c;
-          if (z == (int)rank) {
+          const uint8_t *src = (z == (int)rank ? own_buf
+                  : in_buf + (z - (z > (int)rank ? 1 : 0)) * SLICE_BYTES) + (r_j >> 3) * 128;
 #pragma unroll
-            for (int q = 0; q < NG; q++)
-              pz[z][q] = *(const float4 *)(src + 4 * q);
-          }
-          else {
-            const uint32_t ra = dsmem_addr(src, (uint32_t)z);
-#pragma unroll
-            for (int q = 0; q < NG; q++)
-              pz[z][q] = ld_dsmem_v4(ra + 16 * q);
+          for (int q = 0; q < NG; q++) {
+            const int row = r_row0 + q * RPI;
+            pz[z][q] = *(const float4 *)(src + (size_t)row * (CPR * 4) +
+                (((r_j & 7) ^ (row & 7)) << 4));
           }
         }
 #pragma unroll
@@ -1509,48 +1727,55 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           a[q].x *= inv_scale; a[q].y *= inv_scale; a[q].z *= inv_scale; a[q].w *= inv_scale;
         }
       }
-      const bool live = r_ok && s_live[r_row];
-      float sq = 0.0f;
-      const size_t eoff = ((size_t)(k + 1) * v.cap + r_s) * I;
-      const size_t poff = ((size_t)(k + 1) * v.cap + r_s) * g.E.pitch;
-      if (live) {
+      if (TIMING && threadIdx.x == 0 && a[0].x != 123.456f && a[NG - 1].w != 123.456f)
+        CH_STAMP(15);
 #pragma unroll
-        for (int q = 0; q < NG; q += 2) {
-          const int c = n0 + r_c + 4 * q;
-          if (c >= I)
-            break;
-          float4 o0 = plain ? chain_mask4<true>(v, a[q], xq[q], c, r_s, sq)
-                            : chain_mask4<false>(v, a[q], xq[q], c, r_s, sq);
-          uint2 h0, l0;
-          rb_split4(o0, e_scale, h0, l0);
-          __stcg((float4 *)(v.E + eoff + c), o0);
-          if (c + 4 < I) {
-            float4 o1 = plain ? chain_mask4<true>(v, a[q + 1], xq[q + 1], c + 4, r_s, sq)
-                              : chain_mask4<false>(v, a[q + 1], xq[q + 1], c + 4, r_s, sq);
-            uint2 h1, l1;
-            rb_split4(o1, e_scale, h1, l1);
-            __stcg((float4 *)(v.E + eoff + c + 4), o1);
-            __stcg((uint4 *)(g.E.hi + poff + c), make_uint4(h0.x, h0.y, h1.x, h1.y));
-            __stcg((uint4 *)(g.E.lo + poff + c), make_uint4(l0.x, l0.y, l1.x, l1.y));
-          }
-          else {
-            __stcg((uint2 *)(g.E.hi + poff + c), h0);
-            __stcg((uint2 *)(g.E.lo + poff + c), l0);
-          }
+      for (int q = 0; q < NG; q++) {
+        const int row = r_row0 + q * RPI;
+        const bool live = m0 + row < v.n && s_live[row];
+        const int rs = v.base + (m0 + row < v.n ? m0 + row : 0);
+        float sq = 0.0f;
+        if (live && r_col < I) {
+          float4 o = plain ? chain_mask4<true>(v, a[q], xq[q], r_col, rs, sq)
+                           : chain_mask4<false>(v, a[q], xq[q], r_col, rs, sq);
+          if (TIMING && threadIdx.x == 0 && q == 0 && o.x != 123.456f && sq != 123.456f)
+            CH_STAMP(16);
+          uint2 h, l;
+          rb_split4(o, e_scale, h, l);
+          if (TIMING && threadIdx.x == 0 && q == 0 && h.x != 12345u && l.y != 12345u)
+            CH_STAMP(17);
+          __stcg((float4 *)(v.E + ((size_t)(k + 1) * v.cap + rs) * I + r_col), o);
+          const size_t poff = ((size_t)(k + 1) * v.cap + rs) * g.E.pitch + r_col;
+          __stcg((uint2 *)(g.E.hi + poff), h);
+          __stcg((uint2 *)(g.E.lo + poff), l);
+          if (TIMING && threadIdx.x == 0 && q == 0)
+            CH_STAMP(18);
         }
+        /* the row's LPR threads sit side by side in a warp */
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+          sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (live && r_j == 0)
+          __stcg(sq_grp + (size_t)par * sq_par + (size_t)row * CH_SQ_SLOTS + grp_cta, sq);
+        if (TIMING && threadIdx.x == 0 && q == 0)
+          CH_STAMP(19);
       }
-      sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-      if (live && (threadIdx.x & 1) == 0)
-        __stcg(sq_grp + (size_t)par * sq_par + (size_t)r_row * CH_SQ_SLOTS + grp_cta, sq);
     }
-    if (threadIdx.x == 0)
+    if (threadIdx.x == 0) {
       s_any[par ^ 1] = 0; /* the next step's verdicts start from "nobody" */
+      CH_STAMP(11);
+    }
     /* E(k+1)'s planes were written through the generic proxy; the next step's
        TMA reads them through the async proxy */
     asm volatile("fence.proxy.async;" ::: "memory");
-    __syncthreads();
     if (threadIdx.x == 0)
+      CH_STAMP(12);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      CH_STAMP(13);
       asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(gsync), "r"(1u) : "memory");
+      CH_STAMP(9);
+    }
   }
 
   if (!finished) {
@@ -1559,26 +1784,21 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
       wait_counter(gsync, (unsigned int)depth * grp_ctas);
     __syncthreads();
     if (d_valid && dsc.live) {
-      const float *sp = sq_grp + (size_t)((depth - 1) & 1) * sq_par + (size_t)di * CH_SQ_SLOTS;
-      float es = 0.0f;
-      for (int q = 0; q < n_slots; q += 4) {
-        float4 t = __ldcg((const float4 *)(sp + q));
-        es += t.x;
-        if (q + 1 < n_slots) es += t.y;
-        if (q + 2 < n_slots) es += t.z;
-        if (q + 3 < n_slots) es += t.w;
-      }
+      float es = sum_sq_parts(sq_grp + (size_t)((depth - 1) & 1) * sq_par +
+          (size_t)di * CH_SQ_SLOTS, n_slots);
       chain_decide(dsc, es, depth - 1, depth);
       if (owner)
         v.sc[v.base + m0 + di] = dsc;
     }
   }
-  /* (on the early exit the speculative K loop's accumulator was drained like
-     any other before the verdict was looked at: no MMA is in flight) */
+  /* (on the early exit the speculative K loop's accumulator was waited for
+     like any other before the verdict was looked at: no MMA is in flight, and
+     no slice was exchanged in that step) */
   if (owner && d_valid)
     atomicMax(s_kmax, dsc.n_steps);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all(); /* nobody leaves while a peer may still signal its barriers */
   if (owner && threadIdx.x == 0)
     atomicMax(g.kmax, (unsigned int)*s_kmax);
   if (warp == 1) {
@@ -2027,7 +2247,9 @@ chain_clusters_fit(int n_clusters, dim3 grid)
 {
   static int attr_done = 0, coop = -1;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(k_tc_chain_persistent<SPLITS>,
+    if (cudaFuncSetAttribute(k_tc_chain_persistent<SPLITS, false>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_tc_chain_persistent<SPLITS, true>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES) != cudaSuccess) {
       cudaGetLastError();
       return 0;
@@ -2051,7 +2273,7 @@ chain_clusters_fit(int n_clusters, dim3 grid)
   cfg.attrs = at;
   cfg.numAttrs = 1;
   int max_clusters = 0;
-  if (cudaOccupancyMaxActiveClusters(&max_clusters, k_tc_chain_persistent<SPLITS>, &cfg) !=
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, k_tc_chain_persistent<SPLITS, false>, &cfg) !=
       cudaSuccess) {
     cudaGetLastError();
     return 0;
@@ -2122,8 +2344,9 @@ launch_chain(RbTc *t, const ChainPlan *pl, ChainArgs *ca)
   at[1].val.cooperative = cooperative;
   cfg.attrs = at;
   cfg.numAttrs = 2;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_tc_chain_persistent<SPLITS>, t->mEhi_k, t->mElo_k,
-      t->mWhi_k, t->mWlo_k, *ca);
+  auto kernel = ca->dbg ? k_tc_chain_persistent<SPLITS, true> : k_tc_chain_persistent<SPLITS, false>;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k,
+      *ca);
   if (e != cudaSuccess && cooperative) {
     /* a driver that does not combine cooperative launches with clusters:
        co-residency then rests on cudaOccupancyMaxActiveClusters (chain_plan)
@@ -2133,8 +2356,7 @@ launch_chain(RbTc *t, const ChainPlan *pl, ChainArgs *ca)
         "persistent chain kernel plainly\n", cudaGetErrorString(e));
     cooperative = 0;
     at[1].val.cooperative = 0;
-    e = cudaLaunchKernelEx(&cfg, k_tc_chain_persistent<SPLITS>, t->mEhi_k, t->mElo_k,
-        t->mWhi_k, t->mWlo_k, *ca);
+    e = cudaLaunchKernelEx(&cfg, kernel, t->mEhi_k, t->mElo_k, t->mWhi_k, t->mWlo_k, *ca);
   }
   if (e != cudaSuccess)
     rb_die("recur-b200: launch of k_tc_chain_persistent failed: %s", cudaGetErrorString(e));
@@ -2187,6 +2409,16 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     ca.nkb_total = pl.nkb_total;
     ca.kb_per = pl.kb_per;
     ca.tail0 = pl.tail0;
+    ca.dbg = NULL;
+    static unsigned long long *dbg_dev = NULL;
+    static int dbg_calls = 0;
+    const bool timing = getenv("RECUR_B200_CHAIN_TIMING") != NULL;
+    if (timing) {
+      if (!dbg_dev)
+        CUDA_OR_DIE(cudaMalloc((void **)&dbg_dev, 64 * 32 * sizeof(unsigned long long)));
+      CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, 64 * 32 * sizeof(unsigned long long), rb_stream));
+      ca.dbg = dbg_dev;
+    }
     rb_prof_begin(RB_PROF_CHAIN);
     if (pl.splits == 4)
       launch_chain<4>(t, &pl, &ca);
@@ -2194,6 +2426,30 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
       launch_chain<2>(t, &pl, &ca);
     LAUNCH_CHECK("k_tc_chain_persistent");
     rb_prof_end(RB_PROF_CHAIN);
+    if (timing && (++dbg_calls % 100) == 60) {
+      static unsigned long long h[64 * 32];
+      CUDA_OR_DIE(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, rb_stream));
+      CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
+      static const char *names[20] = {"step start", "barrier seen", "first block landed",
+        "MMAs issued", "accumulator ready", "slices parked + fenced", "tail done", "verdicts in",
+        "cluster's K loops over", "arrived", "peers' slices in", "rows stored", "proxy fence",
+        "block barrier", "tensor memory drained", "slices summed", "row 0 masked", "row 0 split",
+        "row 0 stores issued", "row 0 done"};
+      static const int order[19] = {1, 7, 2, 3, 4, 14, 5, 6, 8, 10, 15, 16, 17, 18, 19, 11, 12, 13, 9};
+      double sum[20] = {0};
+      int steps = 0;
+      for (int k = 2; k < 64 && h[k * 32 + 9]; k++, steps++)
+        for (int q = 1; q < 20; q++)
+          if (h[k * 32 + q])
+            sum[q] += (double)(h[k * 32 + q] - h[k * 32]);
+      fprintf(stderr, "chain timing, CTA 0, mean over %d steps, us after the step's start:", steps);
+      for (int q = 0; q < 19 && steps; q++)
+        fprintf(stderr, " %s %.2f;", names[order[q]], sum[order[q]] / steps * 1e-3);
+      if (steps > 1)
+        fprintf(stderr, " step period %.2f\n", (double)(h[(steps + 1) * 32] - h[2 * 32]) / (steps - 1) * 1e-3);
+      else
+        fprintf(stderr, "\n");
+    }
   }
   else if (resident) {
     rbk_walk_resident(v, &Ep);

@@ -110,7 +110,9 @@ def _compare_steps(lib, ref, tmp_path, n, warm, steps, expect_kernel, text, g, r
                            ("min_error_threshold", "min_error_threshold")):
             a = np.array([getattr(got[j], field) for j in range(n) if j not in masked])
             b = np.array([logs[j][key] for j in range(n) if j not in masked])
-            np.testing.assert_allclose(a, b, rtol=2e-4, atol=1e-6 * np.abs(b).max(),
+            # 1e-3: a confident stream's error 1 - p cancels (p near 1), so the
+            # forward pass's 1e-6 comes back multiplied by p / (1 - p)
+            np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-6 * np.abs(b).max(),
                                        err_msg="%s step %d" % (key, s))
         flips = [j for j in range(n) if got[j].n_steps != want_depths[j]]
         for j in flips:
