@@ -19,9 +19,16 @@ random-initialised weights (rnn_randomise_weights_auto, seed 1).
   roofline / cpu_baseline: see DESIGN.md "Measurement".
 
 N > 1: one process per GPU (torchrun), streams sharded 512 per rank (weak
-scaling), [ih_delta | ho_delta] all-reduced over NCCL each step.  The only
-thing torch.distributed carries is the NCCL unique id, the barriers and the
-max-over-ranks of the timings.
+scaling: `value`), [ih_delta | ho_delta] summed over the ranks each step by
+the library's own exchange kernel over NVLink peer memory (NCCL with
+--no-p2p).  The line also carries a `strong` sub-record - the SAME 512
+streams split 512/N per GPU, as BASELINE.json words configs[1] - and a
+`trained` sub-record (the job after 2000 more positions, when the adaptive
+BPTT walk has deepened).  The learn rate is LEARN_RATE / N: the reference sums
+the deltas over all streams, so N times the streams at the same rate is N
+times the step (1e-5 at 512 streams already diverges).  The only
+thing torch.distributed carries is the bootstrap (NCCL id, IPC handles), the
+barriers and the max-over-ranks of the timings.
 
 --impl reference times the reference's own CPU implementation of the same
 loop (oracle/_ref, the unmodified reference compiled in place) on the host
@@ -209,7 +216,7 @@ def run_reference(args):
     total_chars = 0
     t0 = time.time()
     steps_done = 0
-    timed = max(4, min(per_step * args.steps, 48))   # bounded: ~10-20 s of CPU work
+    timed = max(4, min(per_step * args.steps, 96))   # bounded: ~10-20 s of CPU work
     rate, wall = reference_cpu_throughput(cores, n_streams, warm, timed)
     ms_per_step = 1e3 * (per_step * n_streams * cores) / rate
     line = {
@@ -230,18 +237,26 @@ def run_reference(args):
     return 0
 
 
-def workload_config(n_gpus, scaling="weak"):
+def workload_config(n_gpus, exchange=None):
+    if n_gpus > 1:
+        par = ("streams sharded over %d GPUs, one process each; [ih_delta | ho_delta] summed "
+               "over ranks every step by: %s" % (n_gpus, exchange or "see gradient_exchange"))
+    else:
+        par = "1 GPU"
     return {
         "workload": "text-predict BPTT training, hidden %d, %d synchronic streams per GPU, "
                     "BPTT depth %d, %d-symbol alphabet (BASELINE.json configs[1])"
                     % (HIDDEN, STREAMS, DEPTH, ALPHABET),
         "hidden": HIDDEN, "streams_per_gpu": STREAMS, "global_streams": STREAMS * n_gpus,
-        "bptt_depth": DEPTH, "alphabet": ALPHABET, "learn_rate": LEARN_RATE,
+        "bptt_depth": DEPTH, "alphabet": ALPHABET,
+        "learn_rate": LEARN_RATE / n_gpus,
+        "learn_rate_note": "%g / n_gpus: deltas are summed over all streams of all ranks"
+                           % LEARN_RATE,
         "learning_style": "weighted momentum 0.95", "text": "order-1 Markov chain, seed 2",
-        "parallelism": "streams sharded over %d GPU(s), deltas all-reduced (NCCL)" % n_gpus
-        if n_gpus > 1 else "1 GPU",
-        "l2": "working set per step (history ring 66 MB + error chain 66 MB + weights, "
-              "momentum, deltas 18 MB) exceeds the 126 MB L2; no explicit flush",
+        "parallelism": par,
+        "l2": "working set per step (history ring 66 MB + error chain 66 MB + their FP16 "
+              "operand planes + weights, momentum, deltas 18 MB) exceeds the 126 MB L2; "
+              "no explicit flush",
     }
 
 
@@ -288,25 +303,43 @@ def run_ours(args):
     lo, hi = rdist.shard_bounds(len(text), rank, world)
     my_text = np.ascontiguousarray(text[lo:hi])
 
-    def make_job():
+    def make_job(n_streams=None, lr=None):
         """A freshly initialised net (same seed every time), its training set
         and batch, the peer exchange attached, the text in HBM."""
+        n_streams = n_streams or n
         devnull_fd = os.dup(2)
         os.dup2(os.open(os.devnull, os.O_WRONLY), 2)   # the reference-style init chatter
         net = make_net(L, input_size=ALPHABET, hidden=args.hidden, output=ALPHABET, depth=DEPTH,
-                       seed=1, lr=LEARN_RATE / world)
+                       seed=1, lr=lr or LEARN_RATE / world)
         os.dup2(devnull_fd, 2)
         os.close(devnull_fd)
-        nets = L.rnn_new_training_set(net, n)
-        batch = L.rnn_batch_new(nets, n)
+        nets = L.rnn_new_training_set(net, n_streams)
+        batch = L.rnn_batch_new(nets, n_streams)
         exchange = attach_exchange(batch)
         L.rnn_batch_text_upload(batch, u8ptr(my_text), len(my_text))
-        return net, nets, batch, exchange
+        return net, nets, batch, exchange, n_streams
 
     def drop_job(job):
-        net, nets, batch, _ = job
+        net, nets, batch, _, n_streams = job
         L.rnn_batch_delete(batch)
-        L.rnn_delete_training_set(nets, n, 0)   # nets[0] is the prototype: it goes too
+        L.rnn_delete_training_set(nets, n_streams, 0)   # nets[0] is the prototype: it goes too
+
+    def time_resident(batch, pos, steps, stats=None):
+        """`steps` positions of rnn_batch_text_train between CUDA events on the
+        library's stream: (ms, max over ranks; next position)."""
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record(stream)
+        pos = L.rnn_batch_text_train(batch, pos, steps, style, MOMENTUM, SOFT_START,
+                                     C.byref(stats) if stats is not None else None)
+        b.record(stream)
+        barrier()
+        return max_over_ranks(a.elapsed_time(b)), pos
+
+    def executed_depths(batch, n_streams):
+        d = (C.c_int32 * n_streams)()
+        L.rnn_batch_bptt_depths(batch, d)
+        return np.array(list(d), dtype=np.float64)
 
     def attach_exchange(batch):
       exchange = "none"
@@ -347,7 +380,7 @@ def run_ours(args):
 
     # ---- device-resident arm (value) ---------------------------------------
     job = make_job()
-    net, nets, batch, exchange = job
+    net, nets, batch, exchange, _ = job
     pos = warm_up(batch)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -357,17 +390,25 @@ def run_ours(args):
         time.sleep(0.05)          # nvidia-smi takes a moment to print its first line
     sampler.samples.clear()
     launches0 = L.rnn_b200_kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stats = api.RnnBatchCharStats()
-    barrier()
-    ev0.record(stream)
-    pos = L.rnn_batch_text_train(batch, pos, args.steps, style, MOMENTUM, SOFT_START,
-                                 C.byref(stats))
-    ev1.record(stream)
-    barrier()
+    ms, pos = time_resident(batch, pos, args.steps, stats)
     launches = L.rnn_b200_kernel_launches() - launches0
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
     value = (args.steps * n * world) / (ms * 1e-3)
+
+    # ---- the same job once training has gone on: the adaptive walk deepens ----
+    trained = None
+    if args.trained_after > 0:
+        pos = L.rnn_batch_text_train(batch, pos, args.trained_after, style, MOMENTUM, SOFT_START,
+                                     None)
+        t_steps = min(args.steps, 300)
+        tstats = api.RnnBatchCharStats()
+        tms, pos = time_resident(batch, pos, t_steps, tstats)
+        td = executed_depths(batch, n)
+        trained = {"positions_before": DEPTH + args.steps + args.trained_after,
+                   "steps": t_steps, "value": (t_steps * n * world) / (tms * 1e-3), "unit": UNIT,
+                   "ms_per_step": tms / t_steps, "mean_executed_depth": float(td.mean()),
+                   "max_executed_depth": float(td.max()),
+                   "t_entropy": -tstats.entropy / max(tstats.count, 1)}
 
     # ---- end-to-end arm (host symbols in, report sums out, every step) -----
     # the SAME job again from the same initial weights, so that both arms do
@@ -375,7 +416,7 @@ def run_ours(args):
     barrier()
     drop_job(job)
     job = make_job()
-    net, nets, batch, exchange = job
+    net, nets, batch, exchange, _ = job
     pos = warm_up(batch)
     spacing = (len(my_text) - 1) // n
     offs = (np.arange(n, dtype=np.int64) * spacing)
@@ -460,18 +501,18 @@ def run_ours(args):
         alg["bptt_chain"] = flops_pair * n
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_bf16 = float(peaks["bf16_tflops_sustained"])
-        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)"
+        peak_f16 = float(peaks["bf16_tflops_sustained"])
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit MMA rate, sustained)"
     except Exception:
-        peak_bf16 = 1400.0
-        peak_src = "fallback 1.4 PFLOP/s sustained bf16 / 2"
+        peak_f16 = 1400.0
+        peak_src = "fallback 1.4 PFLOP/s sustained dense 16-bit MMA"
     dominant = max((k for k in kernels if k in alg), key=lambda k: kernels[k]["ms_total"],
                    default=None)
     traffic = None
     try:   # DRAM bytes per launch of that kernel from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
-        kname = {"bptt_chain": "k_tc_chain_persistent<128, 3>", "weight_grad": "k_tc_dw_pair",
-                 "forward": "k_tc_nt<128, 3>"}.get(dominant)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+        kname = {"bptt_chain": "k_tc_chain_persistent", "weight_grad": "k_tc_dw_pair",
+                 "forward": "k_tc_nt"}.get(dominant)
         if kname in tr:
             traffic = tr[kname]["dram_bytes_per_launch"]
     except Exception:
@@ -480,14 +521,35 @@ def run_ours(args):
     if dominant:
         per_launch_s = kernels[dominant]["ms_per_launch"] * 1e-3
         achieved = alg[dominant] / per_launch_s / 1e12
-        peak = peak_bf16 / 2.0
-        roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+        roofline = {"bound": "tensor", "kernel": dominant, "achieved": achieved, "peak": peak_f16,
+                    "unit": "TFLOP/s", "frac": achieved / peak_f16, "traffic": traffic,
                     "peak_source": peak_src,
-                    "note": "achieved = algorithmic FP32 FLOPs (unpadded, 2 per multiply-add) "
-                            "per launch / CUDA-event time per launch; a 3xTF32 kernel issues 3 "
-                            "MMAs per logical one, so its ceiling against this peak is 1/3",
+                    "frac_vs_tf32_peak": achieved / (peak_f16 / 2.0),
+                    "note": "achieved = algorithmic FP32 FLOPs (unpadded, 2 per multiply-add, "
+                            "only the BPTT steps each stream executed) per launch / CUDA-event "
+                            "time per launch.  The kernels issue kind::f16 MMAs on FP16 hi/lo "
+                            "operand planes, three per logical product, so the ceiling against "
+                            "`peak` is 1/3.  Round 1 issued kind::tf32 MMAs and reported against "
+                            "peak / 2 (the TF32 rate the north star names): frac_vs_tf32_peak "
+                            "continues that series",
                     "kernels": kernels}
+
+    # ---- strong scaling: the SAME 512 streams split over the GPUs ------------
+    strong = None
+    if world > 1 and n == STREAMS and (STREAMS // world) >= 64 and not args.no_strong:
+        barrier()
+        drop_job(job)
+        n_strong = STREAMS // world
+        job = make_job(n_strong, LEARN_RATE)   # 512 streams in all: the N = 1 job's rate
+        net, nets, batch, exchange, _ = job
+        spos = warm_up(batch)
+        s_steps = min(args.steps, 500)
+        sms, spos = time_resident(batch, spos, s_steps)
+        sd = executed_depths(batch, n_strong)
+        strong = {"scaling": "strong", "global_streams": STREAMS, "streams_per_gpu": n_strong,
+                  "steps": s_steps, "value": (s_steps * STREAMS) / (sms * 1e-3), "unit": UNIT,
+                  "ms_per_step": sms / s_steps, "mean_executed_depth": float(sd.mean()),
+                  "learn_rate": LEARN_RATE}
 
     line = None
     if rank == 0:
@@ -497,7 +559,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world),
+            "config": workload_config(world, exchange),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * n,
                     "d2h_bytes_per_step": C.sizeof(api.RnnBatchCharStats),
                     "ms_per_step": e2e_ms / e2e_steps},
@@ -512,13 +574,15 @@ def run_ours(args):
                       "accuracy": stats.correct / max(stats.count, 1)},
             "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],
             "gradient_exchange": exchange,
+            "trained": trained,
+            "strong": strong,
             "opinion": {"value": opinion_rate, "unit": "stream-steps/s (rnn_opinion only, "
                         "one-hot input, %d steps)" % fwd_steps,
                         "ms_per_step": fwd_ms / fwd_steps},
         }
         if args.hidden != HIDDEN or n != STREAMS:
             line["config"]["workload"] += " [OVERRIDDEN: hidden %d streams %d]" % (args.hidden, n)
-    L.rnn_batch_delete(batch)
+    drop_job(job)
     if dist:
         barrier()
     L.rnn_b200_comm_leave()
@@ -528,12 +592,17 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cores = host_cores()
-                rate, wall = reference_cpu_throughput(cores, 8, DEPTH, 24)
+                one, wall1 = reference_cpu_throughput(1, 8, DEPTH, 48)
+                rate, wall = reference_cpu_throughput(cores, 8, DEPTH, 96)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": UNIT, "cores": cores, "kind": "reference",
+                    "one_core": one,
                     "sample": "%d independent replicas (one per core) of the reference multi-tap "
-                              "loop, H%d D%d, 8 streams each, %d warm-up + 24 timed positions, "
-                              "%.1f s wall" % (cores, HIDDEN, DEPTH, DEPTH, wall)}
+                              "loop, H%d D%d, 8 streams each, %d warm-up + 96 timed positions, "
+                              "%.1f s wall; one_core: a single replica alone on the host, "
+                              "%d + 48 positions, %.1f s (the reference is single-threaded: "
+                              "streams alias shared delta arrays)"
+                              % (cores, HIDDEN, DEPTH, DEPTH, wall, DEPTH, wall1)}
             except Exception as e:  # the oracle .so did not travel
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
                                         "kind": "reference", "sample": "unavailable: %s" % e}
@@ -557,6 +626,9 @@ def main():
     ap.add_argument("--cold", action="store_true", help="do not pre-fill the BPTT ring")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-p2p", action="store_true", help="exchange deltas with NCCL only")
+    ap.add_argument("--trained-after", type=int, default=2000,
+                    help="positions to train before the `trained` sub-record (0: skip it)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

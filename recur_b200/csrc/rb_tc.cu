@@ -1767,7 +1767,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
     }
     /* E(k+1)'s planes were written through the generic proxy; the next step's
        TMA reads them through the async proxy */
-    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     if (threadIdx.x == 0)
       CH_STAMP(12);
     __syncthreads();
