@@ -637,7 +637,7 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
   }
   /* the update follows at once: the weight gradient may stay in its split-K
      planes until then (single GPU; an exchange needs the finished sum) */
-  rb_tc_defer_delta_reduce(rb_comm_size() <= 1);
+  rb_tc_defer_delta_reduce(rb_comm_size() <= 1 || rb_p2p_ready(b->p2p));
   calc_deltas_async(b, 0);
   rb_tc_defer_delta_reduce(0);
   rb_apply_learning_async(proto, learning_style, momentum);

@@ -165,8 +165,11 @@ void *rb_p2p_new(size_t n_floats);
 int rb_p2p_export(void *state, void *handles_out);
 int rb_p2p_attach(void *state, const void *all_handles, int rank, int n_ranks);
 int rb_p2p_ready(void *state);
-void rb_p2p_reduce(void *state, const float *partial, int splits, int ih_size, int ho_size,
-    float *ih_delta, int accumulate);
+void rb_p2p_exchange(void *state, const float *partial, int splits, int ih_size, int ho_size,
+    const float *ho_delta);
+void rb_p2p_result(void *state, const float **result, const unsigned int **flags,
+    unsigned int *epoch, int *n);
+void rb_p2p_copy_out(void *state, float *ih_delta);
 void rb_p2p_delete(void *state);
 
 #ifdef __cplusplus

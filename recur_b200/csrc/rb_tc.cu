@@ -400,8 +400,11 @@ typedef struct RbTc {
   unsigned int *sync;   /* barrier counters of the persistent chain + kmax, two areas */
   size_t sync_words;
   int sync_flip;
-  int delta_pending;    /* the last weight gradient still sits in `partial`, unsummed */
+  int delta_pending;    /* the last weight gradient is not in ih_delta yet: 1 = unsummed in
+                           `partial`, 2 = summed over all ranks in the peer exchange's result
+                           block (both deltas), behind its second flag round */
   int pending_accumulate;
+  void *pending_p2p;
   const float *w_src;   /* weights the planes were made from */
   uint64_t w_version;
   /* tensor maps */
@@ -2033,19 +2036,48 @@ struct UpdateArgs {
   /* the output matrix rides along */
   float *ho_W, *ho_mom, *ho_aux;
   const float *ho_delta;
+  float *ho_delta_out;  /* where the API shows ho_delta, when ho_delta is read elsewhere */
   int ho_size;
   float ho_rate;
   int n_tiles_x, n_tiles;
+  /* multi-GPU: `partial` and `ho_delta` are the peer exchange's result block;
+     every rank's second epoch must be in before it is read */
+  const unsigned int *wait_flags;
+  unsigned int wait_epoch;
+  int wait_n;
 };
+
+__device__ __forceinline__ unsigned int
+ld_acquire_sys_u32(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void __launch_bounds__(256)
 k_update_split(UpdateArgs a)
 {
+  if (a.wait_flags) {
+    if ((int)threadIdx.x < a.wait_n) {
+      const unsigned int *f = a.wait_flags + 8 /* second round */ + threadIdx.x;
+      unsigned int spins = 0;
+      while (ld_acquire_sys_u32(f) < a.wait_epoch) {
+        if (++spins > (1u << 24))
+          __trap();
+      }
+    }
+    __syncthreads();
+  }
   if ((int)blockIdx.x >= a.n_tiles) {
     int i = ((int)blockIdx.x - a.n_tiles) * 256 + threadIdx.x;
-    if (i < a.ho_size)
-      a.ho_W[i] = rb_optimiser_step(a.method, a.ho_W[i], a.ho_delta[i], a.ho_mom, a.ho_aux, i,
+    if (i < a.ho_size) {
+      float d = a.wait_flags ? __ldcv(a.ho_delta + i) : a.ho_delta[i];
+      if (a.ho_delta_out)
+        a.ho_delta_out[i] = d;
+      a.ho_W[i] = rb_optimiser_step(a.method, a.ho_W[i], d, a.ho_mom, a.ho_aux, i,
           a.ho_rate, a.momentum, a.momentum_weight);
+    }
     return;
   }
   __shared__ rb_h16 th[32][34], tl[32][34];
@@ -2066,10 +2098,14 @@ k_update_split(UpdateArgs a)
       w[q] = a.W[i];
       if (a.partial) {
         float t = a.accumulate ? a.delta[i] : 0.0f;
+        if (a.wait_flags)
+          t = __ldcv(a.partial + i); /* written by peers: past the caches */
+        else {
 #pragma unroll
-        for (int z = 0; z < TC_DW_SPLITS; z++)
-          if (z < a.splits)
-            t += __ldcg(a.partial + (size_t)z * size + i);
+          for (int z = 0; z < TC_DW_SPLITS; z++)
+            if (z < a.splits)
+              t += __ldcg(a.partial + (size_t)z * size + i);
+        }
         d[q] = t;
       }
       else
@@ -2524,9 +2560,16 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     t->dw_splits = 1;
   }
   if (rb_p2p_ready(v->p2p)) {
-    /* multi-GPU: the split-K sum is the first phase of the exchange kernel */
-    rb_p2p_reduce(v->p2p, t->partial, t->dw_splits, size, v->d.h_size * v->d.o_size, ih_delta,
-        accumulate);
+    /* multi-GPU: the split-K sum is the first phase of the exchange kernel;
+       whoever consumes the result waits for the peers' last stores */
+    if (accumulate)
+      rb_die("recur-b200: accumulate != 0 across GPUs (see recur_b200.h)");
+    rb_p2p_exchange(v->p2p, t->partial, t->dw_splits, size, v->d.h_size * v->d.o_size, ho_delta);
+    t->delta_pending = 2;
+    t->pending_accumulate = 0;
+    t->pending_p2p = v->p2p;
+    if (!defer_delta_reduce)
+      rb_tc_materialise_delta(p, ih_delta);
   }
   else if (defer_delta_reduce) {
     /* the caller applies the update next: rb_tc_fused_update sums the
@@ -2559,6 +2602,11 @@ rb_tc_materialise_delta(RbPool *p, float *ih_delta)
     return;
   const RbDims *d = &p->group->d;
   int size = d->i_size * d->h_size;
+  if (t->delta_pending == 2) {
+    rb_p2p_copy_out(t->pending_p2p, ih_delta); /* [ih_delta | ho_delta] are adjacent */
+    t->delta_pending = 0;
+    return;
+  }
   k_dw_reduce<<<cdiv(size / 4, 256), 256, 0, rb_stream>>>(ih_delta, t->partial, size,
       t->dw_splits, t->pending_accumulate);
   LAUNCH_CHECK("k_dw_reduce");
@@ -2588,6 +2636,20 @@ rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum, float mo
   a.partial = t->delta_pending ? t->partial : NULL;
   a.splits = t->dw_splits;
   a.accumulate = t->pending_accumulate;
+  a.ho_delta = b->ho_delta;
+  a.ho_delta_out = NULL;
+  a.wait_flags = NULL;
+  a.wait_epoch = 0;
+  a.wait_n = 0;
+  if (t->delta_pending == 2) {
+    const float *result;
+    rb_p2p_result(t->pending_p2p, &result, &a.wait_flags, &a.wait_epoch, &a.wait_n);
+    a.partial = result;
+    a.splits = 1;
+    a.accumulate = 0;
+    a.ho_delta = result + net->ih_size;
+    a.ho_delta_out = b->ho_delta;
+  }
   a.I = d->i_size;
   a.H = d->h_size;
   a.method = method;
@@ -2603,7 +2665,6 @@ rb_tc_fused_update(RbPool *p, RecurNN *net, int method, float momentum, float mo
   a.ho_W = net->ho_weights;
   a.ho_mom = b->ho_momentum;
   a.ho_aux = b->ho_aux;
-  a.ho_delta = b->ho_delta;
   a.ho_size = net->ho_size;
   a.ho_rate = b->learn_rate * b->ho_scale;
   a.n_tiles_x = cdiv(a.H, 32);
