@@ -616,8 +616,13 @@ char_step_device(RnnBatch *b, int learning_style, float momentum, int from_text,
   }
   else {
     /* the output kernel may take the softmax error and its sums along */
+    if (b->masked) { /* skip bits a masked call left behind: this step trains every stream */
+      rbk_mask_streams(&v, NULL);
+      b->masked = 0;
+    }
     rbk_request_fused_loss(b->next_dev, b->err_dev, b->winner_dev, b->accum_dev, b->accum_host,
         b->accum_reset);
+    rbk_request_fused_top(1);
     rb_char_forward_dispatch(&v, from_text ? b->text_dev : NULL, b->text_len, pos,
         from_text ? (b->text_len - 1) / b->n : 0, b->cur_dev, b->next_dev, noise, 1,
         continues);

@@ -648,12 +648,16 @@ k_out(RbView v)
 
 __device__ __forceinline__ void
 softmax_error_warp(const RbView &v, int j, int lane, const u8 *target, float *err_out,
-    int *winner_out)
+    int *winner_out, const float *y_row = NULL, float *work_row = NULL)
 {
+  /* y_row / work_row: the stream's outputs and a scratch row in shared memory,
+     when the caller has them there (the error row is then left in work_row as
+     well as in the pool) */
   int s = v.slots[j];
   const int len = v.d.output_size, O = v.d.o_size;
-  const float *src = v.Y + (size_t)s * O;
-  float *err = v.OE + (size_t)s * O;
+  const float *src = y_row ? y_row : v.Y + (size_t)s * O;
+  float *out = v.OE + (size_t)s * O;
+  float *err = work_row ? work_row : out;
 
   float mx = -INFINITY, mn = INFINITY;
   for (int i = lane; i < len; i += 32) {
@@ -693,9 +697,14 @@ softmax_error_warp(const RbView &v, int j, int lane, const u8 *target, float *er
       e_t = e;
     }
     err[i] = e;
+    if (work_row)
+      out[i] = e;
   }
-  for (int i = len + lane; i < O; i += 32)
+  for (int i = len + lane; i < O; i += 32) {
     err[i] = 0.0f;
+    if (work_row)
+      out[i] = 0.0f;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -727,20 +736,24 @@ __device__ __forceinline__ void
 char_accum_block(const float *err, const int *winner, const u8 *target, int n,
     RbCharAccum *acc, RbCharAccum *snapshot = NULL, int reset = 0)
 {
+  /* the first 256 threads of the block do the sums (a fixed order whatever
+     the block size); the others only keep the barriers company */
   __shared__ double s_err[256], s_ent[256];
   __shared__ int s_cor[256];
   double e = 0.0, h = 0.0;
   int c = 0;
-  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+  for (int j = threadIdx.x; j < n && threadIdx.x < 256; j += 256) {
     float ej = __ldcg(err + j); /* written by other blocks of the same kernel in the fused case */
     e += ej;
     float x = 1.0f - ej;
     h += (x < 1e-30f) ? -100.0f : log2f(x);
     c += (__ldcg(winner + j) == (int)target[j]);
   }
-  s_err[threadIdx.x] = e;
-  s_ent[threadIdx.x] = h;
-  s_cor[threadIdx.x] = c;
+  if (threadIdx.x < 256) {
+    s_err[threadIdx.x] = e;
+    s_ent[threadIdx.x] = h;
+    s_cor[threadIdx.x] = c;
+  }
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) {
@@ -972,6 +985,52 @@ slot_of(const RbView &v, int j)
   return v.contiguous ? v.base + j : v.slots[j];
 }
 
+/* A matrix into shared memory as bulk asynchronous copies (TMA, no tensor
+   map): one thread issues them, the copy engine keeps the SM's L2 port full
+   without a register or a warp being involved, everybody waits on the
+   mbarrier when the data is needed.  n_floats * 4 must be a multiple of 16. */
+__device__ __forceinline__ void
+bulk_stage_begin(unsigned long long *bar, float *dst, const float *src, int n_floats)
+{
+  const unsigned int b = (unsigned int)__cvta_generic_to_shared(bar);
+  unsigned int d = (unsigned int)__cvta_generic_to_shared(dst);
+  const char *g = (const char *)src;
+  unsigned int left = (unsigned int)n_floats * 4u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(left)
+      : "memory");
+  while (left) {
+    const unsigned int chunk = left < 32768u ? left : 32768u;
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(d), "l"(g), "r"(chunk), "r"(b) : "memory");
+    d += chunk;
+    g += chunk;
+    left -= chunk;
+  }
+}
+
+__device__ __forceinline__ void
+bulk_stage_init(unsigned long long *bar)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(
+          (unsigned int)__cvta_generic_to_shared(bar)));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void
+bulk_stage_wait(unsigned long long *bar)
+{
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"((unsigned int)__cvta_generic_to_shared(bar)) : "memory");
+}
+
 __device__ __forceinline__ void
 stage_matrix(float *dst, const float *__restrict__ src, int n_floats)
 {
@@ -1045,12 +1104,24 @@ struct RbLossArgs {
   RbCharAccum *accum;
   RbCharAccum *snapshot; /* pinned host copy of the sums, or NULL */
   int reset;             /* start the sums from zero */
+  int fuse_top;          /* go on to the top layer's back-propagation (a7, a8) */
+  unsigned long long *dbg; /* RECUR_B200_OUT_TIMING: globaltimer stamps of block 0 */
 };
+
+#define OUT_STAMP(slot) do {                                            \
+    if (loss.dbg && blockIdx.x == 0 && threadIdx.x == 0) {              \
+      unsigned long long t_;                                            \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));             \
+      loss.dbg[slot] = t_;                                              \
+    }                                                                   \
+  } while (0)
 
 __device__ unsigned int rb_loss_ticket;
 
+#define OUT_NT 512 /* threads of k_out_multi: sixteen warps to hide its many short dependent phases */
+
 template <bool FROM_PARTIALS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(OUT_NT)
 k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
 {
   extern __shared__ __align__(16) float sh[]; /* Who | OS hidden rows | reduction space */
@@ -1060,6 +1131,15 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
   float *who = sh;
   float *hid = sh + (size_t)H * O;
   float *red = hid + (size_t)OS * H;
+  float *ysm = red + OS * OUT_NT;  /* [OS][O] the block's output rows, for the loss */
+  float *soe = ysm + OS * O;    /* [OS][O] ... and their error rows */
+  __shared__ __align__(8) unsigned long long who_bar;
+  OUT_STAMP(0);
+  if (threadIdx.x == 0)
+    bulk_stage_init(&who_bar);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    bulk_stage_begin(&who_bar, who, v.Who, H * O);
   if (FROM_PARTIALS) {
     /* every load of the block's rows is issued before the weights are staged */
     constexpr int MAXZ = 4;
@@ -1075,8 +1155,6 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
               pz[q][z] = __ldcg((const float4 *)(row + z * fp.split_stride));
         }
       }
-      if (c == (int)threadIdx.x * 4)
-        stage_matrix(who, v.Who, H * O);
 #pragma unroll
       for (int q = 0; q < OS; q++) {
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1095,11 +1173,8 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
         *(float4 *)(hid + (size_t)q * H + c) = h;
       }
     }
-    if ((int)threadIdx.x * 4 >= H)
-      stage_matrix(who, v.Who, H * O);
   }
   else {
-    stage_matrix(who, v.Who, H * O);
     for (int q = 0; q < OS; q++) {
       if (q < ns)
         stage_matrix(hid + (size_t)q * H, v.Hd + (size_t)slot_of(v, j0 + q) * H, H);
@@ -1108,9 +1183,12 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
           hid[(size_t)q * H + i] = 0.0f;
     }
   }
+  OUT_STAMP(1);
+  bulk_stage_wait(&who_bar);
   __syncthreads();
-  const int CW = (O >= 256) ? 256 : O;
-  const int G = 256 / CW;
+  OUT_STAMP(2);
+  const int CW = (O >= OUT_NT) ? OUT_NT : O;
+  const int G = OUT_NT / CW;
   const int col = threadIdx.x % CW, grp = threadIdx.x / CW;
   for (int c0 = 0; c0 < O; c0 += CW) {
     int c = c0 + col;
@@ -1151,26 +1229,143 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
           for (int gq = 0; gq < G; gq++)
             t += red[(gq * OS + q) * CW + col];
           v.Y[(size_t)slot_of(v, j0 + q) * O + c] = t;
+          if (loss.target)
+            ysm[q * O + c] = t;
         }
       }
       __syncthreads();
     }
     else if (c < O) {
-      for (int q = 0; q < ns; q++)
+      for (int q = 0; q < ns; q++) {
         v.Y[(size_t)slot_of(v, j0 + q) * O + c] = acc[q];
+        if (loss.target)
+          ysm[q * O + c] = acc[q];
+      }
     }
   }
+  OUT_STAMP(3);
   if (loss.target) {
     __shared__ int s_last;
     __syncthreads(); /* the block's rows of Y are written */
     const int w = threadIdx.x >> 5;
     if (w < ns)
-      softmax_error_warp(v, j0 + w, threadIdx.x & 31, loss.target, loss.err, loss.winner);
+      softmax_error_warp(v, j0 + w, threadIdx.x & 31, loss.target, loss.err, loss.winner,
+          ysm + w * O, soe + w * O);
+    else if (w < OS)
+      for (int i = threadIdx.x & 31; i < O; i += 32)
+        soe[w * O + i] = 0.0f;
+    OUT_STAMP(4);
+    if (loss.fuse_top) {
+      /* a7/a8 for the block's streams while Who, their hidden rows and now
+         their error rows are in shared memory (recur-nn.c:199-228, 318-322,
+         719-721): what k_gemm<TOP> + k_top_finish do for the general case */
+      float *part = red;  /* [warps][4 * OS] */
+      __syncthreads();    /* the error rows are in soe */
+      OUT_STAMP(7);
+      constexpr int YR = 2048 / OUT_NT; /* h_size <= 2048 on this path */
+      float e[YR][OS];
+      float st[4 * OS]; /* per stream: |e| sum, hidden sum, squares, zeros */
+#pragma unroll
+      for (int u = 0; u < 4 * OS; u++)
+        st[u] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < YR; r++) {
+        const int y = threadIdx.x + OUT_NT * r;
+#pragma unroll
+        for (int q = 0; q < OS; q++)
+          e[r][q] = 0.0f;
+        if (y < H) {
+          float h[OS];
+          bool any = false;
+#pragma unroll
+          for (int q = 0; q < OS; q++) {
+            h[q] = hid[q * H + y];
+            st[4 * q + 1] += h[q];
+            st[4 * q + 2] += h[q] * h[q];
+            st[4 * q + 3] += (h[q] == 0.0f);
+            any = any || h[q] != 0.0f;
+          }
+          if (y >= 1 && y <= v.d.hidden_size && any) {
+            const float *wrow = who + (size_t)y * O;
+            for (int x = 0; x < O; x += 4) {
+              float4 wv = *(const float4 *)(wrow + x);
+#pragma unroll
+              for (int q = 0; q < OS; q++) {
+                const float4 oq = *(const float4 *)(soe + q * O + x);
+                e[r][q] += wv.x * oq.x + wv.y * oq.y + wv.z * oq.z + wv.w * oq.w;
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < OS; q++) {
+              if (h[q] == 0.0f)
+                e[r][q] = 0.0f;
+              st[4 * q] += fabsf(e[r][q]);
+            }
+          }
+        }
+      }
+      OUT_STAMP(8);
+#pragma unroll
+      for (int u = 0; u < 4 * OS; u++) {
+        float t = st[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+          t += __shfl_xor_sync(0xffffffffu, t, o);
+        if ((threadIdx.x & 31) == 0)
+          part[(threadIdx.x >> 5) * (4 * OS) + u] = t;
+      }
+      __syncthreads();
+      OUT_STAMP(9);
+      float scale[OS];
+#pragma unroll
+      for (int q = 0; q < OS; q++) {
+        float total = 0.0f;
+        for (int wq = 0; wq < OUT_NT / 32; wq++)
+          total += part[wq * (4 * OS) + 4 * q];
+        const float halfmax = H * MAX_TOP_ERROR_FACTOR;
+        scale[q] = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
+        if ((int)threadIdx.x == q && q < ns) {
+          float hsum = 0.0f, hmag = 0.0f, hz = 0.0f;
+          for (int wq = 0; wq < OUT_NT / 32; wq++) {
+            hsum += part[wq * (4 * OS) + 4 * q + 1];
+            hmag += part[wq * (4 * OS) + 4 * q + 2];
+            hz += part[wq * (4 * OS) + 4 * q + 3];
+          }
+          RbScalars *sc = v.sc + slot_of(v, j0 + q);
+          const float top_scaled = (total > halfmax) ? scale[q] * total : total;
+          sc->top_raw = total;
+          sc->top_scaled = top_scaled;
+          sc->hidden_sum = hsum;
+          sc->hidden_mag = sqrtf(hmag);
+          sc->hidden_zeros = (int)(hz + 0.5f);
+          sc->min_sum = fminf(sc->mef / sc->lr, MIN_ERROR_GAIN * top_scaled);
+          sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
+          sc->cum_error = 0.0f;
+          sc->err_sum = 0.0f;
+          sc->live = (v.depth > 0) && !(sc->adaptive & 2);
+          sc->n_steps = 0;
+          sc->t_left = v.depth;
+          sc->ih_scale = 1.0f;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < YR; r++) {
+        const int y = threadIdx.x + OUT_NT * r;
+        if (y < H) {
+#pragma unroll
+          for (int q = 0; q < OS; q++)
+            if (q < ns)
+              e_row(v, slot_of(v, j0 + q), 0)[y] = e[r][q] * scale[q];
+        }
+      }
+    }
+    OUT_STAMP(5);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0)
       s_last = (atomicAdd(&rb_loss_ticket, 1u) == gridDim.x - 1);
     __syncthreads();
+    OUT_STAMP(6);
     if (s_last) {
       __threadfence();
       char_accum_block((const float *)loss.err, (const int *)loss.winner, loss.target, v.n,
@@ -1264,6 +1459,112 @@ k_ho_delta_slab(RbView v, float *ho_delta, int accumulate)
       t += red[((size_t)q * HO_ROWS + y) * (n_cg * 12) + o];
     size_t idx = (size_t)(y0 + y) * O + o;
     ho_delta[idx] = (accumulate ? ho_delta[idx] : 0.0f) + t;
+  }
+}
+
+/* The same with the streams split over blockIdx.y as well, for batches whose
+   slab would keep a block to itself on an SM: every block leaves its part in
+   `parts[z]`, the last block of a row group to finish (ticket) adds the parts
+   in split order - a fixed order, whoever that block is. */
+__global__ void __launch_bounds__(256)
+k_ho_delta_split(RbView v, float *ho_delta, int accumulate, float *parts, unsigned int *tickets)
+{
+  extern __shared__ float sh[]; /* nz x HO_ROWS hidden, nz x o_size errors, reduction space */
+  __shared__ int s_last;
+  const int H = v.d.h_size, O = v.d.o_size;
+  const int y0 = blockIdx.x * HO_ROWS;
+  const int Z = gridDim.y, z = blockIdx.y;
+  const int per_z = (v.n + Z - 1) / Z;
+  const int b0 = z * per_z, nz = max(0, min(v.n, b0 + per_z) - b0);
+  float *sH = sh;
+  float *sO = sh + (size_t)per_z * HO_ROWS;
+  float *red = sO + (size_t)per_z * O + 16;
+  {
+    const int per = HO_ROWS / 4;
+    for (int i0 = threadIdx.x; i0 < nz * per; i0 += 4 * blockDim.x) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + u * blockDim.x;
+        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nz * per) {
+          int b = i / per, q = (i - b * per) * 4;
+          if (y0 + q < H)
+            t[u] = __ldg((const float4 *)(v.Hd + (size_t)slot_of(v, b0 + b) * H + y0 + q));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        int i = i0 + u * blockDim.x;
+        if (i < nz * per)
+          *(float4 *)(sH + (size_t)i * 4) = t[u];
+      }
+    }
+    if (v.contiguous) {
+      stage_matrix(sO, v.OE + (size_t)(v.base + b0) * O, nz * O);
+    }
+    else {
+      for (int i = threadIdx.x; i < nz * (O / 4); i += blockDim.x) {
+        int b = i / (O / 4), q = (i - b * (O / 4)) * 4;
+        *(float4 *)(sO + (size_t)b * O + q) =
+          *(const float4 *)(v.OE + (size_t)v.slots[b0 + b] * O + q);
+      }
+    }
+  }
+  __syncthreads();
+  const int n_cg = (O + 11) / 12;
+  const int S = 256 / (HO_ROWS * n_cg);
+  const int yl = threadIdx.x % HO_ROWS;
+  const int cg = (threadIdx.x / HO_ROWS) % n_cg;
+  const int sl = threadIdx.x / (HO_ROWS * n_cg);
+  float acc[12];
+#pragma unroll
+  for (int u = 0; u < 12; u++)
+    acc[u] = 0.0f;
+  if (sl < S) {
+    for (int b = sl; b < nz; b += S) {
+      float h = sH[b * HO_ROWS + yl];
+      const float4 *e4 = (const float4 *)(sO + (size_t)b * O + cg * 12);
+      float4 e0 = e4[0], e1 = e4[1], e2 = e4[2];
+      acc[0] += h * e0.x; acc[1] += h * e0.y; acc[2] += h * e0.z; acc[3] += h * e0.w;
+      acc[4] += h * e1.x; acc[5] += h * e1.y; acc[6] += h * e1.z; acc[7] += h * e1.w;
+      acc[8] += h * e2.x; acc[9] += h * e2.y; acc[10] += h * e2.z; acc[11] += h * e2.w;
+    }
+#pragma unroll
+    for (int u = 0; u < 12; u++)
+      red[((size_t)sl * HO_ROWS + yl) * (n_cg * 12) + cg * 12 + u] = acc[u];
+  }
+  __syncthreads();
+  float *mine = parts + (size_t)z * H * O;
+  for (int i = threadIdx.x; i < HO_ROWS * O; i += blockDim.x) {
+    int y = i / O, o = i - y * O;
+    if (y0 + y >= H)
+      continue;
+    float t = 0.0f;
+    for (int q = 0; q < S; q++)
+      t += red[((size_t)q * HO_ROWS + y) * (n_cg * 12) + o];
+    __stcg(mine + (size_t)(y0 + y) * O + o, t);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s_last = (atomicAdd(tickets + blockIdx.x, 1u) == (unsigned int)Z - 1);
+    if (s_last)
+      tickets[blockIdx.x] = 0u;
+  }
+  __syncthreads();
+  if (!s_last)
+    return;
+  __threadfence();
+  for (int i = threadIdx.x; i < HO_ROWS * O; i += blockDim.x) {
+    int y = i / O, o = i - y * O;
+    if (y0 + y >= H)
+      continue;
+    size_t idx = (size_t)(y0 + y) * O + o;
+    float t = accumulate ? ho_delta[idx] : 0.0f;
+    for (int q = 0; q < Z; q++)
+      t += __ldcg(parts + (size_t)q * H * O + idx);
+    ho_delta[idx] = t;
   }
 }
 
@@ -1730,14 +2031,14 @@ rbk_prepare_x(const RbView *v)
 static size_t
 out_multi_smem(const RbView *v)
 {
-  return ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.h_size + (size_t)OS * 256 + 8) *
-      sizeof(float);
+  return ((size_t)v->d.h_size * v->d.o_size + (size_t)OS * v->d.h_size + (size_t)OS * OUT_NT +
+      (size_t)2 * OS * v->d.o_size + 8) * sizeof(float);
 }
 
 static int
 out_multi_usable(const RbView *v)
 {
-  return v->n >= 4 * OS && out_multi_smem(v) <= 200 * 1024;
+  return v->n >= 4 * OS && out_multi_smem(v) <= 220 * 1024;
 }
 
 static void
@@ -1745,10 +2046,12 @@ out_multi_attr(void)
 {
   static int attr_done = 0;
   if (!attr_done) {
-    cudaFuncSetAttribute(k_out_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        200 * 1024);
-    cudaFuncSetAttribute(k_out_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-        200 * 1024);
+    /* 227 KB per block less the kernel's static shared memory */
+    if (cudaFuncSetAttribute(k_out_multi<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            220 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_out_multi<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            220 * 1024) != cudaSuccess)
+      rb_die("recur-b200: k_out_multi cannot have 220 KB of shared memory");
     attr_done = 1;
   }
 }
@@ -1767,7 +2070,14 @@ rbk_output_takes_partials(const RbView *v, int splits)
 static struct {
   RbLossArgs args;
   int armed, done;
+  int want_top; /* the caller trains on this forward pass: fuse the top layer too */
 } loss_request;
+
+extern "C" void
+rbk_request_fused_top(int on)
+{
+  loss_request.want_top = on;
+}
 
 extern "C" void
 rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
@@ -1775,6 +2085,8 @@ rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
 {
   loss_request.args.snapshot = snapshot_host;
   loss_request.args.reset = reset;
+  loss_request.args.fuse_top = 0;
+  loss_request.want_top = 0;
   loss_request.args.target = target_dev;
   loss_request.args.err = err_dev;
   loss_request.args.winner = winner_dev;
@@ -1791,19 +2103,64 @@ rbk_fused_loss_done(void)
   return done;
 }
 
+static int top_fused_pending = 0;
+static const RbPool *top_fused_pool = NULL;
+static int top_fused_base = 0, top_fused_n = 0;
+
+/* did the last forward pass already run the top layer for this batch (E(0),
+   its clip and the walk's thresholds)?  Asked once by whoever would otherwise
+   launch it. */
+extern "C" int
+rbk_top_was_fused(const RbView *v)
+{
+  int f = top_fused_pending && top_fused_pool == v->pool && top_fused_base == v->base &&
+      top_fused_n == v->n && v->contiguous;
+  top_fused_pending = 0;
+  return f;
+}
+
 extern "C" void
 rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
 {
-  RbLossArgs loss = {NULL, NULL, NULL, NULL, NULL, 0};
+  RbLossArgs loss = {NULL, NULL, NULL, NULL, NULL, 0, 0, NULL};
+  top_fused_pending = 0;
+  static unsigned long long *dbg_dev = NULL;
+  static int dbg_calls = 0;
+  const bool timing = getenv("RECUR_B200_OUT_TIMING") != NULL;
   if (loss_request.armed && v->contiguous) {
     loss = loss_request.args;
     loss_request.done = 1;
+    /* training step of the char model on a batch: the top layer rides along */
+    if (loss_request.want_top && v->pool && v->pool->has_bptt && v->n >= 4 * OS &&
+        v->d.h_size <= 2048 && !v->CIE && !getenv("RECUR_B200_NO_FUSED_TOP")) {
+      loss.fuse_top = 1;
+      top_fused_pending = 1;
+      top_fused_pool = v->pool;
+      top_fused_base = v->base;
+      top_fused_n = v->n;
+    }
+  }
+  if (timing) {
+    if (!dbg_dev)
+      cudaMalloc((void **)&dbg_dev, 16 * sizeof(unsigned long long));
+    loss.dbg = dbg_dev;
   }
   out_multi_attr();
   rb_prof_begin(RB_PROF_OUT);
-  k_out_multi<true><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, *fp, loss);
+  k_out_multi<true><<<cdiv(v->n, OS), OUT_NT, out_multi_smem(v), rb_stream>>>(*v, *fp, loss);
   LAUNCH_CHECK("k_out_multi<partials>");
   rb_prof_end(RB_PROF_OUT);
+  if (timing && loss.target && (++dbg_calls % 100) == 60) {
+    unsigned long long h[16];
+    cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, rb_stream);
+    cudaStreamSynchronize(rb_stream);
+    fprintf(stderr, "k_out_multi block 0, us after its start: rows summed %.2f, Who landed %.2f, "
+        "outputs done %.2f, softmax done %.2f, (error rows in %.2f, dot products %.2f, "
+        "sums %.2f) top layer done %.2f, ticket taken %.2f\n",
+        (h[1] - h[0]) * 1e-3, (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3, (h[4] - h[0]) * 1e-3,
+        (h[7] - h[0]) * 1e-3, (h[8] - h[0]) * 1e-3, (h[9] - h[0]) * 1e-3,
+        (h[5] - h[0]) * 1e-3, (h[6] - h[0]) * 1e-3);
+  }
 }
 
 extern "C" void
@@ -1811,10 +2168,10 @@ rbk_output(const RbView *v)
 {
   if (out_multi_usable(v)) {
     RbFwdPartials none = {NULL, 0, 0, 0, 0};
-    RbLossArgs no_loss = {NULL, NULL, NULL, NULL, NULL, 0};
+    RbLossArgs no_loss = {NULL, NULL, NULL, NULL, NULL, 0, 0, NULL};
     out_multi_attr();
     rb_prof_begin(RB_PROF_OUT);
-    k_out_multi<false><<<cdiv(v->n, OS), 256, out_multi_smem(v), rb_stream>>>(*v, none, no_loss);
+    k_out_multi<false><<<cdiv(v->n, OS), OUT_NT, out_multi_smem(v), rb_stream>>>(*v, none, no_loss);
     LAUNCH_CHECK("k_out_multi");
     rb_prof_end(RB_PROF_OUT);
     return;
@@ -1902,39 +2259,112 @@ rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
 }
 
 static int ho_slab_attr_done = 0;
+static cudaStream_t top_side = NULL;
+static cudaEvent_t top_ev_fork = NULL, top_ev_join = NULL;
+static int top_forked = 0;
+
+/* ho_delta for a batch, on `stream` */
+static void
+launch_ho_delta_batch(const RbView *v, float *ho_delta, int accumulate, cudaStream_t stream)
+{
+  /* big batches: the streams are split over blocks too, so that several
+     small blocks share an SM instead of one slab owning it */
+  int Z = v->n / 128;
+  if (Z > 4)
+    Z = 4;
+  if (Z >= 2) {
+    static float *parts = NULL;
+    static unsigned int *tickets = NULL;
+    static size_t parts_cap = 0;
+    const size_t need = (size_t)4 * v->d.h_size * v->d.o_size;
+    if (parts_cap < need) {
+      cudaStreamSynchronize(rb_stream);
+      if (top_side)
+        cudaStreamSynchronize(top_side);
+      cudaFree(parts);
+      cudaFree(tickets);
+      if (cudaMalloc(&parts, need * sizeof(float)) != cudaSuccess ||
+          cudaMalloc(&tickets, 4096 * sizeof(unsigned int)) != cudaSuccess)
+        rb_die("recur-b200: out of device memory for the ho_delta parts");
+      cudaMemset(tickets, 0, 4096 * sizeof(unsigned int));
+      parts_cap = need;
+    }
+    const int per_z = (v->n + Z - 1) / Z;
+    size_t smem = ((size_t)per_z * (HO_ROWS + v->d.o_size) + 16 + (size_t)256 * 12) * sizeof(float);
+    static int attr_done = 0;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_ho_delta_split, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          100 * 1024);
+      attr_done = 1;
+    }
+    if (smem <= 100 * 1024 && cdiv(v->d.h_size, HO_ROWS) <= 4096) {
+      k_ho_delta_split<<<dim3(cdiv(v->d.h_size, HO_ROWS), Z), 256, smem, stream>>>(*v, ho_delta,
+          accumulate, parts, tickets);
+      LAUNCH_CHECK("k_ho_delta_split");
+      return;
+    }
+  }
+  size_t slab = ((size_t)v->n * (HO_ROWS + v->d.o_size) + 16 + (size_t)256 * 12) * sizeof(float);
+  if (!ho_slab_attr_done) {
+    cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        200 * 1024);
+    ho_slab_attr_done = 1;
+  }
+  k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, stream>>>(*v, ho_delta, accumulate);
+  LAUNCH_CHECK("k_ho_delta_slab");
+}
+
+/* wait (on the library stream) for what rbk_top_layer_begin left running
+   beside it */
+extern "C" void
+rbk_top_layer_join(void)
+{
+  if (top_forked)
+    cudaStreamWaitEvent(rb_stream, top_ev_join, 0);
+  top_forked = 0;
+}
 
 extern "C" void
 rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges)
+{
+  rbk_top_layer_begin(v, ho_delta, accumulate, ranges_dev, n_ranges);
+  rbk_top_layer_join();
+}
+
+/* a7..a9.  Returns with the top-layer kernels queued on the library stream
+   and, for a batch, ho_delta possibly still running on a side stream:
+   rbk_top_layer_join() before anything reads ho_delta. */
+extern "C" void
+rbk_top_layer_begin(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges)
 {
   /* a9 reads the hidden rows and the output errors, a7/a8 the same plus Who:
      neither needs the other, both are too small to fill the GPU.  In a batch
      the ho_delta kernel runs on a side stream next to the top-layer kernels
      (not while the per-class profiler is timing them). */
-  static cudaStream_t side = NULL;
-  static cudaEvent_t ev_fork = NULL, ev_join = NULL;
+  const bool fused = rbk_top_was_fused(v) && n_ranges == 0; /* the forward pass did a7/a8 */
   size_t slab = ((size_t)v->n * (HO_ROWS + v->d.o_size) + 16 + (size_t)256 * 12) * sizeof(float);
   const bool slab_ok = ho_delta && n_ranges == 0 && v->n >= 8 && slab <= 200 * 1024 &&
       v->d.o_size <= 384;
   bool forked = false;
   if (slab_ok && v->n >= 4 * OS && !rb_prof_active()) {
-    if (!side) {
-      cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking);
-      cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
-      cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    if (!top_side) {
+      cudaStreamCreateWithFlags(&top_side, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&top_ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&top_ev_join, cudaEventDisableTiming);
     }
-    if (!ho_slab_attr_done) {
-      cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
-          200 * 1024);
-      ho_slab_attr_done = 1;
-    }
-    cudaEventRecord(ev_fork, rb_stream);
-    cudaStreamWaitEvent(side, ev_fork, 0);
-    k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, side>>>(*v, ho_delta, accumulate);
-    LAUNCH_CHECK("k_ho_delta_slab");
-    cudaEventRecord(ev_join, side);
+    cudaEventRecord(top_ev_fork, rb_stream);
+    cudaStreamWaitEvent(top_side, top_ev_fork, 0);
+    launch_ho_delta_batch(v, ho_delta, accumulate, top_side);
+    cudaEventRecord(top_ev_join, top_side);
     forked = true;
+    top_forked = 1;
   }
+  if (fused) {
+    /* E(0), its clip and the thresholds are in place already */
+  }
+  else
   if (n_ranges == 0 && v->n >= 4 * OS && v->pool && v->pool->has_bptt) {
     /* a batch: E(0) = mask * (o_error . Who^T) as a tiled contraction */
     GemmArgs g;
@@ -1958,20 +2388,12 @@ rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
     LAUNCH_CHECK("k_top");
     rb_prof_end(RB_PROF_TOP);
   }
-  if (forked) {
-    cudaStreamWaitEvent(rb_stream, ev_join, 0);
+  if (forked)
     return;
-  }
   /* hidden slab + errors + slack + per-slice partial sums */
   if (slab_ok) {
-    if (!ho_slab_attr_done) {
-      cudaFuncSetAttribute(k_ho_delta_slab, cudaFuncAttributeMaxDynamicSharedMemorySize,
-          200 * 1024);
-      ho_slab_attr_done = 1;
-    }
     rb_prof_begin(RB_PROF_HO);
-    k_ho_delta_slab<<<cdiv(v->d.h_size, HO_ROWS), 256, slab, rb_stream>>>(*v, ho_delta, accumulate);
-    LAUNCH_CHECK("k_ho_delta_slab");
+    launch_ho_delta_batch(v, ho_delta, accumulate, rb_stream);
     rb_prof_end(RB_PROF_HO);
   }
   else if (ho_delta && n_ranges == 0 && v->n >= 8) {

@@ -113,6 +113,11 @@ void rbk_softmax_error(const RbView *v, const u8 *target_dev, float *err_dev,
     int *winner_dev, RbCharAccum *accum_dev);              /* a6 */
 void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges);       /* a7..a9 */
+void rbk_top_layer_begin(const RbView *v, float *ho_delta, int accumulate,
+    const RecurErrorRange *ranges_dev, int n_ranges);
+void rbk_top_layer_join(void);
+void rbk_request_fused_top(int on);
+int rbk_top_was_fused(const RbView *v);
 void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */
 void rbk_set_params(const RbView *v, const float *lr_dev, const float *mef_dev, int adaptive);
 void rbk_mask_streams(const RbView *v, const u8 *active_dev);

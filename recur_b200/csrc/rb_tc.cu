@@ -2416,11 +2416,12 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     p->x_planes_stale = 0;
   }
   /* top layer: E(0), then its planes and the scale of this walk's planes */
-  rbk_top_layer(v, ho_delta, accumulate, NULL, 0);
+  rbk_top_layer_begin(v, ho_delta, accumulate, NULL, 0);
   rb_prof_begin(RB_PROF_TOP);
   k_e0_planes<<<v->n, 256, 0, rb_stream>>>(*v, Ep, t->escale);
   LAUNCH_CHECK("k_e0_planes");
   rb_prof_end(RB_PROF_TOP);
+  rbk_top_layer_join(); /* ho_delta ran beside the planes kernel */
 
   /* small nets: every stream walks alone with the weights resident in its SM */
   const bool resident = rbk_walk_resident_usable(v);

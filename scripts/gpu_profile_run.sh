@@ -13,13 +13,13 @@ rm -f $out/*_${tag}.ncu-rep $out/launches_${tag}.csv $out/bench_${tag}_*.json
 #    (10 launches per training step; ncu slows every skipped launch, so only 70 steps are skipped)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 100 --csv \
   --log-file $out/launches_${tag}.csv \
-  python bench.py --steps 100 --warmup 30 --no-cpu-baseline > $out/ncu_launches_${tag}.log 2>&1
+  python bench.py --steps 100 --warmup 30 --no-cpu-baseline --trained-after 0 > $out/ncu_launches_${tag}.log 2>&1
 
 # 2. one --set full capture per hot kernel, 120 training steps in (ncu slows every
 #    intercepted launch, deeper captures cost minutes of box time each)
 for k in k_tc_chain_persistent k_tc_dw_pair k_tc_nt k_update_split k_out_multi; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 120 -c 1 \
-    -f -o $out/${k}_${tag} python bench.py --steps 140 --warmup 30 --no-cpu-baseline \
+    -f -o $out/${k}_${tag} python bench.py --steps 140 --warmup 30 --no-cpu-baseline --trained-after 0 \
     > $out/ncu_${k}_${tag}.log 2>&1
 done
 
