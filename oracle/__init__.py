@@ -81,11 +81,34 @@ def load_ref(strict=True):
                                          c_double_p, c_double_p, c_int_p]
     lib.ref_opinion_steps.restype = C.c_double
     lib.ref_opinion_steps.argtypes = [P, u8_p, C.c_int, C.c_int]
+    lib.ref_multi_entropy_step.restype = None
+    lib.ref_multi_entropy_step.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, c_double_p]
+    lib.rnn_char_multi_cross_entropy.restype = None
+    lib.rnn_char_multi_cross_entropy.argtypes = [P, u8_p, C.c_int, C.c_int, c_double_p, C.c_int]
     for name in ("ref_sizeof_RecurNN", "ref_sizeof_RecurNNBPTT",
                  "ref_sizeof_RecurExtraLayer"):
         getattr(lib, name).restype = C.c_size_t
         getattr(lib, name).argtypes = []
     _cache[path] = lib
+    return lib
+
+
+CHARMULTI_B200 = os.path.join(HERE, "_ref", "libcharmulti_b200.so")
+FIXTURE_NET = os.path.join(HERE, "_ref", "fixtures", "multi-text-6c34c563i73-h99-o3650.net")
+
+
+def load_charmulti_b200():
+    """The reference's charmodel-multi-predict.c, unmodified, linked against
+    librecur_b200.so (oracle/Makefile): its rnn_char_multi_cross_entropy calls
+    this repo's rnn_opinion."""
+    from recur_b200 import abi
+    if CHARMULTI_B200 in _cache:
+        return _cache[CHARMULTI_B200]
+    lib = C.CDLL(CHARMULTI_B200, mode=os.RTLD_LOCAL)
+    lib.rnn_char_multi_cross_entropy.restype = None
+    lib.rnn_char_multi_cross_entropy.argtypes = [abi.RecurNN_p, u8_p, C.c_int, C.c_int,
+                                                 c_double_p, C.c_int]
+    _cache[CHARMULTI_B200] = lib
     return lib
 
 

@@ -65,6 +65,22 @@ ref_one_hot_error(RecurNN *net, int c, int next, int *correct)
   return error[next];
 }
 
+/* The body of rnn_char_multi_cross_entropy's loop (charmodel-multi-predict.c:
+   361-368) for output vectors that did not come from rnn_opinion on a
+   reference net: per class group the reference's own softmax and capped log. */
+void
+ref_multi_entropy_step(const float *answer, int n_classes, int alphabet_len, int next,
+    double *entropy)
+{
+  float error[alphabet_len];
+  for (int j = 0; j < n_classes; j++){
+    const float *group = answer + alphabet_len * j;
+    softmax(error, group, alphabet_len);
+    float e = error[next];
+    entropy[j] -= capped_log2f_(e);
+  }
+}
+
 /* Replays the synchronic multi-tap loop of rnn_char_epoch
    (charmodel-predict.c:288-311) for `steps` character positions starting at
    text position `start`.  Accumulates the same three report sums.  Returns

@@ -5,12 +5,13 @@ rnnca per-cell forward (config 5), replayed over the reference API on the CPU
 elements themselves need GStreamer and cannot be built, so
 the loops are restated here in the order the reference runs them."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
 
 from recur_b200 import abi
-from helpers import make_net, weights, arr, fptr, rel_err, copy_weights, STD_FLAGS
+from helpers import make_net, weights, arr, fptr, u8ptr, rel_err, copy_weights, STD_FLAGS
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -26,13 +27,15 @@ def grouped_softmax_error(out, target):
     return err.astype(np.float32)
 
 
-@pytest.mark.parametrize("n_channels", [10, 96])
-def test_config3_classify_training_loop(gpu_lib, ref, n_channels):
+@pytest.mark.parametrize("n_channels,depth,chunks", [(10, 10, 6), (96, 10, 6), (256, 30, 34)])
+def test_config3_classify_training_loop(gpu_lib, ref, n_channels, depth, chunks):
     """gstclassify.c:2201-2239: clear deltas; per channel forward on dense
     features, grouped softmax error, rnn_bptt_calc_deltas(net, 1, NULL),
-    advance; then Nesterov update and rnn_condition_net."""
+    advance; then Nesterov update and rnn_condition_net.  The last case is
+    BASELINE.json configs[2] at its own size: 256 channels, BPTT depth 30, run
+    until the ring is full and the walks are as deep as they get."""
     lib = gpu_lib
-    F, Hn, classes, depth, chunks = 32, 199, 4, 10, 6
+    F, Hn, classes = 32, 199, 4
     rs = np.random.RandomState(3)
     feats = np.log1p(rs.random_sample((chunks, n_channels, F)) * 400).astype(np.float32)
     targets = rs.randint(0, classes, size=(chunks, n_channels))
@@ -117,6 +120,62 @@ def test_config4_multi_head_forward(gpu_lib, ref):
                     p /= p.sum()
                     dst[j, k] -= np.log2(max(p[text[j, t + 1]], 1e-30))
     assert rel_err(ent_got, ent_ref) < TOL
+    lib.rnn_batch_delete(batch)
+
+
+def test_config4_fixture_net_entropies_match_reference(gpu_lib, ref):
+    """BASELINE.json configs[3] on the reference's own saved net
+    (test/multi-text-6c34c563i73-h99-o3650.net, the CDB fixture), loaded by
+    each side's rnn_load_net: the double[50] class entropies of
+    rnn_char_multi_cross_entropy (charmodel-multi-predict.c:350-372) over
+    synthetic texts, three ways - the reference; the reference's unmodified
+    function linked against librecur_b200.so (its per-net rnn_opinion); and
+    the array-of-nets calls with the reference's softmax on the outputs."""
+    import oracle
+    lib = gpu_lib
+    if not (os.path.exists(oracle.FIXTURE_NET) and os.path.exists(oracle.CHARMULTI_B200)):
+        pytest.skip("oracle/_ref fixtures not built")
+    ours = oracle.load_charmulti_b200()
+    n_texts, length, skip, alpha = 4, 300, 10, 73
+    r = ref.rnn_load_net(oracle.FIXTURE_NET.encode())
+    a = lib.rnn_load_net(oracle.FIXTURE_NET.encode())
+    assert r and a
+    n_classes = r.contents.output_size // alpha
+    assert (r.contents.input_size, r.contents.hidden_size, n_classes) == (73, 99, 50)
+    assert r.contents.activation == abi.RNN_RESQRT
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    rs = np.random.RandomState(7)
+    text = rs.randint(0, alpha, size=(n_texts, length)).astype(np.uint8)
+    want = np.zeros((n_texts, n_classes))
+    per_net = np.zeros((n_texts, n_classes))
+    dp = C.POINTER(C.c_double)
+    for j in range(n_texts):
+        rc = ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None)
+        ref.rnn_char_multi_cross_entropy(rc, u8ptr(text[j]), length, alpha,
+                                         want[j].ctypes.data_as(dp), skip)
+        ac = lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None)
+        ours.rnn_char_multi_cross_entropy(ac, u8ptr(text[j]), length, alpha,
+                                          per_net[j].ctypes.data_as(dp), skip)
+    assert want.min() > 0 and np.isfinite(want).all()
+    assert rel_err(per_net, want) < TOL
+    # the batch calls: all texts at once
+    clones = [lib.rnn_clone(a, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n_texts)]
+    arr_t = (abi.RecurNN_p * n_texts)(*clones)
+    batch = lib.rnn_batch_new(arr_t, n_texts)
+    got = np.zeros((n_texts, n_classes))
+    outs = np.zeros((n_texts, n_classes * alpha), dtype=np.float32)
+    for t in range(length - 1):
+        hot = np.ascontiguousarray(text[:, t])
+        lib.rnn_batch_set_one_hot(batch, hot.ctypes.data_as(abi.u8_p))
+        lib.rnn_batch_opinion(batch, 0.0)
+        if t < skip:
+            continue
+        lib.rnn_batch_get_outputs(batch, fptr(outs))
+        for j in range(n_texts):
+            ref.ref_multi_entropy_step(fptr(outs[j]), n_classes, alpha, int(text[j, t + 1]),
+                                       got[j].ctypes.data_as(dp))
+    got /= (length - skip - 1)
+    assert rel_err(got, want) < TOL
     lib.rnn_batch_delete(batch)
 
 
