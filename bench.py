@@ -513,8 +513,10 @@ def run_ours(args):
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
         kname = {"bptt_chain": "k_tc_chain_persistent", "weight_grad": "k_tc_dw_pair",
                  "forward": "k_tc_nt"}.get(dominant)
-        if kname in tr:
-            traffic = tr[kname]["dram_bytes_per_launch"]
+        for key in tr:   # ncu prints template arguments after the name
+            if kname and key.startswith(kname):
+                traffic = tr[key]["dram_bytes_per_launch"]
+                break
     except Exception:
         pass
     roofline = None
