@@ -616,8 +616,255 @@ def run_ours(args):
     return 0
 
 
+# ---------------------------------------------------------------------------
+# --config rnnca: BASELINE.json configs[4], the cellular automaton at 1080p
+
+RNNCA_W, RNNCA_H = 1920, 1080
+RNNCA_HIDDEN, RNNCA_LEN_POS, RNNCA_EDGES = 51, 2, 0
+RNNCA_METRIC = "rnnca_frames_per_second"
+RNNCA_UNIT = "frames/s"
+
+
+def rnnca_pattern():
+    """17 luma + 8 chroma neighbours, the size of RNNCA_DEFAULT_PATTERN
+    (gstrnnca.h:49-51)."""
+    off_y = np.array([(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)
+                      if abs(dx) + abs(dy) <= 2 or (abs(dx), abs(dy)) == (2, 2)][:17],
+                     dtype=np.int32)
+    off_c = np.array([(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)],
+                     dtype=np.int32)
+    return off_y, off_c
+
+
+def rnnca_config(n_gpus):
+    return {"workload": "rnnca fill_frame (gstrnnca.c:805-830), %dx%d cells, one I35/H%d/O3 ReLU "
+                        "net per pixel sharing the trainers' weights; a step = one frame of the "
+                        "automaton (every cell: gather 17 luma + 2x8 chroma neighbours + 2 position "
+                        "terms, rnn_opinion, fast_sigmoid, bytes); BASELINE.json configs[4]"
+                        % (RNNCA_W, RNNCA_H, RNNCA_HIDDEN),
+            "cells": RNNCA_W * RNNCA_H, "n_gpus": n_gpus,
+            "parallelism": "replicas only (an automaton per GPU; no collective)" if n_gpus > 1
+                           else "single GPU",
+            "cache": "per-frame working set 453 MB of hidden state > 126 MB L2: no flush needed"}
+
+
+def _rnnca_ref_band(args):
+    seed, first, n_cells, frames, frame0 = args
+    import oracle
+    from recur_b200 import abi
+    from helpers import make_net
+    ref = oracle.load_ref(strict=False)
+    port = oracle.load_port()
+    os.dup2(os.open(os.devnull, os.O_WRONLY), 2)
+    off_y, off_c = rnnca_pattern()
+    n_in = len(off_y) + 2 * len(off_c) + RNNCA_LEN_POS
+    net = make_net(ref, input_size=n_in, hidden=RNNCA_HIDDEN, output=3, depth=10, seed=seed, lr=3e-3)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    clones = (abi.RecurNN_p * n_cells)(*[ref.rnn_clone(net, fwd, abi.RECUR_RNG_SUBSEED, None)
+                                         for _ in range(n_cells)])
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    frame = frame0.copy()
+    out = frame0.copy()
+    fill = C.cast(port.oracle_rnnca_fill_inputs, C.c_void_p)
+    secs = 0.0
+    for f in range(frames):
+        secs += ref.ref_rnnca_cells(clones, first, n_cells, frame.ctypes.data_as(u8p),
+                                    out.ctypes.data_as(u8p), RNNCA_W, RNNCA_H, fill,
+                                    off_y.ctypes.data_as(ip), len(off_y), off_c.ctypes.data_as(ip),
+                                    len(off_c), RNNCA_LEN_POS, RNNCA_EDGES)
+        frame, out = out, frame
+    return secs, n_cells * frames
+
+
+def rnnca_reference_throughput(cores, rows_per_core, frames):
+    """frames/s of the reference's fill_frame with its cells split into bands
+    over `cores` processes (the element itself is single-threaded; the cells
+    of one frame are independent, so this is the most the host could do)."""
+    import oracle
+    if not oracle.have_ref():
+        raise RuntimeError("oracle/_ref is not built")
+    rs = np.random.RandomState(3)
+    frame0 = rs.randint(0, 256, size=3 * RNNCA_W * RNNCA_H).astype(np.uint8)
+    n_cells = rows_per_core * RNNCA_W
+    jobs = [(11, (r * rows_per_core % (RNNCA_H - rows_per_core)) * RNNCA_W, n_cells, frames, frame0)
+            for r in range(cores)]
+    t0 = time.time()
+    if cores == 1:
+        res = [_rnnca_ref_band(jobs[0])]
+    else:
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_rnnca_ref_band, jobs)
+    wall = time.time() - t0
+    cells_per_s = sum(c / s for s, c in res)
+    return cells_per_s / (RNNCA_W * RNNCA_H), wall
+
+
+def run_rnnca_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    cores = host_cores()
+    rows, frames = 64, 12
+    rate, wall = rnnca_reference_throughput(cores, rows, frames)
+    line = {"impl": "reference", "metric": RNNCA_METRIC, "value": rate, "unit": RNNCA_UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": rnnca_config(args.gpus),
+            "cpu_baseline": {"value": rate, "unit": RNNCA_UNIT, "cores": cores, "kind": "reference",
+                             "sample": "%d processes, each a band of %d rows x %d cells of the "
+                                       "1080p frame for %d frames: reference rnn_opinion + "
+                                       "fast_sigmoid_array around the oracle's fill_net_inputs "
+                                       "(gstrnnca.c itself needs GStreamer); %.1f s wall"
+                                       % (cores, rows, RNNCA_W, frames, wall)},
+            "e2e": {"value": rate, "unit": RNNCA_UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_rnnca(args):
+    import torch
+    from recur_b200 import api
+    from helpers import make_net
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    L = api.load_library()
+    if L.rnn_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if L.rnn_b200_set_device(local_rank) != 0:
+        raise SystemExit("cannot select GPU %d" % local_rank)
+    from recur_b200 import dist as rdist
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        L.rnn_b200_synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    off_y, off_c = rnnca_pattern()
+    len_y, len_c = len(off_y), len(off_c)
+    n_in = len_y + 2 * len_c + RNNCA_LEN_POS
+    n = RNNCA_W * RNNCA_H
+    net = make_net(L, input_size=n_in, hidden=RNNCA_HIDDEN, output=3, depth=10, seed=11, lr=3e-3)
+    cells = L.rnn_cells_new(net, RNNCA_W, RNNCA_H)
+    if not cells:
+        raise SystemExit("rnn_cells_new failed")
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    oy, oc = off_y.ctypes.data_as(ip), off_c.ctypes.data_as(ip)
+    rs = np.random.RandomState(3)
+    host_in = torch.from_numpy(rs.randint(0, 256, size=3 * n).astype(np.uint8)).pin_memory()
+    host_out = torch.empty(3 * n, dtype=torch.uint8).pin_memory()
+    pin = C.cast(host_in.data_ptr(), u8p)
+    pout = C.cast(host_out.data_ptr(), u8p)
+    stream = torch.cuda.ExternalStream(L.rnn_b200_stream())
+    warm = max(args.warmup, 3)
+    steps = min(args.steps, 400)
+
+    def run(k, first=None, last=None):
+        L.rnn_cells_rnnca_run(cells, first, k, last, oy, len_y, oc, len_c, RNNCA_LEN_POS, RNNCA_EDGES)
+
+    run(warm, pin, None)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(stream)
+    run(steps)
+    b.record(stream)
+    barrier()
+    ms = rdist.max_over_ranks(dist, a.elapsed_time(b), device="cuda")
+    # end to end: a host frame in, a host frame out, every step
+    e2e_steps = min(steps, 100)
+    for _ in range(3):
+        L.rnn_cells_rnnca_frame(cells, pin, pout, oy, len_y, oc, len_c, RNNCA_LEN_POS, RNNCA_EDGES)
+    barrier()
+    a.record(stream)
+    for _ in range(e2e_steps):
+        L.rnn_cells_rnnca_frame(cells, pin, pout, oy, len_y, oc, len_c, RNNCA_LEN_POS, RNNCA_EDGES)
+        host_in, host_out = host_out, host_in
+        pin, pout = pout, pin
+    b.record(stream)
+    barrier()
+    e2e_ms = rdist.max_over_ranks(dist, a.elapsed_time(b), device="cuda")
+    sampler.stop()
+    L.rnn_cells_delete(cells)
+
+    line = None
+    if rank == 0:
+        c = net.contents
+        # per cell and frame: hidden state read once and written once, 3 bytes in, 3 out
+        # (neighbour bytes and the second pass over the state come from L1/L2)
+        alg_bytes = n * (2 * c.h_size * 4 + 6)
+        alg_flops = 2.0 * n * (c.i_size * c.h_size + c.h_size * 3)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            peak = float(peaks["hbm_gbs"])
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            peak, peak_src = 6550.0, "fallback (B200_PROFILING.md)"
+        per_launch = ms / steps * 1e-3
+        achieved = alg_bytes / per_launch / 1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
+            traffic = next((v for k, v in tr.items() if k.startswith("k_cells_frame")), None)
+        except Exception:
+            pass
+        line = {"metric": RNNCA_METRIC, "value": world * steps / (ms * 1e-3), "unit": RNNCA_UNIT,
+                "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": rnnca_config(world),
+                "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": RNNCA_UNIT,
+                        "h2d_bytes_per_step": 3 * n, "d2h_bytes_per_step": 3 * n,
+                        "ms_per_step": e2e_ms / e2e_steps},
+                "gpu_launches": steps, "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "k_cells_frame", "achieved": achieved,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes,
+                             "fp32_tflops": alg_flops / per_launch / 1e12,
+                             "note": "algorithmic bytes = cells x (2 x h_size x 4 state + 6 frame "
+                                     "bytes).  The kernel is FP32 CUDA-core work (%.1f GFLOP per "
+                                     "frame): fp32_tflops against the 148 SM x 128 lane x 2 x clock "
+                                     "FMA ceiling is the tighter bound" % (alg_flops / 1e9)}}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                cores = host_cores()
+                rate, wall = rnnca_reference_throughput(cores, 64, 12)
+                one, wall1 = rnnca_reference_throughput(1, 64, 12)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": RNNCA_UNIT, "cores": cores, "kind": "reference",
+                    "one_core": one,
+                    "sample": "%d processes, each a band of 64 rows x %d cells for 12 frames: "
+                              "reference rnn_opinion + fast_sigmoid_array around the oracle's "
+                              "fill_net_inputs; %.1f s wall (one_core: one band alone, %.1f s; the "
+                              "element itself runs fill_frame on one thread)"
+                              % (cores, RNNCA_W, wall, wall1)}
+            except Exception as e:
+                line["cpu_baseline"] = {"value": None, "unit": RNNCA_UNIT, "cores": 0,
+                                        "kind": "reference", "sample": "unavailable: %s" % e}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="text", choices=["text", "rnnca"],
+                    help="text: the headline (BASELINE configs[1]); rnnca: configs[4]")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=30)
@@ -632,6 +879,8 @@ def main():
                     help="positions to train before the `trained` sub-record (0: skip it)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
     args = ap.parse_args()
+    if args.config == "rnnca":
+        return run_rnnca_reference(args) if args.impl == "reference" else run_rnnca(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -193,6 +193,37 @@ void rnn_batch_rnnca_frame(RnnBatch *cells, const unsigned char *frame_in,
     unsigned char *frame_out, int width, int height, const int *offsets_y, int len_y,
     const int *offsets_c, int len_c, int len_pos, int edges);
 
+/* ---- a net per pixel without a struct per pixel ---------------------------- */
+
+/* gstrnnca runs one forward-only net per pixel, all with the trainers' weights
+   (gstrnnca.c:805-830); at 1080p that is two million RecurNN clones whose only
+   content is 52 floats of hidden state.  RnnCells keeps that state on the
+   device and nothing on the host: `prototype` lends its weights (they are read
+   afresh on every call, so training the prototype in between is seen), the
+   cells start with zeroed hidden layers like fresh clones.  Nets of up to 63
+   hidden units, 40 inputs, at least 3 outputs, no bottom layer; NULL (with a
+   line on stderr) otherwise. */
+typedef struct RnnCells RnnCells;
+RnnCells *rnn_cells_new(RecurNN *prototype, int width, int height);
+void rnn_cells_delete(RnnCells *cells);
+/* rnn_forget_history for every cell */
+void rnn_cells_forget(RnnCells *cells);
+
+/* rnn_batch_rnnca_frame on such cells: one frame in (host), one frame out. */
+void rnn_cells_rnnca_frame(RnnCells *cells, const unsigned char *frame_in,
+    unsigned char *frame_out, const int *offsets_y, int len_y, const int *offsets_c, int len_c,
+    int len_pos, int edges);
+
+/* The automaton running by itself: n_frames steps, each frame the input of the
+   next, the pictures staying on the device.  frame_in may be NULL (go on from
+   the last picture), frame_out may be NULL. */
+void rnn_cells_rnnca_run(RnnCells *cells, const unsigned char *frame_in, int n_frames,
+    unsigned char *frame_out, const int *offsets_y, int len_y, const int *offsets_c, int len_c,
+    int len_pos, int edges);
+
+/* One cell's hidden_layer: h_size floats.  Synchronises. */
+void rnn_cells_get_hidden(RnnCells *cells, int cell, float *hidden);
+
 /* Number of BPTT steps each stream executed in the most recent
    rnn_batch_calc_deltas / training step (the value the reference logs as
    "depth", plus one when the walk stopped early; recur-nn.c:387,416): n

@@ -81,6 +81,11 @@ def load_ref(strict=True):
                                          c_double_p, c_double_p, c_int_p]
     lib.ref_opinion_steps.restype = C.c_double
     lib.ref_opinion_steps.argtypes = [P, u8_p, C.c_int, C.c_int]
+    lib.ref_rnnca_cells.restype = C.c_double
+    lib.ref_rnnca_cells.argtypes = [C.POINTER(abi.RecurNN_p), C.c_int, C.c_int,
+                                    C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int, C.c_int,
+                                    C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int),
+                                    C.c_int, C.c_int, C.c_int]
     lib.ref_multi_entropy_step.restype = None
     lib.ref_multi_entropy_step.argtypes = [c_float_p, C.c_int, C.c_int, C.c_int, c_double_p]
     lib.rnn_char_multi_cross_entropy.restype = None

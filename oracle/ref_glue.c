@@ -171,3 +171,40 @@ ref_opinion_steps(RecurNN *net, const u8 *text, int len, int steps)
   clock_gettime(CLOCK_MONOTONIC, &t1);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- gstrnnca's fill_frame (gstrnnca.c:805-830) over a band of cells -------
+   gstrnnca.c needs GStreamer and cannot be compiled here; its frame loop is
+   rnn_opinion + fast_sigmoid_array + UNIT_TO_BYTE around fill_net_inputs.
+   The first three are reference code, called here; fill_net_inputs is the
+   oracle's restatement, handed in as a function pointer; UNIT_TO_BYTE is a
+   one-line macro of gstrnnca.c (:642), spelled out below.  Cells first .. first + n - 1 of a
+   w x h frame; clones[i] is the net of cell first + i.  Returns seconds. */
+typedef void (*ref_fill_inputs_fn)(const unsigned char *frame, int w, int h, int cx, int cy,
+    const int *offsets_y, int len_y, const int *offsets_c, int len_c, int len_pos, int edges,
+    float *inputs);
+
+double
+ref_rnnca_cells(RecurNN **clones, int first, int n, const unsigned char *frame,
+    unsigned char *frame_out, int w, int h, ref_fill_inputs_fn fill, const int *offsets_y,
+    int len_y, const int *offsets_c, int len_c, int len_pos, int edges)
+{
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  int plane = w * h;
+  for (int i = 0; i < n; i++){
+    int cell = first + i;
+    RecurNN *net = clones[i];
+    fill(frame, w, h, cell % w, cell / w, offsets_y, len_y, offsets_c, len_c, len_pos, edges,
+        net->real_inputs);
+    float *answer = rnn_opinion(net, NULL, 0);
+    fast_sigmoid_array(answer, answer, 3);
+  }
+  for (int i = 0; i < n; i++){
+    float *yuv = clones[i]->output_layer;
+    for (int k = 0; k < 3; k++){
+      frame_out[k * plane + first + i] = (unsigned char)(yuv[k] * 255.9f); /* UNIT_TO_BYTE :642 */
+    }
+  }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}

@@ -1,0 +1,809 @@
+/* rb_cells.cu - rnnca at its own scale (BASELINE.json configs[4]): one tiny net
+ * PER PIXEL of a video frame (reference gstrnnca.c:805-830, fill_frame), two
+ * million of them at 1080p, all with the trainers' weights.  As host RecurNN
+ * clones they cost seconds to create and exist only to hold 52 floats of hidden
+ * state each; RnnCells keeps just that state, on the device, column-major
+ * ([hidden unit][cell]) so that a warp's 32 cells read and write whole lines.
+ *
+ * A frame is one kernel.  Two of them are here:
+ *
+ *   k_cells_frame_tc (the one that runs): a CTA takes 128 cells at a time.
+ *     Each thread builds its cell's input vector (bias, old hidden state,
+ *     gathered neighbour bytes, position) straight into the shared-memory image
+ *     of a K-major tcgen05 operand, as FP16 hi/lo planes (rb_split.cuh); the
+ *     weights sit beside it as the B operand, fetched once per CTA; 3 MMAs per
+ *     16 inputs leave the 128 x 64 sums in TMEM, and the same thread reads its
+ *     row back, applies the input soft clip (it is linear in the inputs, so it
+ *     multiplies the sums), the activation, the output layer and the sigmoid,
+ *     and writes the state and the three bytes.  What is left on the CUDA cores
+ *     is the gather and the epilogue: the frame is bounded by HBM (state in,
+ *     state out) rather than by 19.6 GFLOP of FP32 multiply-adds.
+ *
+ *   k_cells_frame (RECUR_B200_CELLS_FMA=1; a second, independent reading the
+ *     tests compare the first with): one thread does a cell in FP32 FMAs in the
+ *     reference's order, weights in constant memory.
+ */
+#include "rb_internal.h"
+#include "rb_kernels.h"
+#include "rb_split.cuh"
+#include "rb_devmath.cuh"
+#include "rb_ptx.cuh"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned char u8;
+
+#define LAUNCH_CHECK(name) do {                                         \
+    cudaError_t e_ = cudaGetLastError();                                \
+    if (e_ != cudaSuccess)                                              \
+      rb_die("recur-b200: launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+    rb_count_launch(1);                                                 \
+  } while (0)
+
+static inline int
+cdiv(int a, int b)
+{
+  return (a + b - 1) / b;
+}
+
+/* ======================================================================== */
+/* the FP32 frame (cross-check)                                               */
+
+#define CELLS_XIN 40 /* most gathered inputs + position terms per cell */
+
+struct CellsArgs {
+  const float *Wih, *Who;
+  int I, H, O, hs, activation;
+  float *state; /* [H][n] */
+  int n;
+  const u8 *frame;
+  u8 *frame_out;
+  int width, height;
+  const int *off_y, *off_c;
+  int len_y, len_c, len_pos, edges;
+};
+
+/* The weights as the kernel reads them: [i_size][HN] and [h_size][4], in
+   CONSTANT memory.  Every thread of a warp wants the same weight at the same
+   time; from shared memory that is an LDS.128 per four FMAs whose 512 bytes of
+   register write-back cost four cycles of the SM's one load path (measured:
+   the kernel ran at 17 % of the FMA rate).  From the constant bank the weight
+   arrives through the uniform datapath and the FMA pipe is what is left. */
+#define CELLS_MAX_I 104
+__constant__ float4 cells_w[CELLS_MAX_I * 16];
+__constant__ float4 cells_wo[64];
+
+__global__ void
+k_cells_pack(const float *__restrict__ Wih, const float *__restrict__ Who, int I, int H, int O,
+    int HN, float *w, float *wo)
+{
+  /* column c of the packed rows is hidden unit c + 1: unit 0 is the bias, its
+     sums are never used (recur-nn.c:144), and without it 51 units fill 13
+     aligned float4s */
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < I * HN) {
+    int y = t / HN, c = t - y * HN + 1;
+    w[t] = (c < H) ? Wih[(size_t)y * H + c] : 0.0f;
+  }
+  if (t < H * 4) {
+    int y = t >> 2, o = t & 3;
+    wo[t] = (o < O) ? Who[(size_t)y * O + o] : 0.0f;
+  }
+}
+
+#define CELLS_NT 128
+
+template <int HN>
+__device__ __forceinline__ void
+cells_row_fma(float (&acc)[HN], float x, const float4 *w4)
+{
+#pragma unroll
+  for (int c = 0; c < HN / 4; c++) {
+    const float4 w = w4[c];
+    acc[4 * c] = fmaf(x, w.x, acc[4 * c]);
+    acc[4 * c + 1] = fmaf(x, w.y, acc[4 * c + 1]);
+    acc[4 * c + 2] = fmaf(x, w.z, acc[4 * c + 2]);
+    acc[4 * c + 3] = fmaf(x, w.w, acc[4 * c + 3]);
+  }
+}
+
+template <int HN>
+__global__ void __launch_bounds__(CELLS_NT, 4)
+k_cells_frame(CellsArgs a)
+{
+  /* each thread's input vector, [row][thread]: written in the first pass (the
+     sum for the soft clip needs every input before any product), read back in
+     the second */
+  extern __shared__ float xs[];
+  float *mine = xs + threadIdx.x;
+  const float4 *W = cells_w;
+  const int hs1 = a.hs + 1;
+  const int n_in = a.len_y + 2 * a.len_c, n_tot = n_in + a.len_pos;
+  const int plane = a.width * a.height;
+  const float unit = 1.0f / 255.0f;
+  for (int cell = blockIdx.x * CELLS_NT + threadIdx.x; cell < a.n; cell += gridDim.x * CELLS_NT) {
+    const int cx = cell % a.width, cy = cell / a.width;
+    const float *st = a.state + cell;
+    float sum = 1.0f; /* input 0, the bias */
+#pragma unroll 10
+    for (int i = 1; i < hs1; i++) {
+      const float v = st[(size_t)i * a.n];
+      mine[i * CELLS_NT] = v;
+      sum += v;
+    }
+    /* fill_net_inputs (gstrnnca.c:670-691) */
+#pragma unroll 1
+    for (int j = 0; j < n_tot; j++) {
+      float val;
+      if (j < a.len_y)
+        val = a.frame[rnnca_offset_point(a.off_y + 2 * j, cx, cy, a.width, a.height, a.edges)] *
+            unit;
+      else if (j < n_in) {
+        const int q = (j - a.len_y) >> 1, which = (j - a.len_y) & 1;
+        const int o = rnnca_offset_point(a.off_c + 2 * q, cx, cy, a.width, a.height, a.edges);
+        val = a.frame[(1 + which) * plane + o] * unit;
+      }
+      else {
+        const int k = j - n_in;
+        const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+        val = (k == 0) ? xx : (k == 1) ? yy
+            : (float)(0.5 - (((double)yy - 0.5) * ((double)yy - 0.5) +
+                  ((double)xx - 0.5) * ((double)xx - 0.5)));
+      }
+      mine[(a.H + j) * CELLS_NT] = val;
+      sum += val;
+    }
+    /* maybe_scale_inputs (recur-nn.c:68-81) */
+    const float softclip = a.I * INPUT_MEAN_SOFT_TOP;
+    const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
+
+    float acc[HN];
+#pragma unroll
+    for (int c = 0; c < HN / 4; c++) {
+      const float4 w = W[c];
+      acc[4 * c] = scale * w.x;
+      acc[4 * c + 1] = scale * w.y;
+      acc[4 * c + 2] = scale * w.z;
+      acc[4 * c + 3] = scale * w.w;
+    }
+#pragma unroll 2
+    for (int i = 1; i < hs1; i++)
+      cells_row_fma<HN>(acc, mine[i * CELLS_NT] * scale, W + i * (HN / 4));
+#pragma unroll 2
+    for (int j = 0; j < n_tot; j++)
+      cells_row_fma<HN>(acc, mine[(a.H + j) * CELLS_NT] * scale, W + (a.H + j) * (HN / 4));
+
+    /* activation (recur-nn.c:121-148), the new state, and the three outputs */
+    const float4 wb = cells_wo[0];
+    float y0 = wb.x, y1 = wb.y, y2 = wb.z; /* hidden unit 0 is 1 */
+    float *sto = a.state + cell;
+    sto[0] = 1.0f;
+#pragma unroll
+    for (int c = 0; c < HN; c++) {
+      float t = acc[c];
+      if (a.activation == RNN_RESQRT)
+        t = (t > 0.0f) ? sqrtf(t + 1.0f) - 1.0f : 0.0f;
+      else {
+        if (a.activation == RNN_RECLIP20)
+          t = t < 20.0f ? t : 20.0f;
+        t = (t > 0.0f) ? t : 0.0f;
+      }
+      if (c + 1 < a.H) {
+        sto[(size_t)(c + 1) * a.n] = t;
+        const float4 wo = cells_wo[c + 1];
+        y0 = fmaf(t, wo.x, y0);
+        y1 = fmaf(t, wo.y, y1);
+        y2 = fmaf(t, wo.z, y2);
+      }
+    }
+    /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE */
+    a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y0)) * 255.9f);
+    a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y1)) * 255.9f);
+    a.frame_out[2 * plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y2)) * 255.9f);
+  }
+}
+
+
+/* ======================================================================== */
+/* the tensor-core frame                                                      */
+
+#define CT_NT 128                    /* threads = cells per tile = MMA rows */
+#define CT_BN 64                     /* hidden units 1..64 = MMA columns */
+#define CT_A_CHUNK (CT_NT * 128)     /* 64 halves of K for 128 rows: 16 KB */
+#define CT_B_CHUNK (CT_BN * 128)     /* 64 halves of K for 64 units: 8 KB */
+#define CT_MAX_CHUNKS 2              /* i_size <= 128 */
+#define CT_X_TOP 8192.0f             /* rows with larger hidden values are pre-scaled */
+
+/* per gathered input j: its neighbour offset, its plane, and for cells whose
+   whole neighbourhood is inside the frame the flat distance to the byte */
+__constant__ int cells_dx[CELLS_XIN], cells_dy[CELLS_XIN], cells_plane[CELLS_XIN],
+    cells_delta[CELLS_XIN];
+
+struct CellsTcArgs {
+  CellsArgs c;
+  const rb_h16 *w_image; /* [hi | lo][chunk][64 units][64 halves], swizzled as in shared memory */
+  float *rowmax;         /* [n] largest hidden value of each cell */
+  int chunks, ksteps, reach, tiles; /* ksteps: bit s = K steps 16 s .. 16 s + 15 hold inputs */
+};
+
+/* K, the inner dimension of the product, is laid out for the kernel's
+   convenience rather than in the order of the net's input vector: [0, 64) the
+   hidden units (the bias first), [64, 104) the gathered bytes, [104, 107) the
+   position terms, zeros elsewhere - every section starts at a place known at
+   compile time, so a thread holds its whole input vector in registers.  The
+   sections are in the net's order, so sums over K ascend like the reference's.
+   This maps a K index to the net's input row, -1 for padding. */
+#define CT_K_BYTES 64
+#define CT_K_POS 104
+#define CT_K_END 112
+__host__ __device__ __forceinline__ int
+cells_k_row(int k, int H, int n_in, int n_pos)
+{
+  if (k < CT_K_BYTES)
+    return k < H ? k : -1;
+  if (k < CT_K_POS)
+    return k - CT_K_BYTES < n_in ? H + k - CT_K_BYTES : -1;
+  return k - CT_K_POS < n_pos ? H + n_in + k - CT_K_POS : -1;
+}
+
+/* The B operand as the kernel's shared memory holds it: unit u + 1's weights
+   along K, 128-byte rows, the 16-byte pieces of a row XORed with the row
+   number (SWIZZLE_128B), as FP16 hi/lo planes of 64 w. */
+__global__ void
+k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, int H, int O,
+    int n_in, int n_pos, int chunks, rb_h16 *image, float *wo)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < CT_BN * chunks * 8) {
+    const int u = t % CT_BN, g = t / CT_BN; /* 8 inputs k = 8g .. 8g + 7 of unit u + 1 */
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int k = cells_k_row(8 * g + e, H, n_in, n_pos);
+      v[e] = (k >= 0 && u + 1 < H) ? Wih[(size_t)k * H + u + 1] : 0.0f;
+    }
+    uint2 h0, l0, h1, l1;
+    rb_split4(make_float4(v[0], v[1], v[2], v[3]), (float)RB_W_SCALE, h0, l0);
+    rb_split4(make_float4(v[4], v[5], v[6], v[7]), (float)RB_W_SCALE, h1, l1);
+    const size_t at = (size_t)(g >> 3) * CT_B_CHUNK + (size_t)u * 128 + (((g & 7) ^ (u & 7)) << 4);
+    char *hi = (char *)image, *lo = (char *)image + (size_t)chunks * CT_B_CHUNK;
+    *(uint4 *)(hi + at) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *(uint4 *)(lo + at) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  }
+  if (t < H * 4) {
+    int y = t >> 2, o = t & 3;
+    wo[t] = (o < O) ? Who[(size_t)y * O + o] : 0.0f;
+  }
+}
+
+/* eight consecutive inputs of this thread's cell -> 16 bytes of each plane, at
+   K = 8 g of row r of the A operand (128-byte rows, SWIZZLE_128B) */
+__device__ __forceinline__ void
+cells_put8(unsigned char *a_hi, unsigned char *a_lo, int g, int r, const float *v, float pre)
+{
+  uint2 h0, l0, h1, l1;
+  rb_split4(make_float4(v[0], v[1], v[2], v[3]), pre, h0, l0);
+  rb_split4(make_float4(v[4], v[5], v[6], v[7]), pre, h1, l1);
+  const uint32_t at = (uint32_t)(g >> 3) * CT_A_CHUNK + (uint32_t)r * 128 +
+      (((g & 7) ^ (r & 7)) << 4);
+  *(uint4 *)(a_hi + at) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *(uint4 *)(a_lo + at) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+}
+
+/* 256 threads, two per cell of the tile: thread r and thread 128 + r share row r.
+   Going in, the first builds the hidden-state half of the row and the second
+   the gathered half; coming out, the first takes hidden units 1..32 and the
+   second 33..64 (warps w and w + 4 reach the same 32 lanes of tensor memory).
+   Two CTAs per SM: 16 warps, 128 registers each. */
+template <int ACT>
+__global__ void __launch_bounds__(2 * CT_NT, 2)
+k_cells_frame_tc(CellsTcArgs t)
+{
+  extern __shared__ __align__(1024) unsigned char ct_smem[];
+  __shared__ __align__(8) uint64_t w_bar, mma_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float s_sum[2][CT_NT];
+  __shared__ float4 s_y[2][CT_NT];
+  const CellsArgs &a = t.c;
+  /* shared memory: A hi [chunks][16 KB], A lo, B hi [chunks][8 KB], B lo */
+  unsigned char *base = (unsigned char *)(((uintptr_t)ct_smem + 1023) & ~(uintptr_t)1023);
+  unsigned char *a_hi = base, *a_lo = base + t.chunks * CT_A_CHUNK;
+  unsigned char *b_hi = base + 2 * t.chunks * CT_A_CHUNK, *b_lo = b_hi + t.chunks * CT_B_CHUNK;
+  const int tid = threadIdx.x, r = tid & (CT_NT - 1), role = tid >> 7, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(&w_bar, 1);
+    mbar_init(&mma_bar, 1);
+    fence_barrier_init();
+    const uint32_t bytes = 2u * t.chunks * CT_B_CHUNK;
+    mbar_expect_tx(&w_bar, bytes);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(b_hi)), "l"(t.w_image), "r"(bytes), "r"(smem_u32(&w_bar)) : "memory");
+  }
+  if (warp == 0)
+    tmem_alloc(&tmem_slot, 2 * CT_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t idesc = umma_idesc_f16(CT_NT, CT_BN, 0, 0);
+
+  const int hs1 = a.hs + 1;
+  const int n_in = a.len_y + 2 * a.len_c;
+  const int plane = a.width * a.height;
+  uint32_t phase = 0;
+  bool w_ready = false;
+
+  for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x) {
+    const bool live = tile * CT_NT + r < a.n;
+    const int cell = live ? tile * CT_NT + r : a.n - 1; /* the ragged end repeats the last cell */
+    /* rows whose hidden values would not fit FP16 go through the tensor cores
+       divided by a power of two, and their sums are multiplied back */
+    float pre = 1.0f, post = 1.0f;
+    {
+      const float m = t.rowmax[cell];
+      if (m > CT_X_TOP) {
+        const int e = ((__float_as_int(m) >> 23) & 0xff) - 127;
+        pre = __int_as_float((127 + 13 - e) << 23);
+        post = __int_as_float((127 - 13 + e) << 23);
+      }
+    }
+    /* a thread's half of the input vector goes into registers, every load
+       issued before any is used */
+    float part = 0.0f; /* ascending, as maybe_scale_inputs does (recur-nn.c:72-75) */
+    if (role == 0) {
+      const float *st = a.state + cell;
+      float hv[CT_K_BYTES];
+#pragma unroll
+      for (int k = 1; k < CT_K_BYTES; k++)
+        hv[k] = (k < hs1) ? st[(size_t)k * a.n] : 0.0f;
+      hv[0] = 1.0f;
+#pragma unroll
+      for (int k = 0; k < CT_K_BYTES; k++)
+        part += hv[k];
+#pragma unroll
+      for (int g = 0; g < CT_K_BYTES / 8; g++)
+        if (8 * g < ((a.H + 15) & ~15)) /* whole K steps: what the MMAs read must be written */
+          cells_put8(a_hi, a_lo, g, r, hv + 8 * g, pre);
+    }
+    else {
+      const int cx = cell % a.width, cy = cell / a.width;
+      const bool interior = cx >= t.reach && cx < a.width - t.reach && cy >= t.reach &&
+          cy < a.height - t.reach;
+      const u8 *fr = a.frame + cell;
+      float bv[CT_K_END - CT_K_BYTES];
+      if (interior) {
+#pragma unroll
+        for (int j = 0; j < CT_K_POS - CT_K_BYTES; j++)
+          bv[j] = (j < n_in) ? fr[cells_delta[j]] * (1.0f / 255.0f) : 0.0f;
+      }
+      else {
+        /* get_offset_point (gstrnnca.c:644-667) at the frame's border */
+#pragma unroll
+        for (int j = 0; j < CT_K_POS - CT_K_BYTES; j++) {
+          int x = cx + cells_dx[j], y = cy + cells_dy[j];
+          if (a.edges) {
+            y = max(0, min(a.height - 1, y));
+            x = max(0, min(a.width - 1, x));
+          }
+          else {
+            y += (y < 0) ? a.height : (y >= a.height) ? -a.height : 0;
+            x += (x < 0) ? a.width : (x >= a.width) ? -a.width : 0;
+          }
+          bv[j] = (j < n_in) ? a.frame[cells_plane[j] * plane + y * a.width + x] * (1.0f / 255.0f)
+                             : 0.0f;
+        }
+      }
+      /* the position terms (gstrnnca.c:685-690) */
+      const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+#pragma unroll
+      for (int q = 0; q < 8; q++)
+        bv[CT_K_POS - CT_K_BYTES + q] = 0.0f;
+      if (a.len_pos > 0)
+        bv[CT_K_POS - CT_K_BYTES] = xx;
+      if (a.len_pos > 1)
+        bv[CT_K_POS - CT_K_BYTES + 1] = yy;
+      if (a.len_pos > 2)
+        bv[CT_K_POS - CT_K_BYTES + 2] = (float)(0.5 - (((double)yy - 0.5) * ((double)yy - 0.5) +
+            ((double)xx - 0.5) * ((double)xx - 0.5)));
+#pragma unroll
+      for (int j = 0; j < CT_K_END - CT_K_BYTES; j++)
+        part += bv[j];
+#pragma unroll
+      for (int g = 0; g < (CT_K_END - CT_K_BYTES) / 8; g++)
+        cells_put8(a_hi, a_lo, CT_K_BYTES / 8 + g, r, bv + 8 * g, pre);
+    }
+    s_sum[role][r] = part;
+
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      if (!w_ready) {
+        mbar_wait(&w_bar, 0);
+        w_ready = true;
+      }
+      tc_fence_after();
+      bool first = true;
+      for (int ks = 0; ks < CT_K_END / 16; ks++) {
+        if (!((t.ksteps >> ks) & 1))
+          continue;
+        const uint32_t ao = (uint32_t)(ks >> 2) * CT_A_CHUNK + (ks & 3) * 32;
+        const uint32_t bo = (uint32_t)(ks >> 2) * CT_B_CHUNK + (ks & 3) * 32;
+        const uint64_t dah = umma_desc(smem_u32(a_hi) + ao, 16, 1024);
+        const uint64_t dal = umma_desc(smem_u32(a_lo) + ao, 16, 1024);
+        const uint64_t dbh = umma_desc(smem_u32(b_hi) + bo, 16, 1024);
+        const uint64_t dbl = umma_desc(smem_u32(b_lo) + bo, 16, 1024);
+        umma_f16(tmem_base, dah, dbh, idesc, !first);
+        umma_f16(tmem_base + CT_BN, dah, dbl, idesc, !first);
+        umma_f16(tmem_base + CT_BN, dal, dbh, idesc, 1u);
+        first = false;
+      }
+      umma_commit(&mma_bar);
+    }
+    /* maybe_scale_inputs (recur-nn.c:68-81): every input times `scale`, so every sum too */
+    const float sum = s_sum[0][r] + s_sum[1][r];
+    const float softclip = a.I * INPUT_MEAN_SOFT_TOP;
+    const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
+    const float unscale = scale * post * (1.0f / RB_W_SCALE);
+    mbar_wait(&mma_bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+
+    /* this thread's half of the row of sums: activation (recur-nn.c:121-148),
+       the new state, its share of the three outputs */
+    float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, biggest = 0.0f;
+    float *sto = a.state + cell;
+    if (role == 0) {
+      const float4 wb = cells_wo[0]; /* hidden unit 0 is 1 */
+      y0 = wb.x;
+      y1 = wb.y;
+      y2 = wb.z;
+      if (live)
+        sto[0] = 1.0f;
+    }
+    if (role * 32 + 1 < a.H) {
+      float mn[32], cr[32];
+      tmem_ld32_nowait(tmem_lane + role * 32, mn);
+      tmem_ld32_nowait(tmem_lane + CT_BN + role * 32, cr);
+      tmem_wait_ld();
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int unit = role * 32 + q + 1;
+        float x = (mn[q] + cr[q] * (1.0f / RB_LO_GAIN)) * unscale;
+        if (ACT == RNN_RESQRT)
+          x = (x > 0.0f) ? sqrtf(x + 1.0f) - 1.0f : 0.0f;
+        else {
+          if (ACT == RNN_RECLIP20)
+            x = fminf(x, 20.0f);
+          x = fmaxf(x, 0.0f);
+        }
+        if (unit < hs1) { /* the pad units after them stay zero (rnn_cells_new) */
+          if (live)
+            sto[(size_t)unit * a.n] = x;
+          biggest = fmaxf(biggest, x);
+          const float4 wo = cells_wo[unit];
+          y0 = fmaf(x, wo.x, y0);
+          y1 = fmaf(x, wo.y, y1);
+          y2 = fmaf(x, wo.z, y2);
+        }
+      }
+    }
+    s_y[role][r] = make_float4(y0, y1, y2, biggest);
+    tc_fence_before(); /* the next tile's MMAs overwrite TMEM after the next barrier */
+    __syncthreads();
+    const float4 other = s_y[role ^ 1][r];
+    if (live) {
+      /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642) */
+      if (role == 0) {
+        t.rowmax[cell] = fmaxf(biggest, other.w);
+        a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(y0 + other.x))) * 255.9f);
+      }
+      else {
+        a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(other.y + y1))) * 255.9f);
+        a.frame_out[2 * plane + cell] =
+            (u8)(1.0f / (1.0f + fast_expf_dev(-(other.z + y2))) * 255.9f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * CT_BN);
+  }
+}
+
+struct RnnCells {
+  RecurNN *proto;
+  int width, height, n;
+  float *state;               /* device [h_size][n] */
+  u8 *frames;                 /* device: two frames of 3 n bytes, ping-pong */
+  int *off_dev;
+  int off_ints;
+  u8 *host;                   /* pinned staging, 3 n bytes */
+  int cur;                    /* which of the two frames holds the newest picture */
+  rb_h16 *w_image;            /* device: the weights as k_cells_frame_tc's B operand */
+  float *rowmax;              /* device [n]: largest hidden value of each cell */
+  int reach;                  /* largest |dx|, |dy| of the neighbourhood */
+};
+
+extern "C" RnnCells *
+rnn_cells_new(RecurNN *prototype, int width, int height)
+{
+  rb_require_device("rnn_cells_new");
+  if (!prototype || width < 1 || height < 1) {
+    fprintf(stderr, "rnn_cells_new: need a prototype net and a frame size\n");
+    return NULL;
+  }
+  if (prototype->h_size > 64 || prototype->output_size < 3 || prototype->bottom_layer ||
+      prototype->input_size > CELLS_XIN || prototype->i_size > CELLS_MAX_I) {
+    fprintf(stderr, "rnn_cells_new: the cell kernel takes nets of up to 63 hidden units, "
+        "%d inputs, at least 3 outputs and no bottom layer\n", CELLS_XIN);
+    return NULL;
+  }
+  rb_net_of(prototype); /* aborts on a foreign pointer */
+  RnnCells *c = (RnnCells *)calloc(1, sizeof(RnnCells));
+  c->proto = prototype;
+  c->width = width;
+  c->height = height;
+  c->n = width * height;
+  size_t n = (size_t)c->n;
+  if (cudaMalloc((void **)&c->state, n * prototype->h_size * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void **)&c->frames, 2 * 3 * n + 64) != cudaSuccess ||
+      cudaMalloc((void **)&c->off_dev, 4 * CELLS_XIN * sizeof(int)) != cudaSuccess ||
+      cudaMalloc((void **)&c->w_image, 2 * CT_MAX_CHUNKS * CT_B_CHUNK) != cudaSuccess ||
+      cudaMalloc((void **)&c->rowmax, n * sizeof(float)) != cudaSuccess ||
+      cudaHostAlloc((void **)&c->host, 3 * n, cudaHostAllocDefault) != cudaSuccess)
+    rb_die("recur-b200: out of memory for %d cells", c->n);
+  cudaMemsetAsync(c->state, 0, n * prototype->h_size * sizeof(float), rb_stream);
+  cudaMemsetAsync(c->frames, 0, 2 * 3 * n, rb_stream);
+  cudaMemsetAsync(c->rowmax, 0, n * sizeof(float), rb_stream);
+  cudaStreamSynchronize(rb_stream);
+  return c;
+}
+
+extern "C" void
+rnn_cells_delete(RnnCells *c)
+{
+  if (!c)
+    return;
+  cudaStreamSynchronize(rb_stream);
+  cudaFree(c->state);
+  cudaFree(c->frames);
+  cudaFree(c->off_dev);
+  cudaFree(c->w_image);
+  cudaFree(c->rowmax);
+  cudaFreeHost(c->host);
+  free(c);
+}
+
+extern "C" void
+rnn_cells_forget(RnnCells *c)
+{
+  cudaMemsetAsync(c->state, 0, (size_t)c->n * c->proto->h_size * sizeof(float), rb_stream);
+  cudaMemsetAsync(c->rowmax, 0, (size_t)c->n * sizeof(float), rb_stream);
+}
+
+static void
+cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_pos, int edges)
+{
+  RecurNN *p = c->proto;
+  CellsArgs a;
+  a.Wih = p->ih_weights;
+  a.Who = p->ho_weights;
+  a.I = p->i_size;
+  a.H = p->h_size;
+  a.O = p->o_size;
+  a.hs = p->hidden_size;
+  a.activation = p->activation;
+  a.state = c->state;
+  a.n = c->n;
+  a.frame = in;
+  a.frame_out = out;
+  a.width = c->width;
+  a.height = c->height;
+  a.off_y = c->off_dev;
+  a.off_c = c->off_dev + 2 * len_y;
+  a.len_y = len_y;
+  a.len_c = len_c;
+  a.len_pos = len_pos;
+  a.edges = edges;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static float *w_dev, *wo_dev;
+  if (!w_dev) {
+    cudaGetSymbolAddress((void **)&w_dev, cells_w);
+    cudaGetSymbolAddress((void **)&wo_dev, cells_wo);
+  }
+  const char *env = getenv("RECUR_B200_CELLS_FMA"); /* read per frame: tests flip it */
+  const int use_fma = (env && *env && *env != '0');
+  rb_prof_begin(RB_PROF_FWD);
+  if (!use_fma) {
+    CellsTcArgs t;
+    t.c = a;
+    t.w_image = c->w_image;
+    t.rowmax = c->rowmax;
+    const int n_in = len_y + 2 * len_c;
+    t.chunks = CT_MAX_CHUNKS;
+    t.ksteps = 0;
+    for (int k = 0; k < CT_K_END; k++)
+      if (cells_k_row(k, p->h_size, n_in, len_pos) >= 0)
+        t.ksteps |= 1 << (k / 16);
+    t.reach = c->reach;
+    t.tiles = cdiv(c->n, CT_NT);
+    const size_t sh = (size_t)2 * t.chunks * (CT_A_CHUNK + CT_B_CHUNK) + 1024;
+    void (*kernel)(CellsTcArgs) = p->activation == RNN_RESQRT ? k_cells_frame_tc<RNN_RESQRT>
+        : p->activation == RNN_RECLIP20 ? k_cells_frame_tc<RNN_RECLIP20>
+        : k_cells_frame_tc<RNN_RELU>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            2 * CT_MAX_CHUNKS * (CT_A_CHUNK + CT_B_CHUNK) + 1024) != cudaSuccess)
+      rb_die("recur-b200: k_cells_frame_tc: cannot reserve shared memory");
+    /* the prototype may have been trained since the last frame: repack every time (2 us) */
+    k_cells_pack_tc<<<cdiv(CT_BN * t.chunks * 8, 256), 256, 0, rb_stream>>>(p->ih_weights,
+        p->ho_weights, p->h_size, p->o_size, n_in, len_pos, t.chunks, c->w_image, wo_dev);
+    /* two CTAs of 128 TMEM columns and <= 97 KB fit an SM */
+    int blocks = t.tiles < 2 * sms ? t.tiles : 2 * sms;
+    kernel<<<blocks, 2 * CT_NT, sh, rb_stream>>>(t);
+    LAUNCH_CHECK("k_cells_frame_tc");
+    rb_prof_end(RB_PROF_FWD);
+    return;
+  }
+  static int per_sm[2];
+  const int big = p->h_size > 52;
+  const int HN = big ? 64 : 52;
+  const size_t sh = (size_t)p->i_size * CELLS_NT * sizeof(float);
+  if (!per_sm[big]) {
+    if (cudaFuncSetAttribute(big ? k_cells_frame<64> : k_cells_frame<52>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, CELLS_MAX_I * CELLS_NT * sizeof(float)) !=
+        cudaSuccess)
+      rb_die("recur-b200: k_cells_frame: cannot reserve shared memory");
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[big],
+        big ? k_cells_frame<64> : k_cells_frame<52>, CELLS_NT, sh);
+    if (per_sm[big] < 1)
+      per_sm[big] = 1;
+  }
+  int blocks = cdiv(c->n, CELLS_NT);
+  if (blocks > sms * per_sm[big])
+    blocks = sms * per_sm[big];
+  k_cells_pack<<<cdiv(p->i_size * HN, 256), 256, 0, rb_stream>>>(p->ih_weights, p->ho_weights,
+      p->i_size, p->h_size, p->o_size, HN, w_dev, wo_dev);
+  if (!big)
+    k_cells_frame<52><<<blocks, CELLS_NT, sh, rb_stream>>>(a);
+  else
+    k_cells_frame<64><<<blocks, CELLS_NT, sh, rb_stream>>>(a);
+  LAUNCH_CHECK("k_cells_frame");
+  rb_prof_end(RB_PROF_FWD);
+}
+
+static void
+cells_check(RnnCells *c, int len_y, int len_c, int len_pos)
+{
+  if (c->proto->input_size != len_y + 2 * len_c + len_pos || len_y < 0 || len_c < 0 ||
+      len_pos < 0 || len_pos > 3)
+    rb_die("recur-b200: rnn_cells: a net of %d inputs does not match %d + 2*%d + %d",
+        c->proto->input_size, len_y, len_c, len_pos);
+}
+
+static void
+cells_offsets(RnnCells *c, const int *offsets_y, int len_y, const int *offsets_c, int len_c)
+{
+  int off[4 * CELLS_XIN];
+  memcpy(off, offsets_y, 2 * (size_t)len_y * sizeof(int));
+  memcpy(off + 2 * len_y, offsets_c, 2 * (size_t)len_c * sizeof(int));
+  cudaMemcpyAsync(c->off_dev, off, 2 * (size_t)(len_y + len_c) * sizeof(int),
+      cudaMemcpyHostToDevice, rb_stream);
+  /* the same per gathered input, in the order of fill_net_inputs (gstrnnca.c:672-684) */
+  int dx[CELLS_XIN], dy[CELLS_XIN], pl[CELLS_XIN], delta[CELLS_XIN];
+  const int plane = c->width * c->height;
+  int reach = 0, j = 0;
+  for (int i = 0; i < len_y; i++, j++) {
+    dx[j] = offsets_y[2 * i];
+    dy[j] = offsets_y[2 * i + 1];
+    pl[j] = 0;
+  }
+  for (int i = 0; i < len_c; i++) {
+    for (int k = 1; k <= 2; k++, j++) {
+      dx[j] = offsets_c[2 * i];
+      dy[j] = offsets_c[2 * i + 1];
+      pl[j] = k;
+    }
+  }
+  for (int i = 0; i < j; i++) {
+    delta[i] = pl[i] * plane + dy[i] * c->width + dx[i];
+    reach = abs(dx[i]) > reach ? abs(dx[i]) : reach;
+    reach = abs(dy[i]) > reach ? abs(dy[i]) : reach;
+  }
+  c->reach = reach;
+  cudaMemcpyToSymbolAsync(cells_dx, dx, j * sizeof(int), 0, cudaMemcpyHostToDevice, rb_stream);
+  cudaMemcpyToSymbolAsync(cells_dy, dy, j * sizeof(int), 0, cudaMemcpyHostToDevice, rb_stream);
+  cudaMemcpyToSymbolAsync(cells_plane, pl, j * sizeof(int), 0, cudaMemcpyHostToDevice, rb_stream);
+  cudaMemcpyToSymbolAsync(cells_delta, delta, j * sizeof(int), 0, cudaMemcpyHostToDevice,
+      rb_stream);
+  cudaStreamSynchronize(rb_stream); /* the tables are on this stack */
+}
+
+static bool
+cells_is_pinned(const void *p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+/* One frame (reference gstrnnca.c:805-830, fill_frame): host frame in, host
+   frame out; the hidden state of every cell stays on the device. */
+extern "C" void
+rnn_cells_rnnca_frame(RnnCells *c, const unsigned char *frame_in, unsigned char *frame_out,
+    const int *offsets_y, int len_y, const int *offsets_c, int len_c, int len_pos, int edges)
+{
+  cells_check(c, len_y, len_c, len_pos);
+  rb_matrices_to_device(c->proto);
+  cells_offsets(c, offsets_y, len_y, offsets_c, len_c);
+  const size_t fb = 3 * (size_t)c->n;
+  u8 *in = c->frames, *out = c->frames + fb;
+  /* frames in page-locked memory (cudaHostAlloc / cudaHostRegister, a video
+     pipeline's buffer pool) are copied from and to in place; pageable ones go
+     through the staging buffer */
+  const bool in_pinned = cells_is_pinned(frame_in), out_pinned = cells_is_pinned(frame_out);
+  if (!in_pinned)
+    memcpy(c->host, frame_in, fb);
+  cudaMemcpyAsync(in, in_pinned ? frame_in : c->host, fb, cudaMemcpyHostToDevice, rb_stream);
+  cells_launch(c, in, out, len_y, len_c, len_pos, edges);
+  cudaMemcpyAsync(out_pinned ? frame_out : c->host, out, fb, cudaMemcpyDeviceToHost, rb_stream);
+  cudaStreamSynchronize(rb_stream);
+  if (!out_pinned)
+    memcpy(frame_out, c->host, fb);
+  c->cur = 1;
+}
+
+/* The automaton running by itself, as the element does between key frames:
+   n_frames steps, every frame the input of the next, the pictures never
+   leaving the device.  frame_in (may be NULL: go on from the last picture) is
+   uploaded first, frame_out (may be NULL) receives the last picture. */
+extern "C" void
+rnn_cells_rnnca_run(RnnCells *c, const unsigned char *frame_in, int n_frames,
+    unsigned char *frame_out, const int *offsets_y, int len_y, const int *offsets_c, int len_c,
+    int len_pos, int edges)
+{
+  cells_check(c, len_y, len_c, len_pos);
+  rb_matrices_to_device(c->proto);
+  cells_offsets(c, offsets_y, len_y, offsets_c, len_c);
+  const size_t fb = 3 * (size_t)c->n;
+  if (frame_in) {
+    memcpy(c->host, frame_in, fb);
+    cudaMemcpyAsync(c->frames + (size_t)c->cur * fb, c->host, fb, cudaMemcpyHostToDevice,
+        rb_stream);
+  }
+  for (int f = 0; f < n_frames; f++) {
+    cells_launch(c, c->frames + (size_t)c->cur * fb, c->frames + (size_t)(c->cur ^ 1) * fb, len_y,
+        len_c, len_pos, edges);
+    c->cur ^= 1;
+  }
+  if (frame_out) {
+    cudaMemcpyAsync(c->host, c->frames + (size_t)c->cur * fb, fb, cudaMemcpyDeviceToHost,
+        rb_stream);
+    cudaStreamSynchronize(rb_stream);
+    memcpy(frame_out, c->host, fb);
+  }
+}
+
+/* one cell's hidden_layer (h_size floats) */
+extern "C" void
+rnn_cells_get_hidden(RnnCells *c, int cell, float *hidden)
+{
+  cudaMemcpy2DAsync(hidden, sizeof(float), c->state + cell, (size_t)c->n * sizeof(float),
+      sizeof(float), c->proto->h_size, cudaMemcpyDeviceToHost, rb_stream);
+  cudaStreamSynchronize(rb_stream);
+}

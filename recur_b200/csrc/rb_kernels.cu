@@ -29,6 +29,7 @@
  */
 #include "rb_kernels.h"
 #include "rb_split.cuh"
+#include "rb_devmath.cuh"
 #include "rb_rng.h"
 #include "rb_optim.cuh"
 #include <math.h>
@@ -91,38 +92,6 @@ block_sum(float v, float *scratch /* >= 33 floats */)
   }
   __syncthreads();
   return scratch[32];
-}
-
-/* recur-nn-helpers.h:104-113: 2x / (1 + x^2 (0.99 + x^2/100)), x = sum/halfmax */
-__device__ __forceinline__ float
-soft_clip_dev(float sum, float halfmax)
-{
-  if (halfmax == 0.0f)
-    return sum;
-  float x = sum / halfmax;
-  float fudge = (float)(0.99 + (double)(x * x / 100.0f));
-  return 2.0f * x / (1.0f + x * x * fudge);
-}
-
-/* badmaths.h:14-29: Pade(2,2) of exp on |x| < 0.2 after dividing by 8^count,
-   then count rounds of three squarings.  The comparison in the reference is
-   made in double against 0.2, which for a float means >= 0.2f. */
-__device__ __forceinline__ float
-fast_expf_dev(float x)
-{
-  int count = 0;
-  while (fabsf(x) >= 0.2f && count < 48) {
-    x *= 0.125f;
-    count++;
-  }
-  float a = ((x + 3.0f) * (x + 3.0f) + 3.0f) / ((x - 3.0f) * (x - 3.0f) + 3.0f);
-  while (count) {
-    a *= a;
-    a *= a;
-    a *= a;
-    count--;
-  }
-  return a;
 }
 
 __device__ __forceinline__ float *
@@ -3474,27 +3443,6 @@ struct RnncaArgs {
   const int *off_y, *off_c; /* (dx, dy) pairs */
   int len_y, len_c, len_pos, edges;
 };
-
-__device__ __forceinline__ int
-rnnca_offset_point(const int *off, int cx, int cy, int w, int h, int edges)
-{
-  int x = cx + off[0], y = cy + off[1];
-  if (edges) {
-    y = max(0, min(h - 1, y));
-    x = max(0, min(w - 1, x));
-  }
-  else {
-    if (y < 0)
-      y += h;
-    else if (y >= h)
-      y -= h;
-    if (x < 0)
-      x += w;
-    else if (x >= w)
-      x -= w;
-  }
-  return y * w + x;
-}
 
 __global__ void __launch_bounds__(128)
 k_rnnca_gather(RnncaArgs a)

@@ -71,17 +71,29 @@ rb_pack2(rb_h16 a, rb_h16 b)
   return (uint32_t)a | ((uint32_t)b << 16);
 }
 
+/* two consecutive values (already multiplied by the plane scale) -> 4 bytes of
+   each plane; the packed conversions round like rb_f2h */
+__device__ __forceinline__ void
+rb_split2(float a0, float a1, uint32_t &hi, uint32_t &lo)
+{
+  float f0, f1;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(a1), "f"(a0));
+  asm("{\n\t"
+      ".reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t"
+      "}" : "=f"(f0), "=f"(f1) : "r"(hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;"
+      : "=r"(lo) : "f"((a1 - f1) * RB_LO_GAIN), "f"((a0 - f0) * RB_LO_GAIN));
+}
+
 /* four consecutive values -> 8 bytes of each plane */
 __device__ __forceinline__ void
 rb_split4(float4 a, float scale, uint2 &hi, uint2 &lo)
 {
-  rb_h16 h0, h1, h2, h3, l0, l1, l2, l3;
-  rb_split_f16(a.x * scale, h0, l0);
-  rb_split_f16(a.y * scale, h1, l1);
-  rb_split_f16(a.z * scale, h2, l2);
-  rb_split_f16(a.w * scale, h3, l3);
-  hi = make_uint2(rb_pack2(h0, h1), rb_pack2(h2, h3));
-  lo = make_uint2(rb_pack2(l0, l1), rb_pack2(l2, l3));
+  rb_split2(a.x * scale, a.y * scale, hi.x, lo.x);
+  rb_split2(a.z * scale, a.w * scale, hi.y, lo.y);
 }
 
 #endif

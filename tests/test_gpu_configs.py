@@ -445,3 +445,207 @@ def test_f4_rnnca_frame_on_device(gpu_lib, ref, port, edges, len_pos, cells_kern
         frame = want  # both sides continue from the reference's frame
     assert n_off <= 0.01 * 3 * 3 * n, n_off
     lib.rnn_batch_delete(batch)
+
+
+def _rnnca_pattern():
+    # 17 luma and 8 chroma neighbours like the default pattern (gstrnnca.h:49-51)
+    off_y = np.array([(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)
+                      if abs(dx) + abs(dy) <= 2 or (abs(dx), abs(dy)) == (2, 2)][:17],
+                     dtype=np.int32)
+    off_c = np.array([(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)],
+                     dtype=np.int32)
+    return off_y, off_c
+
+
+def _rnnca_cpu_frame(L, port, clones, frame, W, Hh, off_y, off_c, len_pos, edges, n_in):
+    """fill_frame (gstrnnca.c:805-830) on the CPU with library L's rnn_opinion
+    and fast_sigmoid, the oracle's fill_net_inputs and UNIT_TO_BYTE."""
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    n = W * Hh
+    want = np.zeros(3 * n, dtype=np.uint8)
+    inputs = np.zeros(n_in, dtype=np.float32)
+    for cell in range(n):
+        port.oracle_rnnca_fill_inputs(frame.ctypes.data_as(u8p), W, Hh, cell % W, cell // W,
+                                      off_y.ctypes.data_as(ip), len(off_y),
+                                      off_c.ctypes.data_as(ip), len(off_c), len_pos, edges,
+                                      fptr(inputs))
+        out = arr(L.rnn_opinion(clones[cell], fptr(inputs), 0.0), 3)
+        for i in range(3):
+            want[i * n + cell] = port.oracle_rnnca_unit_to_byte(L.ref_fast_sigmoid(float(out[i])))
+    return want
+
+
+@pytest.mark.parametrize("kernel", ["tensor", "fma"])
+@pytest.mark.parametrize("edges,len_pos,gain", [(1, 2, 1.0), (0, 3, 1.0), (0, 2, 12.0)])
+def test_config5_device_cells_frame(gpu_lib, ref, ref_fast, port, edges, len_pos, gain, kernel,
+                                    monkeypatch):
+    """BASELINE configs[4] at its own shape: RnnCells (hidden state of every
+    cell on the device, no host clone per pixel) through rnn_cells_rnnca_frame
+    against fill_frame replayed on the CPU with BOTH builds of the reference.
+
+    The bytes are truncations of fast_sigmoid(y) * 255.9 (gstrnnca.c:642), so
+    a last-place difference in y moves a byte across an integer boundary, by
+    one, never further.  The reference does that to itself: its shipped build
+    (-Ofast -ffast-math -DVECTOR, what `ref_fast` is) and its IEEE build differ
+    in some bytes by one; the tolerance here is that same +-1, and no more
+    differing bytes than three times what the two reference builds show
+    between themselves (plus a handful for tiny frames).
+
+    gain 12 makes the hidden sums large enough for maybe_scale_inputs
+    (recur-nn.c:68-81) to engage in every cell."""
+    lib = gpu_lib
+    monkeypatch.setenv("RECUR_B200_CELLS_FMA", "1" if kernel == "fma" else "0")
+    W, Hh = 24, 17      # 408 cells: three full tiles of 128 and a ragged one
+    n = W * Hh
+    off_y, off_c = _rnnca_pattern()
+    len_y, len_c = len(off_y), len(off_c)
+    n_in = len_y + 2 * len_c + len_pos
+    shape = dict(input_size=n_in, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    a = make_net(lib, **shape)
+    nets, clones = {}, {}
+    for name, L in (("strict", ref), ("fast", ref_fast)):
+        nets[name] = make_net(L, **shape)
+        clones[name] = [L.rnn_clone(nets[name], fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+    for net in [a] + list(nets.values()):
+        ih, ho = weights(net)
+        ih *= gain
+    cells = lib.rnn_cells_new(a, W, Hh)
+    assert cells
+    rs = np.random.RandomState(9)
+    frame = rs.randint(0, 256, size=3 * n).astype(np.uint8)
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    ours_off = builds_off = 0
+    clipped = 0
+    for f in range(4 if gain > 1 else 3):
+        got = np.zeros(3 * n, dtype=np.uint8)
+        lib.rnn_cells_rnnca_frame(cells, frame.ctypes.data_as(u8p), got.ctypes.data_as(u8p),
+                                  off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                                  len_pos, edges)
+        want = {k: _rnnca_cpu_frame(L, port, clones[k], frame, W, Hh, off_y, off_c, len_pos, edges,
+                                    n_in) for k, L in (("strict", ref), ("fast", ref_fast))}
+        d_ours = np.abs(got.astype(np.int32) - want["strict"].astype(np.int32))
+        d_builds = np.abs(want["fast"].astype(np.int32) - want["strict"].astype(np.int32))
+        assert d_ours.max() <= 1, (f, d_ours.max())
+        assert d_builds.max() <= 1, (f, d_builds.max())
+        ours_off += int((d_ours != 0).sum())
+        builds_off += int((d_builds != 0).sum())
+        # hidden state of a few cells against the strict clones
+        for cell in (0, 1, W + 3, n - 1):
+            h = np.zeros(52, dtype=np.float32)
+            lib.rnn_cells_get_hidden(cells, cell, fptr(h))
+            c = clones["strict"][cell].contents
+            assert rel_err(h, arr(c.hidden_layer, c.h_size)) < TOL, (f, cell)
+            x = arr(c.input_layer, c.i_size)
+            clipped += bool(abs(x[0] - 1.0) > 1e-6)
+        frame = want["strict"]
+    assert ours_off <= 3 * builds_off + 12, (ours_off, builds_off)
+    if gain > 1:
+        assert clipped >= 4, clipped
+    # rnn_cells_forget = fresh clones; rnn_cells_rnnca_run = the same frames chained
+    lib.rnn_cells_forget(cells)
+    start = rs.randint(0, 256, size=3 * n).astype(np.uint8)
+    step = start.copy()
+    for f in range(3):
+        nxt = np.zeros_like(step)
+        lib.rnn_cells_rnnca_frame(cells, step.ctypes.data_as(u8p), nxt.ctypes.data_as(u8p),
+                                  off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                                  len_pos, edges)
+        step = nxt
+    lib.rnn_cells_forget(cells)
+    ran = np.zeros_like(step)
+    lib.rnn_cells_rnnca_run(cells, start.ctypes.data_as(u8p), 3, ran.ctypes.data_as(u8p),
+                            off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                            len_pos, edges)
+    assert np.array_equal(ran, step)
+    lib.rnn_cells_delete(cells)
+
+
+def test_config5_rnnca_trainer_step(gpu_lib, ref, port):
+    """maybe_learn / train_net (gstrnnca.c:693-733) with the element's 200
+    trainers (gstrnnca.h:36): clear the deltas; every trainer gathers its
+    neighbourhood from the previous frame, runs forward (no rnn_bptt_advance:
+    the element never calls it, the walk sees one live step and an empty
+    ring), takes slope * (target - sigmoid) as the error and accumulates its
+    deltas; then the weighted-momentum update with the soft start and
+    rnn_condition_net.  On the device: the same calls as batch calls."""
+    lib = gpu_lib
+    W, Hh, n_tr, frames = 48, 32, 200, 12
+    off_y, off_c = _rnnca_pattern()
+    len_y, len_c, len_pos = len(off_y), len(off_c), 2
+    n_in = len_y + 2 * len_c + len_pos
+    flags = abi.RNN_NET_FLAG_STANDARD | abi.RNN_COND_USE_SCALE | abi.RNN_NET_FLAG_LOG_WEIGHT_SUM
+    shape = dict(input_size=n_in, hidden=51, output=3, depth=10, seed=11, lr=3e-3, momentum=0.5,
+                 flags=flags)
+    rs = np.random.RandomState(21)
+    pos = np.stack([rs.randint(2, W - 2, size=n_tr), rs.randint(2, Hh - 2, size=n_tr)], axis=1)
+    yy, xx = np.mgrid[0:Hh, 0:W]
+    movie = []
+    for f in range(frames + 1):
+        planes = [127 + 120 * np.sin(0.3 * xx + 0.2 * f + p) * np.cos(0.25 * yy - 0.1 * f * p)
+                  for p in range(3)]
+        movie.append(np.clip(np.stack(planes), 0, 255).astype(np.uint8).reshape(-1))
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    plane = W * Hh
+    soft_start = 2000.0
+
+    def gather(prev):
+        x = np.zeros((n_tr, n_in), dtype=np.float32)
+        for t in range(n_tr):
+            port.oracle_rnnca_fill_inputs(prev.ctypes.data_as(u8p), W, Hh, int(pos[t, 0]),
+                                          int(pos[t, 1]), off_y.ctypes.data_as(ip), len_y,
+                                          off_c.ctypes.data_as(ip), len_c, len_pos, 1, fptr(x[t]))
+        return x
+
+    def errors(answers, now):
+        err = np.zeros((n_tr, 4), dtype=np.float32)
+        for t in range(n_tr):
+            o = int(pos[t, 1]) * W + int(pos[t, 0])
+            for i in range(3):
+                a_ = np.float32(ref.ref_fast_sigmoid(float(answers[t, i])))
+                target = np.float32(now[o + plane * i]) * np.float32(1.0 / 255.0)
+                err[t, i] = a_ * (np.float32(1.0) - a_) * (target - a_)
+        return err
+
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    rn = ref.rnn_new_training_set(r, n_tr)
+    an = lib.rnn_new_training_set(a, n_tr)
+    batch = lib.rnn_batch_new(an, n_tr)
+    for f in range(frames):
+        prev, now = movie[f], movie[f + 1]
+        x = gather(prev)
+        # the reference, trainer by trainer
+        ref.rnn_bptt_clear_deltas(r)
+        answers = np.zeros((n_tr, 3), dtype=np.float32)
+        for t in range(n_tr):
+            c = rn[t].contents
+            arr(c.real_inputs, n_in)[:] = x[t]
+            answers[t] = arr(ref.rnn_opinion(rn[t], None, c.presynaptic_noise), 3)
+        err_r = errors(answers, now)
+        for t in range(n_tr):
+            c = rn[t].contents
+            arr(c.bptt.contents.o_error, c.o_size)[:] = err_r[t, :c.o_size]
+            ref.rnn_bptt_calc_deltas(rn[t], 1, None)
+        m = ref.rnn_calculate_momentum_soft_start(float(r.contents.generation),
+                                                  r.contents.bptt.contents.momentum, soft_start)
+        ref.rnn_apply_learning(r, abi.RNN_MOMENTUM_WEIGHTED, m)
+        ref.rnn_condition_net(r)
+        # the device, as batch calls
+        lib.rnn_bptt_clear_deltas(a)
+        lib.rnn_batch_set_inputs(batch, fptr(x))
+        lib.rnn_batch_opinion(batch, 0.0)
+        outs = np.zeros((n_tr, 3), dtype=np.float32)
+        lib.rnn_batch_get_outputs(batch, fptr(outs))
+        assert rel_err(outs, answers) < TOL, f
+        err_a = np.ascontiguousarray(errors(outs, now)[:, :3])   # n x output_size
+        lib.rnn_batch_set_errors(batch, fptr(err_a))
+        lib.rnn_batch_calc_deltas(batch, 1)
+        m = lib.rnn_calculate_momentum_soft_start(float(a.contents.generation),
+                                                  a.contents.bptt.contents.momentum, soft_start)
+        lib.rnn_apply_learning(a, abi.RNN_MOMENTUM_WEIGHTED, m)
+        lib.rnn_condition_net(a)
+        for p, q in zip(weights(a), weights(r)):
+            assert rel_err(p, q) < TOL, f
+        assert a.contents.generation == r.contents.generation
+    lib.rnn_batch_delete(batch)
