@@ -48,6 +48,15 @@ cdiv(int a, int b)
   return (a + b - 1) / b;
 }
 
+static float
+rb_half_to_float(rb_h16 h)
+{
+  const int sign = h >> 15, e = (h >> 10) & 31, m = h & 1023;
+  float v = e == 0 ? ldexpf((float)m, -24) : e == 31 ? (m ? NAN : INFINITY)
+      : ldexpf((float)(m | 1024), e - 25);
+  return sign ? -v : v;
+}
+
 /* ======================================================================== */
 /* the FP32 frame (cross-check)                                               */
 
@@ -209,54 +218,106 @@ k_cells_frame(CellsArgs a)
 /* ======================================================================== */
 /* the tensor-core frame                                                      */
 
-#define CT_NT 128                    /* threads = cells per tile = MMA rows */
+#define CT_NT 128                    /* cells per tile = MMA rows */
 #define CT_BN 64                     /* hidden units 1..64 = MMA columns */
 #define CT_A_CHUNK (CT_NT * 128)     /* 64 halves of K for 128 rows: 16 KB */
 #define CT_B_CHUNK (CT_BN * 128)     /* 64 halves of K for 64 units: 8 KB */
-#define CT_MAX_CHUNKS 2              /* i_size <= 128 */
-#define CT_X_TOP 8192.0f             /* rows with larger hidden values are pre-scaled */
-
-/* per gathered input j: its neighbour offset, its plane, and for cells whose
-   whole neighbourhood is inside the frame the flat distance to the byte */
-__constant__ int cells_dx[CELLS_XIN], cells_dy[CELLS_XIN], cells_plane[CELLS_XIN],
-    cells_delta[CELLS_XIN];
-
-struct CellsTcArgs {
-  CellsArgs c;
-  const rb_h16 *w_image; /* [hi | lo][chunk][64 units][64 halves], swizzled as in shared memory */
-  float *rowmax;         /* [n] largest hidden value of each cell */
-  int chunks, ksteps, reach, tiles; /* ksteps: bit s = K steps 16 s .. 16 s + 15 hold inputs */
-};
+#define CT_X_TOP 8192.0f             /* rows with larger hidden values are stored scaled down */
+#define CT_TILE_BYTES (2 * CT_A_CHUNK) /* a tile's hidden state in HBM: hi plane, lo plane */
 
 /* K, the inner dimension of the product, is laid out for the kernel's
-   convenience rather than in the order of the net's input vector: [0, 64) the
-   hidden units (the bias first), [64, 104) the gathered bytes, [104, 107) the
-   position terms, zeros elsewhere - every section starts at a place known at
-   compile time, so a thread holds its whole input vector in registers.  The
-   sections are in the net's order, so sums over K ascend like the reference's.
-   This maps a K index to the net's input row, -1 for padding. */
+   convenience rather than in the order of the net's input vector:
+     [0, 63)    hidden units 1..63 (unit u at u - 1)
+     63         the bias (input 0, always 1)
+     [64, 104)  the gathered bytes
+     [104, 107) the position terms
+   and zeros elsewhere.  Every section starts at a place known at compile time;
+   the first 64 are exactly what a cell carries from frame to frame.  This maps
+   a K index to the net's input row, -1 for padding. */
 #define CT_K_BYTES 64
 #define CT_K_POS 104
 #define CT_K_END 112
 __host__ __device__ __forceinline__ int
 cells_k_row(int k, int H, int n_in, int n_pos)
 {
-  if (k < CT_K_BYTES)
-    return k < H ? k : -1;
+  if (k < CT_K_BYTES - 1)
+    return k + 1 < H ? k + 1 : -1;
+  if (k == CT_K_BYTES - 1)
+    return 0;
   if (k < CT_K_POS)
     return k - CT_K_BYTES < n_in ? H + k - CT_K_BYTES : -1;
   return k - CT_K_POS < n_pos ? H + n_in + k - CT_K_POS : -1;
 }
 
-/* The B operand as the kernel's shared memory holds it: unit u + 1's weights
-   along K, 128-byte rows, the 16-byte pieces of a row XORed with the row
-   number (SWIZZLE_128B), as FP16 hi/lo planes of 64 w. */
+/* per gathered input j: its neighbour offset, its plane, and for cells whose
+   whole neighbourhood is inside the frame the flat distance to the byte */
+__constant__ int cells_dx[CT_K_END - CT_K_BYTES], cells_dy[CT_K_END - CT_K_BYTES],
+    cells_plane[CT_K_END - CT_K_BYTES], cells_delta[CT_K_END - CT_K_BYTES];
+
+/* The hidden state of the cells lives in HBM as the tensor cores read it: per
+   tile of 128 cells the first K chunk of the A operand, FP16 hi plane then lo
+   plane, 128-byte rows with their 16-byte pieces XORed with the row number
+   (SWIZZLE_128B) - so a tile's state is two bulk copies into shared memory
+   going in and two going out, and no thread touches it in between.  Beside it
+   per cell: the sum of its hidden values (for the input soft clip) and their
+   largest (rows that would not fit FP16 are stored divided by a power of two). */
+struct CellsAux {
+  float hsum, hmax;
+};
+
+struct CellsTcArgs {
+  CellsArgs c;
+  const rb_h16 *w_image; /* [hi | lo][chunk][64 units][64 halves], swizzled as in shared memory */
+  unsigned char *planes; /* [tiles][hi 16 KB | lo 16 KB] */
+  CellsAux *aux;         /* [tiles * 128] */
+  int ksteps, reach, tiles; /* ksteps: bit s = K steps 16 s .. 16 s + 15 hold inputs */
+};
+
+/* the power of two a row with largest value m is stored divided by, and back */
+__host__ __device__ __forceinline__ void
+cells_row_scale(float m, float &pre, float &post)
+{
+  pre = post = 1.0f;
+  if (m > CT_X_TOP) {
+    union { float f; int i; } u;
+    u.f = m;
+    const int e = ((u.i >> 23) & 0xff) - 127;
+    u.i = (127 + 13 - e) << 23;
+    pre = u.f;
+    u.i = (127 - 13 + e) << 23;
+    post = u.f;
+  }
+}
+
+/* fresh clones: hidden state zero, the bias one */
+__global__ void
+k_cells_reset(unsigned char *planes, CellsAux *aux, int tiles)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; /* one 16-byte piece each */
+  const size_t pieces = (size_t)tiles * CT_TILE_BYTES / 16;
+  if (i < pieces) {
+    const int in_tile = (int)(i % (CT_TILE_BYTES / 16));
+    const int plane = in_tile / (CT_A_CHUNK / 16), r = (in_tile % (CT_A_CHUNK / 16)) >> 3;
+    const int piece = in_tile & 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (plane == 0 && (piece ^ (r & 7)) == 7)
+      v.w = 0x3C000000u; /* K 63 = 1.0 in the hi plane */
+    ((uint4 *)planes)[i] = v;
+  }
+  if (i < (size_t)tiles * CT_NT) {
+    aux[i].hsum = 0.0f;
+    aux[i].hmax = 0.0f;
+  }
+}
+
+/* The B operand as the kernel's shared memory holds it: a unit's weights
+   along K, 128-byte rows, SWIZZLE_128B, as FP16 hi/lo planes of 64 w. */
 __global__ void
 k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, int H, int O,
-    int n_in, int n_pos, int chunks, rb_h16 *image, float *wo)
+    int n_in, int n_pos, rb_h16 *image, float *wo)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < CT_BN * chunks * 8) {
+  if (t < CT_BN * 2 * 8) {
     const int u = t % CT_BN, g = t / CT_BN; /* 8 inputs k = 8g .. 8g + 7 of unit u + 1 */
     float v[8];
 #pragma unroll
@@ -268,7 +329,7 @@ k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, in
     rb_split4(make_float4(v[0], v[1], v[2], v[3]), (float)RB_W_SCALE, h0, l0);
     rb_split4(make_float4(v[4], v[5], v[6], v[7]), (float)RB_W_SCALE, h1, l1);
     const size_t at = (size_t)(g >> 3) * CT_B_CHUNK + (size_t)u * 128 + (((g & 7) ^ (u & 7)) << 4);
-    char *hi = (char *)image, *lo = (char *)image + (size_t)chunks * CT_B_CHUNK;
+    char *hi = (char *)image, *lo = (char *)image + 2 * CT_B_CHUNK;
     *(uint4 *)(hi + at) = make_uint4(h0.x, h0.y, h1.x, h1.y);
     *(uint4 *)(lo + at) = make_uint4(l0.x, l0.y, l1.x, l1.y);
   }
@@ -278,113 +339,125 @@ k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, in
   }
 }
 
-/* eight consecutive inputs of this thread's cell -> 16 bytes of each plane, at
-   K = 8 g of row r of the A operand (128-byte rows, SWIZZLE_128B) */
+/* eight consecutive inputs of a row -> 16 bytes of each plane, at K = 8 g of
+   row r of an operand chunk (128-byte rows, SWIZZLE_128B) */
 __device__ __forceinline__ void
-cells_put8(unsigned char *a_hi, unsigned char *a_lo, int g, int r, const float *v, float pre)
+cells_put8(unsigned char *hi, unsigned char *lo, int g, int r, const float *v, float pre)
 {
   uint2 h0, l0, h1, l1;
   rb_split4(make_float4(v[0], v[1], v[2], v[3]), pre, h0, l0);
   rb_split4(make_float4(v[4], v[5], v[6], v[7]), pre, h1, l1);
-  const uint32_t at = (uint32_t)(g >> 3) * CT_A_CHUNK + (uint32_t)r * 128 +
-      (((g & 7) ^ (r & 7)) << 4);
-  *(uint4 *)(a_hi + at) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-  *(uint4 *)(a_lo + at) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+  const uint32_t at = (uint32_t)r * 128 + (((g & 7) ^ (r & 7)) << 4);
+  *(uint4 *)(hi + at) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+  *(uint4 *)(lo + at) = make_uint4(l0.x, l0.y, l1.x, l1.y);
 }
 
-/* 256 threads, two per cell of the tile: thread r and thread 128 + r share row r.
-   Going in, the first builds the hidden-state half of the row and the second
-   the gathered half; coming out, the first takes hidden units 1..32 and the
-   second 33..64 (warps w and w + 4 reach the same 32 lanes of tensor memory).
-   Two CTAs per SM: 16 warps, 128 registers each. */
+__device__ __forceinline__ void
+bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void
+bulk_s2g(void *dst, const void *src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+      ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+/* A CTA per SM, four kinds of warp, two tiles in flight:
+ *
+ *   warp 17     one thread fetches the tile's hidden state, two bulk copies
+ *               from HBM into the first K chunk of A[buf];
+ *   warps 0-7   gather: two threads per cell read its neighbourhood's bytes and
+ *               write them, with the position terms, as the second K chunk;
+ *   warp 16     one thread issues the tile's MMAs into TMEM[buf];
+ *   warps 8-15  drain: two threads per row (hidden units 1..32 and 33..64;
+ *               warps w and w + 4 reach the same 32 TMEM lanes): soft clip,
+ *               activation, output layer, sigmoid, bytes; the new state goes
+ *               back to HBM as planes through a staging tile and bulk copies.
+ *
+ * While the drain warps finish tile i, the tensor core does tile i + 1 and
+ * the copies and the gather for tile i + 2 are under way. */
+#define CW_GATHER 256
+#define CW_GATHER_SLOTS ((CT_K_END - CT_K_BYTES) / 2) /* K slots a gather thread fills: 24 */
+#define CW_DRAIN 256
+#define CW_MMA_THREAD (CW_GATHER + CW_DRAIN)
+#define CW_TMA_THREAD (CW_GATHER + CW_DRAIN + 32)
+#define CW_THREADS (CW_GATHER + CW_DRAIN + 64)
+#define CW_A_BUF (4 * CT_A_CHUNK) /* one tile's operand: hi chunks 0, 1, lo chunks 0, 1 */
+#define CW_SMEM (2 * CW_A_BUF + 4 * CT_B_CHUNK + CT_TILE_BYTES + 1024)
+
 template <int ACT>
-__global__ void __launch_bounds__(2 * CT_NT, 2)
+__global__ void __launch_bounds__(CW_THREADS, 1)
 k_cells_frame_tc(CellsTcArgs t)
 {
   extern __shared__ __align__(1024) unsigned char ct_smem[];
-  __shared__ __align__(8) uint64_t w_bar, mma_bar;
+  __shared__ __align__(8) uint64_t w_bar, h_full[2], a_full[2], a_empty[2], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[2][CT_NT];
-  __shared__ float4 s_y[2][CT_NT];
+  __shared__ float s_sum[2][2][CT_NT]; /* [buf][gather role][row]: halves of the soft clip's sum */
+  __shared__ float s_post[2][CT_NT];  /* [buf][row]: what the stored row must be multiplied by */
+  __shared__ float4 s_y[2][2][CT_NT]; /* [buf][drain role][row]: halves of the outputs, max */
+  __shared__ float s_h[2][2][CT_NT];  /* [buf][drain role][row]: halves of the new hidden sum */
   const CellsArgs &a = t.c;
-  /* shared memory: A hi [chunks][16 KB], A lo, B hi [chunks][8 KB], B lo */
+  /* A[buf]: hi chunk 0 (state), hi chunk 1 (gathered), lo chunk 0, lo chunk 1 */
   unsigned char *base = (unsigned char *)(((uintptr_t)ct_smem + 1023) & ~(uintptr_t)1023);
-  unsigned char *a_hi = base, *a_lo = base + t.chunks * CT_A_CHUNK;
-  unsigned char *b_hi = base + 2 * t.chunks * CT_A_CHUNK, *b_lo = b_hi + t.chunks * CT_B_CHUNK;
-  const int tid = threadIdx.x, r = tid & (CT_NT - 1), role = tid >> 7, warp = tid >> 5;
+  unsigned char *b_hi = base + 2 * CW_A_BUF, *b_lo = b_hi + 2 * CT_B_CHUNK;
+  unsigned char *stage = b_lo + 2 * CT_B_CHUNK; /* the new state of a tile on its way out */
+  const int tid = threadIdx.x, warp = tid >> 5;
 
   if (tid == 0) {
     mbar_init(&w_bar, 1);
-    mbar_init(&mma_bar, 1);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&h_full[i], 1);
+      mbar_init(&a_full[i], CW_GATHER);
+      mbar_init(&a_empty[i], 1);
+      mbar_init(&t_full[i], 1);
+      mbar_init(&t_empty[i], CW_DRAIN);
+    }
     fence_barrier_init();
-    const uint32_t bytes = 2u * t.chunks * CT_B_CHUNK;
-    mbar_expect_tx(&w_bar, bytes);
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(smem_u32(b_hi)), "l"(t.w_image), "r"(bytes), "r"(smem_u32(&w_bar)) : "memory");
+    mbar_expect_tx(&w_bar, 4 * CT_B_CHUNK);
+    bulk_g2s(b_hi, t.w_image, 4 * CT_B_CHUNK, &w_bar);
   }
   if (warp == 0)
-    tmem_alloc(&tmem_slot, 2 * CT_BN);
+    tmem_alloc(&tmem_slot, 4 * CT_BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t idesc = umma_idesc_f16(CT_NT, CT_BN, 0, 0);
-
-  const int hs1 = a.hs + 1;
-  const int n_in = a.len_y + 2 * a.len_c;
   const int plane = a.width * a.height;
-  uint32_t phase = 0;
-  bool w_ready = false;
 
-  for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x) {
-    const bool live = tile * CT_NT + r < a.n;
-    const int cell = live ? tile * CT_NT + r : a.n - 1; /* the ragged end repeats the last cell */
-    /* rows whose hidden values would not fit FP16 go through the tensor cores
-       divided by a power of two, and their sums are multiplied back */
-    float pre = 1.0f, post = 1.0f;
-    {
-      const float m = t.rowmax[cell];
-      if (m > CT_X_TOP) {
-        const int e = ((__float_as_int(m) >> 23) & 0xff) - 127;
-        pre = __int_as_float((127 + 13 - e) << 23);
-        post = __int_as_float((127 - 13 + e) << 23);
-      }
-    }
-    /* a thread's half of the input vector goes into registers, every load
-       issued before any is used */
-    float part = 0.0f; /* ascending, as maybe_scale_inputs does (recur-nn.c:72-75) */
-    if (role == 0) {
-      const float *st = a.state + cell;
-      float hv[CT_K_BYTES];
-#pragma unroll
-      for (int k = 1; k < CT_K_BYTES; k++)
-        hv[k] = (k < hs1) ? st[(size_t)k * a.n] : 0.0f;
-      hv[0] = 1.0f;
-#pragma unroll
-      for (int k = 0; k < CT_K_BYTES; k++)
-        part += hv[k];
-#pragma unroll
-      for (int g = 0; g < CT_K_BYTES / 8; g++)
-        if (8 * g < ((a.H + 15) & ~15)) /* whole K steps: what the MMAs read must be written */
-          cells_put8(a_hi, a_lo, g, r, hv + 8 * g, pre);
-    }
-    else {
+  if (tid < CW_GATHER) {
+    /* ---- gather ------------------------------------------------------------ */
+    /* two threads per cell: K 64..87 (the first 24 bytes) and K 88..111 (the
+       other bytes and the position terms) */
+    const int r = tid & (CT_NT - 1), role = tid >> 7;
+    const int n_in = a.len_y + 2 * a.len_c;
+    const int j0 = role * CW_GATHER_SLOTS;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const bool live = tile * CT_NT + r < a.n;
+      const int cell = live ? tile * CT_NT + r : a.n - 1; /* the ragged end repeats a cell */
+      unsigned char *a_hi = base + buf * CW_A_BUF + CT_A_CHUNK, *a_lo = a_hi + 2 * CT_A_CHUNK;
+      const CellsAux ax = t.aux[tile * CT_NT + r];
       const int cx = cell % a.width, cy = cell / a.width;
       const bool interior = cx >= t.reach && cx < a.width - t.reach && cy >= t.reach &&
           cy < a.height - t.reach;
       const u8 *fr = a.frame + cell;
-      float bv[CT_K_END - CT_K_BYTES];
+      float bv[CW_GATHER_SLOTS];
       if (interior) {
 #pragma unroll
-        for (int j = 0; j < CT_K_POS - CT_K_BYTES; j++)
-          bv[j] = (j < n_in) ? fr[cells_delta[j]] * (1.0f / 255.0f) : 0.0f;
+        for (int q = 0; q < CW_GATHER_SLOTS; q++)
+          bv[q] = (j0 + q < n_in) ? fr[cells_delta[j0 + q]] * (1.0f / 255.0f) : 0.0f;
       }
       else {
         /* get_offset_point (gstrnnca.c:644-667) at the frame's border */
 #pragma unroll
-        for (int j = 0; j < CT_K_POS - CT_K_BYTES; j++) {
+        for (int q = 0; q < CW_GATHER_SLOTS; q++) {
+          const int j = j0 + q;
           int x = cx + cells_dx[j], y = cy + cells_dy[j];
           if (a.edges) {
             y = max(0, min(a.height - 1, y));
@@ -394,143 +467,229 @@ k_cells_frame_tc(CellsTcArgs t)
             y += (y < 0) ? a.height : (y >= a.height) ? -a.height : 0;
             x += (x < 0) ? a.width : (x >= a.width) ? -a.width : 0;
           }
-          bv[j] = (j < n_in) ? a.frame[cells_plane[j] * plane + y * a.width + x] * (1.0f / 255.0f)
-                             : 0.0f;
+          bv[q] = (j0 + q < n_in)
+              ? a.frame[cells_plane[j] * plane + y * a.width + x] * (1.0f / 255.0f) : 0.0f;
         }
       }
-      /* the position terms (gstrnnca.c:685-690) */
-      const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
-#pragma unroll
-      for (int q = 0; q < 8; q++)
-        bv[CT_K_POS - CT_K_BYTES + q] = 0.0f;
-      if (a.len_pos > 0)
-        bv[CT_K_POS - CT_K_BYTES] = xx;
-      if (a.len_pos > 1)
-        bv[CT_K_POS - CT_K_BYTES + 1] = yy;
-      if (a.len_pos > 2)
-        bv[CT_K_POS - CT_K_BYTES + 2] = (float)(0.5 - (((double)yy - 0.5) * ((double)yy - 0.5) +
-            ((double)xx - 0.5) * ((double)xx - 0.5)));
-#pragma unroll
-      for (int j = 0; j < CT_K_END - CT_K_BYTES; j++)
-        part += bv[j];
-#pragma unroll
-      for (int g = 0; g < (CT_K_END - CT_K_BYTES) / 8; g++)
-        cells_put8(a_hi, a_lo, CT_K_BYTES / 8 + g, r, bv + 8 * g, pre);
-    }
-    s_sum[role][r] = part;
-
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      if (!w_ready) {
-        mbar_wait(&w_bar, 0);
-        w_ready = true;
+      /* the sum maybe_scale_inputs takes (recur-nn.c:72-75): bias, hidden, inputs */
+      float sum = 0.0f;
+      if (role == 0)
+        sum = 1.0f + ax.hsum;
+      else if (a.len_pos > 0) {
+        /* the position terms (gstrnnca.c:685-690) */
+        const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+        bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS] = xx;
+        if (a.len_pos > 1)
+          bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS + 1] = yy;
+        if (a.len_pos > 2)
+          bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS + 2] = (float)(0.5 -
+              (((double)yy - 0.5) * ((double)yy - 0.5) + ((double)xx - 0.5) * ((double)xx - 0.5)));
       }
+      float pre, post;
+      cells_row_scale(ax.hmax, pre, post);
+#pragma unroll
+      for (int q = 0; q < CW_GATHER_SLOTS; q++)
+        sum += bv[q];
+      if (it >= 2) { /* the MMAs of two tiles ago have read A[buf], its drain s_sum[buf] */
+        mbar_wait(&a_empty[buf], ((it >> 1) - 1) & 1);
+        mbar_wait(&t_empty[buf], ((it >> 1) - 1) & 1);
+      }
+#pragma unroll
+      for (int g = 0; g < CW_GATHER_SLOTS / 8; g++)
+        cells_put8(a_hi, a_lo, role * (CW_GATHER_SLOTS / 8) + g, r, bv + 8 * g, pre);
+      s_sum[buf][role][r] = sum;
+      if (role == 0)
+        s_post[buf][r] = post;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&a_full[buf]);
+    }
+  }
+  else if (tid < CW_GATHER + CW_DRAIN) {
+    /* ---- drain ------------------------------------------------------------- */
+    const int dt = tid - CW_GATHER, r = dt & (CT_NT - 1), role = dt >> 7;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float softclip = a.I * INPUT_MEAN_SOFT_TOP;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      const bool live = tile * CT_NT + r < a.n;
+      const int cell = live ? tile * CT_NT + r : a.n - 1;
+      mbar_wait(&a_full[buf], par); /* the gather's sums are in s_sum */
+      /* maybe_scale_inputs (recur-nn.c:68-81): every input times `scale`, so every sum too */
+      const float sum = s_sum[buf][0][r] + s_sum[buf][1][r];
+      const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
+      const float unscale = scale * s_post[buf][r] * (1.0f / RB_W_SCALE);
+      float x[32];
+      mbar_wait(&t_full[buf], par);
       tc_fence_after();
+      {
+        float cr[32];
+        tmem_ld32_nowait(tmem_lane + buf * 2 * CT_BN + role * 32, x);
+        tmem_ld32_nowait(tmem_lane + buf * 2 * CT_BN + CT_BN + role * 32, cr);
+        tmem_wait_ld();
+        tc_fence_before();
+        mbar_arrive(&t_empty[buf]); /* the sums are in registers: TMEM[buf] may be overwritten */
+#pragma unroll
+        for (int q = 0; q < 32; q++)
+          x[q] = (x[q] + cr[q] * (1.0f / RB_LO_GAIN)) * unscale;
+      }
+      /* this thread's half of the row: activation (recur-nn.c:121-148), its
+         share of the three outputs, of the new row's sum and maximum */
+      float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, biggest = 0.0f, hsum = 0.0f;
+      if (role == 0) {
+        const float4 wb = cells_wo[0]; /* hidden unit 0 is 1 */
+        y0 = wb.x;
+        y1 = wb.y;
+        y2 = wb.z;
+      }
+#pragma unroll
+      for (int q = 0; q < 32; q++) {
+        const int unit = role * 32 + q + 1;
+        float v = x[q];
+        if (ACT == RNN_RESQRT)
+          v = (v > 0.0f) ? sqrtf(v + 1.0f) - 1.0f : 0.0f;
+        else {
+          if (ACT == RNN_RECLIP20)
+            v = fminf(v, 20.0f);
+          v = fmaxf(v, 0.0f);
+        }
+        if (unit <= a.hs) {
+          biggest = fmaxf(biggest, v);
+          hsum += v;
+          const float4 wo = cells_wo[unit];
+          y0 = fmaf(v, wo.x, y0);
+          y1 = fmaf(v, wo.y, y1);
+          y2 = fmaf(v, wo.z, y2);
+        }
+        else
+          v = 0.0f; /* pad units */
+        x[q] = v;
+      }
+      if (role == 1)
+        x[31] = 1.0f; /* K 63 is the bias */
+      s_y[buf][role][r] = make_float4(y0, y1, y2, biggest);
+      s_h[buf][role][r] = hsum;
+      if (dt == 0) /* the staging tile's last journey to HBM has read it */
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(CW_DRAIN) : "memory");
+      const float4 other = s_y[buf][role ^ 1][r];
+      const float hmax = fmaxf(biggest, other.w);
+      float pre, post;
+      cells_row_scale(hmax, pre, post);
+#pragma unroll
+      for (int g = 0; g < 4; g++)
+        cells_put8(stage, stage + CT_A_CHUNK, role * 4 + g, r, x + 8 * g, pre);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(CW_DRAIN) : "memory");
+      if (dt == 0) {
+        bulk_s2g(t.planes + (size_t)tile * CT_TILE_BYTES, stage, CT_TILE_BYTES);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642) */
+      if (role == 0) {
+        CellsAux ax;
+        ax.hsum = s_h[buf][0][r] + s_h[buf][1][r];
+        ax.hmax = hmax;
+        t.aux[tile * CT_NT + r] = ax;
+        if (live)
+          a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(y0 + other.x))) * 255.9f);
+      }
+      else if (live) {
+        a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(other.y + y1))) * 255.9f);
+        a.frame_out[2 * plane + cell] =
+            (u8)(1.0f / (1.0f + fast_expf_dev(-(other.z + y2))) * 255.9f);
+      }
+    }
+    if (dt == 0)
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  else if (tid == CW_MMA_THREAD) {
+    /* ---- the MMA thread ---------------------------------------------------- */
+    const uint32_t idesc = umma_idesc_f16(CT_NT, CT_BN, 0, 0);
+    mbar_wait(&w_bar, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const uint32_t par = (it >> 1) & 1;
+      mbar_wait(&h_full[buf], par);
+      mbar_wait(&a_full[buf], par);
+      if (it >= 2)
+        mbar_wait(&t_empty[buf], par ^ 1);
+      tc_fence_after();
+      const uint32_t a_hi = smem_u32(base + buf * CW_A_BUF);
+      const uint32_t a_lo = a_hi + 2 * CT_A_CHUNK;
+      const uint32_t acc = tmem_base + buf * 2 * CT_BN;
       bool first = true;
       for (int ks = 0; ks < CT_K_END / 16; ks++) {
         if (!((t.ksteps >> ks) & 1))
           continue;
         const uint32_t ao = (uint32_t)(ks >> 2) * CT_A_CHUNK + (ks & 3) * 32;
         const uint32_t bo = (uint32_t)(ks >> 2) * CT_B_CHUNK + (ks & 3) * 32;
-        const uint64_t dah = umma_desc(smem_u32(a_hi) + ao, 16, 1024);
-        const uint64_t dal = umma_desc(smem_u32(a_lo) + ao, 16, 1024);
+        const uint64_t dah = umma_desc(a_hi + ao, 16, 1024);
+        const uint64_t dal = umma_desc(a_lo + ao, 16, 1024);
         const uint64_t dbh = umma_desc(smem_u32(b_hi) + bo, 16, 1024);
         const uint64_t dbl = umma_desc(smem_u32(b_lo) + bo, 16, 1024);
-        umma_f16(tmem_base, dah, dbh, idesc, !first);
-        umma_f16(tmem_base + CT_BN, dah, dbl, idesc, !first);
-        umma_f16(tmem_base + CT_BN, dal, dbh, idesc, 1u);
+        umma_f16(acc, dah, dbh, idesc, !first);
+        umma_f16(acc + CT_BN, dah, dbl, idesc, !first);
+        umma_f16(acc + CT_BN, dal, dbh, idesc, 1u);
         first = false;
       }
-      umma_commit(&mma_bar);
+      umma_commit(&a_empty[buf]);
+      umma_commit(&t_full[buf]);
     }
-    /* maybe_scale_inputs (recur-nn.c:68-81): every input times `scale`, so every sum too */
-    const float sum = s_sum[0][r] + s_sum[1][r];
-    const float softclip = a.I * INPUT_MEAN_SOFT_TOP;
-    const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
-    const float unscale = scale * post * (1.0f / RB_W_SCALE);
-    mbar_wait(&mma_bar, phase);
-    phase ^= 1;
-    tc_fence_after();
-
-    /* this thread's half of the row of sums: activation (recur-nn.c:121-148),
-       the new state, its share of the three outputs */
-    float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, biggest = 0.0f;
-    float *sto = a.state + cell;
-    if (role == 0) {
-      const float4 wb = cells_wo[0]; /* hidden unit 0 is 1 */
-      y0 = wb.x;
-      y1 = wb.y;
-      y2 = wb.z;
-      if (live)
-        sto[0] = 1.0f;
-    }
-    if (role * 32 + 1 < a.H) {
-      float mn[32], cr[32];
-      tmem_ld32_nowait(tmem_lane + role * 32, mn);
-      tmem_ld32_nowait(tmem_lane + CT_BN + role * 32, cr);
-      tmem_wait_ld();
-#pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int unit = role * 32 + q + 1;
-        float x = (mn[q] + cr[q] * (1.0f / RB_LO_GAIN)) * unscale;
-        if (ACT == RNN_RESQRT)
-          x = (x > 0.0f) ? sqrtf(x + 1.0f) - 1.0f : 0.0f;
-        else {
-          if (ACT == RNN_RECLIP20)
-            x = fminf(x, 20.0f);
-          x = fmaxf(x, 0.0f);
-        }
-        if (unit < hs1) { /* the pad units after them stay zero (rnn_cells_new) */
-          if (live)
-            sto[(size_t)unit * a.n] = x;
-          biggest = fmaxf(biggest, x);
-          const float4 wo = cells_wo[unit];
-          y0 = fmaf(x, wo.x, y0);
-          y1 = fmaf(x, wo.y, y1);
-          y2 = fmaf(x, wo.z, y2);
-        }
-      }
-    }
-    s_y[role][r] = make_float4(y0, y1, y2, biggest);
-    tc_fence_before(); /* the next tile's MMAs overwrite TMEM after the next barrier */
-    __syncthreads();
-    const float4 other = s_y[role ^ 1][r];
-    if (live) {
-      /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642) */
-      if (role == 0) {
-        t.rowmax[cell] = fmaxf(biggest, other.w);
-        a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(y0 + other.x))) * 255.9f);
-      }
-      else {
-        a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(other.y + y1))) * 255.9f);
-        a.frame_out[2 * plane + cell] =
-            (u8)(1.0f / (1.0f + fast_expf_dev(-(other.z + y2))) * 255.9f);
-      }
+  }
+  else if (tid == CW_TMA_THREAD) {
+    /* ---- the state's way in ------------------------------------------------ */
+    int it = 0;
+    for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      if (it >= 2)
+        mbar_wait(&a_empty[buf], ((it >> 1) - 1) & 1);
+      unsigned char *a_hi = base + buf * CW_A_BUF;
+      const unsigned char *src = t.planes + (size_t)tile * CT_TILE_BYTES;
+      mbar_expect_tx(&h_full[buf], CT_TILE_BYTES);
+      bulk_g2s(a_hi, src, CT_A_CHUNK, &h_full[buf]);
+      bulk_g2s(a_hi + 2 * CT_A_CHUNK, src + CT_A_CHUNK, CT_A_CHUNK, &h_full[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * CT_BN);
+    tmem_dealloc(tmem_base, 4 * CT_BN);
   }
 }
 
 struct RnnCells {
   RecurNN *proto;
-  int width, height, n;
-  float *state;               /* device [h_size][n] */
+  int width, height, n, tiles;
+  unsigned char *planes;      /* device [tiles][32 KB]: the hidden state (see CellsTcArgs) */
+  CellsAux *aux;              /* device [tiles * 128] */
+  float *state;               /* device [h_size][n]: the FP32 cross-check kernel's state */
   u8 *frames;                 /* device: two frames of 3 n bytes, ping-pong */
   int *off_dev;
-  int off_ints;
   u8 *host;                   /* pinned staging, 3 n bytes */
   int cur;                    /* which of the two frames holds the newest picture */
   rb_h16 *w_image;            /* device: the weights as k_cells_frame_tc's B operand */
-  float *rowmax;              /* device [n]: largest hidden value of each cell */
   int reach;                  /* largest |dx|, |dy| of the neighbourhood */
+  int fma;                    /* this object runs the FP32 kernel (RECUR_B200_CELLS_FMA at creation) */
+  long frames_run;            /* since the last rnn_cells_forget */
 };
+
+static void
+cells_reset(RnnCells *c)
+{
+  if (c->fma)
+    cudaMemsetAsync(c->state, 0, (size_t)c->n * c->proto->h_size * sizeof(float), rb_stream);
+  else {
+    const size_t pieces = (size_t)c->tiles * CT_TILE_BYTES / 16;
+    k_cells_reset<<<(unsigned)((pieces + 255) / 256), 256, 0, rb_stream>>>(c->planes, c->aux,
+        c->tiles);
+    LAUNCH_CHECK("k_cells_reset");
+  }
+  c->frames_run = 0;
+}
 
 extern "C" RnnCells *
 rnn_cells_new(RecurNN *prototype, int width, int height)
@@ -552,17 +711,22 @@ rnn_cells_new(RecurNN *prototype, int width, int height)
   c->width = width;
   c->height = height;
   c->n = width * height;
+  c->tiles = cdiv(c->n, CT_NT);
+  const char *env = getenv("RECUR_B200_CELLS_FMA");
+  c->fma = (env && *env && *env != '0');
   size_t n = (size_t)c->n;
-  if (cudaMalloc((void **)&c->state, n * prototype->h_size * sizeof(float)) != cudaSuccess ||
+  cudaError_t e = c->fma
+      ? cudaMalloc((void **)&c->state, n * prototype->h_size * sizeof(float))
+      : cudaMalloc((void **)&c->planes, (size_t)c->tiles * CT_TILE_BYTES);
+  if (e != cudaSuccess ||
+      cudaMalloc((void **)&c->aux, (size_t)c->tiles * CT_NT * sizeof(CellsAux)) != cudaSuccess ||
       cudaMalloc((void **)&c->frames, 2 * 3 * n + 64) != cudaSuccess ||
       cudaMalloc((void **)&c->off_dev, 4 * CELLS_XIN * sizeof(int)) != cudaSuccess ||
-      cudaMalloc((void **)&c->w_image, 2 * CT_MAX_CHUNKS * CT_B_CHUNK) != cudaSuccess ||
-      cudaMalloc((void **)&c->rowmax, n * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void **)&c->w_image, 4 * CT_B_CHUNK) != cudaSuccess ||
       cudaHostAlloc((void **)&c->host, 3 * n, cudaHostAllocDefault) != cudaSuccess)
     rb_die("recur-b200: out of memory for %d cells", c->n);
-  cudaMemsetAsync(c->state, 0, n * prototype->h_size * sizeof(float), rb_stream);
+  cells_reset(c);
   cudaMemsetAsync(c->frames, 0, 2 * 3 * n, rb_stream);
-  cudaMemsetAsync(c->rowmax, 0, n * sizeof(float), rb_stream);
   cudaStreamSynchronize(rb_stream);
   return c;
 }
@@ -574,10 +738,11 @@ rnn_cells_delete(RnnCells *c)
     return;
   cudaStreamSynchronize(rb_stream);
   cudaFree(c->state);
+  cudaFree(c->planes);
+  cudaFree(c->aux);
   cudaFree(c->frames);
   cudaFree(c->off_dev);
   cudaFree(c->w_image);
-  cudaFree(c->rowmax);
   cudaFreeHost(c->host);
   free(c);
 }
@@ -585,8 +750,7 @@ rnn_cells_delete(RnnCells *c)
 extern "C" void
 rnn_cells_forget(RnnCells *c)
 {
-  cudaMemsetAsync(c->state, 0, (size_t)c->n * c->proto->h_size * sizeof(float), rb_stream);
-  cudaMemsetAsync(c->rowmax, 0, (size_t)c->n * sizeof(float), rb_stream);
+  cells_reset(c);
 }
 
 static void
@@ -624,35 +788,33 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
     cudaGetSymbolAddress((void **)&w_dev, cells_w);
     cudaGetSymbolAddress((void **)&wo_dev, cells_wo);
   }
-  const char *env = getenv("RECUR_B200_CELLS_FMA"); /* read per frame: tests flip it */
-  const int use_fma = (env && *env && *env != '0');
+  c->frames_run++;
   rb_prof_begin(RB_PROF_FWD);
-  if (!use_fma) {
+  if (!c->fma) {
     CellsTcArgs t;
     t.c = a;
     t.w_image = c->w_image;
-    t.rowmax = c->rowmax;
+    t.planes = c->planes;
+    t.aux = c->aux;
     const int n_in = len_y + 2 * len_c;
-    t.chunks = CT_MAX_CHUNKS;
     t.ksteps = 0;
     for (int k = 0; k < CT_K_END; k++)
       if (cells_k_row(k, p->h_size, n_in, len_pos) >= 0)
         t.ksteps |= 1 << (k / 16);
     t.reach = c->reach;
-    t.tiles = cdiv(c->n, CT_NT);
-    const size_t sh = (size_t)2 * t.chunks * (CT_A_CHUNK + CT_B_CHUNK) + 1024;
+    t.tiles = c->tiles;
     void (*kernel)(CellsTcArgs) = p->activation == RNN_RESQRT ? k_cells_frame_tc<RNN_RESQRT>
         : p->activation == RNN_RECLIP20 ? k_cells_frame_tc<RNN_RECLIP20>
         : k_cells_frame_tc<RNN_RELU>;
-    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-            2 * CT_MAX_CHUNKS * (CT_A_CHUNK + CT_B_CHUNK) + 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CW_SMEM) !=
+        cudaSuccess)
       rb_die("recur-b200: k_cells_frame_tc: cannot reserve shared memory");
     /* the prototype may have been trained since the last frame: repack every time (2 us) */
-    k_cells_pack_tc<<<cdiv(CT_BN * t.chunks * 8, 256), 256, 0, rb_stream>>>(p->ih_weights,
-        p->ho_weights, p->h_size, p->o_size, n_in, len_pos, t.chunks, c->w_image, wo_dev);
-    /* two CTAs of 128 TMEM columns and <= 97 KB fit an SM */
-    int blocks = t.tiles < 2 * sms ? t.tiles : 2 * sms;
-    kernel<<<blocks, 2 * CT_NT, sh, rb_stream>>>(t);
+    k_cells_pack_tc<<<cdiv(CT_BN * 2 * 8, 256), 256, 0, rb_stream>>>(p->ih_weights,
+        p->ho_weights, p->h_size, p->o_size, n_in, len_pos, c->w_image, wo_dev);
+    /* a CTA per SM (194 KB of shared memory, 256 TMEM columns) */
+    int blocks = t.tiles < sms ? t.tiles : sms;
+    kernel<<<blocks, CW_THREADS, CW_SMEM, rb_stream>>>(t);
     LAUNCH_CHECK("k_cells_frame_tc");
     rb_prof_end(RB_PROF_FWD);
     return;
@@ -803,7 +965,27 @@ rnn_cells_rnnca_run(RnnCells *c, const unsigned char *frame_in, int n_frames,
 extern "C" void
 rnn_cells_get_hidden(RnnCells *c, int cell, float *hidden)
 {
-  cudaMemcpy2DAsync(hidden, sizeof(float), c->state + cell, (size_t)c->n * sizeof(float),
-      sizeof(float), c->proto->h_size, cudaMemcpyDeviceToHost, rb_stream);
+  const int H = c->proto->h_size;
+  if (c->fma) {
+    cudaMemcpy2DAsync(hidden, sizeof(float), c->state + cell, (size_t)c->n * sizeof(float),
+        sizeof(float), H, cudaMemcpyDeviceToHost, rb_stream);
+    cudaStreamSynchronize(rb_stream);
+    return;
+  }
+  /* the row of the cell's tile, out of both planes */
+  const int tile = cell / CT_NT, r = cell % CT_NT;
+  rb_h16 hi[64], lo[64];
+  CellsAux ax;
+  const unsigned char *src = c->planes + (size_t)tile * CT_TILE_BYTES + (size_t)r * 128;
+  cudaMemcpyAsync(hi, src, 128, cudaMemcpyDeviceToHost, rb_stream);
+  cudaMemcpyAsync(lo, src + CT_A_CHUNK, 128, cudaMemcpyDeviceToHost, rb_stream);
+  cudaMemcpyAsync(&ax, c->aux + cell, sizeof(ax), cudaMemcpyDeviceToHost, rb_stream);
   cudaStreamSynchronize(rb_stream);
+  float pre, post;
+  cells_row_scale(ax.hmax, pre, post);
+  hidden[0] = c->frames_run ? 1.0f : 0.0f; /* rnn_opinion sets it (recur-nn.c:144) */
+  for (int u = 1; u < H; u++) {
+    const int k = u - 1, at = (((k >> 3) ^ (r & 7)) << 3) + (k & 7);
+    hidden[u] = (rb_half_to_float(hi[at]) + rb_half_to_float(lo[at]) * (1.0f / RB_LO_GAIN)) * post;
+  }
 }
