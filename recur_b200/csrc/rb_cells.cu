@@ -367,22 +367,50 @@ bulk_s2g(void *dst, const void *src, uint32_t bytes)
       ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 
+/* The state streams through once per frame, a gigabyte of it; the frame's six
+   megabytes are read 33 times per cell.  The streams are marked evict-first so
+   that the frame stays in L2 under them. */
+__device__ __forceinline__ uint64_t
+l2_evict_first(void)
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+__device__ __forceinline__ void
+bulk_g2s_hint(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void
+bulk_s2g_hint(void *dst, const void *src, uint32_t bytes, uint64_t pol)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+      ::"l"(dst), "r"(smem_u32(src)), "r"(bytes), "l"(pol) : "memory");
+}
+
 /* A CTA per SM, four kinds of warp, two tiles in flight:
  *
- *   warp 17     one thread fetches the tile's hidden state, two bulk copies
+ *   warp 21     one thread fetches the tile's hidden state, two bulk copies
  *               from HBM into the first K chunk of A[buf];
- *   warps 0-7   gather: two threads per cell read its neighbourhood's bytes and
+ *   warps 0-11  gather: three threads per cell read its neighbourhood's bytes and
  *               write them, with the position terms, as the second K chunk;
- *   warp 16     one thread issues the tile's MMAs into TMEM[buf];
- *   warps 8-15  drain: two threads per row (hidden units 1..32 and 33..64;
+ *   warp 20     one thread issues the tile's MMAs into TMEM[buf];
+ *   warps 12-19 drain: two threads per row (hidden units 1..32 and 33..64;
  *               warps w and w + 4 reach the same 32 TMEM lanes): soft clip,
  *               activation, output layer, sigmoid, bytes; the new state goes
  *               back to HBM as planes through a staging tile and bulk copies.
  *
  * While the drain warps finish tile i, the tensor core does tile i + 1 and
  * the copies and the gather for tile i + 2 are under way. */
-#define CW_GATHER 256
-#define CW_GATHER_SLOTS ((CT_K_END - CT_K_BYTES) / 2) /* K slots a gather thread fills: 24 */
+#define CW_GATHER_ROLES 3
+#define CW_GATHER (CW_GATHER_ROLES * CT_NT)
+#define CW_GATHER_SLOTS ((CT_K_END - CT_K_BYTES) / CW_GATHER_ROLES) /* K slots per gather thread: 16 */
 #define CW_DRAIN 256
 #define CW_MMA_THREAD (CW_GATHER + CW_DRAIN)
 #define CW_TMA_THREAD (CW_GATHER + CW_DRAIN + 32)
@@ -397,7 +425,7 @@ k_cells_frame_tc(CellsTcArgs t)
   extern __shared__ __align__(1024) unsigned char ct_smem[];
   __shared__ __align__(8) uint64_t w_bar, h_full[2], a_full[2], a_empty[2], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_sum[2][2][CT_NT]; /* [buf][gather role][row]: halves of the soft clip's sum */
+  __shared__ float s_sum[2][CW_GATHER_ROLES][CT_NT]; /* [buf][gather role][row]: parts of the soft clip's sum */
   __shared__ float s_post[2][CT_NT];  /* [buf][row]: what the stored row must be multiplied by */
   __shared__ float4 s_y[2][2][CT_NT]; /* [buf][drain role][row]: halves of the outputs, max */
   __shared__ float s_h[2][2][CT_NT];  /* [buf][drain role][row]: halves of the new hidden sum */
@@ -431,8 +459,8 @@ k_cells_frame_tc(CellsTcArgs t)
 
   if (tid < CW_GATHER) {
     /* ---- gather ------------------------------------------------------------ */
-    /* two threads per cell: K 64..87 (the first 24 bytes) and K 88..111 (the
-       other bytes and the position terms) */
+    /* three threads per cell, 16 K slots each: K 64..79, 80..95 (bytes) and
+       96..111 (the last bytes and the position terms) */
     const int r = tid & (CT_NT - 1), role = tid >> 7;
     const int n_in = a.len_y + 2 * a.len_c;
     const int j0 = role * CW_GATHER_SLOTS;
@@ -475,14 +503,15 @@ k_cells_frame_tc(CellsTcArgs t)
       float sum = 0.0f;
       if (role == 0)
         sum = 1.0f + ax.hsum;
-      else if (a.len_pos > 0) {
+      else if (role == CW_GATHER_ROLES - 1 && a.len_pos > 0) {
         /* the position terms (gstrnnca.c:685-690) */
         const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
-        bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS] = xx;
+        const int at = CT_K_POS - CT_K_BYTES - (CW_GATHER_ROLES - 1) * CW_GATHER_SLOTS;
+        bv[at] = xx;
         if (a.len_pos > 1)
-          bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS + 1] = yy;
+          bv[at + 1] = yy;
         if (a.len_pos > 2)
-          bv[CT_K_POS - CT_K_BYTES - CW_GATHER_SLOTS + 2] = (float)(0.5 -
+          bv[at + 2] = (float)(0.5 -
               (((double)yy - 0.5) * ((double)yy - 0.5) + ((double)xx - 0.5) * ((double)xx - 0.5)));
       }
       float pre, post;
@@ -517,7 +546,7 @@ k_cells_frame_tc(CellsTcArgs t)
       const int cell = live ? tile * CT_NT + r : a.n - 1;
       mbar_wait(&a_full[buf], par); /* the gather's sums are in s_sum */
       /* maybe_scale_inputs (recur-nn.c:68-81): every input times `scale`, so every sum too */
-      const float sum = s_sum[buf][0][r] + s_sum[buf][1][r];
+      const float sum = s_sum[buf][0][r] + s_sum[buf][1][r] + s_sum[buf][2][r];
       const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
       const float unscale = scale * s_post[buf][r] * (1.0f / RB_W_SCALE);
       float x[32];
@@ -583,7 +612,8 @@ k_cells_frame_tc(CellsTcArgs t)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 2, %0;" ::"n"(CW_DRAIN) : "memory");
       if (dt == 0) {
-        bulk_s2g(t.planes + (size_t)tile * CT_TILE_BYTES, stage, CT_TILE_BYTES);
+        bulk_s2g_hint(t.planes + (size_t)tile * CT_TILE_BYTES, stage, CT_TILE_BYTES,
+            l2_evict_first());
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642) */
@@ -641,6 +671,7 @@ k_cells_frame_tc(CellsTcArgs t)
   }
   else if (tid == CW_TMA_THREAD) {
     /* ---- the state's way in ------------------------------------------------ */
+    const uint64_t pol = l2_evict_first();
     int it = 0;
     for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
@@ -649,8 +680,8 @@ k_cells_frame_tc(CellsTcArgs t)
       unsigned char *a_hi = base + buf * CW_A_BUF;
       const unsigned char *src = t.planes + (size_t)tile * CT_TILE_BYTES;
       mbar_expect_tx(&h_full[buf], CT_TILE_BYTES);
-      bulk_g2s(a_hi, src, CT_A_CHUNK, &h_full[buf]);
-      bulk_g2s(a_hi + 2 * CT_A_CHUNK, src + CT_A_CHUNK, CT_A_CHUNK, &h_full[buf]);
+      bulk_g2s_hint(a_hi, src, CT_A_CHUNK, &h_full[buf], pol);
+      bulk_g2s_hint(a_hi + 2 * CT_A_CHUNK, src + CT_A_CHUNK, CT_A_CHUNK, &h_full[buf], pol);
     }
   }
   tc_fence_before();
