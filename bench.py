@@ -536,6 +536,14 @@ def run_ours(args):
                             "continues that series",
                     "kernels": kernels}
 
+    # ---- the exchange alone (no skew from unequal BPTT depths) ---------------
+    exchange_us = None
+    if world > 1 and exchange and exchange.startswith("fused"):
+        barrier()
+        us = float(L.rnn_batch_p2p_probe(batch, 200))
+        exchange_us = max_over_ranks(us) if us > 0 else None
+        barrier()
+
     # ---- strong scaling: the SAME 512 streams split over the GPUs ------------
     strong = None
     if world > 1 and n == STREAMS and (STREAMS // world) >= 64 and not args.no_strong:
@@ -576,6 +584,7 @@ def run_ours(args):
                       "accuracy": stats.correct / max(stats.count, 1)},
             "engine": {0: "auto", 1: "fma", 2: "tensor"}[L.rnn_b200_set_engine(-1)],
             "gradient_exchange": exchange,
+            "gradient_exchange_us": exchange_us,
             "trained": trained,
             "strong": strong,
             "opinion": {"value": opinion_rate, "unit": "stream-steps/s (rnn_opinion only, "
@@ -645,7 +654,7 @@ def rnnca_config(n_gpus):
             "cells": RNNCA_W * RNNCA_H, "n_gpus": n_gpus,
             "parallelism": "replicas only (an automaton per GPU; no collective)" if n_gpus > 1
                            else "single GPU",
-            "cache": "per-frame working set 453 MB of hidden state > 126 MB L2: no flush needed"}
+            "cache": "per-frame working set 1.1 GB of hidden state > 126 MB L2: no flush needed"}
 
 
 def _rnnca_ref_band(args):
@@ -816,7 +825,8 @@ def run_rnnca(args):
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
-            traffic = next((v for k, v in tr.items() if k.startswith("k_cells_frame")), None)
+            traffic = next((v["dram_bytes_per_launch"] for k, v in tr.items()
+                            if k.startswith("k_cells_frame_tc")), None)
         except Exception:
             pass
         line = {"metric": RNNCA_METRIC, "value": world * steps / (ms * 1e-3), "unit": RNNCA_UNIT,
@@ -827,15 +837,20 @@ def run_rnnca(args):
                         "h2d_bytes_per_step": 3 * n, "d2h_bytes_per_step": 3 * n,
                         "ms_per_step": e2e_ms / e2e_steps},
                 "gpu_launches": steps, "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "kernel": "k_cells_frame", "achieved": achieved,
+                "roofline": {"bound": "hbm", "kernel": "k_cells_frame_tc", "achieved": achieved,
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "fp32_tflops": alg_flops / per_launch / 1e12,
-                             "note": "algorithmic bytes = cells x (2 x h_size x 4 state + 6 frame "
-                                     "bytes).  The kernel is FP32 CUDA-core work (%.1f GFLOP per "
-                                     "frame): fp32_tflops against the 148 SM x 128 lane x 2 x clock "
-                                     "FMA ceiling is the tighter bound" % (alg_flops / 1e9)}}
+                             "bytes_moved_per_launch": n * (2 * 256 + 2 * 8 + 6),
+                             "note": "algorithmic bytes = cells x (hidden state once in and once "
+                                     "out as FP32, 2 x h_size x 4, + 3 frame bytes in + 3 out).  "
+                                     "The kernel keeps the state as FP16 hi/lo operand planes "
+                                     "padded to 64 units (256 B per cell each way) plus 8 B of "
+                                     "per-cell sums: bytes_moved_per_launch is what it must move "
+                                     "in that layout, `traffic` what ncu saw.  The %.1f GFLOP of "
+                                     "multiply-adds per frame run on the tensor cores "
+                                     "(fp32_tflops = algorithmic FLOPs / time)" % (alg_flops / 1e9)}}
         if not args.no_cpu_baseline and world == 1:
             try:
                 cores = host_cores()

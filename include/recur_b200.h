@@ -280,6 +280,14 @@ int rnn_b200_comm_size(void);
 #define RNN_B200_P2P_HANDLE_BYTES 192
 int rnn_batch_p2p_export(RnnBatch *batch, void *handles_out);
 int rnn_batch_p2p_attach(RnnBatch *batch, const void *all_handles, int rank, int n_ranks);
+/* Measurement aid (collective: every rank calls it with the same `rounds`,
+   after at least one training step on the tensor engine): `rounds` exchanges
+   back to back with nothing else on the stream; returns the mean microseconds
+   of one (exchange kernel + the consumer's wait and copy-out), -1 without an
+   attached exchange.  ih_delta / ho_delta are overwritten with sums of stale
+   split-K planes: call it between training steps, not between calc_deltas
+   and apply_learning. */
+float rnn_batch_p2p_probe(RnnBatch *batch, int rounds);
 
 #ifdef __cplusplus
 }

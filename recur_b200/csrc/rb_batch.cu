@@ -230,6 +230,16 @@ rnn_batch_p2p_attach(RnnBatch *b, const void *all_handles, int rank, int n_ranks
   return rb_p2p_attach(b->p2p, all_handles, rank, n_ranks);
 }
 
+extern "C" float rb_tc_exchange_probe(RbPool *p, void *p2p, RecurNN *net, int rounds);
+
+extern "C" float
+rnn_batch_p2p_probe(RnnBatch *b, int rounds)
+{
+  if (!b->p2p)
+    return -1.0f;
+  return rb_tc_exchange_probe(b->pool, b->p2p, &b->nets[0]->pub, rounds);
+}
+
 extern "C" int
 rnn_batch_size(const RnnBatch *b)
 {
@@ -509,8 +519,6 @@ calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
 {
   RecurNN *proto = &b->nets[0]->pub;
   RecurNNBPTT *bp = proto->bptt;
-  if (proto->bottom_layer && rb_comm_size() > 1)
-    rb_die("recur-b200: the bottom layer's deltas are not exchanged between GPUs yet");
   if (accumulate && rb_comm_size() > 1)
     rb_die("recur-b200: accumulate != 0 across GPUs would exchange the previous sum again "
         "(see recur_b200.h)");
@@ -531,8 +539,16 @@ calc_deltas_async(RnnBatch *b, int accumulate, const u8 *active = NULL)
     b->masked = active != NULL;
   }
   rb_top_and_bptt_dispatch(&v, bp->ho_delta, bp->ih_delta, accumulate);
-  if (proto->bottom_layer)
+  if (proto->bottom_layer) {
     rb_bottom_backward(&v, proto, accumulate);
+    /* the bottom layer's weight gradient (recur-nn.c:395-401) is summed over
+       every rank's streams like the other two; it is small (input_size x
+       bottom size) and not on the headline path: NCCL */
+    if (rb_comm_size() > 1) {
+      RecurExtraLayer *bl = proto->bottom_layer;
+      rb_comm_allreduce_sum(bl->delta, (size_t)bl->i_size * bl->o_size);
+    }
+  }
   /* [ih_delta | ho_delta] are adjacent in the prototype's delta block; when
      the peer-memory exchange is attached and the tensor engine ran, the sum
      over ranks already happened inside the weight-gradient reduction */

@@ -16,6 +16,7 @@
  */
 #include "rb_kernels.h"
 #include "rb_host.h"
+#include "rb_comm.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -210,6 +211,65 @@ k_bottom_accumulate(RbView v, float *shared_o_error)
   }
 }
 
+/* Several GPUs: the accumulator's walk over the streams goes on through the
+   ranks in rank order, as if the reference had all the streams in one array.
+   What a rank's streams do to the accumulator is affine in the value they
+   start from, running -> A * running + B per output; every rank works out its
+   own (A, B), the ranks swap them, and each then knows the value its first
+   stream starts from and the value the last rank's last stream ends with. */
+__global__ void
+k_bottom_affine(RbView v, float *ab /* [2][bl_o]: this rank's A, B */)
+{
+  for (int x = threadIdx.x; x < v.bl_o; x += blockDim.x) {
+    float A = 1.0f, B = 0.0f;
+    for (int j = 0; j < v.n; j++) {
+      int s = slot_at(v, j);
+      const RbScalars sc = v.sc[s];
+      if (sc.adaptive & 2)
+        continue;
+      if (x < v.d.input_size)
+        B += v.CIE[(size_t)s * v.bl_o + x];
+      if (sc.err_sum > ERROR_GAIN_CEILING * sc.top_scaled && x < v.d.input_size) {
+        const float m = sc.ih_scale * sc.ih_scale;
+        A *= m;
+        B *= m;
+      }
+    }
+    ab[x] = A;
+    ab[v.bl_o + x] = B;
+  }
+}
+
+/* shared_o_error: in, the value before rank 0's first stream; out, the value
+   this rank's first stream starts from.  after[x]: what to apply after this
+   rank's streams to arrive where the last rank ends. */
+__global__ void
+k_bottom_compose(const float *all_ab /* [ranks][2][bl_o] */, int bl_o, int rank, int ranks,
+    float *shared_o_error, float *after /* [2][bl_o] */)
+{
+  for (int x = threadIdx.x; x < bl_o; x += blockDim.x) {
+    float running = shared_o_error[x];
+    for (int q = 0; q < rank; q++)
+      running = all_ab[(size_t)q * 2 * bl_o + x] * running + all_ab[(size_t)q * 2 * bl_o + bl_o + x];
+    shared_o_error[x] = running;
+    float A = 1.0f, B = 0.0f;
+    for (int q = rank + 1; q < ranks; q++) {
+      const float a = all_ab[(size_t)q * 2 * bl_o + x], b = all_ab[(size_t)q * 2 * bl_o + bl_o + x];
+      A *= a;
+      B = a * B + b;
+    }
+    after[x] = A;
+    after[bl_o + x] = B;
+  }
+}
+
+__global__ void
+k_bottom_finish(float *shared_o_error, const float *after, int bl_o)
+{
+  for (int x = threadIdx.x; x < bl_o; x += blockDim.x)
+    shared_o_error[x] = after[x] * shared_o_error[x] + after[bl_o + x];
+}
+
 /* delta[y, x] (+)= sum_j inputs_j[y] * accumulator_after_j[x] (recur-nn.c:755) */
 __global__ void __launch_bounds__(256)
 k_bottom_delta(RbView v, float *delta, int accumulate)
@@ -260,8 +320,33 @@ extern "C" void
 rb_bottom_backward(const RbView *v, RecurNN *net, int accumulate)
 {
   RecurExtraLayer *bl = net->bottom_layer;
+  const int ranks = rb_comm_size(), rank = rb_comm_rank();
+  static float *ab_dev = NULL;
+  static size_t ab_floats = 0;
+  float *after = NULL;
+  if (ranks > 1) {
+    /* [ranks][2][bl_o] gathered, then [2][bl_o] of "what comes after us" */
+    const size_t need = ((size_t)ranks + 1) * 2 * v->bl_o;
+    if (need > ab_floats) {
+      cudaFree(ab_dev);
+      CUDA_OR_DIE(cudaMalloc((void **)&ab_dev, need * sizeof(float)));
+      ab_floats = need;
+    }
+    after = ab_dev + (size_t)ranks * 2 * v->bl_o;
+    CUDA_OR_DIE(cudaMemsetAsync(ab_dev, 0, (size_t)ranks * 2 * v->bl_o * sizeof(float), rb_stream));
+    k_bottom_affine<<<1, 128, 0, rb_stream>>>(*v, ab_dev + (size_t)rank * 2 * v->bl_o);
+    LAUNCH_CHECK("k_bottom_affine");
+    /* an all-gather spelt as a sum: every rank's rows are zero but its own */
+    rb_comm_allreduce_sum(ab_dev, (size_t)ranks * 2 * v->bl_o);
+    k_bottom_compose<<<1, 128, 0, rb_stream>>>(ab_dev, v->bl_o, rank, ranks, bl->o_error, after);
+    LAUNCH_CHECK("k_bottom_compose");
+  }
   k_bottom_accumulate<<<1, 128, 0, rb_stream>>>(*v, bl->o_error);
   LAUNCH_CHECK("k_bottom_accumulate");
+  if (ranks > 1) {
+    k_bottom_finish<<<1, 128, 0, rb_stream>>>(bl->o_error, after, v->bl_o);
+    LAUNCH_CHECK("k_bottom_finish");
+  }
   int total = v->bl_i * v->bl_o;
   k_bottom_delta<<<(total + 255) / 256, 256, 0, rb_stream>>>(*v, bl->delta, accumulate);
   LAUNCH_CHECK("k_bottom_delta");

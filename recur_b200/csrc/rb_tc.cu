@@ -2292,6 +2292,42 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   rb_prof_end(RB_PROF_DW);
 }
 
+/* Measurement aid: `rounds` gradient exchanges back to back on whatever the
+   split-K planes hold, nothing else on the stream; mean microseconds of one.
+   The exchanges synchronise the ranks among themselves (each waits for every
+   peer's stores), so after the first the figure is the exchange's own latency
+   without the ranks' skew from unequal BPTT depths.  A round = the exchange
+   kernel + the consumer's wait and 4.4 MB local copy-out (the training step's
+   consumer is the update kernel, which waits the same way). */
+extern "C" float
+rb_tc_exchange_probe(RbPool *p, void *p2p, RecurNN *net, int rounds)
+{
+  RbTc *t = (RbTc *)p->tc;
+  if (!t || !rb_p2p_ready(p2p) || t->dw_splits < 1 || rounds < 1)
+    return -1.0f;
+  cudaEvent_t e0, e1;
+  CUDA_OR_DIE(cudaEventCreate(&e0));
+  CUDA_OR_DIE(cudaEventCreate(&e1));
+  rb_p2p_exchange(p2p, t->partial, t->dw_splits, net->ih_size, net->ho_size,
+      net->bptt->ho_delta); /* lines the ranks up */
+  CUDA_OR_DIE(cudaEventRecord(e0, rb_stream));
+  for (int i = 0; i < rounds; i++) {
+    /* the consumer's wait for every rank's result stores is part of a round:
+       it is what makes the inboxes free for the next one */
+    rb_p2p_copy_out(p2p, net->bptt->ih_delta);
+    rb_p2p_exchange(p2p, t->partial, t->dw_splits, net->ih_size, net->ho_size,
+        net->bptt->ho_delta);
+  }
+  CUDA_OR_DIE(cudaEventRecord(e1, rb_stream));
+  rb_p2p_copy_out(p2p, net->bptt->ih_delta);
+  CUDA_OR_DIE(cudaEventSynchronize(e1));
+  float ms = 0.0f;
+  CUDA_OR_DIE(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms * 1e3f / rounds;
+}
+
 /* A caller that runs the update right after the deltas (the char step) lets
    the weight gradient stay in its split-K planes in between. */
 extern "C" void

@@ -29,8 +29,15 @@ done
 
 unset RECUR_B200_PLAIN_LAUNCH
 
+# 2b. the cell automaton's frame kernel (BASELINE configs[4])
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_cells_frame_tc -s 8 -c 1 \
+  -f -o $out/k_cells_frame_tc_${tag} python bench.py --config rnnca --steps 20 --warmup 5 --no-cpu-baseline \
+  > $out/ncu_k_cells_frame_tc_${tag}.log 2>&1
+
 # 3. the bench lines themselves, un-profiled
 timeout 900 python bench.py > $out/bench_${tag}_n1.json 2> $out/bench_${tag}_n1.err
 timeout 900 python bench.py --impl reference > $out/bench_${tag}_ref.json 2> $out/bench_${tag}_ref.err
+timeout 600 python bench.py --config rnnca > $out/bench_${tag}_rnnca.json 2> $out/bench_${tag}_rnnca.err
+timeout 600 python bench.py --config rnnca --impl reference > $out/bench_${tag}_rnnca_ref.json 2> $out/bench_${tag}_rnnca_ref.err
 tail -c 600 $out/bench_${tag}_n1.json
 tail -c 400 $out/bench_${tag}_ref.json

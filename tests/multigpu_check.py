@@ -63,6 +63,66 @@ def main():
         L.rnn_batch_delete(batch)
         L.rnn_delete_training_set(nets, n, 0)
         dist.barrier()
+    # ---- a bottom layer in front (the gstclassify / parrot shape): its deltas
+    # are summed over the ranks too
+    nb, F, bsteps = 8, 12, 5
+    bshape = (F, 7, 67, 4)   # n_inputs, r_inputs, hidden, output
+    from helpers import STD_FLAGS
+
+    def make_bottom(lib):
+        net = lib.rnn_new_with_bottom_layer(bshape[0], bshape[1], bshape[2], bshape[3], STD_FLAGS,
+                                            8, None, 4, 0.01, 0.9, 0.0, abi.RNN_RELU, 0)
+        lib.rnn_randomise_weights_auto(net)
+        return net
+
+    def all_weights(net):
+        bl = net.contents.bottom_layer.contents
+        return [w.copy() for w in weights(net)] + [arr(bl.weights, bl.i_size * bl.o_size).copy()]
+
+    rs = np.random.RandomState(5)
+    feats = rs.random_sample((bsteps, world * nb, F)).astype(np.float32)
+    tgt = rs.randint(0, 4, size=(bsteps, world * nb)).astype(np.uint8)
+    bnet = make_bottom(L)
+    bnets = L.rnn_new_training_set(bnet, nb)
+    bbatch = L.rnn_batch_new(bnets, nb)
+    mine = slice(rank * nb, (rank + 1) * nb)
+    for t in range(bsteps):
+        L.rnn_bptt_clear_deltas(bnet) if t % 2 == 0 else None   # the accumulator grows on odd steps
+        L.rnn_batch_set_inputs(bbatch, fptr(np.ascontiguousarray(feats[t, mine])))
+        L.rnn_batch_opinion(bbatch, 0.0)
+        L.rnn_batch_softmax_error(bbatch, u8ptr(np.ascontiguousarray(tgt[t, mine])), None, None)
+        L.rnn_batch_calc_deltas(bbatch, 0)
+        L.rnn_batch_advance(bbatch)
+        L.rnn_apply_learning(bnet, abi.RNN_MOMENTUM_NESTEROV, 0.9)
+    L.rnn_b200_synchronize()
+    bgot = all_weights(bnet)
+    tb = torch.tensor(bgot[2], device="cuda")
+    bmax, bmin = tb.clone(), tb.clone()
+    dist.all_reduce(bmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(bmin, op=dist.ReduceOp.MIN)
+    bottom_equal = bool(torch.equal(bmax, bmin))
+    L.rnn_batch_delete(bbatch)
+    dist.barrier()
+    bottom = None
+    if rank == 0 and oracle.have_ref():
+        ref = oracle.load_ref(strict=True)
+        r = make_bottom(ref)
+        rn = ref.rnn_new_training_set(r, world * nb)
+        for t in range(bsteps):
+            if t % 2 == 0:
+                ref.rnn_bptt_clear_deltas(r)
+            for j in range(world * nb):
+                c = rn[j].contents
+                out = ref.rnn_opinion(rn[j], fptr(feats[t, j]), 0.0)
+                ref.ref_softmax_best_guess(c.bptt.contents.o_error, out, 4)
+                arr(c.bptt.contents.o_error, c.o_size)[tgt[t, j]] += 1.0
+                # rnn_bptt_calc_deltas(net, j ? 1 : 0): the deltas start afresh, the
+                # bottom layer's shared error accumulator does not (recur-nn.c:751-755)
+                ref.rnn_bptt_calc_deltas(rn[j], 1 if j else 0, None)
+                ref.rnn_bptt_advance(rn[j])
+            ref.rnn_apply_learning(r, abi.RNN_MOMENTUM_NESTEROV, 0.9)
+        want = all_weights(r)
+        bottom = {"rel": [rel_err(g, w) for g, w in zip(bgot, want)], "replicas_equal": bottom_equal}
     if rank == 0:
         port = oracle.load_port()
         s = port.oracle_set_new(42, 127, 42, n * world, 12, lr, abi.RNN_RELU, 1,
@@ -84,6 +144,7 @@ def main():
         for variant, r in results.items():
             out[variant] = {"ih_rel": rel_err(r["ih"], want_ih), "ho_rel": rel_err(r["ho"], want_ho),
                             "replicas_equal": r["replicas_equal"]}
+        out["bottom"] = bottom
         print("MULTIGPU_CHECK " + json.dumps(out))
     dist.barrier()
     L.rnn_b200_comm_leave()
