@@ -652,7 +652,8 @@ def rnnca_config(n_gpus):
                         "terms, rnn_opinion, fast_sigmoid, bytes); BASELINE.json configs[4]"
                         % (RNNCA_W, RNNCA_H, RNNCA_HIDDEN),
             "cells": RNNCA_W * RNNCA_H, "n_gpus": n_gpus,
-            "parallelism": "replicas only (an automaton per GPU; no collective)" if n_gpus > 1
+            "parallelism": "one automaton, rows sharded over %d GPUs, the frame's bands "
+                           "all-gathered (NCCL) after every frame" % n_gpus if n_gpus > 1
                            else "single GPU",
             "cache": "per-frame working set 1.1 GB of hidden state > 126 MB L2: no flush needed"}
 
@@ -752,6 +753,7 @@ def run_rnnca(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        rdist.join_comm(L, dist, rank, world, device="cuda")
 
     def barrier():
         L.rnn_b200_synchronize()
@@ -764,7 +766,8 @@ def run_rnnca(args):
     n_in = len_y + 2 * len_c + RNNCA_LEN_POS
     n = RNNCA_W * RNNCA_H
     net = make_net(L, input_size=n_in, hidden=RNNCA_HIDDEN, output=3, depth=10, seed=11, lr=3e-3)
-    cells = L.rnn_cells_new(net, RNNCA_W, RNNCA_H)
+    # N > 1: ONE automaton, its rows shared between the GPUs (strong scaling)
+    cells = (L.rnn_cells_new_sharded if world > 1 else L.rnn_cells_new)(net, RNNCA_W, RNNCA_H)
     if not cells:
         raise SystemExit("rnn_cells_new failed")
     u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
@@ -806,14 +809,17 @@ def run_rnnca(args):
     e2e_ms = rdist.max_over_ranks(dist, a.elapsed_time(b), device="cuda")
     sampler.stop()
     L.rnn_cells_delete(cells)
+    if dist:
+        barrier()
+        L.rnn_b200_comm_leave()
 
     line = None
     if rank == 0:
         c = net.contents
         # per cell and frame: hidden state read once and written once, 3 bytes in, 3 out
         # (neighbour bytes and the second pass over the state come from L1/L2)
-        alg_bytes = n * (2 * c.h_size * 4 + 6)
-        alg_flops = 2.0 * n * (c.i_size * c.h_size + c.h_size * 3)
+        alg_bytes = n // world * (2 * c.h_size * 4 + 6)     # per GPU: its band of cells
+        alg_flops = 2.0 * (n // world) * (c.i_size * c.h_size + c.h_size * 3)
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             peak = float(peaks["hbm_gbs"])
@@ -829,20 +835,21 @@ def run_rnnca(args):
                             if k.startswith("k_cells_frame_tc")), None)
         except Exception:
             pass
-        line = {"metric": RNNCA_METRIC, "value": world * steps / (ms * 1e-3), "unit": RNNCA_UNIT,
+        line = {"metric": RNNCA_METRIC, "value": steps / (ms * 1e-3), "unit": RNNCA_UNIT,
                 "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": rnnca_config(world),
-                "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": RNNCA_UNIT,
+                "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": RNNCA_UNIT,
                         "h2d_bytes_per_step": 3 * n, "d2h_bytes_per_step": 3 * n,
                         "ms_per_step": e2e_ms / e2e_steps},
-                "gpu_launches": steps, "clocks": sampler.summary(),
+                "gpu_launches": 2 * steps, "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "k_cells_frame_tc", "achieved": achieved,
                              "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "fp32_tflops": alg_flops / per_launch / 1e12,
-                             "bytes_moved_per_launch": n * (2 * 256 + 2 * 8 + 6),
+                             "bytes_moved_per_launch": n // world * (2 * 256 + 2 * 8 + 6),
                              "note": "algorithmic bytes = cells x (hidden state once in and once "
                                      "out as FP32, 2 x h_size x 4, + 3 frame bytes in + 3 out).  "
                                      "The kernel keeps the state as FP16 hi/lo operand planes "

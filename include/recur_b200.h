@@ -205,6 +205,11 @@ void rnn_batch_rnnca_frame(RnnBatch *cells, const unsigned char *frame_in,
    line on stderr) otherwise. */
 typedef struct RnnCells RnnCells;
 RnnCells *rnn_cells_new(RecurNN *prototype, int width, int height);
+/* The same frame shared by the GPUs of rnn_b200_comm_join: rank r of n keeps
+   and computes rows [r height/n, (r+1) height/n); after every frame the bands
+   are gathered, so the frame calls below - now collective - still take and
+   return whole pictures on every rank.  height must be a multiple of n. */
+RnnCells *rnn_cells_new_sharded(RecurNN *prototype, int width, int height);
 void rnn_cells_delete(RnnCells *cells);
 /* rnn_forget_history for every cell */
 void rnn_cells_forget(RnnCells *cells);
@@ -221,7 +226,8 @@ void rnn_cells_rnnca_run(RnnCells *cells, const unsigned char *frame_in, int n_f
     unsigned char *frame_out, const int *offsets_y, int len_y, const int *offsets_c, int len_c,
     int len_pos, int edges);
 
-/* One cell's hidden_layer: h_size floats.  Synchronises. */
+/* One cell's hidden_layer: h_size floats (on a sharded object: a cell of this
+   rank's band).  Synchronises. */
 void rnn_cells_get_hidden(RnnCells *cells, int cell, float *hidden);
 
 /* Number of BPTT steps each stream executed in the most recent

@@ -28,6 +28,7 @@
 #include "rb_split.cuh"
 #include "rb_devmath.cuh"
 #include "rb_ptx.cuh"
+#include "rb_comm.h"
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -66,7 +67,8 @@ struct CellsArgs {
   const float *Wih, *Who;
   int I, H, O, hs, activation;
   float *state; /* [H][n] */
-  int n;
+  int n;        /* cells this GPU runs */
+  int cell0;    /* the first of them in the frame (a band of rows, when several GPUs share it) */
   const u8 *frame;
   u8 *frame_out;
   int width, height;
@@ -133,7 +135,8 @@ k_cells_frame(CellsArgs a)
   const int plane = a.width * a.height;
   const float unit = 1.0f / 255.0f;
   for (int cell = blockIdx.x * CELLS_NT + threadIdx.x; cell < a.n; cell += gridDim.x * CELLS_NT) {
-    const int cx = cell % a.width, cy = cell / a.width;
+    const int gcell = a.cell0 + cell;
+    const int cx = gcell % a.width, cy = gcell / a.width;
     const float *st = a.state + cell;
     float sum = 1.0f; /* input 0, the bias */
 #pragma unroll 10
@@ -208,9 +211,9 @@ k_cells_frame(CellsArgs a)
       }
     }
     /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE */
-    a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y0)) * 255.9f);
-    a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y1)) * 255.9f);
-    a.frame_out[2 * plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y2)) * 255.9f);
+    a.frame_out[gcell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y0)) * 255.9f);
+    a.frame_out[plane + gcell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y1)) * 255.9f);
+    a.frame_out[2 * plane + gcell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y2)) * 255.9f);
   }
 }
 
@@ -468,7 +471,7 @@ k_cells_frame_tc(CellsTcArgs t)
     for (int tile = blockIdx.x; tile < t.tiles; tile += gridDim.x, it++) {
       const int buf = it & 1;
       const bool live = tile * CT_NT + r < a.n;
-      const int cell = live ? tile * CT_NT + r : a.n - 1; /* the ragged end repeats a cell */
+      const int cell = a.cell0 + (live ? tile * CT_NT + r : a.n - 1); /* the ragged end repeats a cell */
       unsigned char *a_hi = base + buf * CW_A_BUF + CT_A_CHUNK, *a_lo = a_hi + 2 * CT_A_CHUNK;
       const CellsAux ax = t.aux[tile * CT_NT + r];
       const int cx = cell % a.width, cy = cell / a.width;
@@ -543,7 +546,7 @@ k_cells_frame_tc(CellsTcArgs t)
       const int buf = it & 1;
       const uint32_t par = (it >> 1) & 1;
       const bool live = tile * CT_NT + r < a.n;
-      const int cell = live ? tile * CT_NT + r : a.n - 1;
+      const int cell = a.cell0 + (live ? tile * CT_NT + r : a.n - 1);
       mbar_wait(&a_full[buf], par); /* the gather's sums are in s_sum */
       /* maybe_scale_inputs (recur-nn.c:68-81): every input times `scale`, so every sum too */
       const float sum = s_sum[buf][0][r] + s_sum[buf][1][r] + s_sum[buf][2][r];
@@ -694,7 +697,11 @@ k_cells_frame_tc(CellsTcArgs t)
 
 struct RnnCells {
   RecurNN *proto;
-  int width, height, n, tiles;
+  int width, height;
+  int n, tiles;               /* cells this GPU runs: all of them, or a band of rows */
+  int cell0;                  /* the band's first cell */
+  int frame_n;                /* width * height */
+  int ranks;                  /* > 1: the bands of all ranks are gathered after every frame */
   unsigned char *planes;      /* device [tiles][32 KB]: the hidden state (see CellsTcArgs) */
   CellsAux *aux;              /* device [tiles * 128] */
   float *state;               /* device [h_size][n]: the FP32 cross-check kernel's state */
@@ -722,8 +729,8 @@ cells_reset(RnnCells *c)
   c->frames_run = 0;
 }
 
-extern "C" RnnCells *
-rnn_cells_new(RecurNN *prototype, int width, int height)
+static RnnCells *
+cells_new(RecurNN *prototype, int width, int height, int rank, int ranks)
 {
   rb_require_device("rnn_cells_new");
   if (!prototype || width < 1 || height < 1) {
@@ -741,13 +748,16 @@ rnn_cells_new(RecurNN *prototype, int width, int height)
   c->proto = prototype;
   c->width = width;
   c->height = height;
-  c->n = width * height;
+  c->frame_n = width * height;
+  c->ranks = ranks;
+  c->n = (height / ranks) * width;
+  c->cell0 = rank * c->n;
   c->tiles = cdiv(c->n, CT_NT);
   const char *env = getenv("RECUR_B200_CELLS_FMA");
   c->fma = (env && *env && *env != '0');
-  size_t n = (size_t)c->n;
+  size_t n = (size_t)c->frame_n; /* frames are whole on every rank */
   cudaError_t e = c->fma
-      ? cudaMalloc((void **)&c->state, n * prototype->h_size * sizeof(float))
+      ? cudaMalloc((void **)&c->state, (size_t)c->n * prototype->h_size * sizeof(float))
       : cudaMalloc((void **)&c->planes, (size_t)c->tiles * CT_TILE_BYTES);
   if (e != cudaSuccess ||
       cudaMalloc((void **)&c->aux, (size_t)c->tiles * CT_NT * sizeof(CellsAux)) != cudaSuccess ||
@@ -760,6 +770,28 @@ rnn_cells_new(RecurNN *prototype, int width, int height)
   cudaMemsetAsync(c->frames, 0, 2 * 3 * n, rb_stream);
   cudaStreamSynchronize(rb_stream);
   return c;
+}
+
+extern "C" RnnCells *
+rnn_cells_new(RecurNN *prototype, int width, int height)
+{
+  return cells_new(prototype, width, height, 0, 1);
+}
+
+/* The same frame shared by the ranks of rnn_b200_comm_join:
+   rank r of n keeps the hidden state of rows [r h/n, (r+1) h/n) and computes
+   those; after every frame the bands are gathered (NCCL all-gather of the
+   three planes), so every rank holds, and returns, the whole picture.  The
+   frame calls become collective. */
+extern "C" RnnCells *
+rnn_cells_new_sharded(RecurNN *prototype, int width, int height)
+{
+  const int ranks = rb_comm_size();
+  if (height % ranks) {
+    fprintf(stderr, "rnn_cells_new_sharded: %d rows do not divide among %d GPUs\n", height, ranks);
+    return NULL;
+  }
+  return cells_new(prototype, width, height, rb_comm_rank(), ranks);
 }
 
 extern "C" void
@@ -798,6 +830,7 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
   a.activation = p->activation;
   a.state = c->state;
   a.n = c->n;
+  a.cell0 = c->cell0;
   a.frame = in;
   a.frame_out = out;
   a.width = c->width;
@@ -877,6 +910,16 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
   rb_prof_end(RB_PROF_FWD);
 }
 
+/* every rank's band of the new picture, to every rank */
+static void
+cells_gather(RnnCells *c, u8 *out)
+{
+  if (c->ranks <= 1)
+    return;
+  unsigned char *planes[3] = {out, out + c->frame_n, out + 2 * (size_t)c->frame_n};
+  rb_comm_allgather_inplace(planes, 3, (size_t)c->n);
+}
+
 static void
 cells_check(RnnCells *c, int len_y, int len_c, int len_pos)
 {
@@ -896,7 +939,7 @@ cells_offsets(RnnCells *c, const int *offsets_y, int len_y, const int *offsets_c
       cudaMemcpyHostToDevice, rb_stream);
   /* the same per gathered input, in the order of fill_net_inputs (gstrnnca.c:672-684) */
   int dx[CELLS_XIN], dy[CELLS_XIN], pl[CELLS_XIN], delta[CELLS_XIN];
-  const int plane = c->width * c->height;
+  const int plane = c->frame_n;
   int reach = 0, j = 0;
   for (int i = 0; i < len_y; i++, j++) {
     dx[j] = offsets_y[2 * i];
@@ -944,7 +987,7 @@ rnn_cells_rnnca_frame(RnnCells *c, const unsigned char *frame_in, unsigned char 
   cells_check(c, len_y, len_c, len_pos);
   rb_matrices_to_device(c->proto);
   cells_offsets(c, offsets_y, len_y, offsets_c, len_c);
-  const size_t fb = 3 * (size_t)c->n;
+  const size_t fb = 3 * (size_t)c->frame_n;
   u8 *in = c->frames, *out = c->frames + fb;
   /* frames in page-locked memory (cudaHostAlloc / cudaHostRegister, a video
      pipeline's buffer pool) are copied from and to in place; pageable ones go
@@ -954,6 +997,7 @@ rnn_cells_rnnca_frame(RnnCells *c, const unsigned char *frame_in, unsigned char 
     memcpy(c->host, frame_in, fb);
   cudaMemcpyAsync(in, in_pinned ? frame_in : c->host, fb, cudaMemcpyHostToDevice, rb_stream);
   cells_launch(c, in, out, len_y, len_c, len_pos, edges);
+  cells_gather(c, out);
   cudaMemcpyAsync(out_pinned ? frame_out : c->host, out, fb, cudaMemcpyDeviceToHost, rb_stream);
   cudaStreamSynchronize(rb_stream);
   if (!out_pinned)
@@ -973,7 +1017,7 @@ rnn_cells_rnnca_run(RnnCells *c, const unsigned char *frame_in, int n_frames,
   cells_check(c, len_y, len_c, len_pos);
   rb_matrices_to_device(c->proto);
   cells_offsets(c, offsets_y, len_y, offsets_c, len_c);
-  const size_t fb = 3 * (size_t)c->n;
+  const size_t fb = 3 * (size_t)c->frame_n;
   if (frame_in) {
     memcpy(c->host, frame_in, fb);
     cudaMemcpyAsync(c->frames + (size_t)c->cur * fb, c->host, fb, cudaMemcpyHostToDevice,
@@ -982,6 +1026,7 @@ rnn_cells_rnnca_run(RnnCells *c, const unsigned char *frame_in, int n_frames,
   for (int f = 0; f < n_frames; f++) {
     cells_launch(c, c->frames + (size_t)c->cur * fb, c->frames + (size_t)(c->cur ^ 1) * fb, len_y,
         len_c, len_pos, edges);
+    cells_gather(c, c->frames + (size_t)(c->cur ^ 1) * fb);
     c->cur ^= 1;
   }
   if (frame_out) {
@@ -997,6 +1042,9 @@ extern "C" void
 rnn_cells_get_hidden(RnnCells *c, int cell, float *hidden)
 {
   const int H = c->proto->h_size;
+  cell -= c->cell0; /* on a sharded object: cells of this rank's band only */
+  if (cell < 0 || cell >= c->n)
+    rb_die("recur-b200: rnn_cells_get_hidden: cell %d is not on this GPU", cell + c->cell0);
   if (c->fma) {
     cudaMemcpy2DAsync(hidden, sizeof(float), c->state + cell, (size_t)c->n * sizeof(float),
         sizeof(float), H, cudaMemcpyDeviceToHost, rb_stream);

@@ -9,13 +9,16 @@
 /* the handful of NCCL declarations used, as in nccl.h (ABI-stable since 2.x) */
 typedef struct { char internal[128]; } rb_ncclUniqueId;
 typedef void *rb_ncclComm_t;
-enum { RB_NCCL_FLOAT = 7, RB_NCCL_SUM = 0 };
+enum { RB_NCCL_UINT8 = 1, RB_NCCL_FLOAT = 7, RB_NCCL_SUM = 0 };
 
 static struct {
   void *lib;
   int (*GetUniqueId)(rb_ncclUniqueId *);
   int (*CommInitRank)(rb_ncclComm_t *, int, rb_ncclUniqueId, int);
   int (*AllReduce)(const void *, void *, size_t, int, int, rb_ncclComm_t, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int, rb_ncclComm_t, cudaStream_t);
+  int (*GroupStart)(void);
+  int (*GroupEnd)(void);
   int (*CommDestroy)(rb_ncclComm_t);
   const char *(*GetErrorString)(int);
   rb_ncclComm_t comm;
@@ -47,6 +50,9 @@ load_nccl(void)
   SYM(GetUniqueId, "ncclGetUniqueId");
   SYM(CommInitRank, "ncclCommInitRank");
   SYM(AllReduce, "ncclAllReduce");
+  SYM(AllGather, "ncclAllGather");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
   SYM(CommDestroy, "ncclCommDestroy");
   SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
@@ -129,4 +135,22 @@ rb_comm_allreduce_sum(float *buf, size_t n)
   int r = g_nccl.AllReduce(buf, buf, n, RB_NCCL_FLOAT, RB_NCCL_SUM, g_nccl.comm, rb_stream);
   if (r)
     rb_die("recur-b200: ncclAllReduce failed: %s", g_nccl.GetErrorString(r));
+}
+
+/* `count` equal pieces of `bytes_each` per rank, piece k of rank r living at
+   bufs[k] + r * bytes_each on every rank: afterwards every rank holds all of
+   every buffer.  One NCCL group, queued on the library stream. */
+extern "C" void
+rb_comm_allgather_inplace(unsigned char **bufs, int count, size_t bytes_each)
+{
+  if (g_nccl.size <= 1 || !g_nccl.comm)
+    return;
+  int r = g_nccl.GroupStart();
+  for (int k = 0; k < count && !r; k++)
+    r = g_nccl.AllGather(bufs[k] + (size_t)g_nccl.rank * bytes_each, bufs[k], bytes_each,
+        RB_NCCL_UINT8, g_nccl.comm, rb_stream);
+  if (!r)
+    r = g_nccl.GroupEnd();
+  if (r)
+    rb_die("recur-b200: ncclAllGather failed: %s", g_nccl.GetErrorString(r));
 }

@@ -15,6 +15,9 @@ int rb_comm_rank(void);
 /* in-place sum over ranks of n floats at a device-accessible address, queued
    on the library stream */
 void rb_comm_allreduce_sum(float *buf, size_t n);
+/* in-place all-gather of `count` buffers, each rank owning bytes_each bytes at
+   offset rank * bytes_each of every buffer */
+void rb_comm_allgather_inplace(unsigned char **bufs, int count, size_t bytes_each);
 #ifdef __cplusplus
 }
 #endif

@@ -103,6 +103,41 @@ def main():
     bottom_equal = bool(torch.equal(bmax, bmin))
     L.rnn_batch_delete(bbatch)
     dist.barrier()
+    # ---- the cell automaton with its rows shared between the ranks: every
+    # rank's gathered picture equals the one a single GPU computes
+    W, Hh = 24, 8 * world
+    off_y = np.array([(dx, dy) for dy in range(-2, 3) for dx in range(-2, 3)
+                      if abs(dx) + abs(dy) <= 2 or (abs(dx), abs(dy)) == (2, 2)][:17], dtype=np.int32)
+    off_c = np.array([(dx, dy) for dy in (-1, 0, 1) for dx in (-1, 0, 1) if (dx, dy) != (0, 0)],
+                     dtype=np.int32)
+    cnet = make_net(L, input_size=35, hidden=51, output=3, depth=10, seed=11, lr=3e-3)
+    whole = L.rnn_cells_new(cnet, W, Hh)
+    banded = L.rnn_cells_new_sharded(cnet, W, Hh)
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    frame = np.random.RandomState(9).randint(0, 256, size=3 * W * Hh).astype(np.uint8)
+    start = frame.copy()
+    cells_ok = bool(whole) and bool(banded)
+    for f in range(3):
+        a_out, b_out = np.zeros_like(frame), np.zeros_like(frame)
+        for obj, out_ in ((whole, a_out), (banded, b_out)):
+            L.rnn_cells_rnnca_frame(obj, frame.ctypes.data_as(u8p), out_.ctypes.data_as(u8p),
+                                    off_y.ctypes.data_as(ip), len(off_y), off_c.ctypes.data_as(ip),
+                                    len(off_c), 2, f % 2)
+        cells_ok = cells_ok and bool(np.array_equal(a_out, b_out)) and bool(a_out.any())
+        frame = a_out
+    L.rnn_cells_forget(banded)
+    ran = np.zeros_like(frame)
+    for f in range(3):   # the same three frames, the pictures staying on the device
+        L.rnn_cells_rnnca_run(banded, start.ctypes.data_as(u8p) if f == 0 else None, 1,
+                              ran.ctypes.data_as(u8p), off_y.ctypes.data_as(ip), len(off_y),
+                              off_c.ctypes.data_as(ip), len(off_c), 2, f % 2)
+    cells_ok = cells_ok and bool(np.array_equal(ran, frame))
+    tc = torch.tensor([1 if cells_ok else 0], device="cuda")
+    dist.all_reduce(tc, op=dist.ReduceOp.MIN)
+    cells_ok = bool(tc.item())
+    L.rnn_cells_delete(whole)
+    L.rnn_cells_delete(banded)
+    dist.barrier()
     bottom = None
     if rank == 0 and oracle.have_ref():
         ref = oracle.load_ref(strict=True)
@@ -145,6 +180,7 @@ def main():
             out[variant] = {"ih_rel": rel_err(r["ih"], want_ih), "ho_rel": rel_err(r["ho"], want_ho),
                             "replicas_equal": r["replicas_equal"]}
         out["bottom"] = bottom
+        out["cells_sharded_equal"] = cells_ok
         print("MULTIGPU_CHECK " + json.dumps(out))
     dist.barrier()
     L.rnn_b200_comm_leave()

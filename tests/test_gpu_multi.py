@@ -26,6 +26,8 @@ def test_two_gpu_training_matches_oracle(gpu_lib):
     for variant in ("nccl", "p2p"):
         assert out[variant]["replicas_equal"], variant
         assert out[variant]["ih_rel"] < 1e-4 and out[variant]["ho_rel"] < 1e-4, out
+    # the cell automaton row-sharded over the ranks: bit-identical pictures
+    assert out["cells_sharded_equal"]
     # a bottom layer in front: its deltas are summed across the ranks as well
     # (against the compiled reference replaying every rank's streams)
     if out.get("bottom") is not None:
