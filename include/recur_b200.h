@@ -230,6 +230,30 @@ void rnn_cells_rnnca_run(RnnCells *cells, const unsigned char *frame_in, int n_f
    rank's band).  Synchronises. */
 void rnn_cells_get_hidden(RnnCells *cells, int cell, float *hidden);
 
+/* ---- the audio front end of gstclassify ------------------------------------- */
+
+/* mfcc.c:9-94 for every channel's window in one launch: window function, real
+   FFT, overlapping triangular mel bins, log(1 + power), and optionally the
+   DCT (recur_extract_log_freq_bins / recur_extract_mfccs).  rnn_mfcc_new takes
+   recur_audio_binner_new's arguments (mfcc.c:308-337; window_type as in mfcc.h:
+   0 none, 1 Hann, 2 Vorbis, 3 MP3) and builds the same tables on the host.
+   Windows are powers of two from 16 to 4096 samples; NULL (with a line on
+   stderr) otherwise. */
+typedef struct RnnMfcc RnnMfcc;
+RnnMfcc *rnn_mfcc_new(int window_size, int window_type, int n_bins, float min_freq,
+    float max_freq, float knee_freq, float focus_freq, float audio_rate, float scale,
+    int value_size);
+void rnn_mfcc_delete(RnnMfcc *mfcc);
+/* n_windows windows of window_size samples in, n_windows rows of n_bins floats
+   out (host memory; synchronises).  dct != 0: the bins' DCT. */
+void rnn_mfcc_extract(RnnMfcc *mfcc, const float *pcm, int n_windows, float *out, int dct);
+/* The same with both ends in device memory, queued on the library's stream. */
+void rnn_mfcc_extract_device(RnnMfcc *mfcc, const float *pcm_dev, int n_windows, float *out_dev,
+    int dct);
+/* The tables rnn_mfcc_new built: window_size mask values and n_bins + 1 slopes. */
+void rnn_mfcc_tables(RnnMfcc *mfcc, float *mask, int *left, int *right, float *left_fraction,
+    float *right_fraction, float *slope);
+
 /* Number of BPTT steps each stream executed in the most recent
    rnn_batch_calc_deltas / training step (the value the reference logs as
    "depth", plus one when the walk stopped early; recur-nn.c:387,416): n

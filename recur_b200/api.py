@@ -41,7 +41,8 @@ B200_API_SYMBOLS = [
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
     "rnn_batch_text_forward", "rnn_batch_rnnca_frame", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_batch_bptt_log",
-    "rnn_batch_p2p_probe", "rnn_cells_new", "rnn_cells_new_sharded", "rnn_cells_delete", "rnn_cells_forget", "rnn_cells_rnnca_frame",
+    "rnn_batch_p2p_probe", "rnn_mfcc_new", "rnn_mfcc_delete", "rnn_mfcc_extract",
+    "rnn_mfcc_extract_device", "rnn_mfcc_tables", "rnn_cells_new", "rnn_cells_new_sharded", "rnn_cells_delete", "rnn_cells_forget", "rnn_cells_rnnca_frame",
     "rnn_cells_rnnca_run", "rnn_cells_get_hidden",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
     "rnn_b200_comm_size", "rnn_batch_p2p_export", "rnn_batch_p2p_attach",
@@ -128,6 +129,17 @@ def _declare_b200(lib):
     ip, bp = C.POINTER(C.c_int), C.POINTER(C.c_uint8)
     lib.rnn_cells_new.restype = vp
     lib.rnn_cells_new.argtypes = [P, C.c_int, C.c_int]
+    lib.rnn_mfcc_new.restype = vp
+    lib.rnn_mfcc_new.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_float, C.c_float, C.c_int]
+    lib.rnn_mfcc_delete.restype = None
+    lib.rnn_mfcc_delete.argtypes = [vp]
+    lib.rnn_mfcc_extract.restype = None
+    lib.rnn_mfcc_extract.argtypes = [vp, c_float_p, C.c_int, c_float_p, C.c_int]
+    lib.rnn_mfcc_extract_device.restype = None
+    lib.rnn_mfcc_extract_device.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+    lib.rnn_mfcc_tables.restype = None
+    lib.rnn_mfcc_tables.argtypes = [vp, c_float_p, ip, ip, c_float_p, c_float_p, c_float_p]
     lib.rnn_cells_new_sharded.restype = vp
     lib.rnn_cells_new_sharded.argtypes = [P, C.c_int, C.c_int]
     lib.rnn_cells_delete.restype = None
