@@ -883,10 +883,69 @@ def run_rnnca(args):
     return 0
 
 
+# ---------------------------------------------------------------------------
+# --config default | classify | multi: BASELINE.json configs[0], [2], [3] through
+# the calls their reference callers make (scripts/configs_speed.py holds the
+# loops; tests/test_gpu_configs.py checks the same loops for parity)
+
+SMALL_CONFIGS = {
+    "default": ("config1", "chars_per_second_default_net", "BASELINE.json configs[0]"),
+    "classify": ("config3", "channel_frames_per_second", "BASELINE.json configs[2]"),
+    "multi": ("config4", "text_chars_per_second", "BASELINE.json configs[3]"),
+}
+
+
+def run_small_config(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import configs_speed
+    fn_name, metric, where = SMALL_CONFIGS[args.config]
+    reference = args.impl == "reference"
+    if not reference:
+        from recur_b200 import api
+        L = api.load_library()
+        if L.rnn_b200_device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        n0 = L.rnn_b200_kernel_launches()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(2)
+    os.dup2(devnull, 2)     # the reference's chatter at net creation
+    try:
+        name, unit, ours_v, ref_v = getattr(configs_speed, fn_name)(
+            ours=not reference, theirs=reference or not args.no_cpu_baseline)
+    finally:
+        os.dup2(saved, 2)
+    v = ref_v if reference else ours_v
+    line = {"metric": metric, "value": v, "unit": unit, "n_gpus": 1, "steps": None,
+            "warmup": None, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name + " [" + where + "]",
+                       "timing": "wall clock around the host-driven loop, inputs from and results "
+                                 "to host memory every step (these are latency-bound API paths: "
+                                 "the value IS the end-to-end number)"},
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": None,
+                    "d2h_bytes_per_step": None},
+            "roofline": None,
+            "cpu_baseline": {"value": ref_v, "unit": unit, "cores": 1, "kind": "reference",
+                             "sample": "the same loop over the compiled reference on one host "
+                                       "core (the reference is single-threaded)"}
+            if ref_v is not None else None}
+    if reference:
+        line["impl"] = "reference"
+        line["gpu_launches"] = 0
+    else:
+        line["gpu_launches"] = int(L.rnn_b200_kernel_launches() - n0)
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="text", choices=["text", "rnnca"],
-                    help="text: the headline (BASELINE configs[1]); rnnca: configs[4]")
+    ap.add_argument("--config", default="text",
+                    choices=["text", "rnnca", "default", "classify", "multi"],
+                    help="text: the headline (BASELINE configs[1]); rnnca: configs[4]; "
+                         "default / classify / multi: configs[0] / [2] / [3]")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=30)
@@ -901,6 +960,8 @@ def main():
                     help="positions to train before the `trained` sub-record (0: skip it)")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record")
     args = ap.parse_args()
+    if args.config in SMALL_CONFIGS:
+        return run_small_config(args)
     if args.config == "rnnca":
         return run_rnnca_reference(args) if args.impl == "reference" else run_rnnca(args)
     if args.impl == "reference":
