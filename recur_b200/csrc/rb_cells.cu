@@ -29,6 +29,7 @@
 #include "rb_devmath.cuh"
 #include "rb_ptx.cuh"
 #include "rb_comm.h"
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -327,6 +328,11 @@ k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, in
     for (int e = 0; e < 8; e++) {
       const int k = cells_k_row(8 * g + e, H, n_in, n_pos);
       v[e] = (k >= 0 && u + 1 < H) ? Wih[(size_t)k * H + u + 1] : 0.0f;
+      /* the bytes go through the tensor cores as the integers they are (exact
+         in FP16, no low plane): BYTE_TO_UNIT's 1/255 (gstrnnca.c:640) rides
+         on their weights */
+      if (8 * g + e >= CT_K_BYTES && 8 * g + e < CT_K_POS)
+        v[e] *= 1.0f / 255.0f;
     }
     uint2 h0, l0, h1, l1;
     rb_split4(make_float4(v[0], v[1], v[2], v[3]), (float)RB_W_SCALE, h0, l0);
@@ -478,11 +484,11 @@ k_cells_frame_tc(CellsTcArgs t)
       const bool interior = cx >= t.reach && cx < a.width - t.reach && cy >= t.reach &&
           cy < a.height - t.reach;
       const u8 *fr = a.frame + cell;
-      float bv[CW_GATHER_SLOTS];
+      unsigned int bb[CW_GATHER_SLOTS]; /* this thread's bytes; slots past the inputs are 0 */
       if (interior) {
 #pragma unroll
         for (int q = 0; q < CW_GATHER_SLOTS; q++)
-          bv[q] = (j0 + q < n_in) ? fr[cells_delta[j0 + q]] * (1.0f / 255.0f) : 0.0f;
+          bb[q] = (j0 + q < n_in) ? fr[cells_delta[j0 + q]] : 0u;
       }
       else {
         /* get_offset_point (gstrnnca.c:644-667) at the frame's border */
@@ -498,37 +504,67 @@ k_cells_frame_tc(CellsTcArgs t)
             y += (y < 0) ? a.height : (y >= a.height) ? -a.height : 0;
             x += (x < 0) ? a.width : (x >= a.width) ? -a.width : 0;
           }
-          bv[q] = (j0 + q < n_in)
-              ? a.frame[cells_plane[j] * plane + y * a.width + x] * (1.0f / 255.0f) : 0.0f;
+          bb[q] = (j0 + q < n_in) ? a.frame[cells_plane[j] * plane + y * a.width + x] : 0u;
         }
-      }
-      /* the sum maybe_scale_inputs takes (recur-nn.c:72-75): bias, hidden, inputs */
-      float sum = 0.0f;
-      if (role == 0)
-        sum = 1.0f + ax.hsum;
-      else if (role == CW_GATHER_ROLES - 1 && a.len_pos > 0) {
-        /* the position terms (gstrnnca.c:685-690) */
-        const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
-        const int at = CT_K_POS - CT_K_BYTES - (CW_GATHER_ROLES - 1) * CW_GATHER_SLOTS;
-        bv[at] = xx;
-        if (a.len_pos > 1)
-          bv[at + 1] = yy;
-        if (a.len_pos > 2)
-          bv[at + 2] = (float)(0.5 -
-              (((double)yy - 0.5) * ((double)yy - 0.5) + ((double)xx - 0.5) * ((double)xx - 0.5)));
       }
       float pre, post;
       cells_row_scale(ax.hmax, pre, post);
+      /* the sum maybe_scale_inputs takes (recur-nn.c:72-75): bias, hidden, inputs */
+      unsigned int total = 0;
 #pragma unroll
       for (int q = 0; q < CW_GATHER_SLOTS; q++)
-        sum += bv[q];
+        total += bb[q];
+      float sum = (float)total * (1.0f / 255.0f);
+      if (role == 0)
+        sum += 1.0f + ax.hsum;
+      /* bytes as FP16 integers: 0x6400 | b is 1024 + b, minus 1024, times the
+         row's power of two - all exact */
+      const __half2 k1024 = __floats2half2_rn(1024.0f, 1024.0f);
+      const __half2 pre2 = __floats2half2_rn(pre, pre);
+      uint32_t hw[CW_GATHER_SLOTS / 2];
+#pragma unroll
+      for (int q = 0; q < CW_GATHER_SLOTS / 2; q++) {
+        uint32_t u = 0x64006400u | bb[2 * q] | (bb[2 * q + 1] << 16);
+        __half2 h = __hmul2(__hsub2(*(__half2 *)&u, k1024), pre2);
+        hw[q] = *(uint32_t *)&h;
+      }
+      uint4 lo_last = make_uint4(0, 0, 0, 0);
+      if (role == CW_GATHER_ROLES - 1 && a.len_pos > 0) {
+        /* the position terms (gstrnnca.c:685-690), K 104..106: floats, both planes */
+        const float xx = cx * 1.0f / a.width, yy = cy * 1.0f / a.height;
+        float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        pv[0] = xx;
+        if (a.len_pos > 1)
+          pv[1] = yy;
+        if (a.len_pos > 2)
+          pv[2] = (float)(0.5 -
+              (((double)yy - 0.5) * ((double)yy - 0.5) + ((double)xx - 0.5) * ((double)xx - 0.5)));
+        sum += pv[0];
+        sum += pv[1];
+        sum += pv[2];
+        uint2 h0, l0, h1, l1;
+        rb_split4(make_float4(pv[0], pv[1], pv[2], pv[3]), pre, h0, l0);
+        rb_split4(make_float4(pv[4], pv[5], pv[6], pv[7]), pre, h1, l1);
+        hw[4] = h0.x;
+        hw[5] = h0.y;
+        hw[6] = h1.x;
+        hw[7] = h1.y;
+        lo_last = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
       if (it >= 2) { /* the MMAs of two tiles ago have read A[buf], its drain s_sum[buf] */
         mbar_wait(&a_empty[buf], ((it >> 1) - 1) & 1);
         mbar_wait(&t_empty[buf], ((it >> 1) - 1) & 1);
       }
 #pragma unroll
-      for (int g = 0; g < CW_GATHER_SLOTS / 8; g++)
-        cells_put8(a_hi, a_lo, role * (CW_GATHER_SLOTS / 8) + g, r, bv + 8 * g, pre);
+      for (int g = 0; g < CW_GATHER_SLOTS / 8; g++) {
+        const int gg = role * (CW_GATHER_SLOTS / 8) + g;
+        const uint32_t at = (uint32_t)r * 128 + (((gg & 7) ^ (r & 7)) << 4);
+        *(uint4 *)(a_hi + at) = make_uint4(hw[4 * g], hw[4 * g + 1], hw[4 * g + 2], hw[4 * g + 3]);
+        /* the low plane is read only in the K step that holds the position
+           terms (K 96..111): zeros under its bytes, the terms' low halves */
+        if (gg >= 4)
+          *(uint4 *)(a_lo + at) = (gg == 5) ? lo_last : make_uint4(0, 0, 0, 0);
+      }
       s_sum[buf][role][r] = sum;
       if (role == 0)
         s_post[buf][r] = post;
@@ -665,7 +701,8 @@ k_cells_frame_tc(CellsTcArgs t)
         const uint64_t dbl = umma_desc(smem_u32(b_lo) + bo, 16, 1024);
         umma_f16(acc, dah, dbh, idesc, !first);
         umma_f16(acc + CT_BN, dah, dbl, idesc, !first);
-        umma_f16(acc + CT_BN, dal, dbh, idesc, 1u);
+        if (ks < CT_K_BYTES / 16 || ks == CT_K_POS / 16) /* bytes have no low plane */
+          umma_f16(acc + CT_BN, dal, dbh, idesc, 1u);
         first = false;
       }
       umma_commit(&a_empty[buf]);
