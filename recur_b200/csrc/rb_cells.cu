@@ -405,13 +405,13 @@ bulk_s2g_hint(void *dst, const void *src, uint32_t bytes, uint64_t pol)
 
 /* A CTA per SM, four kinds of warp, two tiles in flight:
  *
- *   warp 21     one thread fetches the tile's hidden state, two bulk copies
+ *   warp 29     one thread fetches the tile's hidden state, two bulk copies
  *               from HBM into the first K chunk of A[buf];
  *   warps 0-11  gather: three threads per cell read its neighbourhood's bytes and
  *               write them, with the position terms, as the second K chunk;
- *   warp 20     one thread issues the tile's MMAs into TMEM[buf];
- *   warps 12-19 drain: two threads per row (hidden units 1..32 and 33..64;
- *               warps w and w + 4 reach the same 32 TMEM lanes): soft clip,
+ *   warp 28     one thread issues the tile's MMAs into TMEM[buf];
+ *   warps 12-27 drain: four threads per row, 16 hidden units each (warps w,
+ *               w + 4, w + 8, w + 12 reach the same 32 TMEM lanes): soft clip,
  *               activation, output layer, sigmoid, bytes; the new state goes
  *               back to HBM as planes through a staging tile and bulk copies.
  *
@@ -420,7 +420,9 @@ bulk_s2g_hint(void *dst, const void *src, uint32_t bytes, uint64_t pol)
 #define CW_GATHER_ROLES 3
 #define CW_GATHER (CW_GATHER_ROLES * CT_NT)
 #define CW_GATHER_SLOTS ((CT_K_END - CT_K_BYTES) / CW_GATHER_ROLES) /* K slots per gather thread: 16 */
-#define CW_DRAIN 256
+#define CW_DRAIN_ROLES 4
+#define CW_DRAIN (CW_DRAIN_ROLES * CT_NT)
+#define CW_DRAIN_COLS (CT_BN / CW_DRAIN_ROLES) /* hidden units a drain thread takes: 16 */
 #define CW_MMA_THREAD (CW_GATHER + CW_DRAIN)
 #define CW_TMA_THREAD (CW_GATHER + CW_DRAIN + 32)
 #define CW_THREADS (CW_GATHER + CW_DRAIN + 64)
@@ -436,8 +438,8 @@ k_cells_frame_tc(CellsTcArgs t)
   __shared__ uint32_t tmem_slot;
   __shared__ float s_sum[2][CW_GATHER_ROLES][CT_NT]; /* [buf][gather role][row]: parts of the soft clip's sum */
   __shared__ float s_post[2][CT_NT];  /* [buf][row]: what the stored row must be multiplied by */
-  __shared__ float4 s_y[2][2][CT_NT]; /* [buf][drain role][row]: halves of the outputs, max */
-  __shared__ float s_h[2][2][CT_NT];  /* [buf][drain role][row]: halves of the new hidden sum */
+  __shared__ float4 s_y[2][CW_DRAIN_ROLES][CT_NT]; /* [buf][drain role][row]: parts of the outputs, max */
+  __shared__ float s_h[2][CW_DRAIN_ROLES][CT_NT];  /* [buf][drain role][row]: parts of the new hidden sum */
   const CellsArgs &a = t.c;
   /* A[buf]: hi chunk 0 (state), hi chunk 1 (gathered), lo chunk 0, lo chunk 1 */
   unsigned char *base = (unsigned char *)(((uintptr_t)ct_smem + 1023) & ~(uintptr_t)1023);
@@ -588,21 +590,21 @@ k_cells_frame_tc(CellsTcArgs t)
       const float sum = s_sum[buf][0][r] + s_sum[buf][1][r] + s_sum[buf][2][r];
       const float scale = (sum > softclip) ? soft_clip_dev(sum, softclip) : 1.0f;
       const float unscale = scale * s_post[buf][r] * (1.0f / RB_W_SCALE);
-      float x[32];
+      float x[CW_DRAIN_COLS];
       mbar_wait(&t_full[buf], par);
       tc_fence_after();
       {
-        float cr[32];
-        tmem_ld32_nowait(tmem_lane + buf * 2 * CT_BN + role * 32, x);
-        tmem_ld32_nowait(tmem_lane + buf * 2 * CT_BN + CT_BN + role * 32, cr);
+        float cr[CW_DRAIN_COLS];
+        tmem_ld16_nowait(tmem_lane + buf * 2 * CT_BN + role * CW_DRAIN_COLS, x);
+        tmem_ld16_nowait(tmem_lane + buf * 2 * CT_BN + CT_BN + role * CW_DRAIN_COLS, cr);
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&t_empty[buf]); /* the sums are in registers: TMEM[buf] may be overwritten */
 #pragma unroll
-        for (int q = 0; q < 32; q++)
+        for (int q = 0; q < CW_DRAIN_COLS; q++)
           x[q] = (x[q] + cr[q] * (1.0f / RB_LO_GAIN)) * unscale;
       }
-      /* this thread's half of the row: activation (recur-nn.c:121-148), its
+      /* this thread's quarter of the row: activation (recur-nn.c:121-148), its
          share of the three outputs, of the new row's sum and maximum */
       float y0 = 0.0f, y1 = 0.0f, y2 = 0.0f, biggest = 0.0f, hsum = 0.0f;
       if (role == 0) {
@@ -612,8 +614,8 @@ k_cells_frame_tc(CellsTcArgs t)
         y2 = wb.z;
       }
 #pragma unroll
-      for (int q = 0; q < 32; q++) {
-        const int unit = role * 32 + q + 1;
+      for (int q = 0; q < CW_DRAIN_COLS; q++) {
+        const int unit = role * CW_DRAIN_COLS + q + 1;
         float v = x[q];
         if (ACT == RNN_RESQRT)
           v = (v > 0.0f) ? sqrtf(v + 1.0f) - 1.0f : 0.0f;
@@ -634,20 +636,21 @@ k_cells_frame_tc(CellsTcArgs t)
           v = 0.0f; /* pad units */
         x[q] = v;
       }
-      if (role == 1)
-        x[31] = 1.0f; /* K 63 is the bias */
+      if (role == CW_DRAIN_ROLES - 1)
+        x[CW_DRAIN_COLS - 1] = 1.0f; /* K 63 is the bias */
       s_y[buf][role][r] = make_float4(y0, y1, y2, biggest);
       s_h[buf][role][r] = hsum;
       if (dt == 0) /* the staging tile's last journey to HBM has read it */
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, %0;" ::"n"(CW_DRAIN) : "memory");
-      const float4 other = s_y[buf][role ^ 1][r];
-      const float hmax = fmaxf(biggest, other.w);
+      const float4 p0 = s_y[buf][0][r], p1 = s_y[buf][1][r], p2 = s_y[buf][2][r],
+                   p3 = s_y[buf][3][r];
+      const float hmax = fmaxf(fmaxf(p0.w, p1.w), fmaxf(p2.w, p3.w));
       float pre, post;
       cells_row_scale(hmax, pre, post);
 #pragma unroll
-      for (int g = 0; g < 4; g++)
-        cells_put8(stage, stage + CT_A_CHUNK, role * 4 + g, r, x + 8 * g, pre);
+      for (int g = 0; g < CW_DRAIN_COLS / 8; g++)
+        cells_put8(stage, stage + CT_A_CHUNK, role * (CW_DRAIN_COLS / 8) + g, r, x + 8 * g, pre);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       asm volatile("bar.sync 2, %0;" ::"n"(CW_DRAIN) : "memory");
       if (dt == 0) {
@@ -655,19 +658,18 @@ k_cells_frame_tc(CellsTcArgs t)
             l2_evict_first());
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
-      /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642) */
-      if (role == 0) {
+      /* fast_sigmoid (badmaths.h:31-44) and UNIT_TO_BYTE (gstrnnca.c:642); the
+         parts summed in the order of the hidden units */
+      if (role == 3) {
         CellsAux ax;
-        ax.hsum = s_h[buf][0][r] + s_h[buf][1][r];
+        ax.hsum = ((s_h[buf][0][r] + s_h[buf][1][r]) + s_h[buf][2][r]) + s_h[buf][3][r];
         ax.hmax = hmax;
         t.aux[tile * CT_NT + r] = ax;
-        if (live)
-          a.frame_out[cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(y0 + other.x))) * 255.9f);
       }
       else if (live) {
-        a.frame_out[plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-(other.y + y1))) * 255.9f);
-        a.frame_out[2 * plane + cell] =
-            (u8)(1.0f / (1.0f + fast_expf_dev(-(other.z + y2))) * 255.9f);
+        const float y = role == 0 ? ((p0.x + p1.x) + p2.x) + p3.x
+            : role == 1 ? ((p0.y + p1.y) + p2.y) + p3.y : ((p0.z + p1.z) + p2.z) + p3.z;
+        a.frame_out[role * plane + cell] = (u8)(1.0f / (1.0f + fast_expf_dev(-y)) * 255.9f);
       }
     }
     if (dt == 0)

@@ -261,6 +261,20 @@ tmem_ld32_nowait(uint32_t taddr, float *v)
       : "r"(taddr));
 }
 
+/* 16 consecutive accumulator columns of this thread's TMEM lane, no wait */
+__device__ __forceinline__ void
+tmem_ld16_nowait(uint32_t taddr, float *v)
+{
+  uint32_t *r = (uint32_t *)v;
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
 __device__ __forceinline__ void
 tmem_wait_ld(void)
 {
