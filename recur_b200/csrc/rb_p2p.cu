@@ -66,6 +66,12 @@ st_release_sys(unsigned int *p, unsigned int v)
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void
+st_relaxed_sys(unsigned int *p, unsigned int v)
+{
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned int
 ld_acquire_sys(const unsigned int *p)
 {
@@ -87,9 +93,13 @@ publish_epoch(const P2PArgs &a, int which)
     unsigned int done = atomicAdd(counter, 1u) + 1;
     if (done == gridDim.x) {
       *counter = 0;
+      /* ONE fence orders every CTA's stores (observed through the counter)
+         before the flags; the flags themselves go out relaxed, all n in
+         flight at once - a release per flag would wait for the flag before it
+         to cross NVLink, n round trips in a row */
       __threadfence_system();
       for (int q = 0; q < a.n; q++)
-        st_release_sys(a.flags[q] + which * RB_P2P_MAX + a.rank, a.epoch);
+        st_relaxed_sys(a.flags[q] + which * RB_P2P_MAX + a.rank, a.epoch);
     }
   }
 }
