@@ -165,7 +165,7 @@ k_cells_frame(CellsArgs a)
             : (float)(0.5 - (((double)yy - 0.5) * ((double)yy - 0.5) +
                   ((double)xx - 0.5) * ((double)xx - 0.5)));
       }
-      mine[(a.H + j) * CELLS_NT] = val;
+      mine[(hs1 + j) * CELLS_NT] = val; /* real_inputs = input_layer + hidden_size + 1 */
       sum += val;
     }
     /* maybe_scale_inputs (recur-nn.c:68-81) */
@@ -186,7 +186,7 @@ k_cells_frame(CellsArgs a)
       cells_row_fma<HN>(acc, mine[i * CELLS_NT] * scale, W + i * (HN / 4));
 #pragma unroll 2
     for (int j = 0; j < n_tot; j++)
-      cells_row_fma<HN>(acc, mine[(a.H + j) * CELLS_NT] * scale, W + (a.H + j) * (HN / 4));
+      cells_row_fma<HN>(acc, mine[(hs1 + j) * CELLS_NT] * scale, W + (hs1 + j) * (HN / 4));
 
     /* activation (recur-nn.c:121-148), the new state, and the three outputs */
     const float4 wb = cells_wo[0];
@@ -242,15 +242,17 @@ k_cells_frame(CellsArgs a)
 #define CT_K_POS 104
 #define CT_K_END 112
 __host__ __device__ __forceinline__ int
-cells_k_row(int k, int H, int n_in, int n_pos)
+cells_k_row(int k, int hs, int n_in, int n_pos)
 {
+  /* the net's input vector: [1 | hidden 1..hs | inputs | pad]: the inputs start
+     at hidden_size + 1, not at the aligned h_size (recur-nn-init.c:110-126) */
   if (k < CT_K_BYTES - 1)
-    return k + 1 < H ? k + 1 : -1;
+    return k + 1 <= hs ? k + 1 : -1;
   if (k == CT_K_BYTES - 1)
     return 0;
   if (k < CT_K_POS)
-    return k - CT_K_BYTES < n_in ? H + k - CT_K_BYTES : -1;
-  return k - CT_K_POS < n_pos ? H + n_in + k - CT_K_POS : -1;
+    return k - CT_K_BYTES < n_in ? hs + 1 + k - CT_K_BYTES : -1;
+  return k - CT_K_POS < n_pos ? hs + 1 + n_in + k - CT_K_POS : -1;
 }
 
 /* per gathered input j: its neighbour offset, its plane, and for cells whose
@@ -317,8 +319,8 @@ k_cells_reset(unsigned char *planes, CellsAux *aux, int tiles)
 /* The B operand as the kernel's shared memory holds it: a unit's weights
    along K, 128-byte rows, SWIZZLE_128B, as FP16 hi/lo planes of 64 w. */
 __global__ void
-k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, int H, int O,
-    int n_in, int n_pos, rb_h16 *image, float *wo)
+k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, int H, int hs,
+    int O, int n_in, int n_pos, rb_h16 *image, float *wo)
 {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < CT_BN * 2 * 8) {
@@ -326,7 +328,7 @@ k_cells_pack_tc(const float *__restrict__ Wih, const float *__restrict__ Who, in
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const int k = cells_k_row(8 * g + e, H, n_in, n_pos);
+      const int k = cells_k_row(8 * g + e, hs, n_in, n_pos);
       v[e] = (k >= 0 && u + 1 < H) ? Wih[(size_t)k * H + u + 1] : 0.0f;
       /* the bytes go through the tensor cores as the integers they are (exact
          in FP16, no low plane): BYTE_TO_UNIT's 1/255 (gstrnnca.c:640) rides
@@ -902,7 +904,7 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
     const int n_in = len_y + 2 * len_c;
     t.ksteps = 0;
     for (int k = 0; k < CT_K_END; k++)
-      if (cells_k_row(k, p->h_size, n_in, len_pos) >= 0)
+      if (cells_k_row(k, p->hidden_size, n_in, len_pos) >= 0)
         t.ksteps |= 1 << (k / 16);
     t.reach = c->reach;
     t.tiles = c->tiles;
@@ -914,7 +916,7 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
       rb_die("recur-b200: k_cells_frame_tc: cannot reserve shared memory");
     /* the prototype may have been trained since the last frame: repack every time (2 us) */
     k_cells_pack_tc<<<cdiv(CT_BN * 2 * 8, 256), 256, 0, rb_stream>>>(p->ih_weights,
-        p->ho_weights, p->h_size, p->o_size, n_in, len_pos, c->w_image, wo_dev);
+        p->ho_weights, p->h_size, p->hidden_size, p->o_size, n_in, len_pos, c->w_image, wo_dev);
     /* a CTA per SM (194 KB of shared memory, 256 TMEM columns) */
     int blocks = t.tiles < sms ? t.tiles : sms;
     kernel<<<blocks, CW_THREADS, CW_SMEM, rb_stream>>>(t);

@@ -649,3 +649,56 @@ def test_config5_rnnca_trainer_step(gpu_lib, ref, port):
             assert rel_err(p, q) < TOL, f
         assert a.contents.generation == r.contents.generation
     lib.rnn_batch_delete(batch)
+
+
+@pytest.mark.parametrize("activation,hidden,n_pos", [(abi.RNN_RESQRT, 51, 2), (abi.RNN_RECLIP20, 63, 0),
+                                                     (abi.RNN_RELU, 20, 3)])
+def test_device_cells_other_shapes(gpu_lib, ref, port, activation, hidden, n_pos):
+    """RnnCells beyond rnnca's own shape: the other two activations
+    (recur-nn.c:123-140), the widest net the kernel takes (63 hidden units: every
+    column of the MMA tile in use), a narrow one (K steps skipped), no position
+    terms / all three.  Tensor-core kernel against the reference cell by cell:
+    hidden state of EVERY cell and the bytes."""
+    lib = gpu_lib
+    W, Hh = 20, 13      # 260 cells: two tiles and a ragged one
+    n = W * Hh
+    off_y, off_c = _rnnca_pattern()
+    off_y = off_y[:9]
+    len_y, len_c = len(off_y), len(off_c)
+    n_in = len_y + 2 * len_c + n_pos
+    shape = dict(input_size=n_in, hidden=hidden, output=3, depth=4, seed=3, lr=3e-3,
+                 activation=activation)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    a, r = make_net(lib, **shape), make_net(ref, **shape)
+    for net in (a, r):
+        ih, ho = weights(net)
+        ih *= 8.0 if activation == abi.RNN_RECLIP20 else 3.0   # the ceiling / the curve in play
+    clones = [ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+    cells = lib.rnn_cells_new(a, W, Hh)
+    assert cells
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    frame = np.random.RandomState(4).randint(0, 256, size=3 * n).astype(np.uint8)
+    h_size = a.contents.h_size
+    for f in range(4):
+        got = np.zeros(3 * n, dtype=np.uint8)
+        lib.rnn_cells_rnnca_frame(cells, frame.ctypes.data_as(u8p), got.ctypes.data_as(u8p),
+                                  off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                                  n_pos, f % 2)
+        want = _rnnca_cpu_frame(ref, port, clones, frame, W, Hh, off_y, off_c, n_pos, f % 2, n_in)
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).sum() <= 0.01 * d.size + 3, (f, d.max(), (d != 0).sum())
+        worst = 0.0
+        for cell in range(n):
+            h = np.zeros(h_size, dtype=np.float32)
+            lib.rnn_cells_get_hidden(cells, cell, fptr(h))
+            c = clones[cell].contents
+            worst = max(worst, rel_err(h, arr(c.hidden_layer, c.h_size)))
+        assert worst < TOL, (f, worst)
+        if activation == abi.RNN_RECLIP20 and f == 3:
+            hs = np.concatenate([arr(cl.contents.hidden_layer, h_size) for cl in clones[:40]])
+            assert (hs == 20.0).any()      # the ceiling was reached
+        frame = want
+    lib.rnn_cells_delete(cells)
+    # shapes the kernel does not take are refused with a message, not mangled
+    big = make_net(lib, input_size=n_in, hidden=100, output=3, depth=4, seed=3)
+    assert not lib.rnn_cells_new(big, W, Hh)
