@@ -357,6 +357,42 @@ def test_other_activations_match_reference(gpu_lib, ref, activation):
         assert rel_err(x, y) < TOL
 
 
+@pytest.mark.parametrize("n", [70, 128])
+def test_reclip20_batch_with_saturated_units(gpu_lib, ref, n):
+    """with ReCLIP20 the reference leaves rows with x >= 20 out of
+    BOTH the back-propagated error and the weight gradient (recur-nn.c:347).
+    The batch paths compute the gradient as a GEMM over ring rows; saturated
+    hidden units (exactly 20.0) must be masked there too.  70 streams: the FMA
+    engine's GEMMs; 128: a size the tensor engine would take, which ReCLIP20
+    nets are kept off (rb_tc_usable)."""
+    lib = gpu_lib
+    from helpers import u8ptr
+    text = markov_text(2000, 11, seed=12)
+    shape = dict(input_size=11, hidden=66, output=11, depth=6, seed=6, lr=0.003,
+                 activation=abi.RNN_RECLIP20)
+    r = make_net(ref, **shape)
+    a = make_net(lib, **shape)
+    for net in (r, a):
+        ih, ho = weights(net)
+        ih *= 8.0
+    rn = ref.rnn_new_training_set(r, n)
+    an = lib.rnn_new_training_set(a, n)
+    batch = lib.rnn_batch_new(an, n)
+    steps = 6
+    ref.ref_multi_tap_train(rn, n, u8ptr(text), len(text), 0, steps, 0, 0.9, 0.0, None, None, None)
+    lib.rnn_batch_text_upload(batch, u8ptr(text), len(text))
+    lib.rnn_batch_text_train(batch, 0, steps, 0, 0.9, 0.0, None)
+    lib.rnn_batch_pull(batch)
+    saturated = sum(int((arr(rn[j].contents.hidden_layer, 68) == 20.0).sum()) for j in range(n))
+    assert saturated > n, saturated      # the ceiling is in play in most streams
+    for x, y in zip(weights(a), weights(r)):
+        assert rel_err(x, y) < TOL
+    for j in (0, n // 2, n - 1):
+        ca, cr = an[j].contents, rn[j].contents
+        assert rel_err(arr(ca.hidden_layer, ca.h_size), arr(cr.hidden_layer, cr.h_size)) < TOL
+    lib.rnn_batch_delete(batch)
+
+
 def char_loop_ref_softmax(L, ref, nets, n, text, steps):
     length = len(text)
     spacing = (length - 1) // n
