@@ -1280,6 +1280,11 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           for (int z = 0; z < SPLITS; z++) {
             if (z == (int)rank)
               continue;
+            /* (all CTAs send to rank 0 first, so ranks 2 and 3 get their slices and
+               arrive at the group barrier half a microsecond after 0 and 1 -
+               RECUR_B200_CHAIN_TIMING prints it; starting every CTA with its
+               right-hand neighbour evened the arrivals out and made the step
+               1 us SLOWER: measured, kept as it was) */
             /* at the receiver: senders in rank order, the receiver left out */
             const int out_slot = z - (z > (int)rank ? 1 : 0);
             const int in_slot = (int)rank - ((int)rank > z ? 1 : 0);
@@ -1471,6 +1476,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
       CH_STAMP(13);
       asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(gsync), "r"(1u) : "memory");
       CH_STAMP(9);
+      if (TIMING && k == 6) /* every CTA's arrival in one step: who is late */
+        g.dbg[64 * 32 + blockIdx.y * gridDim.x + blockIdx.x] = globaltimer_ns();
     }
   }
 
@@ -2145,8 +2152,8 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     const bool timing = getenv("RECUR_B200_CHAIN_TIMING") != NULL;
     if (timing) {
       if (!dbg_dev)
-        CUDA_OR_DIE(cudaMalloc((void **)&dbg_dev, 64 * 32 * sizeof(unsigned long long)));
-      CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, 64 * 32 * sizeof(unsigned long long), rb_stream));
+        CUDA_OR_DIE(cudaMalloc((void **)&dbg_dev, (64 * 32 + 256) * sizeof(unsigned long long)));
+      CUDA_OR_DIE(cudaMemsetAsync(dbg_dev, 0, (64 * 32 + 256) * sizeof(unsigned long long), rb_stream));
       ca.dbg = dbg_dev;
     }
     rb_prof_begin(RB_PROF_CHAIN);
@@ -2157,7 +2164,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     LAUNCH_CHECK("k_tc_chain_persistent");
     rb_prof_end(RB_PROF_CHAIN);
     if (timing && (++dbg_calls % 100) == 60) {
-      static unsigned long long h[64 * 32];
+      static unsigned long long h[64 * 32 + 256];
       CUDA_OR_DIE(cudaMemcpyAsync(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost, rb_stream));
       CUDA_OR_DIE(cudaStreamSynchronize(rb_stream));
       static const char *names[20] = {"step start", "barrier seen", "first block landed",
@@ -2179,6 +2186,20 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
         fprintf(stderr, " step period %.2f\n", (double)(h[(steps + 1) * 32] - h[2 * 32]) / (steps - 1) * 1e-3);
       else
         fprintf(stderr, "\n");
+      {
+        unsigned long long first = ~0ull;
+        for (int i = 0; i < 256; i++)
+          if (h[64 * 32 + i] && h[64 * 32 + i] < first)
+            first = h[64 * 32 + i];
+        fprintf(stderr, "  arrivals of step 6, ns after the first (rows: m tile; columns: CTA x):\n");
+        const int gx = pl.n_tiles * pl.splits;
+        for (int y = 0; y < pl.m_tiles; y++) {
+          fprintf(stderr, "   ");
+          for (int x = 0; x < gx; x++)
+            fprintf(stderr, " %4llu", h[64 * 32 + y * gx + x] ? h[64 * 32 + y * gx + x] - first : 0ull);
+          fprintf(stderr, "\n");
+        }
+      }
     }
   }
   else if (resident) {
