@@ -54,90 +54,95 @@ struct RnnMfcc {
           __LINE__, cudaGetErrorString(e_));                            \
   } while (0)
 
-/* mfcc.c:101-108 */
+/* ---- set-up on the host ---------------------------------------------------
+ * The tables decide which FFT bin a fraction of a triangle belongs to, so they
+ * are computed with the reference's arithmetic (float where it uses float,
+ * double where it uses double, same sequence): the warped mel scale
+ * (mfcc.c:101-108), its inverse by damped fixed-point iteration (:115-133),
+ * the slope edges (:134-178), the window masks (:272-305). */
+
 static float
-hz_to_mel(float hz, float knee, float focus)
+warped_mel(float hz, float knee, float focus)
 {
-  float mel = 1127.0f * logf(1.0f + hz / knee);
-  if (focus)
-    mel /= 1.0f + expf(3.0f * (1.0f - hz / focus));
-  return mel;
+  const float plain = 1127.0f * logf(1.0f + hz / knee);
+  if (!focus)
+    return plain;
+  return plain / (1.0f + expf(3.0f * (1.0f - hz / focus)));
 }
 
-/* mfcc.c:115-133: the inverse by iteration, as the reference does it */
+/* the frequency whose warped_mel is `target`: start from (target / 34)^2 and
+   step by gain * residual, halving the gain whenever the residual changes
+   sign; stop within 1e-4 mel or when the estimate no longer moves */
 static float
-mel_to_hz(float mel, float knee, float focus)
+warped_mel_inverse(float target, float knee, float focus)
 {
-  float hz = (mel / 34) * (mel / 34);
-  float approx;
-  float prev = hz_to_mel(hz, knee, focus) - 1;
-  float mul = 2.0f;
+  float hz = (target / 34) * (target / 34);
+  float gain = 2.0f;
+  float last = warped_mel(hz, knee, focus) - 1;
   for (;;) {
-    approx = hz_to_mel(hz, knee, focus);
-    if (fabs(mel - approx) < 0.0001 || prev == approx)
+    const float now = warped_mel(hz, knee, focus);
+    if (fabs(target - now) < 0.0001 || last == now)
       return hz;
-    float next = hz + mul * (mel - approx);
-    hz = next > 0 ? next : 0;
-    if ((prev > mel) != (approx > mel))
-      mul *= 0.5;
-    prev = approx;
+    const float moved = hz + gain * (target - now);
+    hz = moved > 0 ? moved : 0;
+    if ((last > target) != (now > target))
+      gain *= 0.5;
+    last = now;
   }
 }
 
-/* mfcc.c:134-178 */
+/* n_bins + 1 slopes between n_bins + 2 edges equally spaced in warped mel;
+   edges in units of FFT bins (fft_len * 2 / rate per Hz) */
 static void
 make_slopes(MfccSlope *slopes, int n_bins, int fft_len, float fmin, float fmax, float fknee,
     float ffocus, float audio_rate)
 {
   const int n_slopes = n_bins + 1;
-  const float mmin = hz_to_mel(fmin, fknee, ffocus);
-  const float mmax = hz_to_mel(fmax, fknee, ffocus);
-  const float step = (mmax - mmin) / n_slopes;
-  float hz_to_samples = fft_len * 2 / audio_rate;
-  float hz = fmin;
-  float mel = mmin;
-  float right = hz * hz_to_samples;
+  const float mel_lo = warped_mel(fmin, fknee, ffocus);
+  const float mel_hi = warped_mel(fmax, fknee, ffocus);
+  const float mel_step = (mel_hi - mel_lo) / n_slopes;
+  const float bins_per_hz = fft_len * 2 / audio_rate;
+  float *edge = (float *)malloc((n_slopes + 1) * sizeof(float));
+  float mel = mel_lo;
+  edge[0] = fmin * bins_per_hz;
+  for (int i = 1; i <= n_slopes; i++) {
+    mel += mel_step;
+    edge[i] = warped_mel_inverse(mel, fknee, ffocus) * bins_per_hz;
+  }
   for (int i = 0; i < n_slopes; i++) {
     MfccSlope *s = &slopes[i];
-    float left = right;
-    s->left = (int)left;
-    s->left_fraction = 1.0 - (left - s->left);
-    mel += step;
-    hz = mel_to_hz(mel, fknee, ffocus);
-    right = hz * hz_to_samples;
-    s->right = (int)right;
-    s->right_fraction = right - s->right;
-    s->slope = 1.0 / (right - left);
-    if (s->left == s->right) {
-      s->left_fraction = (right - left);
+    const float from = edge[i], to = edge[i + 1];
+    s->left = (int)from;
+    s->right = (int)to;
+    s->slope = 1.0 / (to - from);
+    if (s->left != s->right) {
+      s->left_fraction = 1.0 - (from - s->left); /* what of bin `left` lies inside */
+      s->right_fraction = to - s->right;
+    }
+    else { /* the whole triangle side inside one bin */
+      s->left_fraction = to - from;
       s->right_fraction = 0;
     }
   }
+  free(edge);
 }
 
-/* mfcc.c:272-305 */
 static void
 make_window(float *mask, int len, int type, float scale)
 {
   const double pi = 3.1415926535897932384626433832795028841971693993751;
-  const double half_pi = pi * 0.5;
-  const double pi_norm = pi / len;
+  const double per_sample = pi / len;
   for (int i = 0; i < len; i++) {
-    switch (type) {
-    case 1: /* RECUR_WINDOW_HANN */
-      mask[i] = (0.5 - 0.5 * cos(2.0 * pi_norm * i)) * scale;
-      break;
-    case 3: /* RECUR_WINDOW_MP3 */
-      mask[i] = sin(pi_norm * (i + 0.5f)) * scale;
-      break;
-    case 2: { /* RECUR_WINDOW_VORBIS */
-      double z = pi_norm * (i + 0.5);
-      mask[i] = sin(half_pi * sin(z) * sin(z)) * scale;
-      break;
+    double w = 1.0;
+    if (type == 1)                      /* Hann */
+      w = 0.5 - 0.5 * cos(2.0 * per_sample * i);
+    else if (type == 3)                 /* MP3's sine window */
+      w = sin(per_sample * (i + 0.5f));
+    else if (type == 2) {               /* Vorbis' power-complementary window */
+      const double z = per_sample * (i + 0.5);
+      w = sin(pi * 0.5 * sin(z) * sin(z));
     }
-    default:
-      mask[i] = 1.0f;
-    }
+    mask[i] = (type >= 1 && type <= 3) ? (float)(w * scale) : 1.0f;
   }
 }
 
