@@ -1228,7 +1228,17 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
       /* a7/a8 for the block's streams while Who, their hidden rows and now
          their error rows are in shared memory (recur-nn.c:199-228, 318-322,
          719-721): what k_gemm<TOP> + k_top_finish do for the general case */
-      float *part = red;  /* [warps][4 * OS] */
+      float *part = red;  /* [warps][4 * OS], then [4 * OS] totals */
+      float *tot = red + (OUT_NT / 32) * (4 * OS);
+      /* what the scalars at the end need from global memory, asked for now */
+      float pre_mef = 0.0f, pre_lr = 1.0f;
+      int pre_adaptive = 0;
+      if ((int)threadIdx.x < ns) {
+        const RbScalars *sc = v.sc + slot_of(v, j0 + threadIdx.x);
+        pre_mef = sc->mef;
+        pre_lr = sc->lr;
+        pre_adaptive = sc->adaptive;
+      }
       __syncthreads();    /* the error rows are in soe */
       OUT_STAMP(7);
       constexpr int YR = 2048 / OUT_NT; /* h_size <= 2048 on this path */
@@ -1285,21 +1295,22 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
       }
       __syncthreads();
       OUT_STAMP(9);
+      /* the warps' parts, summed in warp order by one thread per value */
+      if (threadIdx.x < 4 * OS) {
+        float t = 0.0f;
+        for (int wq = 0; wq < OUT_NT / 32; wq++)
+          t += part[wq * (4 * OS) + threadIdx.x];
+        tot[threadIdx.x] = t;
+      }
+      __syncthreads();
       float scale[OS];
 #pragma unroll
       for (int q = 0; q < OS; q++) {
-        float total = 0.0f;
-        for (int wq = 0; wq < OUT_NT / 32; wq++)
-          total += part[wq * (4 * OS) + 4 * q];
+        const float total = tot[4 * q];
         const float halfmax = H * MAX_TOP_ERROR_FACTOR;
         scale[q] = (total > halfmax) ? soft_clip_dev(total, halfmax) : 1.0f;
         if ((int)threadIdx.x == q && q < ns) {
-          float hsum = 0.0f, hmag = 0.0f, hz = 0.0f;
-          for (int wq = 0; wq < OUT_NT / 32; wq++) {
-            hsum += part[wq * (4 * OS) + 4 * q + 1];
-            hmag += part[wq * (4 * OS) + 4 * q + 2];
-            hz += part[wq * (4 * OS) + 4 * q + 3];
-          }
+          const float hsum = tot[4 * q + 1], hmag = tot[4 * q + 2], hz = tot[4 * q + 3];
           RbScalars *sc = v.sc + slot_of(v, j0 + q);
           const float top_scaled = (total > halfmax) ? scale[q] * total : total;
           sc->top_raw = total;
@@ -1307,16 +1318,17 @@ k_out_multi(RbView v, RbFwdPartials fp, RbLossArgs loss)
           sc->hidden_sum = hsum;
           sc->hidden_mag = sqrtf(hmag);
           sc->hidden_zeros = (int)(hz + 0.5f);
-          sc->min_sum = fminf(sc->mef / sc->lr, MIN_ERROR_GAIN * top_scaled);
+          sc->min_sum = fminf(pre_mef / pre_lr, MIN_ERROR_GAIN * top_scaled);
           sc->max_sum = MAX_ERROR_GAIN * top_scaled + 1.0f;
           sc->cum_error = 0.0f;
           sc->err_sum = 0.0f;
-          sc->live = (v.depth > 0) && !(sc->adaptive & 2);
+          sc->live = (v.depth > 0) && !(pre_adaptive & 2);
           sc->n_steps = 0;
           sc->t_left = v.depth;
           sc->ih_scale = 1.0f;
         }
       }
+      OUT_STAMP(10);
 #pragma unroll
       for (int r = 0; r < YR; r++) {
         const int y = threadIdx.x + OUT_NT * r;
@@ -2125,9 +2137,9 @@ rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
     cudaStreamSynchronize(rb_stream);
     fprintf(stderr, "k_out_multi block 0, us after its start: rows summed %.2f, Who landed %.2f, "
         "outputs done %.2f, softmax done %.2f, (error rows in %.2f, dot products %.2f, "
-        "sums %.2f) top layer done %.2f, ticket taken %.2f\n",
+        "sums %.2f, clip + scalars %.2f) top layer done %.2f, ticket taken %.2f\n",
         (h[1] - h[0]) * 1e-3, (h[2] - h[0]) * 1e-3, (h[3] - h[0]) * 1e-3, (h[4] - h[0]) * 1e-3,
-        (h[7] - h[0]) * 1e-3, (h[8] - h[0]) * 1e-3, (h[9] - h[0]) * 1e-3,
+        (h[7] - h[0]) * 1e-3, (h[8] - h[0]) * 1e-3, (h[9] - h[0]) * 1e-3, (h[10] - h[0]) * 1e-3,
         (h[5] - h[0]) * 1e-3, (h[6] - h[0]) * 1e-3);
   }
 }
