@@ -702,3 +702,48 @@ def test_device_cells_other_shapes(gpu_lib, ref, port, activation, hidden, n_pos
     # shapes the kernel does not take are refused with a message, not mangled
     big = make_net(lib, input_size=n_in, hidden=100, output=3, depth=4, seed=3)
     assert not lib.rnn_cells_new(big, W, Hh)
+
+
+def test_device_cells_rows_beyond_fp16(gpu_lib, ref, port):
+    """Hidden values past FP16's range: the kernel stores such a cell's row
+    divided by a power of two (CT_X_TOP, rb_cells.cu) and multiplies its sums
+    back.  Weights x 3000 drive the hidden state of every cell past 65504 (the
+    input soft clip, recur-nn.c:68-81, keeps it finite) - the reference, all
+    in FP32, is matched to the usual tolerance."""
+    lib = gpu_lib
+    W, Hh = 16, 9
+    n = W * Hh
+    off_y, off_c = _rnnca_pattern()
+    len_y, len_c, n_pos = len(off_y), len(off_c), 2
+    n_in = len_y + 2 * len_c + n_pos
+    shape = dict(input_size=n_in, hidden=51, output=3, depth=4, seed=5, lr=3e-3)
+    fwd = abi.RNN_NET_FLAG_STANDARD & ~(abi.RNN_NET_FLAG_OWN_BPTT | abi.RNN_NET_FLAG_OWN_WEIGHTS)
+    a, r = make_net(lib, **shape), make_net(ref, **shape)
+    for net in (a, r):
+        ih, ho = weights(net)
+        ih *= 3000.0
+        ho *= 1e-5      # keep the outputs in the sigmoid's interesting range
+    clones = [ref.rnn_clone(r, fwd, abi.RECUR_RNG_SUBSEED, None) for _ in range(n)]
+    cells = lib.rnn_cells_new(a, W, Hh)
+    u8p, ip = C.POINTER(C.c_uint8), C.POINTER(C.c_int)
+    frame = np.random.RandomState(8).randint(0, 256, size=3 * n).astype(np.uint8)
+    biggest = 0.0
+    for f in range(4):
+        got = np.zeros(3 * n, dtype=np.uint8)
+        lib.rnn_cells_rnnca_frame(cells, frame.ctypes.data_as(u8p), got.ctypes.data_as(u8p),
+                                  off_y.ctypes.data_as(ip), len_y, off_c.ctypes.data_as(ip), len_c,
+                                  n_pos, 1)
+        want = _rnnca_cpu_frame(ref, port, clones, frame, W, Hh, off_y, off_c, n_pos, 1, n_in)
+        worst = 0.0
+        for cell in range(n):
+            h = np.zeros(52, dtype=np.float32)
+            lib.rnn_cells_get_hidden(cells, cell, fptr(h))
+            want_h = arr(clones[cell].contents.hidden_layer, 52)
+            worst = max(worst, rel_err(h, want_h))
+            biggest = max(biggest, float(want_h.max()))
+        assert worst < TOL, (f, worst)
+        d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert d.max() <= 1 and (d != 0).sum() <= 0.02 * d.size + 3, (f, d.max(), (d != 0).sum())
+        frame = want
+    assert biggest > 65504.0, biggest
+    lib.rnn_cells_delete(cells)
