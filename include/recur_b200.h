@@ -11,8 +11,12 @@
  *   charmodel-predict.c:293-311 (text-predict)     rnn_batch_char_step / rnn_batch_text_train
  *   gstclassify.c:2201-2239 (classify train)       rnn_batch_opinion + rnn_batch_set_errors
  *                                                  + rnn_batch_calc_deltas + rnn_batch_advance
- *   gstrnnca.c:723-728, 811-820 (rnnca)            rnn_batch_opinion / rnn_batch_get_outputs
+ *   gstrnnca.c:718-733 (rnnca trainers)            rnn_batch_set_inputs + rnn_batch_opinion
+ *                                                  + rnn_batch_set_errors + rnn_batch_calc_deltas
+ *   gstrnnca.c:805-830 (rnnca fill_frame)          rnn_cells_rnnca_frame / rnn_cells_rnnca_run
+ *                                                  (or rnn_batch_rnnca_frame on cloned nets)
  *   charmodel-multi-predict.c:350-372              rnn_batch_opinion + rnn_batch_get_outputs
+ *   mfcc.c:9-94 per channel (gstclassify.c:1984-1995)   rnn_mfcc_extract
  *
  * Every function is plain C: pointers and sizes only.  Host arrays passed in
  * are read before the call returns unless stated; nothing here is reentrant
