@@ -742,7 +742,11 @@ struct RnnCells {
   int n, tiles;               /* cells this GPU runs: all of them, or a band of rows */
   int cell0;                  /* the band's first cell */
   int frame_n;                /* width * height */
-  int ranks;                  /* > 1: the bands of all ranks are gathered after every frame */
+  int ranks;                  /* > 1: this rank computes a band; rows are exchanged between frames */
+  int whole;                  /* the newest frame on this rank is a whole picture */
+  unsigned char *halo;        /* device [ranks][3 planes][2 sides][reach rows][width] */
+  int halo_each;              /* bytes per rank it has room for */
+  int edges_now;
   unsigned char *planes;      /* device [tiles][32 KB]: the hidden state (see CellsTcArgs) */
   CellsAux *aux;              /* device [tiles * 128] */
   float *state;               /* device [h_size][n]: the FP32 cross-check kernel's state */
@@ -807,6 +811,12 @@ cells_new(RecurNN *prototype, int width, int height, int rank, int ranks)
       cudaMalloc((void **)&c->w_image, 4 * CT_B_CHUNK) != cudaSuccess ||
       cudaHostAlloc((void **)&c->host, 3 * n, cudaHostAllocDefault) != cudaSuccess)
     rb_die("recur-b200: out of memory for %d cells", c->n);
+  if (ranks > 1) {
+    c->halo_each = 3 * 2 * 8 * width; /* neighbourhoods up to 8 rows away */
+    if (cudaMalloc((void **)&c->halo, (size_t)ranks * c->halo_each) != cudaSuccess)
+      rb_die("recur-b200: out of memory for the halo rows");
+  }
+  c->whole = 1;
   cells_reset(c);
   cudaMemsetAsync(c->frames, 0, 2 * 3 * n, rb_stream);
   cudaStreamSynchronize(rb_stream);
@@ -847,6 +857,7 @@ rnn_cells_delete(RnnCells *c)
   cudaFree(c->frames);
   cudaFree(c->off_dev);
   cudaFree(c->w_image);
+  cudaFree(c->halo);
   cudaFreeHost(c->host);
   free(c);
 }
@@ -951,14 +962,84 @@ cells_launch(RnnCells *c, const u8 *in, u8 *out, int len_y, int len_c, int len_p
   rb_prof_end(RB_PROF_FWD);
 }
 
-/* every rank's band of the new picture, to every rank */
+/* every rank's band of the picture, to every rank */
 static void
 cells_gather(RnnCells *c, u8 *out)
 {
-  if (c->ranks <= 1)
+  if (c->ranks <= 1 || c->whole)
     return;
   unsigned char *planes[3] = {out, out + c->frame_n, out + 2 * (size_t)c->frame_n};
   rb_comm_allgather_inplace(planes, 3, (size_t)c->n);
+  c->whole = 1;
+}
+
+/* [plane][side: top rows, bottom rows][reach][width] of this rank's band */
+__global__ void
+k_cells_halo_pack(const u8 *__restrict__ frame, u8 *__restrict__ mine, int width, int frame_n,
+    int row0, int rows, int reach)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * 2 * reach * width)
+    return;
+  const int x = i % width, row = (i / width) % reach, side = (i / (width * reach)) & 1;
+  const int plane = i / (2 * width * reach);
+  const int g = side ? row0 + rows - reach + row : row0 + row;
+  mine[i] = frame[(size_t)plane * frame_n + (size_t)g * width + x];
+}
+
+/* the rows just above this rank's band (the bottom rows of the rank before) and
+   just below it (the top rows of the rank after), around the frame's edge when
+   it wraps (get_offset_point's edges == 0, gstrnnca.c:655-664) */
+__global__ void
+k_cells_halo_unpack(u8 *__restrict__ frame, const u8 *__restrict__ all, int width, int height,
+    int frame_n, int row0, int rows, int reach, int rank, int ranks, int edges)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * 2 * reach * width)
+    return;
+  const int x = i % width, row = (i / width) % reach, below = (i / (width * reach)) & 1;
+  const int plane = i / (2 * width * reach);
+  int g = below ? row0 + rows + row : row0 - reach + row;
+  if (g < 0 || g >= height) {
+    if (edges)
+      return; /* clamped edges never look past the frame */
+    g += g < 0 ? height : -height;
+  }
+  const int from = below ? (rank + 1) % ranks : (rank + ranks - 1) % ranks;
+  const size_t per_rank = (size_t)3 * 2 * reach * width;
+  /* the neighbour's side facing us: its top rows if it is below us */
+  const size_t at = (((size_t)plane * 2 + (below ? 0 : 1)) * reach + row) * width + x;
+  frame[(size_t)plane * frame_n + (size_t)g * width + x] = all[from * per_rank + at];
+}
+
+/* Between frames nobody needs the whole picture: a cell reads `reach` rows
+   past its band at most, so the ranks swap just those rows (SURVEY.md 8e's
+   "2-row halo exchange") and gather whole pictures only when one is asked
+   for. */
+static void
+cells_halo(RnnCells *c, u8 *out)
+{
+  if (c->ranks <= 1)
+    return;
+  const int rows = c->n / c->width;
+  if (c->reach > rows || c->reach * c->width * 6 > c->halo_each) {
+    c->whole = 0;
+    cells_gather(c, out); /* neighbourhoods wider than a band: everything to everybody */
+    return;
+  }
+  c->whole = 0;
+  if (c->reach == 0)
+    return;
+  const int count = 3 * 2 * c->reach * c->width;
+  const size_t each = (size_t)count;
+  unsigned char *all = c->halo;
+  k_cells_halo_pack<<<cdiv(count, 256), 256, 0, rb_stream>>>(out, all + (size_t)rb_comm_rank() * each,
+      c->width, c->frame_n, c->cell0 / c->width, rows, c->reach);
+  LAUNCH_CHECK("k_cells_halo_pack");
+  rb_comm_allgather_inplace(&all, 1, each);
+  k_cells_halo_unpack<<<cdiv(count, 256), 256, 0, rb_stream>>>(out, all, c->width, c->height,
+      c->frame_n, c->cell0 / c->width, rows, c->reach, rb_comm_rank(), c->ranks, c->edges_now);
+  LAUNCH_CHECK("k_cells_halo_unpack");
 }
 
 static void
@@ -1038,7 +1119,8 @@ rnn_cells_rnnca_frame(RnnCells *c, const unsigned char *frame_in, unsigned char 
     memcpy(c->host, frame_in, fb);
   cudaMemcpyAsync(in, in_pinned ? frame_in : c->host, fb, cudaMemcpyHostToDevice, rb_stream);
   cells_launch(c, in, out, len_y, len_c, len_pos, edges);
-  cells_gather(c, out);
+  c->whole = 0;
+  cells_gather(c, out); /* the caller wants the picture */
   cudaMemcpyAsync(out_pinned ? frame_out : c->host, out, fb, cudaMemcpyDeviceToHost, rb_stream);
   cudaStreamSynchronize(rb_stream);
   if (!out_pinned)
@@ -1063,14 +1145,17 @@ rnn_cells_rnnca_run(RnnCells *c, const unsigned char *frame_in, int n_frames,
     memcpy(c->host, frame_in, fb);
     cudaMemcpyAsync(c->frames + (size_t)c->cur * fb, c->host, fb, cudaMemcpyHostToDevice,
         rb_stream);
+    c->whole = 1;
   }
+  c->edges_now = edges;
   for (int f = 0; f < n_frames; f++) {
     cells_launch(c, c->frames + (size_t)c->cur * fb, c->frames + (size_t)(c->cur ^ 1) * fb, len_y,
         len_c, len_pos, edges);
-    cells_gather(c, c->frames + (size_t)(c->cur ^ 1) * fb);
+    cells_halo(c, c->frames + (size_t)(c->cur ^ 1) * fb);
     c->cur ^= 1;
   }
   if (frame_out) {
+    cells_gather(c, c->frames + (size_t)c->cur * fb); /* collective: every rank asks or none */
     cudaMemcpyAsync(c->host, c->frames + (size_t)c->cur * fb, fb, cudaMemcpyDeviceToHost,
         rb_stream);
     cudaStreamSynchronize(rb_stream);

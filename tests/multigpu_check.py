@@ -132,6 +132,24 @@ def main():
                               ran.ctypes.data_as(u8p), off_y.ctypes.data_as(ip), len(off_y),
                               off_c.ctypes.data_as(ip), len(off_c), 2, f % 2)
     cells_ok = cells_ok and bool(np.array_equal(ran, frame))
+    # several frames in one call: between them the ranks swap only the rows
+    # next to their bands; wrapped and clamped edges; then on from there
+    for edges in (0, 1):
+        pics = []
+        for obj in (whole, banded):
+            L.rnn_cells_forget(obj)
+            p1, p2 = np.zeros_like(frame), np.zeros_like(frame)
+            L.rnn_cells_rnnca_run(obj, start.ctypes.data_as(u8p), 4, p1.ctypes.data_as(u8p),
+                                  off_y.ctypes.data_as(ip), len(off_y), off_c.ctypes.data_as(ip),
+                                  len(off_c), 2, edges)
+            L.rnn_cells_rnnca_run(obj, None, 3, None, off_y.ctypes.data_as(ip), len(off_y),
+                                  off_c.ctypes.data_as(ip), len(off_c), 2, edges)
+            L.rnn_cells_rnnca_run(obj, None, 2, p2.ctypes.data_as(u8p), off_y.ctypes.data_as(ip),
+                                  len(off_y), off_c.ctypes.data_as(ip), len(off_c), 2, edges)
+            pics.append((p1, p2))
+        cells_ok = cells_ok and bool(np.array_equal(pics[0][0], pics[1][0])) \
+            and bool(np.array_equal(pics[0][1], pics[1][1])) and bool(pics[0][1].any()) \
+            and not bool(np.array_equal(pics[0][0], pics[0][1]))
     tc = torch.tensor([1 if cells_ok else 0], device="cuda")
     dist.all_reduce(tc, op=dist.ReduceOp.MIN)
     cells_ok = bool(tc.item())
