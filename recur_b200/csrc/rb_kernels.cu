@@ -2331,7 +2331,10 @@ rbk_top_layer_begin(const RbView *v, float *ho_delta, int accumulate,
   bool forked = false;
   if (slab_ok && v->n >= 4 * OS && !rb_prof_active()) {
     if (!top_side) {
-      cudaStreamCreateWithFlags(&top_side, cudaStreamNonBlocking);
+      /* lowest priority: when the walk's kernel is waiting for SMs too, it goes first */
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      cudaStreamCreateWithPriority(&top_side, cudaStreamNonBlocking, lo);
       cudaEventCreateWithFlags(&top_ev_fork, cudaEventDisableTiming);
       cudaEventCreateWithFlags(&top_ev_join, cudaEventDisableTiming);
     }

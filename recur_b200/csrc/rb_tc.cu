@@ -2121,7 +2121,8 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
   k_e0_planes<<<v->n, 256, 0, rb_stream>>>(*v, Ep, t->escale);
   LAUNCH_CHECK("k_e0_planes");
   rb_prof_end(RB_PROF_TOP);
-  rbk_top_layer_join(); /* ho_delta ran beside the planes kernel */
+  /* (ho_delta goes on beside the walk, on the SMs the chain kernel leaves
+     free: nothing reads it before the exchange / the update, joined below) */
 
   /* small nets: every stream walks alone with the weights resident in its SM */
   const bool resident = rbk_walk_resident_usable(v);
@@ -2274,6 +2275,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     rbk_dw_fma(v, t->partial, 0);
     t->dw_splits = 1;
   }
+  rbk_top_layer_join(); /* ho_delta: whatever is queued from here on may read it */
   if (rb_p2p_ready(v->p2p)) {
     /* multi-GPU: the split-K sum is the first phase of the exchange kernel;
        whoever consumes the result waits for the peers' last stores */
