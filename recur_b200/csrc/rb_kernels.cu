@@ -2243,6 +2243,9 @@ static int ho_slab_attr_done = 0;
 static cudaStream_t top_side = NULL;
 static cudaEvent_t top_ev_fork = NULL, top_ev_join = NULL;
 static int top_forked = 0;
+static int top_defer = 0, top_deferred = 0, top_deferred_accumulate = 0;
+static RbView top_deferred_v;
+static float *top_deferred_delta = NULL;
 
 /* ho_delta for a batch, on `stream` */
 static void
@@ -2295,6 +2298,38 @@ launch_ho_delta_batch(const RbView *v, float *ho_delta, int accumulate, cudaStre
   LAUNCH_CHECK("k_ho_delta_slab");
 }
 
+/* The tensor engine's walk is one kernel on most of the SMs: ho_delta is
+   launched after it (so that the walk's CTAs are placed first) and runs on the
+   rest.  rbk_top_layer_defer_ho_delta(1) before rbk_top_layer_begin, then
+   rbk_top_layer_ho_delta_now() once the walk is queued. */
+extern "C" void
+rbk_top_layer_defer_ho_delta(int on)
+{
+  top_defer = on;
+}
+
+/* move the point the deferred ho_delta waits for to "now" on the library
+   stream: with it right in front of the walk's kernel, both become ready at
+   the same moment and the stream priorities decide who gets the SMs first */
+extern "C" void
+rbk_top_layer_mark(void)
+{
+  if (top_deferred)
+    cudaEventRecord(top_ev_fork, rb_stream);
+}
+
+extern "C" void
+rbk_top_layer_ho_delta_now(void)
+{
+  if (!top_deferred)
+    return;
+  top_deferred = 0;
+  cudaStreamWaitEvent(top_side, top_ev_fork, 0);
+  launch_ho_delta_batch(&top_deferred_v, top_deferred_delta, top_deferred_accumulate, top_side);
+  cudaEventRecord(top_ev_join, top_side);
+  top_forked = 1;
+}
+
 /* wait (on the library stream) for what rbk_top_layer_begin left running
    beside it */
 extern "C" void
@@ -2339,11 +2374,21 @@ rbk_top_layer_begin(const RbView *v, float *ho_delta, int accumulate,
       cudaEventCreateWithFlags(&top_ev_join, cudaEventDisableTiming);
     }
     cudaEventRecord(top_ev_fork, rb_stream);
-    cudaStreamWaitEvent(top_side, top_ev_fork, 0);
-    launch_ho_delta_batch(v, ho_delta, accumulate, top_side);
-    cudaEventRecord(top_ev_join, top_side);
+    if (top_defer) {
+      /* the caller launches its walk first and lets ho_delta follow it on to
+         the SMs the walk leaves free: rbk_top_layer_ho_delta_now() */
+      top_deferred_v = *v;
+      top_deferred_delta = ho_delta;
+      top_deferred_accumulate = accumulate;
+      top_deferred = 1;
+    }
+    else {
+      cudaStreamWaitEvent(top_side, top_ev_fork, 0);
+      launch_ho_delta_batch(v, ho_delta, accumulate, top_side);
+      cudaEventRecord(top_ev_join, top_side);
+      top_forked = 1;
+    }
     forked = true;
-    top_forked = 1;
   }
   if (fused) {
     /* E(0), its clip and the thresholds are in place already */

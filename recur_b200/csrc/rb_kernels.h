@@ -116,6 +116,9 @@ void rbk_top_layer(const RbView *v, float *ho_delta, int accumulate,
 void rbk_top_layer_begin(const RbView *v, float *ho_delta, int accumulate,
     const RecurErrorRange *ranges_dev, int n_ranges);
 void rbk_top_layer_join(void);
+void rbk_top_layer_defer_ho_delta(int on);
+void rbk_top_layer_ho_delta_now(void);
+void rbk_top_layer_mark(void);
 void rbk_request_fused_top(int on);
 int rbk_top_was_fused(const RbView *v);
 void rbk_bptt(const RbView *v, float *ih_delta, int accumulate); /* a10, a11 */

@@ -2116,13 +2116,16 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     p->x_planes_stale = 0;
   }
   /* top layer: E(0), then its planes and the scale of this walk's planes */
+  rbk_top_layer_defer_ho_delta(1);
   rbk_top_layer_begin(v, ho_delta, accumulate, NULL, 0);
+  rbk_top_layer_defer_ho_delta(0);
   rb_prof_begin(RB_PROF_TOP);
   k_e0_planes<<<v->n, 256, 0, rb_stream>>>(*v, Ep, t->escale);
   LAUNCH_CHECK("k_e0_planes");
   rb_prof_end(RB_PROF_TOP);
   /* (ho_delta goes on beside the walk, on the SMs the chain kernel leaves
      free: nothing reads it before the exchange / the update, joined below) */
+  rbk_top_layer_mark();
 
   /* small nets: every stream walks alone with the weights resident in its SM */
   const bool resident = rbk_walk_resident_usable(v);
@@ -2236,6 +2239,7 @@ rb_tc_top_and_bptt(RbPool *p, const RbView *v, float *ho_delta, float *ih_delta,
     k_compute_kmax<<<1, 256, 0, rb_stream>>>(*v, kmax_dev);
     LAUNCH_CHECK("k_compute_kmax");
   }
+  rbk_top_layer_ho_delta_now(); /* behind the walk's kernel(s), beside them on the GPU */
   rb_prof_begin(RB_PROF_SMALL);
   k_finalize_rows<<<v->n, 256, 0, rb_stream>>>(*v, Ep, kmax_dev, sync_next, (int)t->sync_words);
   LAUNCH_CHECK("k_finalize_rows");
