@@ -725,6 +725,7 @@ rnn_batch_text_forward(RnnBatch *b, int start, int steps)
   RbView v;
   batch_view(b, &v);
   rb_matrices_to_device(&b->nets[0]->pub);
+  rbk_output_pipeline(1); /* a step's output layer beside the next step's forward GEMM */
   for (int s = 0; s < steps; s++, i++) {
     if (i >= len - 1)
       i = 0;
@@ -732,6 +733,7 @@ rnn_batch_text_forward(RnnBatch *b, int start, int steps)
     rb_char_forward_dispatch(&v, b->text_dev, len, i, spacing, b->cur_dev, b->next_dev, 0.0f, 0,
         0);
   }
+  rbk_output_pipeline(0);
   mark_ahead(b);
   return (i >= len - 1) ? 0 : i;
 }

@@ -2043,6 +2043,48 @@ rbk_output_takes_partials(const RbView *v, int splits)
   return out_multi_usable(v) && splits <= 4 && (v->d.h_size % 4) == 0;
 }
 
+/* The first phase of k_out_multi<true> by itself: the forward GEMM's split-K
+   partial sums -> activation -> hidden rows.  For forward-only runs, where the
+   next step needs the hidden rows and nothing else (below). */
+__global__ void __launch_bounds__(256)
+k_hidden_from_partials(RbView v, RbFwdPartials fp)
+{
+  const int H = v.d.h_size;
+  const int per_row = H / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n * per_row)
+    return;
+  const int j = i / per_row, c = (i - j * per_row) * 4;
+  const int slot = slot_of(v, j);
+  const float *row = fp.part + (size_t)slot * fp.pitch + c;
+  float4 h = __ldcg((const float4 *)row);
+  for (int z = 1; z < fp.splits; z++) {
+    const float4 p = __ldcg((const float4 *)(row + z * fp.split_stride));
+    h.x += p.x; h.y += p.y; h.z += p.z; h.w += p.w;
+  }
+  h = hidden_activation(v, h, c, fp.use_noise ? v.noise + (size_t)slot * H : NULL);
+  *(float4 *)(v.Hd + (size_t)slot * H + c) = h;
+}
+
+/* Forward-only runs (rnn_batch_text_forward: rnn_opinion step after step):
+   step t + 1 needs step t's hidden rows, not its outputs.  With the pipeline
+   on, the hidden rows are finished on the library stream and the output
+   layer of step t runs on a side stream beside step t + 1's input rows and
+   forward GEMM.  rbk_output_pipeline(0) joins. */
+static int out_pipe = 0, out_pipe_pending = 0;
+static cudaStream_t out_side = NULL;
+static cudaEvent_t out_ev_hidden = NULL, out_ev_done = NULL;
+
+extern "C" void
+rbk_output_pipeline(int on)
+{
+  if (!on && out_pipe_pending) {
+    cudaStreamWaitEvent(rb_stream, out_ev_done, 0);
+    out_pipe_pending = 0;
+  }
+  out_pipe = on;
+}
+
 /* hidden activation + output layer from the split-K partial sums of the
    tensor engine's forward GEMM */
 /* A caller about to run a forward pass whose outputs go straight into the
@@ -2127,6 +2169,25 @@ rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp)
     loss.dbg = dbg_dev;
   }
   out_multi_attr();
+  if (out_pipe && !loss.target && !rb_prof_active() && (v->d.h_size % 4) == 0) {
+    if (!out_side) {
+      cudaStreamCreateWithFlags(&out_side, cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&out_ev_hidden, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&out_ev_done, cudaEventDisableTiming);
+    }
+    if (out_pipe_pending) /* the last step's output layer is still reading the hidden rows */
+      cudaStreamWaitEvent(rb_stream, out_ev_done, 0);
+    k_hidden_from_partials<<<cdiv(v->n * (v->d.h_size / 4), 256), 256, 0, rb_stream>>>(*v, *fp);
+    LAUNCH_CHECK("k_hidden_from_partials");
+    cudaEventRecord(out_ev_hidden, rb_stream);
+    cudaStreamWaitEvent(out_side, out_ev_hidden, 0);
+    RbFwdPartials none = {NULL, 0, 0, 0, 0};
+    k_out_multi<false><<<cdiv(v->n, OS), OUT_NT, out_multi_smem(v), out_side>>>(*v, none, loss);
+    LAUNCH_CHECK("k_out_multi");
+    cudaEventRecord(out_ev_done, out_side);
+    out_pipe_pending = 1;
+    return;
+  }
   rb_prof_begin(RB_PROF_OUT);
   k_out_multi<true><<<cdiv(v->n, OS), OUT_NT, out_multi_smem(v), rb_stream>>>(*v, *fp, loss);
   LAUNCH_CHECK("k_out_multi<partials>");

@@ -105,6 +105,7 @@ typedef struct RbFwdPartials {
 } RbFwdPartials;
 int rbk_output_takes_partials(const RbView *v, int splits);
 void rbk_output_from_partials(const RbView *v, const RbFwdPartials *fp);
+void rbk_output_pipeline(int on);
 void rbk_request_fused_loss(const u8 *target_dev, float *err_dev, int *winner_dev,
     RbCharAccum *accum_dev, RbCharAccum *snapshot_host, int reset);
 int rbk_fused_loss_done(void);
