@@ -17,6 +17,7 @@
  *                                                  (or rnn_batch_rnnca_frame on cloned nets)
  *   charmodel-multi-predict.c:350-372              rnn_batch_opinion + rnn_batch_get_outputs
  *   mfcc.c:9-94 per channel (gstclassify.c:1984-1995)   rnn_mfcc_extract
+ *   rescale.c:240-256 per plane (gstrnnca.c:619-637)    rnn_b200_adaptive_downscale
  *
  * Every function is plain C: pointers and sizes only.  Host arrays passed in
  * are read before the call returns unless stated; nothing here is reentrant
@@ -233,6 +234,22 @@ void rnn_cells_rnnca_run(RnnCells *cells, const unsigned char *frame_in, int n_f
 /* One cell's hidden_layer: h_size floats (on a sharded object: a cell of this
    rank's band).  Synchronises. */
 void rnn_cells_get_hidden(RnnCells *cells, int cell, float *hidden);
+
+/* ---- gstrnnca's frame intake ------------------------------------------------ */
+
+/* recur_adaptive_downscale (rescale.c:240-256; remember_frame,
+   gstrnnca.c:619-637): box-filter a byte plane down to another size, bit for
+   bit as the reference does it - every second row and column when shrinking by
+   four or more both ways, a plain copy of width * height bytes for equal
+   sizes, exact sums otherwise; what the reference's rounding leaves unwritten
+   at the right and bottom of `dst` stays as it was.  Host planes (the call
+   synchronises) or device planes (queued on the library's stream).  Returns 0,
+   or -1 with a line on stderr for enlargements and for shrink factors beyond
+   the reference's 16-bit column sums (more than 257 source rows per row). */
+int rnn_b200_adaptive_downscale(const unsigned char *src, int s_width, int s_height, int s_stride,
+    unsigned char *dst, int d_width, int d_height, int d_stride);
+int rnn_b200_adaptive_downscale_device(const unsigned char *src_dev, int s_width, int s_height,
+    int s_stride, unsigned char *dst_dev, int d_width, int d_height, int d_stride);
 
 /* ---- the audio front end of gstclassify ------------------------------------- */
 

@@ -41,7 +41,8 @@ B200_API_SYMBOLS = [
     "rnn_batch_char_step", "rnn_batch_text_upload", "rnn_batch_text_train",
     "rnn_batch_text_forward", "rnn_batch_rnnca_frame", "rnn_batch_pull", "rnn_batch_bptt_depths",
     "rnn_batch_bptt_log",
-    "rnn_batch_p2p_probe", "rnn_mfcc_new", "rnn_mfcc_delete", "rnn_mfcc_extract",
+    "rnn_batch_p2p_probe", "rnn_b200_adaptive_downscale",
+    "rnn_b200_adaptive_downscale_device", "rnn_mfcc_new", "rnn_mfcc_delete", "rnn_mfcc_extract",
     "rnn_mfcc_extract_device", "rnn_mfcc_tables", "rnn_cells_new", "rnn_cells_new_sharded", "rnn_cells_delete", "rnn_cells_forget", "rnn_cells_rnnca_frame",
     "rnn_cells_rnnca_run", "rnn_cells_get_hidden",
     "rnn_b200_comm_unique_id", "rnn_b200_comm_join", "rnn_b200_comm_leave",
@@ -129,6 +130,10 @@ def _declare_b200(lib):
     ip, bp = C.POINTER(C.c_int), C.POINTER(C.c_uint8)
     lib.rnn_cells_new.restype = vp
     lib.rnn_cells_new.argtypes = [P, C.c_int, C.c_int]
+    for name in ("rnn_b200_adaptive_downscale", "rnn_b200_adaptive_downscale_device"):
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int]
     lib.rnn_mfcc_new.restype = vp
     lib.rnn_mfcc_new.argtypes = [C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_float, C.c_float, C.c_int]
