@@ -1032,7 +1032,8 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
   uint64_t *k_done = step_go + 1;   /* every CTA of the cluster is through its K loop */
   uint64_t *data_in = k_done + 1;   /* the peers' slices have landed */
   uint64_t *w_again = data_in + 1;  /* the weights the own slice sat on are back */
-  uint32_t *tmem_slot = (uint32_t *)(w_again + 1);
+  uint64_t *data_in2 = w_again + 1; /* ... and the second half of their rows */
+  uint32_t *tmem_slot = (uint32_t *)(data_in2 + 1);
   int *s_any = (int *)(tmem_slot + 1);      /* [2] a stream walks on, by step parity */
   int *s_kmax = s_any + 2;
   uint8_t *s_live = (uint8_t *)(s_kmax + 1); /* [128] */
@@ -1065,6 +1066,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
     mbar_init(step_go, 1);
     mbar_init(k_done, SPLITS);
     mbar_init(data_in, 1);
+    mbar_init(data_in2, 1);
     mbar_init(w_again, 1);
     fence_barrier_init();
     tma_prefetch_desc(&mEhi);
@@ -1272,24 +1274,30 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
         named_bar_sync(1, 128);
         if (threadIdx.x == 64) {
           CH_STAMP(5);
-          mbar_expect_tx(data_in, (SPLITS - 1) * SLICE_BYTES);
+          mbar_expect_tx(data_in, (SPLITS - 1) * (SLICE_BYTES / 2));
+          mbar_expect_tx(data_in2, (SPLITS - 1) * (SLICE_BYTES / 2));
           /* no peer may still be reading its ring with the tensor core */
           mbar_wait_cluster(k_done, par);
           CH_STAMP(8);
+          /* Rows 0..63 of every slice first, then rows 64..127: the receivers
+             start on the first half while the second is on its way.  (All CTAs
+             send to rank 0 first, so the higher ranks get theirs later - by a
+             whole slice per rank when slices went out in one piece; starting
+             every CTA with its right-hand neighbour instead makes EVERY rank
+             wait for the last position and was measured 1 us slower.) */
 #pragma unroll
-          for (int z = 0; z < SPLITS; z++) {
-            if (z == (int)rank)
-              continue;
-            /* (all CTAs send to rank 0 first, so ranks 2 and 3 get their slices and
-               arrive at the group barrier half a microsecond after 0 and 1 -
-               RECUR_B200_CHAIN_TIMING prints it; starting every CTA with its
-               right-hand neighbour evened the arrivals out and made the step
-               1 us SLOWER: measured, kept as it was) */
-            /* at the receiver: senders in rank order, the receiver left out */
-            const int out_slot = z - (z > (int)rank ? 1 : 0);
-            const int in_slot = (int)rank - ((int)rank > z ? 1 : 0);
-            bulk_copy_to_peer(in_buf + in_slot * SLICE_BYTES, out_buf + out_slot * SLICE_BYTES,
-                SLICE_BYTES, data_in, (uint32_t)z);
+          for (int half = 0; half < 2; half++) {
+#pragma unroll
+            for (int z = 0; z < SPLITS; z++) {
+              if (z == (int)rank)
+                continue;
+              /* at the receiver: senders in rank order, the receiver left out */
+              const int out_slot = z - (z > (int)rank ? 1 : 0);
+              const int in_slot = (int)rank - ((int)rank > z ? 1 : 0);
+              bulk_copy_to_peer(in_buf + in_slot * SLICE_BYTES + half * (SLICE_BYTES / 2),
+                  out_buf + out_slot * SLICE_BYTES + half * (SLICE_BYTES / 2), SLICE_BYTES / 2,
+                  half ? data_in2 : data_in, (uint32_t)z);
+            }
           }
         }
       }
@@ -1399,26 +1407,30 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
 
     /* ---- E(k+1): this CTA's slice of the tile, summed over the K splits:
        the peers' parts have landed in this CTA's own shared memory ---- */
-    {
-      mbar_wait(data_in, par);
-      if (threadIdx.x == 0)
+    /* (the rows' first half arrives, and is worked on, while the second is
+       still in flight) */
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      constexpr int NH = NG / 2;
+      mbar_wait(hh ? data_in2 : data_in, par);
+      if (threadIdx.x == 0 && hh == 1)
         CH_STAMP(10);
-      float4 a[NG];
+      float4 a[NH];
       {
-        float4 pz[SPLITS][NG];
+        float4 pz[SPLITS][NH];
 #pragma unroll
         for (int z = 0; z < SPLITS; z++) {
           const uint8_t *src = (z == (int)rank ? own_buf
                   : in_buf + (z - (z > (int)rank ? 1 : 0)) * SLICE_BYTES) + (r_j >> 3) * 128;
 #pragma unroll
-          for (int q = 0; q < NG; q++) {
-            const int row = r_row0 + q * RPI;
+          for (int q = 0; q < NH; q++) {
+            const int row = r_row0 + (hh * NH + q) * RPI;
             pz[z][q] = *(const float4 *)(src + (size_t)row * (CPR * 4) +
                 (((r_j & 7) ^ (row & 7)) << 4));
           }
         }
 #pragma unroll
-        for (int q = 0; q < NG; q++) {
+        for (int q = 0; q < NH; q++) {
           a[q] = pz[0][q];
 #pragma unroll
           for (int z = 1; z < SPLITS; z++) {
@@ -1428,28 +1440,29 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           a[q].x *= inv_scale; a[q].y *= inv_scale; a[q].z *= inv_scale; a[q].w *= inv_scale;
         }
       }
-      if (TIMING && threadIdx.x == 0 && a[0].x != 123.456f && a[NG - 1].w != 123.456f)
+      if (TIMING && threadIdx.x == 0 && hh == 1 && a[0].x != 123.456f && a[NH - 1].w != 123.456f)
         CH_STAMP(15);
 #pragma unroll
-      for (int q = 0; q < NG; q++) {
-        const int row = r_row0 + q * RPI;
+      for (int q = 0; q < NH; q++) {
+        const int qq = hh * NH + q;
+        const int row = r_row0 + qq * RPI;
         const bool live = m0 + row < v.n && s_live[row];
         const int rs = v.base + (m0 + row < v.n ? m0 + row : 0);
         float sq = 0.0f;
         if (live && r_col < I) {
-          float4 o = plain ? chain_mask4<true>(v, a[q], xq[q], r_col, rs, sq)
-                           : chain_mask4<false>(v, a[q], xq[q], r_col, rs, sq);
-          if (TIMING && threadIdx.x == 0 && q == 0 && o.x != 123.456f && sq != 123.456f)
+          float4 o = plain ? chain_mask4<true>(v, a[q], xq[qq], r_col, rs, sq)
+                           : chain_mask4<false>(v, a[q], xq[qq], r_col, rs, sq);
+          if (TIMING && threadIdx.x == 0 && qq == 0 && o.x != 123.456f && sq != 123.456f)
             CH_STAMP(16);
           uint2 h, l;
           rb_split4(o, e_scale, h, l);
-          if (TIMING && threadIdx.x == 0 && q == 0 && h.x != 12345u && l.y != 12345u)
+          if (TIMING && threadIdx.x == 0 && qq == 0 && h.x != 12345u && l.y != 12345u)
             CH_STAMP(17);
           __stcg((float4 *)(v.E + ((size_t)(k + 1) * v.cap + rs) * I + r_col), o);
           const size_t poff = ((size_t)(k + 1) * v.cap + rs) * g.E.pitch + r_col;
           __stcg((uint2 *)(g.E.hi + poff), h);
           __stcg((uint2 *)(g.E.lo + poff), l);
-          if (TIMING && threadIdx.x == 0 && q == 0)
+          if (TIMING && threadIdx.x == 0 && qq == 0)
             CH_STAMP(18);
         }
         /* the row's LPR threads sit side by side in a warp */
@@ -1458,7 +1471,7 @@ k_tc_chain_persistent(const __grid_constant__ CUtensorMap mEhi,
           sq += __shfl_xor_sync(0xffffffffu, sq, o);
         if (live && r_j == 0)
           __stcg(sq_grp + (size_t)par * sq_par + (size_t)row * CH_SQ_SLOTS + grp_cta, sq);
-        if (TIMING && threadIdx.x == 0 && q == 0)
+        if (TIMING && threadIdx.x == 0 && qq == 0)
           CH_STAMP(19);
       }
     }
