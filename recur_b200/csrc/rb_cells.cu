@@ -736,6 +736,12 @@ k_cells_frame_tc(CellsTcArgs t)
   }
 }
 
+struct RnnCells;
+/* whose neighbourhood tables the constant memory holds, and for which pattern */
+static const struct RnnCells *cells_tables_owner = NULL;
+static size_t cells_tables_bytes = 0;
+static int cells_tables_key[4 * CELLS_XIN + 2];
+
 struct RnnCells {
   RecurNN *proto;
   int width, height;
@@ -850,6 +856,8 @@ rnn_cells_delete(RnnCells *c)
 {
   if (!c)
     return;
+  if (cells_tables_owner == c)
+    cells_tables_owner = NULL; /* a later object may get the same address */
   cudaStreamSynchronize(rb_stream);
   cudaFree(c->state);
   cudaFree(c->planes);
@@ -1054,10 +1062,22 @@ cells_check(RnnCells *c, int len_y, int len_c, int len_pos)
 static void
 cells_offsets(RnnCells *c, const int *offsets_y, int len_y, const int *offsets_c, int len_c)
 {
-  int off[4 * CELLS_XIN];
-  memcpy(off, offsets_y, 2 * (size_t)len_y * sizeof(int));
-  memcpy(off + 2 * len_y, offsets_c, 2 * (size_t)len_c * sizeof(int));
-  cudaMemcpyAsync(c->off_dev, off, 2 * (size_t)(len_y + len_c) * sizeof(int),
+  int off[4 * CELLS_XIN + 2];
+  off[0] = len_y;
+  off[1] = len_c;
+  memcpy(off + 2, offsets_y, 2 * (size_t)len_y * sizeof(int));
+  memcpy(off + 2 + 2 * len_y, offsets_c, 2 * (size_t)len_c * sizeof(int));
+  /* the element passes the same pattern frame after frame: the tables on the
+     device (constant memory: one set for the library) stay while nothing else
+     has written them */
+  const size_t off_bytes = (2 + 2 * (size_t)(len_y + len_c)) * sizeof(int);
+  if (cells_tables_owner == c && cells_tables_bytes == off_bytes &&
+      !memcmp(cells_tables_key, off, off_bytes))
+    return;
+  cells_tables_owner = c;
+  cells_tables_bytes = off_bytes;
+  memcpy(cells_tables_key, off, off_bytes);
+  cudaMemcpyAsync(c->off_dev, off + 2, 2 * (size_t)(len_y + len_c) * sizeof(int),
       cudaMemcpyHostToDevice, rb_stream);
   /* the same per gathered input, in the order of fill_net_inputs (gstrnnca.c:672-684) */
   int dx[CELLS_XIN], dy[CELLS_XIN], pl[CELLS_XIN], delta[CELLS_XIN];
