@@ -2,6 +2,7 @@
 """bench.py — text-predict BPTT chars/sec on B200 (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config text|rnnca|default|classify|multi]
 
 One "step" is one character position of recur's synchronic text-predict loop
 (reference charmodel-predict.c:293-311) over all streams of this rank:
@@ -33,6 +34,15 @@ barriers and the max-over-ranks of the timings.
 --impl reference times the reference's own CPU implementation of the same
 loop (oracle/_ref, the unmodified reference compiled in place) on the host
 cores: one independent replica per core, bounded sample.
+
+--config selects one of the other BASELINE.json configurations instead (each
+with its own --impl reference arm):
+  rnnca     configs[4]: the cell automaton at 1920 x 1080, a step = a frame
+            (rnn_cells_rnnca_run / _frame); N > 1: ONE automaton, its rows
+            shared by the GPUs (strong scaling)
+  default   configs[0]: one default net through the per-net API
+  classify  configs[2]: 256-channel classify training through the batch calls
+  multi     configs[3]: multi-head charmodel forward, 64 texts
 """
 import argparse
 import ctypes as C
