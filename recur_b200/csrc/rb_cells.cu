@@ -2,26 +2,30 @@
  * PER PIXEL of a video frame (reference gstrnnca.c:805-830, fill_frame), two
  * million of them at 1080p, all with the trainers' weights.  As host RecurNN
  * clones they cost seconds to create and exist only to hold 52 floats of hidden
- * state each; RnnCells keeps just that state, on the device, column-major
- * ([hidden unit][cell]) so that a warp's 32 cells read and write whole lines.
+ * state each; RnnCells keeps just that state, on the device.
  *
  * A frame is one kernel.  Two of them are here:
  *
- *   k_cells_frame_tc (the one that runs): a CTA takes 128 cells at a time.
- *     Each thread builds its cell's input vector (bias, old hidden state,
- *     gathered neighbour bytes, position) straight into the shared-memory image
- *     of a K-major tcgen05 operand, as FP16 hi/lo planes (rb_split.cuh); the
- *     weights sit beside it as the B operand, fetched once per CTA; 3 MMAs per
- *     16 inputs leave the 128 x 64 sums in TMEM, and the same thread reads its
- *     row back, applies the input soft clip (it is linear in the inputs, so it
- *     multiplies the sums), the activation, the output layer and the sigmoid,
- *     and writes the state and the three bytes.  What is left on the CUDA cores
- *     is the gather and the epilogue: the frame is bounded by HBM (state in,
- *     state out) rather than by 19.6 GFLOP of FP32 multiply-adds.
+ *   k_cells_frame_tc (the one that runs).  The cells' hidden state lives in HBM
+ *     in the layout the tensor cores read: per tile of 128 cells the first K
+ *     chunk of a K-major tcgen05 A operand, FP16 hi and lo planes (rb_split.cuh),
+ *     SWIZZLE_128B rows.  One persistent CTA per SM, four kinds of warp, two
+ *     tiles in flight: a thread bulk-copies a tile's state into shared memory;
+ *     gather warps read the neighbourhood's bytes and write the second K chunk
+ *     (the bytes as the FP16 integers they are, 1/255 folded into their
+ *     weights); a thread issues the MMAs (the weights are the B operand, fetched
+ *     once per CTA) into tensor memory; drain warps read the sums back, apply
+ *     the input soft clip (linear in the inputs, so it multiplies the sums), the
+ *     activation, the output layer and the sigmoid, write the three bytes, and
+ *     send the new state back as planes through a staging tile and a bulk
+ *     copy.  The frame is bounded by HBM (state in, state out), not by its
+ *     19.6 GFLOP of multiply-adds.  Several GPUs share a frame by rows and swap
+ *     the rows next to their bands between frames (cells_halo).
  *
- *   k_cells_frame (RECUR_B200_CELLS_FMA=1; a second, independent reading the
- *     tests compare the first with): one thread does a cell in FP32 FMAs in the
- *     reference's order, weights in constant memory.
+ *   k_cells_frame (RnnCells created with RECUR_B200_CELLS_FMA=1; a second,
+ *     independent reading the tests compare the first with): one thread does a
+ *     cell in FP32 FMAs in the reference's order, weights in constant memory,
+ *     state as plain floats, column-major ([hidden unit][cell]).
  */
 #include "rb_internal.h"
 #include "rb_kernels.h"
